@@ -1,0 +1,92 @@
+"""ctypes binding of libazb.so (the C ABI declared in include/azb.h).
+
+There is no fallback: on a CUDA device every hot-path call goes through this library, and a
+missing or stale library raises instead of silently running something else.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import torch
+
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libazb.so")
+ABI_VERSION = 1
+
+F32, BF16, F16, I64 = 0, 1, 2, 3
+DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16, torch.int64: I64}
+
+_lib = None
+
+_SIGNATURES = {
+    "azb_version": (c_int, []),
+    "azb_strerror": (c_char_p, [c_int]),
+    "azb_rng_policy": (c_int, [c_int64, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
+    "azb_step_f32": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
+         c_void_p, c_void_p, c_uint64, c_void_p, c_int64, c_int64, c_int64, c_void_p],
+    ),
+    "azb_advance": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int32, c_void_p]),
+    "azb_init_noise_f32": (c_int, [c_void_p, c_int64, c_float, c_float, c_uint64, c_int64, c_int64, c_int64, c_void_p]),
+}
+
+
+class AzbError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Loads libazb.so once; raises AzbError when it is absent (build with __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AzbError(
+                f"{LIB_PATH} is missing: the sm_100a extension is not built "
+                "(run `python -m azula_b200.csrc.build`); azula_b200 has no CPU/eager fallback for CUDA tensors"
+            )
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            try:
+                fn = getattr(handle, name)
+            except AttributeError as e:  # stale build
+                raise AzbError(f"libazb.so lacks symbol {name}; rebuild it") from e
+            fn.restype, fn.argtypes = res, args
+        if handle.azb_version() != ABI_VERSION:
+            raise AzbError(f"libazb.so ABI {handle.azb_version()} != expected {ABI_VERSION}; rebuild it")
+        _lib = handle
+    return _lib
+
+
+def register(signatures: dict) -> None:
+    """Lets engine modules add the signatures of further entry points before the first load."""
+    _SIGNATURES.update(signatures)
+    global _lib
+    if _lib is not None:
+        for name, (res, args) in signatures.items():
+            fn = getattr(_lib, name)
+            fn.restype, fn.argtypes = res, args
+
+
+def check(code: int, what: str = "") -> None:
+    if code != 0:
+        msg = lib().azb_strerror(code).decode()
+        raise AzbError(f"{what or 'libazb'} failed with code {code}: {msg}")
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def rng_policy(numel: int) -> tuple[int, int]:
+    """(T, offset_inc) of the randn launch ATen would use for numel elements on the current device."""
+    T, inc = c_int64(0), c_int64(0)
+    check(lib().azb_rng_policy(numel, ctypes.byref(T), ctypes.byref(inc)), "azb_rng_policy")
+    return T.value, inc.value

@@ -1,0 +1,2 @@
+r"""Execution engine behind the Azula-compatible surface: coefficient tables, the fused
+graph-captured sampling loop and the native sm_100a ADM backbone."""

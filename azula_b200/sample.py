@@ -1,0 +1,267 @@
+r"""Reverse diffusion samplers (interface of ``azula/sample.py``).
+
+Starting from :math:`x_1 \sim p(X_1)`, a sampler simulates :math:`T` transitions
+:math:`x_s \sim q(X_s \mid x_t)` along a time grid from :py:`start` to :py:`stop`.
+
+Execution model (what differs from the reference): for CUDA float32 inputs and a
+:class:`azula_b200.denoise.Preconditioned` denoiser, ``sampler(x)`` does not run a Python
+loop of ~86 tiny kernels per step (``azula/sample.py:151-157``); it runs the
+:class:`azula_b200.engine.loop.FusedLoop` -- backbone forward plus one hand-written sm_100a
+transition kernel per step, captured in a CUDA graph that is replayed for every step.
+Anything the fused loop cannot express (subclasses overriding :meth:`Sampler.step`, denoiser
+wrappers, inputs that require grad, non-float32 state) goes through :meth:`Sampler.step`,
+whose CUDA implementation still performs the whole affine update in that one kernel.  CPU
+tensors use plain torch arithmetic; there is no CPU kernel and no silent fallback for CUDA
+tensors when ``libazb.so`` is missing (the call raises).
+"""
+
+from __future__ import annotations
+
+__all__ = ["Sampler", "DDPMSampler", "DDIMSampler"]
+
+import abc
+import math
+import torch
+
+from collections.abc import Iterable, Sequence
+from torch import Tensor
+from tqdm import tqdm
+
+from . import _lib
+from .denoise import Denoiser
+from .engine import loop as _loop
+from .engine.table import transition_scalars
+
+
+class Sampler(abc.ABC):
+    r"""Abstract reverse diffusion sampler (``azula/sample.py:54-176``).
+
+    Arguments:
+        start: The starting time :math:`t_T`.
+        stop: The stopping time :math:`t_0`.
+        steps: The number of discretization steps :math:`T` (constant step size).
+        silent: Whether to hide the sampling progress bar or not.
+        dtype: The time data type.
+        device: The time device.
+        graph: Engine knob. :py:`None` captures the fused loop in a CUDA graph when possible,
+            :py:`True` insists (errors surface), :py:`False` launches the fused step eagerly.
+        unroll: Engine knob, number of steps captured per graph (:py:`None` = automatic).
+    """
+
+    denoiser: Denoiser
+
+    def __init__(
+        self,
+        start: float = 1.0,
+        stop: float = 0.0,
+        steps: int = 64,
+        silent: bool = False,
+        dtype: torch.dtype | None = None,
+        device: torch.device | None = None,
+        graph: bool | None = None,
+        unroll: int | None = None,
+    ) -> None:
+        self.start = start
+        self.stop = stop
+        self.steps = steps
+        self.silent = silent
+
+        self.dtype = dtype
+        self.device = device
+
+        self.graph = graph
+        self.unroll = unroll
+        self._loops: dict = {}
+
+    @property
+    def timesteps(self) -> Tensor:
+        r"""The :math:`T + 1` grid points :math:`t_T, \dots, t_0`."""
+        return torch.linspace(self.start, self.stop, self.steps + 1, dtype=self.dtype, device=self.device)
+
+    # ------------------------------------------------------------------------------- init
+    @torch.no_grad()
+    def init(
+        self,
+        shape: Sequence[int],
+        mean: float | Tensor = 0.0,
+        var: float | Tensor = 1.0,
+        **kwargs,
+    ) -> Tensor:
+        r"""Draws :math:`x_{t_T} \sim \mathcal{N}(\alpha_{t_T} \mathbb{E}[X], \alpha_{t_T}^2
+        \mathbb{V}[X] + \sigma_{t_T}^2 I)` (``azula/sample.py:96-128``).
+
+        Arguments:
+            shape: The shape :math:`(*)` of the tensor.
+            mean: The mean of :math:`p(X)`, with shape :math:`()` or :math:`(*)`.
+            var: The variance of :math:`p(X)`, with shape :math:`()` or :math:`(*)`.
+            kwargs: Keyword arguments passed to :func:`torch.Tensor.to`.
+        """
+        t_T = self.timesteps[0]
+
+        alpha_T, sigma_T = self.denoiser.schedule(t_T)
+        alpha_T, sigma_T = alpha_T.to(**kwargs), sigma_T.to(**kwargs)
+
+        mean_T, std_T = alpha_T * mean, torch.sqrt(alpha_T**2 * var + sigma_T**2)
+
+        scalar = mean_T.ndim == 0 and std_T.ndim == 0 and mean_T.dtype == torch.float32 == std_T.dtype
+        numel = math.prod(shape)
+        if alpha_T.is_cuda and scalar and numel > 0:
+            # one kernel: Philox draw (same bits as randn_like) + affine map
+            x = torch.empty(tuple(shape), dtype=torch.float32, device=alpha_T.device)
+            with torch.cuda.device(x.device):
+                gen = _loop.default_generator(x.device)
+                threads, inc = _lib.rng_policy(numel)
+                seed, offset = gen.initial_seed(), gen.get_offset()
+                _lib.check(
+                    _lib.lib().azb_init_noise_f32(
+                        x.data_ptr(), numel, float(mean_T), float(std_T), seed, offset, threads, 0,
+                        _lib.stream_ptr(x.device),
+                    ),
+                    "azb_init_noise_f32",
+                )
+                gen.set_offset(offset + inc)
+            return x
+
+        mean_T, std_T = mean_T.expand(shape), std_T.expand(shape)
+        return mean_T + std_T * torch.randn_like(mean_T)
+
+    def progress_bar(self, it: Iterable) -> Iterable:
+        if torch.is_tensor(it):
+            it = it.unbind()
+        if self.silent:
+            return it
+        return tqdm(it, miniters=1, unit="step", ncols=79, ascii=True)
+
+    # ------------------------------------------------------------------------------- loop
+    def _fusable(self, x: Tensor) -> bool:
+        return False
+
+    @torch.no_grad()
+    def __call__(self, x: Tensor, **kwargs) -> Tensor:
+        r"""Simulates the reverse process from :math:`t_T` to :math:`t_0`
+        (``azula/sample.py:139-161``); never mutates :py:`x`."""
+        if self._fusable(x) and _loop.supports(self, x):
+            with torch.cuda.device(x.device):
+                key = _loop.signature(self, x, kwargs)
+                loop = self._loops.get(key)
+                if loop is None:
+                    self._loops.clear()  # one live graph per sampler keeps device memory bounded
+                    loop = self._loops[key] = _loop.FusedLoop(self, x, kwargs, self.graph, self.unroll)
+                return loop.run(x, kwargs, self.progress_bar)
+
+        time_pairs = self.timesteps.unfold(0, 2, 1).to(device=x.device)
+
+        x_t = x
+        for t, s in self.progress_bar(time_pairs):
+            x_t = self.step(x_t, t, s, **kwargs)
+        return x_t
+
+    def step(self, x_t: Tensor, t: Tensor, s: Tensor, **kwargs) -> Tensor:
+        r"""Simulates the reverse process from :math:`t` to :math:`s`; returns
+        :math:`x_s \sim q(X_s \mid x_t)`."""
+        raise NotImplementedError()
+
+
+class _Ancestral(Sampler):
+    r"""Shared implementation of DDPM/DDIM:
+
+    .. math:: x_s = \alpha_s \mu + \sigma_s \sqrt{1 - \tau'} \, \frac{x_t - \alpha_t \mu}{\sigma_t}
+        + \sigma_s \sqrt{\tau'} \, \varepsilon \qquad
+        \tau = 1 - \frac{\alpha_t^2}{\alpha_s^2} \frac{\sigma_s^2}{\sigma_t^2}
+
+    with :math:`\tau' = \tau` (DDPM) or :math:`\mathrm{clip}(\eta \tau, 0, 1)` (DDIM).
+    """
+
+    def __init__(self, denoiser: Denoiser, **kwargs) -> None:
+        super().__init__(**kwargs)
+
+        self.denoiser = denoiser
+
+    def _eta(self) -> float | None:
+        return None
+
+    def _fusable(self, x: Tensor) -> bool:
+        # a subclass that overrides step() (e.g. guidance samplers) must see its own step run
+        return type(self).step is _Ancestral.step
+
+    def step(self, x_t: Tensor, t: Tensor, s: Tensor, **kwargs) -> Tensor:
+        alpha_s, sigma_s = self.denoiser.schedule(s)
+        alpha_t, sigma_t = self.denoiser.schedule(t)
+        k, n = transition_scalars(alpha_t, sigma_t, alpha_s, sigma_s, self._eta())
+
+        mean = self.denoiser(x_t, t, **kwargs).mean
+
+        if _cuda_step_ok(x_t, mean, alpha_s):
+            return _cuda_step(x_t, mean, alpha_s, k, alpha_t, n)
+
+        x_s = alpha_s * mean
+        x_s = x_s + k * (x_t - alpha_t * mean)
+        x_s = x_s + n * torch.randn_like(x_t)
+        return x_s
+
+
+class DDPMSampler(_Ancestral):
+    r"""DDPM sampler (Ho et al., 2020; ``azula/sample.py:179-216``).
+
+    Arguments:
+        denoiser: A denoiser :math:`q_\phi(X \mid X_t)`.
+        kwargs: Keyword arguments passed to :class:`Sampler`.
+    """
+
+
+class DDIMSampler(_Ancestral):
+    r"""DDIM sampler (Song et al., 2021; ``azula/sample.py:219-261``).
+
+    Arguments:
+        denoiser: A denoiser :math:`q_\phi(X \mid X_t)`.
+        eta: The stochasticity :math:`\eta \in \mathbb{R}_+` (1 = DDPM, 0 = deterministic).
+        kwargs: Keyword arguments passed to :class:`Sampler`.
+    """
+
+    def __init__(self, denoiser: Denoiser, eta: float = 0.0, **kwargs) -> None:
+        super().__init__(denoiser, **kwargs)
+
+        self.eta = eta
+
+    def _eta(self) -> float | None:
+        return self.eta
+
+
+# ---------------------------------------------------------------- eager step on a CUDA device
+
+
+def _cuda_step_ok(x_t: Tensor, mean: Tensor, alpha_s: Tensor) -> bool:
+    return (
+        x_t.is_cuda
+        and x_t.dtype == torch.float32
+        and mean.dtype == torch.float32
+        and mean.shape == x_t.shape
+        and alpha_s.ndim == 0
+        and x_t.numel() > 0
+        and not (torch.is_grad_enabled() and (x_t.requires_grad or mean.requires_grad))
+    )
+
+
+def _cuda_step(x_t: Tensor, mean: Tensor, alpha_s, k, alpha_t, n) -> Tensor:
+    r"""The affine update of one generic step as a single ``azb_step_f32`` launch
+    (row = [0, 1, alpha_s, k, alpha_t, n, 1, inf] so that m = F = the posterior mean)."""
+    with torch.cuda.device(x_t.device):
+        zero = torch.zeros((), dtype=torch.float32, device=x_t.device)
+        cols = [zero, zero + 1, alpha_s, k, alpha_t, n, zero + 1, zero + float("inf")]
+        row = torch.stack([c.to(device=x_t.device, dtype=torch.float32).reshape(()) for c in cols])
+        idx = torch.zeros((), dtype=torch.int32, device=x_t.device)
+        x_c, m_c = x_t.contiguous(), mean.contiguous()
+        out = torch.empty_like(x_c)
+        gen = _loop.default_generator(x_t.device)
+        threads, inc = _lib.rng_policy(x_c.numel())
+        seed, offset = gen.initial_seed(), gen.get_offset()
+        _lib.check(
+            _lib.lib().azb_step_f32(
+                x_c.data_ptr(), m_c.data_ptr(), _lib.F32, x_c.numel(), None, out.data_ptr(), None, _lib.F32,
+                x_c.numel(), 1, row.data_ptr(), idx.data_ptr(), seed, None, offset, threads, 0,
+                _lib.stream_ptr(x_t.device),
+            ),
+            "azb_step_f32",
+        )
+        gen.set_offset(offset + inc)
+    return out.reshape(x_t.shape)
