@@ -22,7 +22,9 @@ from . import table as _table
 _F_DTYPES = (torch.float32, torch.bfloat16, torch.float16)
 
 
-def default_generator(device: torch.device) -> torch.Generator:
+def default_generator(device: torch.device | None = None) -> torch.Generator:
+    torch.cuda.init()  # the generator tuple is empty until CUDA is initialised
+    device = torch.device("cuda") if device is None else torch.device(device)
     index = device.index if device.index is not None else torch.cuda.current_device()
     return torch.cuda.default_generators[index]
 

@@ -12,6 +12,7 @@ from conftest import close, load_golden
 
 from azula_b200 import _lib
 from azula_b200.denoise import KarrasDenoiser
+from azula_b200.engine.loop import default_generator
 from azula_b200.noise import VPSchedule
 from azula_b200.sample import DDIMSampler, DDPMSampler
 from oracle import ref_math as RM
@@ -37,7 +38,7 @@ def test_philox_matches_torch_randn_bits(numel):
         torch.manual_seed(seed)
         for _ in range(skip):
             torch.randn(numel, device=DEV)
-        gen = torch.cuda.default_generators[torch.cuda.current_device()]
+        gen = default_generator()
         offset = gen.get_offset()
         ref = torch.randn(numel, device=DEV)
         T, inc = _lib.rng_policy(numel)
@@ -128,7 +129,7 @@ def test_step_learned_variance_stride_and_inkernel_noise():
     out6 = torch.randn(B, 2 * C, H, W, device=DEV, generator=g)
     vals = [100.0, -99.9, 0.7, 0.2, 0.6, 0.3, 1.0, 1.0]
     torch.manual_seed(21)
-    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    gen = default_generator()
     offset = gen.get_offset()
     eps = torch.randn_like(x)
     got, _ = _call_step(x, out6, _row(vals), None, n_per=C * H * W, batch=B, stride=2 * C * H * W, seed=21, offset=offset)
@@ -170,7 +171,7 @@ def test_fused_loop_vs_oracle_mlp(graph):
             torch.manual_seed(1)
             keep = x1.clone()
             got = smp(x1)
-            end_offset = torch.cuda.default_generators[torch.cuda.current_device()].get_offset()
+            end_offset = default_generator().get_offset()
             torch.manual_seed(1)
             again = smp(x1)
         assert torch.equal(x1, keep)
