@@ -101,6 +101,22 @@ int azb_init_noise_f32(float* x, int64_t numel, float mean_T, float std_T, uint6
                        int64_t offset_host, int64_t rng_threads, int64_t rng_elem_offset,
                        void* stream);
 
+/*
+ * Convolution (3x3 pad 1 / 1x1) or linear layer as an implicit GEMM on tcgen05 tensor cores:
+ * replaces the cuDNN/cuBLAS calls behind nn.Conv2d / nn.Conv1d(k=1) / nn.Linear on the ADM
+ * path (azula/plugins/adm/_src/unet.py:182,207,213-215,277,285,471,602).
+ *   act    NHWC bf16, pixel stride act_ld elements (n images of h x w pixels, c_in channels)
+ *   wpack  bf16 [c_out_rows][taps][k_per_tap], k_per_tap = c_in rounded up to 64, zero padded;
+ *          c_out_rows = c_out rounded up to the N tile (16/32/64/128), zero padded
+ *   out    out_mode 0: bf16 NHWC with pixel stride out_ld (+ residual bf16 NHWC, stride res_ld)
+ *          out_mode 1: fp32 NCHW [n][c_out][h][w]
+ *   bias   fp32 [c_out] or NULL.  A linear layer is taps=1 with h=1, w=rows.
+ */
+int azb_conv_gemm_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld,
+                       const void* wpack, int64_t c_out, int64_t c_out_rows, int taps, int64_t k_per_tap,
+                       const float* bias, const void* residual, int64_t res_ld, void* out, int64_t out_ld,
+                       int out_mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

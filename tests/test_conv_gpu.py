@@ -1,0 +1,135 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution (azb_conv_gemm_bf16) through the C ABI.
+
+Checker: torch fp32 convolution (TF32 off) of the SAME bf16-rounded operands -- the only
+differences left are fp32 accumulation order and the final bf16 rounding of the output, so the
+stated tolerance is 2^-8 relative to the output scale (bf16 has 8 significand bits).
+"""
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from azula_b200.engine import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _exact_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _mk(n, h, w, ci, co, k, seed=0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    x = torch.randn(n, h, w, ci, device=DEV, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(co, ci, k, k, device=DEV, generator=g) / (ci * k * k) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(co, device=DEV, generator=g)
+    return x, wt, b
+
+
+def _ref(x, wt, b, residual=None):
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, padding=wt.shape[-1] // 2)
+    y = y.permute(0, 2, 3, 1)
+    if residual is not None:
+        y = y + residual.float()
+    return y
+
+
+def _check(got, ref, what):
+    err = (got.float() - ref).abs()
+    tol = 2.0**-8 * ref.abs() + 2.0**-8 * ref.abs().mean()
+    bad = (err > tol).sum().item()
+    assert bad == 0, (what, bad, err.max().item(), ref.abs().mean().item())
+
+
+SHAPES = [
+    # n, h, w, c_in, c_out, k
+    (2, 16, 16, 64, 128, 3),
+    (1, 8, 8, 128, 128, 3),      # patch spans 2 images, batch 1 -> TMA out-of-bounds rows
+    (2, 32, 32, 256, 256, 3),
+    (1, 64, 64, 64, 64, 3),      # N tile 64
+    (2, 16, 16, 32, 32, 3),      # C_in < 64: zero-padded K, N tile 32
+    (3, 4, 4, 64, 64, 3),
+    (5, 2, 2, 128, 256, 3),
+    (2, 12, 12, 64, 128, 3),     # extent not a multiple of the patch
+    (1, 20, 24, 192, 128, 3),
+    (2, 16, 16, 128, 384, 1),    # 1x1 (attention qkv / skip connection)
+    (1, 32, 32, 512, 512, 1),
+    (1, 128, 128, 256, 256, 3),
+    (1, 16, 16, 768, 512, 3),    # concatenated input
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_conv_matches_torch(shape):
+    n, h, w, ci, co, k = shape
+    x, wt, b = _mk(*shape)
+    pc = ops.pack_conv(wt.float(), b)
+    got = ops.conv(x, pc)
+    torch.cuda.synchronize()
+    assert got.shape == (n, h, w, co)
+    _check(got, _ref(x, wt, b), shape)
+
+
+def test_conv_residual_and_strided_output():
+    """Epilogue adds a residual and writes into a channel slice of a wider (concat) buffer."""
+    n, h, w, ci, co = 2, 16, 16, 128, 128
+    x, wt, b = _mk(n, h, w, ci, co, 3, seed=3)
+    res = torch.randn(n, h, w, co, device=DEV).to(torch.bfloat16)
+    wide = torch.zeros(n, h, w, co + 64, device=DEV, dtype=torch.bfloat16)
+    view = wide[..., 64:]
+    ops.conv(x, ops.pack_conv(wt.float(), b), out=view, residual=res)
+    torch.cuda.synchronize()
+    _check(view, _ref(x, wt, b, res), "residual+slice")
+    assert (wide[..., :64] == 0).all()
+    # strided input: read the convolution input from a channel slice as well
+    xin = torch.zeros(n, h, w, ci + 64, device=DEV, dtype=torch.bfloat16)
+    xin[..., :ci] = x
+    got = ops.conv(xin[..., :ci], ops.pack_conv(wt.float(), b))
+    _check(got, _ref(x, wt, b), "strided input")
+
+
+def test_conv_network_output_nchw_fp32():
+    """The UNet's last conv (256 -> 6, learn_var) written as fp32 NCHW, N tile 16."""
+    n, h, w, ci, co = 2, 32, 32, 256, 6
+    x, wt, b = _mk(n, h, w, ci, co, 3, seed=5)
+    got = ops.conv(x, ops.pack_conv(wt.float(), b), nchw_f32=True)
+    torch.cuda.synchronize()
+    ref = _ref(x, wt, b).permute(0, 3, 1, 2)
+    assert got.shape == (n, co, h, w) and got.dtype == torch.float32
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4), (got - ref).abs().max().item()
+
+
+def test_linear_layer_rows():
+    """nn.Linear as a 1-tap GEMM over rows (time-embedding MLP, attention projections)."""
+    for rows, ci, co in ((1, 256, 1024), (16, 1024, 512), (300, 64, 192)):
+        g = torch.Generator(device=DEV).manual_seed(rows)
+        x = torch.randn(rows, ci, device=DEV, generator=g).to(torch.bfloat16)
+        wt = (torch.randn(co, ci, device=DEV, generator=g) / ci**0.5).to(torch.bfloat16)
+        b = torch.randn(co, device=DEV, generator=g)
+        got = ops.conv(x, ops.pack_conv(wt.float(), b))
+        torch.cuda.synchronize()
+        _check(got, F.linear(x.float(), wt.float(), b), (rows, ci, co))
+
+
+def test_conv_throughput_report():
+    """Not a pass/fail perf gate: prints achieved TFLOP/s of the heaviest ADM shapes."""
+    for (n, h, w, ci, co) in ((4, 256, 256, 256, 256), (16, 64, 64, 512, 512), (16, 16, 16, 1024, 1024)):
+        x, wt, b = _mk(n, h, w, ci, co, 3)
+        pc = ops.pack_conv(wt.float(), b)
+        out = torch.empty(n, h, w, co, device=DEV, dtype=torch.bfloat16)
+        for _ in range(3):
+            ops.conv(x, pc, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.conv(x, pc, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        tf = 2.0 * n * h * w * co * ci * 9 / (ms * 1e-3) / 1e12
+        print(f"conv3x3 {n}x{h}x{w} {ci}->{co}: {ms:.3f} ms, {tf:.0f} TFLOP/s")
