@@ -8,9 +8,10 @@ Nothing here falls back to torch arithmetic: a missing library raises.
 
 from __future__ import annotations
 
+import math
 import torch
 
-from ctypes import c_float, c_int, c_int64, c_void_p
+from ctypes import POINTER, byref, c_float, c_int, c_int64, c_void_p
 from dataclasses import dataclass
 from torch import Tensor
 
@@ -22,6 +23,25 @@ _lib.register({
         [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int64,
          c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p],
     ),
+    "azb_gn_stats_workspace": (c_int, [c_int64, c_int64, c_int64, c_int64, POINTER(c_int64)]),
+    "azb_gn_stats_bf16": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_void_p],
+    ),
+    "azb_gn_apply_bf16": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+         c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p],
+    ),
+    "azb_attention_bf16": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+         c_void_p],
+    ),
+    "azb_im2col3x3_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "azb_timestep_features_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_float, c_void_p, c_void_p]),
+    "azb_linear_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "azb_add_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
 })
 
 
@@ -102,3 +122,146 @@ def conv(x: Tensor, pc: PackedConv, out: Tensor | None = None, residual: Tensor 
         "azb_conv_gemm_bf16",
     )
     return out
+
+
+GN_GROUPS = 32
+GN_EPS = 1e-5
+
+
+class GroupNormScratch:
+    r"""Reusable workspace of the GroupNorm reduction (partials, per-image counters, statistics)."""
+
+    def __init__(self, device, max_n: int = 64, max_partial: int = 1 << 22) -> None:
+        self.partial = torch.empty(max_partial, dtype=torch.float32, device=device)
+        self.counters = torch.zeros(max_n, dtype=torch.int32, device=device)
+
+    def need(self, n: int, hw: int, c: int, groups: int) -> None:
+        want = c_int64(0)
+        _lib.check(_lib.lib().azb_gn_stats_workspace(n, hw, c, groups, byref(want)))
+        if want.value > self.partial.numel() or n > self.counters.numel():
+            raise RuntimeError("GroupNormScratch too small")
+
+
+def gn_stats(x: Tensor, scratch: GroupNormScratch, stats: Tensor | None = None, groups: int = GN_GROUPS,
+             eps: float = GN_EPS) -> Tensor:
+    r"""(N, H, W, C) or (N, T, C) bf16 -> stats (N, groups, 2) = (mean, rstd) in fp32."""
+    n, c = x.shape[0], x.shape[-1]
+    hw = math.prod(x.shape[1:-1])
+    scratch.need(n, hw, c, groups)
+    if stats is None:
+        stats = torch.empty(n, groups, 2, dtype=torch.float32, device=x.device)
+    _lib.check(
+        _lib.lib().azb_gn_stats_bf16(
+            x.data_ptr(), _ld(x), n, hw, c, groups, eps, scratch.partial.data_ptr(), stats.data_ptr(),
+            scratch.counters.data_ptr(), _lib.stream_ptr(x.device),
+        ),
+        "azb_gn_stats_bf16",
+    )
+    return stats
+
+
+def gn_apply(x: Tensor, out: Tensor | None = None, stats: Tensor | None = None, gamma: Tensor | None = None,
+             beta: Tensor | None = None, scale_shift: Tensor | None = None, ss_step: Tensor | None = None,
+             ss_step_stride: int = 0, silu: bool = True, mode: int = 0, groups: int = GN_GROUPS) -> Tensor:
+    r"""Normalise + modulate + activate + resample in one pass (``azb_gn_apply_bf16``).
+
+    x (N, H, W, C) bf16.  ``scale_shift`` is fp32 (rows, 2C) with rows in {1, N} (or a per-step table
+    indexed by the device counter ``ss_step``).  ``mode``: 0 same, 1 nearest x2, 2 average pool 2x2.
+    """
+    n, h, w, c = x.shape
+    ho, wo = (h * 2, w * 2) if mode == 1 else (h // 2, w // 2) if mode == 2 else (h, w)
+    if out is None:
+        out = torch.empty(n, ho, wo, c, dtype=torch.bfloat16, device=x.device)
+    ss_stride = 0
+    if scale_shift is not None:
+        assert scale_shift.dtype == torch.float32 and scale_shift.shape[-1] == 2 * c and scale_shift.is_contiguous()
+        if ss_step is None and scale_shift.ndim == 2 and scale_shift.shape[0] == n and n > 1:
+            ss_stride = 2 * c
+    _lib.check(
+        _lib.lib().azb_gn_apply_bf16(
+            x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), n, h, w, c, groups, _lib.ptr(stats), _lib.ptr(gamma),
+            _lib.ptr(beta), _lib.ptr(scale_shift), ss_stride, _lib.ptr(ss_step), ss_step_stride, int(silu), mode,
+            _lib.stream_ptr(x.device),
+        ),
+        "azb_gn_apply_bf16",
+    )
+    return out
+
+
+def attention(qkv: Tensor, heads: int, new_order: bool = False, out: Tensor | None = None) -> Tensor:
+    r"""(N, T, 3C) bf16 -> (N, T, C) bf16, legacy (per-head q|k|v) or new (q|k|v blocks) channel order."""
+    n, t, c3 = qkv.shape
+    c = c3 // 3
+    d = c // heads
+    if out is None:
+        out = torch.empty(n, t, c, dtype=torch.bfloat16, device=qkv.device)
+    hs, kd, vd = (d, c, 2 * c) if new_order else (3 * d, d, 2 * d)
+    _lib.check(
+        _lib.lib().azb_attention_bf16(
+            qkv.data_ptr(), qkv.stride(1), out.data_ptr(), out.stride(1), n, t, heads, d, hs, kd, vd,
+            _lib.stream_ptr(qkv.device),
+        ),
+        "azb_attention_bf16",
+    )
+    return out
+
+
+def im2col3x3(x: Tensor, k_pad: int = 64, out: Tensor | None = None) -> Tensor:
+    r"""fp32 NCHW network input -> bf16 (N, H, W, k_pad) patches for the first 3x3 convolution."""
+    n, c, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(n, h, w, k_pad, dtype=torch.bfloat16, device=x.device)
+    _lib.check(
+        _lib.lib().azb_im2col3x3_f32(x.data_ptr(), out.data_ptr(), n, c, h, w, k_pad, _lib.stream_ptr(x.device)),
+        "azb_im2col3x3_f32",
+    )
+    return out
+
+
+def pack_first_conv(weight: Tensor, bias: Tensor, k_pad: int = 64) -> PackedConv:
+    r"""(C_out, C, 3, 3) -> a 1-tap GEMM weight over the im2col patches (k = tap*C + c)."""
+    c_out, c = weight.shape[:2]
+    flat = torch.zeros(c_out, k_pad, dtype=torch.float32, device=weight.device)
+    flat[:, : 9 * c] = weight.permute(0, 2, 3, 1).reshape(c_out, 9 * c)
+    return pack_conv(flat, bias)
+
+
+def timestep_features(t: Tensor, dim: int, out: Tensor | None = None, max_period: float = 10000.0) -> Tensor:
+    rows = t.numel()
+    assert t.dtype in (torch.int64, torch.float32) and t.is_contiguous()
+    if out is None:
+        out = torch.empty(rows, dim, dtype=torch.float32, device=t.device)
+    _lib.check(
+        _lib.lib().azb_timestep_features_f32(
+            t.data_ptr(), _lib.DTYPE_CODE[t.dtype], rows, dim, max_period, out.data_ptr(), _lib.stream_ptr(t.device)
+        ),
+        "azb_timestep_features_f32",
+    )
+    return out
+
+
+def linear_f32(x: Tensor, weight: Tensor, bias: Tensor | None, silu_in: bool = False, out: Tensor | None = None) -> Tensor:
+    m, k = x.shape
+    nn_ = weight.shape[0]
+    assert x.dtype == torch.float32 and weight.dtype == torch.float32 and x.is_contiguous() and weight.is_contiguous()
+    if out is None:
+        out = torch.empty(m, nn_, dtype=torch.float32, device=x.device)
+    _lib.check(
+        _lib.lib().azb_linear_f32(
+            x.data_ptr(), weight.data_ptr(), _lib.ptr(bias), out.data_ptr(), m, nn_, k, int(silu_in),
+            _lib.stream_ptr(x.device),
+        ),
+        "azb_linear_f32",
+    )
+    return out
+
+
+def add_rows(y: Tensor, table: Tensor, idx: Tensor) -> Tensor:
+    _lib.check(
+        _lib.lib().azb_add_rows_f32(
+            y.data_ptr(), table.data_ptr(), idx.data_ptr(), y.shape[0], y.shape[1], _lib.stream_ptr(y.device)
+        ),
+        "azb_add_rows_f32",
+    )
+    return y

@@ -117,6 +117,58 @@ int azb_conv_gemm_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t
                        const float* bias, const void* residual, int64_t res_ld, void* out, int64_t out_ld,
                        int out_mode, void* stream);
 
+/*
+ * GroupNorm statistics over NHWC bf16 (N, HW, C), pixel stride ld: stats[n][g] = {mean, rstd}.
+ * With azb_gn_apply_bf16 this replaces native_group_norm + SiLU + scale/shift + resampling
+ * (azula/plugins/adm/_src/nn.py:80-87, _src/unet.py:177-181,203-207,229-243,276,599-601).
+ * `partial` is a float workspace of azb_gn_stats_workspace() elements; `counters` int32[n],
+ * zero-initialised once (the kernel leaves it zeroed).  Deterministic (no float atomics).
+ */
+int azb_gn_stats_workspace(int64_t n, int64_t hw, int64_t c, int64_t groups, int64_t* partial_floats);
+int azb_gn_stats_bf16(const void* x, int64_t ld, int64_t n, int64_t hw, int64_t c, int64_t groups, float eps,
+                      float* partial, float* stats, int32_t* counters, void* stream);
+
+/*
+ * y = act((x - mean) * rstd * gamma + beta) * (1 + scale) + shift ... folded to act(A*x + B):
+ *   stats NULL          -> identity transform (used to resample the residual branch)
+ *   scale_shift         -> fp32 rows [scale(C) | shift(C)]; image n uses row n*ss_stride (0 = shared);
+ *                          when ss_step is given, *ss_step * ss_step_stride is added (per-step table)
+ *   silu                -> SiLU after the affine map
+ *   mode                -> 0 same size, 1 nearest x2 upsample, 2 2x2 average pool (of the activated values)
+ * x (N,H,W,C) stride x_ld -> y (N,Ho,Wo,C) stride y_ld, both bf16 NHWC.
+ */
+int azb_gn_apply_bf16(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t n, int64_t h, int64_t w,
+                      int64_t c, int64_t groups, const float* stats, const float* gamma, const float* beta,
+                      const float* scale_shift, int64_t ss_stride, const int32_t* ss_step, int64_t ss_step_stride,
+                      int silu, int mode, void* stream);
+
+/*
+ * softmax(q k^T / sqrt(d)) v per (image, head) without materialising the T x T logits
+ * (QKVAttentionLegacy / QKVAttention, azula/plugins/adm/_src/unet.py:328-345,361-381).
+ * qkv (N, T, ld) bf16; head hd reads q/k/v at channel hd*head_stride + {0, k_delta, v_delta};
+ * out (N, T, out_ld) bf16, head hd at channel hd*d.  d in {16, 32, 64, 128}.
+ */
+int azb_attention_bf16(const void* qkv, int64_t ld, void* out, int64_t out_ld, int64_t n, int64_t t,
+                       int64_t heads, int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta,
+                       void* stream);
+
+/* im2col of the fp32 NCHW network input for the first 3x3 conv (_src/unet.py:471):
+ * out[n][h][w][k] bf16, k = (kh*3+kw)*c + ch for k < 9c, zero up to k_pad. */
+int azb_im2col3x3_f32(const float* x, void* out, int64_t n, int64_t c, int64_t h, int64_t w, int64_t k_pad,
+                      void* stream);
+
+/* Sinusoidal timestep features [cos | sin] (_src/nn.py:90-108); t is int64 or fp32 [rows]. */
+int azb_timestep_features_f32(const void* t, int t_dtype, int64_t rows, int64_t dim, float max_period,
+                              float* out, void* stream);
+
+/* y[m][n] = b[n] + sum_k act(x[m][k]) w[n][k] in fp32 (act = SiLU when silu_in): the time-embedding
+ * MLP and the per-block emb_layers (_src/unet.py:458-462,198-204). */
+int azb_linear_f32(const float* x, const float* w, const float* b, float* y, int64_t m, int64_t n, int64_t k,
+                   int silu_in, void* stream);
+
+/* y[r][:] += table[idx[r]][:] (class-label embedding, _src/unet.py:621-623). */
+int azb_add_rows_f32(float* y, const float* table, const int64_t* idx, int64_t rows, int64_t dim, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
