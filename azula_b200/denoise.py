@@ -115,6 +115,11 @@ class Preconditioned(Denoiser):
         r"""How this denoiser invokes its backbone; the fused loop calls it directly."""
         return self.backbone(x_in, time, **kwargs)
 
+    def fusable(self) -> bool:
+        r"""Whether :meth:`forward` is the stock one, i.e. fully described by :meth:`coefficients`
+        (a subclass overriding :meth:`forward` must see its own code run)."""
+        return type(self).forward is Preconditioned.forward
+
     def forward(self, x_t: Tensor, t: Tensor, **kwargs) -> DiracPosterior:
         alpha_t, sigma_t = self.schedule(t)
         alpha_t, sigma_t = _unsqueeze_like(alpha_t, x_t.ndim), _unsqueeze_like(sigma_t, x_t.ndim)

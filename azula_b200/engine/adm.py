@@ -1,0 +1,407 @@
+r"""Native sm_100a executor of the ADM U-Net layout (:mod:`azula_b200.plugins.adm.unet`).
+
+Replaces ``UNetModel.forward`` of the reference (``azula/plugins/adm/_src/unet.py:605-634``
+and the blocks it calls, ``:227-247,290-296,328-345``; ~10^3 ATen/cuDNN launches per forward,
+fp32 NCHW, every GroupNorm / SiLU / scale-shift / residual / resample a separate HBM round
+trip) by a *plan*: a flat list of C-ABI launches (``include/azb.h``) over statically allocated
+NHWC bf16 buffers, built once per input signature.
+
+Data layout in HBM
+    * activations: NHWC bf16, pixel stride ``ld`` >= C, so producers write straight into channel
+      slices of the decoder's concatenation buffers -- ``torch.cat`` (``_src/unet.py:631``)
+      disappears: encoder block *i* stores its output in the right half of the buffer that
+      decoder block *L-1-i* normalises and convolves, the previous decoder block in the left half;
+    * weights: bf16 ``[C_out][tap][C_in]`` (K-major, zero padded to the 64-element TMA box),
+      packed once per parameter version; biases, GroupNorm affine and embeddings fp32;
+    * the 42 per-block ``emb_layers`` linears are concatenated into one fp32 matrix, evaluated
+      by one launch per forward; blocks read their ``[scale | shift]`` slice in place.
+
+Per residual unit: stats -> apply(+SiLU, +resample) -> conv3x3 (tcgen05) -> stats ->
+apply(+scale/shift +SiLU, in place) -> conv3x3 (tcgen05, + fused skip residual); attention unit:
+stats -> apply -> qkv GEMM -> flash attention -> proj GEMM (+ fused residual).  No allocation,
+synchronisation or host read happens while a plan runs, so it is CUDA-graph capturable.
+"""
+
+from __future__ import annotations
+
+import math
+import torch
+
+from ctypes import byref, c_int64
+from torch import Tensor
+
+from .. import _lib
+from . import ops
+
+_MAX_PLANS = 2
+
+
+class Packed:
+    r"""Kernel-layout copy of a model's parameters on one device."""
+
+    def __init__(self, model, device: torch.device) -> None:
+        lay = model.layout
+        if not lay.scale_shift:
+            raise NotImplementedError("native ADM path needs use_scale_shift_norm=True (all ADM cards use it)")
+        p = {k: v.detach().to(device) for k, v in model.named_parameters()}
+        f32 = lambda key: p[key].to(torch.float32).contiguous()  # noqa: E731
+        self.fingerprint = fingerprint(model)
+        self.k_pad = -(-9 * lay.in_channels // 64) * 64
+        self.time0 = (f32("time_embed.0.weight"), f32("time_embed.0.bias"))
+        self.time2 = (f32("time_embed.2.weight"), f32("time_embed.2.bias"))
+        self.labels = f32("label_emb.weight") if lay.num_classes is not None else None
+        self.unit: dict[str, dict] = {}
+        emb_w, emb_b, offset = [], [], 0
+        for u in lay.units():
+            if u.kind == "stem":
+                w = ops.pack_first_conv(p[u.path + ".weight"].float(), p[u.path + ".bias"], self.k_pad)
+                self.unit[u.path] = {"conv": w}
+            elif u.kind == "res":
+                self.unit[u.path] = {
+                    "gn1": (f32(u.path + ".in_layers.0.weight"), f32(u.path + ".in_layers.0.bias")),
+                    "conv1": ops.pack_conv(p[u.path + ".in_layers.2.weight"], p[u.path + ".in_layers.2.bias"]),
+                    "gn2": (f32(u.path + ".out_layers.0.weight"), f32(u.path + ".out_layers.0.bias")),
+                    "conv2": ops.pack_conv(p[u.path + ".out_layers.3.weight"], p[u.path + ".out_layers.3.bias"]),
+                    "skip": ops.pack_conv(p[u.path + ".skip_connection.weight"], p[u.path + ".skip_connection.bias"])
+                    if u.cin != u.cout else None,
+                    "emb_offset": offset,
+                }
+                emb_w.append(f32(u.path + ".emb_layers.1.weight"))
+                emb_b.append(f32(u.path + ".emb_layers.1.bias"))
+                offset += 2 * u.cout
+            else:
+                if u.cin // u.heads not in (16, 32, 64, 128):
+                    raise NotImplementedError(f"attention head width {u.cin // u.heads} not in (16, 32, 64, 128)")
+                self.unit[u.path] = {
+                    "gn": (f32(u.path + ".norm.weight"), f32(u.path + ".norm.bias")),
+                    "qkv": ops.pack_conv(p[u.path + ".qkv.weight"], p[u.path + ".qkv.bias"]),
+                    "proj": ops.pack_conv(p[u.path + ".proj_out.weight"], p[u.path + ".proj_out.bias"]),
+                }
+        self.emb_total = offset
+        self.emb_w, self.emb_b = torch.cat(emb_w).contiguous(), torch.cat(emb_b).contiguous()
+        self.out_gn = (f32("out.0.weight"), f32("out.0.bias"))
+        self.out_conv = ops.pack_conv(p["out.2.weight"], p["out.2.bias"])
+
+
+def fingerprint(model) -> tuple:
+    return tuple((q.data_ptr(), q._version) for q in model.parameters())
+
+
+class _Arena:
+    r"""Plan-build-time allocator of bf16 scratch with reuse (one stream => sequential lifetimes)."""
+
+    def __init__(self, device) -> None:
+        self.device = device
+        self.idle: list[Tensor] = []
+        self.owner: dict[int, Tensor] = {}
+        self.bytes = 0
+
+    def take(self, *shape: int) -> Tensor:
+        need = math.prod(shape)
+        fit = [t for t in self.idle if t.numel() >= need]
+        if fit:
+            flat = min(fit, key=Tensor.numel)
+            self.idle = [t for t in self.idle if t is not flat]
+        else:
+            flat = torch.empty(need, dtype=torch.bfloat16, device=self.device)
+            self.bytes += 2 * need
+        view = flat[:need].view(shape)
+        self.owner[id(view)] = flat
+        return view
+
+    def give(self, view: Tensor) -> None:
+        self.idle.append(self.owner.pop(id(view)))
+
+
+class Plan:
+    r"""The launch list of one (batch, height, width, embedding rows) signature."""
+
+    def __init__(self, model, packed: Packed, n: int, h: int, w: int, rows: int, device: torch.device) -> None:
+        self.lay = lay = model.layout
+        self.packed = packed
+        self.n, self.h, self.w, self.rows, self.device = n, h, w, rows, device
+        self.lib = _lib.lib()
+        self.ops: list[tuple] = []
+        self.meta: list[tuple] = []
+        self.keep: list[Tensor] = []  # everything the launch list points into
+        arena = self.arena = _Arena(device)
+        f32 = dict(dtype=torch.float32, device=device)
+
+        # ---- embedding path (fp32): features -> MLP -> (+ label rows) -> all emb_layers at once
+        D = lay.embed_dim
+        self.feat = torch.empty(rows, lay.model_channels, **f32)
+        self.emb1 = torch.empty(rows, D, **f32)
+        self.emb = torch.empty(rows, D, **f32)
+        self.emb_all = torch.empty(rows, packed.emb_total, **f32)
+
+        # ---- GroupNorm workspace sized for the largest site
+        self.gn_partial_need = 0
+        self.counters = torch.zeros(max(n, 1), dtype=torch.int32, device=device)
+
+        # ---- concatenation buffers of the decoder
+        L = len(lay.encoder)
+        assert len(lay.decoder) == L
+        # spatial size of each encoder output
+        sizes, hh, ww = [], h, w
+        for block in lay.encoder:
+            if block[0].kind == "res" and block[0].resample == 2:
+                if hh % 2 or ww % 2:
+                    raise ValueError(f"spatial size {(h, w)} is not divisible by the network's downsampling")
+                hh, ww = hh // 2, ww // 2
+            sizes.append((hh, ww, block[-1].cout))
+        self.cat = []
+        carried = lay.middle[-1].cout
+        for j, block in enumerate(lay.decoder):
+            sh, sw, sc = sizes[L - 1 - j]
+            assert block[0].cin == carried + sc, (block[0], carried, sc)
+            self.cat.append((arena.take(n, sh, sw, carried + sc), carried))
+            carried = block[-1].cout
+        for buf, _ in self.cat:  # concat buffers live for the whole forward
+            arena.owner.pop(id(buf))
+        self.patches = arena.take(n, h, w, packed.k_pad)
+        arena.owner.pop(id(self.patches))
+        self.final = arena.take(n, h, w, lay.final_channels)
+        arena.owner.pop(id(self.final))
+
+        def skip_slot(i: int) -> Tensor:
+            buf, left = self.cat[L - 1 - i]
+            return buf[..., left:]
+
+        # ---- encoder
+        cur = None
+        for i, block in enumerate(lay.encoder):
+            cur = self._block(block, cur, skip_slot(i))
+        # ---- middle
+        cur = self._block(lay.middle, cur, self.cat[0][0][..., : self.cat[0][1]])
+        # ---- decoder
+        for j, block in enumerate(lay.decoder):
+            if j + 1 < L:
+                nxt, left = self.cat[j + 1]
+                dest = nxt[..., :left]
+            else:
+                dest = self.final
+            cur = self._block(block, self.cat[j][0], dest)
+        # ---- head: GroupNorm + SiLU in place; the last convolution is bound per call (output tensor)
+        st = self._stats(self.final)
+        self._apply(self.final, self.final, st, packed.out_gn, None, True, 0)
+
+        self.gn_partial = torch.empty(max(self.gn_partial_need, 1), **f32)
+        self._bind_partial()
+        self.scratch_bytes = arena.bytes
+
+    # ------------------------------------------------------------------------ plan building
+    def _emit(self, kind: str, flops: float, nbytes: float, fn, *args) -> None:
+        r"""Queues one launch; ``flops`` / ``nbytes`` are its ALGORITHMIC work."""
+        self.ops.append((fn, args))
+        self.meta.append((kind, flops, nbytes))
+
+    def _conv(self, x: Tensor, pc: ops.PackedConv, out: Tensor, residual: Tensor | None = None) -> None:
+        n, h, w, _ = x.shape
+        self.keep += [x, out, pc.w] + ([residual] if residual is not None else []) + ([pc.bias] if pc.bias is not None else [])
+        flops = 2.0 * n * h * w * pc.c_out * pc.taps * pc.c_in
+        nbytes = 2.0 * (n * h * w * (pc.c_in + pc.c_out * (2 if residual is not None else 1)) + pc.c_out * pc.taps * pc.c_in)
+        self._emit(
+            "conv3x3" if pc.taps == 9 else "conv1x1", flops, nbytes,
+            self.lib.azb_conv_gemm_bf16, x.data_ptr(), n, h, w, pc.c_in, ops._ld(x), pc.w.data_ptr(), pc.c_out,
+            pc.c_out_rows, pc.taps, pc.k_per_tap, _lib.ptr(pc.bias), _lib.ptr(residual),
+            0 if residual is None else ops._ld(residual), out.data_ptr(), ops._ld(out), 0,
+        )
+
+    def _stats(self, x: Tensor) -> Tensor:
+        n, c = x.shape[0], x.shape[-1]
+        hw = math.prod(x.shape[1:-1])
+        want = c_int64(0)
+        _lib.check(self.lib.azb_gn_stats_workspace(n, hw, c, ops.GN_GROUPS, byref(want)), "azb_gn_stats_workspace")
+        self.gn_partial_need = max(self.gn_partial_need, want.value)
+        stats = torch.empty(n, ops.GN_GROUPS, 2, dtype=torch.float32, device=self.device)
+        self.keep += [x, stats]
+        self._emit(
+            "gn_stats", 0.0, 2.0 * n * hw * c,
+            self.lib.azb_gn_stats_bf16, x.data_ptr(), ops._ld(x), n, hw, c, ops.GN_GROUPS, ops.GN_EPS, "partial",
+            stats.data_ptr(), self.counters.data_ptr(),
+        )
+        return stats
+
+    def _bind_partial(self) -> None:
+        ptr = self.gn_partial.data_ptr()
+        self.ops = [(fn, tuple(ptr if isinstance(a, str) else a for a in args)) for fn, args in self.ops]
+
+    def _apply(self, x: Tensor, out: Tensor, stats: Tensor | None, affine, emb_offset: int | None, silu: bool,
+               mode: int) -> None:
+        n, h, w, c = x.shape
+        gamma, beta = affine if affine is not None else (None, None)
+        ss_ptr, ss_stride = None, 0
+        if emb_offset is not None:
+            ss_ptr = self.emb_all.data_ptr() + 4 * emb_offset
+            ss_stride = self.packed.emb_total if (self.rows == n and n > 1) else 0
+        self.keep += [x, out] + ([stats] if stats is not None else []) + ([gamma, beta] if gamma is not None else [])
+        px_out = n * h * w * (4 if mode == 1 else 1) // (4 if mode == 2 else 1)
+        self._emit(
+            "gn_apply", 0.0, 2.0 * c * (n * h * w + px_out),
+            self.lib.azb_gn_apply_bf16, x.data_ptr(), ops._ld(x), out.data_ptr(), ops._ld(out), n, h, w, c,
+            ops.GN_GROUPS, _lib.ptr(stats), _lib.ptr(gamma), _lib.ptr(beta), ss_ptr, ss_stride, None, 0, int(silu), mode,
+        )
+
+    def _block(self, block, x: Tensor | None, dest: Tensor) -> Tensor:
+        r"""Emits the units of one block; the last unit writes ``dest``."""
+        arena = self.arena
+        temp = None
+        for k, u in enumerate(block):
+            last = k + 1 == len(block)
+            if u.kind == "stem":
+                self._conv(self.patches, self.packed.unit[u.path]["conv"], dest)
+                return dest
+            n, h, w, _ = x.shape
+            ho, wo = (2 * h, 2 * w) if u.resample == 1 else (h // 2, w // 2) if u.resample == 2 else (h, w)
+            out = dest if last else arena.take(n, ho, wo, u.cout)
+            if u.kind == "res":
+                self._res(u, x, out)
+            else:
+                self._attn(u, x, out)
+            if temp is not None:
+                arena.give(temp)
+            temp = None if last else out
+            x = out
+        return dest
+
+    def _res(self, u, x: Tensor, out: Tensor) -> None:
+        r"""``ResBlock._forward`` (``_src/unet.py:227-247``) with ``use_scale_shift_norm``."""
+        w_, arena = self.packed.unit[u.path], self.arena
+        n, ho, wo, _ = out.shape
+        st1 = self._stats(x)
+        h1 = arena.take(n, ho, wo, u.cin)
+        self._apply(x, h1, st1, w_["gn1"], None, True, u.resample)  # SiLU(GN(x)) then up / down
+        if u.resample:
+            xr = arena.take(n, ho, wo, u.cin)
+            self._apply(x, xr, None, None, None, False, u.resample)  # x_upd on the raw input
+        else:
+            xr = x
+        h2 = arena.take(n, ho, wo, u.cout)
+        self._conv(h1, w_["conv1"], h2)
+        arena.give(h1)
+        st2 = self._stats(h2)
+        self._apply(h2, h2, st2, w_["gn2"], w_["emb_offset"], True, 0)  # SiLU(GN(h) (1 + scale) + shift), in place
+        if w_["skip"] is not None:
+            sk = arena.take(n, ho, wo, u.cout)
+            self._conv(xr, w_["skip"], sk)
+        else:
+            sk = xr
+        self._conv(h2, w_["conv2"], out, residual=sk)  # skip_connection(x) + h
+        arena.give(h2)
+        if sk is not xr:
+            arena.give(sk)
+        if xr is not x:
+            arena.give(xr)
+
+    def _attn(self, u, x: Tensor, out: Tensor) -> None:
+        r"""``AttentionBlock._forward`` (``_src/unet.py:290-296``)."""
+        w_, arena = self.packed.unit[u.path], self.arena
+        n, h, w, c = x.shape
+        st = self._stats(x)
+        y = arena.take(n, h, w, c)
+        self._apply(x, y, st, w_["gn"], None, False, 0)
+        qkv = arena.take(n, h, w, 3 * c)
+        self._conv(y, w_["qkv"], qkv)
+        arena.give(y)
+        a = arena.take(n, h, w, c)
+        d = c // u.heads
+        hs, kd, vd = (d, c, 2 * c) if self.lay.new_attention_order else (3 * d, d, 2 * d)
+        self.keep += [qkv, a]
+        t = h * w
+        self._emit("attention", 4.0 * n * u.heads * t * t * d, 2.0 * n * t * 4 * c, self.lib.azb_attention_bf16, qkv.data_ptr(), 3 * c, a.data_ptr(), c, n, h * w, u.heads, d, hs, kd, vd)
+        arena.give(qkv)
+        self._conv(a, w_["proj"], out, residual=x)
+        arena.give(a)
+
+    # ------------------------------------------------------------------------------ running
+    @property
+    def launches(self) -> int:
+        r"""Kernels launched by one :meth:`run` (without the label lookup)."""
+        return len(self.ops) + 6
+
+    def profile(self) -> dict[str, dict]:
+        r"""Times every queued launch with CUDA events on the current stream (buffers keep whatever
+        the last :meth:`run` left in them); returns per kernel kind: launches, ms, flops, bytes."""
+        s = _lib.stream_ptr(self.device)
+        events = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.ops) + 1)]
+        events[0].record()
+        for i, (fn, args) in enumerate(self.ops):
+            _lib.check(fn(*args, s), fn.__name__)
+            events[i + 1].record()
+        torch.cuda.synchronize(self.device)
+        table: dict[str, dict] = {}
+        for i, (kind, flops, nbytes) in enumerate(self.meta):
+            row = table.setdefault(kind, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            row["launches"] += 1
+            row["ms"] += events[i].elapsed_time(events[i + 1])
+            row["flops"] += flops
+            row["bytes"] += nbytes
+        return table
+
+    def run(self, x: Tensor, timesteps: Tensor, y: Tensor | None, out: Tensor) -> Tensor:
+        lib, pk, lay = self.lib, self.packed, self.lay
+        s = _lib.stream_ptr(self.device)
+        chk = _lib.check
+        n, c, h, w = x.shape
+        chk(lib.azb_im2col3x3_f32(x.data_ptr(), self.patches.data_ptr(), n, c, h, w, pk.k_pad, s), "azb_im2col3x3_f32")
+        rows, D = self.rows, lay.embed_dim
+        chk(lib.azb_timestep_features_f32(timesteps.data_ptr(), _lib.DTYPE_CODE[timesteps.dtype], rows,
+                                          lay.model_channels, 10000.0, self.feat.data_ptr(), s), "azb_timestep_features_f32")
+        chk(lib.azb_linear_f32(self.feat.data_ptr(), pk.time0[0].data_ptr(), pk.time0[1].data_ptr(),
+                               self.emb1.data_ptr(), rows, D, lay.model_channels, 0, s), "azb_linear_f32")
+        chk(lib.azb_linear_f32(self.emb1.data_ptr(), pk.time2[0].data_ptr(), pk.time2[1].data_ptr(),
+                               self.emb.data_ptr(), rows, D, D, 1, s), "azb_linear_f32")
+        if y is not None:
+            chk(lib.azb_add_rows_f32(self.emb.data_ptr(), pk.labels.data_ptr(), y.data_ptr(), rows, D, s), "azb_add_rows_f32")
+        chk(lib.azb_linear_f32(self.emb.data_ptr(), pk.emb_w.data_ptr(), pk.emb_b.data_ptr(), self.emb_all.data_ptr(),
+                               rows, pk.emb_total, D, 1, s), "azb_linear_f32")
+        for fn, args in self.ops:
+            rc = fn(*args, s)
+            if rc:
+                chk(rc, fn.__name__)
+        oc = pk.out_conv
+        chk(lib.azb_conv_gemm_bf16(self.final.data_ptr(), n, h, w, oc.c_in, ops._ld(self.final), oc.w.data_ptr(),
+                                   oc.c_out, oc.c_out_rows, oc.taps, oc.k_per_tap, _lib.ptr(oc.bias), None, 0,
+                                   out.data_ptr(), 0, 1, s), "azb_conv_gemm_bf16")
+        return out
+
+
+def forward(model, x: Tensor, timesteps: Tensor, y: Tensor | None = None) -> Tensor:
+    r"""``UNetModel.forward`` on a CUDA device: (N, C, H, W) any float dtype -> (N, C', H, W) same dtype."""
+    device = x.device
+    lay = model.layout
+    if x.ndim != 4 or x.shape[1] != lay.in_channels:
+        raise ValueError(f"expected an input of shape (N, {lay.in_channels}, H, W), got {tuple(x.shape)}")
+    n, _, h, w = x.shape
+    with torch.cuda.device(device):
+        cache = model._native
+        packed = cache.get("packed")
+        if packed is None or packed.fingerprint != fingerprint(model) or packed.emb_w.device != device:
+            cache.clear()
+            packed = cache["packed"] = Packed(model, device)
+
+        timesteps = timesteps.reshape(-1)
+        if timesteps.numel() not in (1, n):
+            raise ValueError(f"timesteps must have 1 or {n} elements, got {timesteps.numel()}")
+        if y is not None and timesteps.numel() != n:
+            timesteps = timesteps.expand(n)
+        tdtype = torch.float32 if timesteps.is_floating_point() else torch.int64
+        timesteps = timesteps.to(device=device, dtype=tdtype).contiguous()
+        rows = timesteps.numel()
+        if y is not None:
+            y = y.reshape(-1).to(device=device, dtype=torch.int64).contiguous()
+            if y.numel() != n:
+                raise ValueError(f"y must have {n} elements")
+
+        key = (n, h, w, rows)
+        plan = cache.get(key)
+        if plan is None:
+            plans = [k for k in cache if k != "packed"]
+            while len(plans) >= _MAX_PLANS:
+                del cache[plans.pop(0)]
+            plan = cache[key] = Plan(model, packed, n, h, w, rows, device)
+
+        xin = x.to(torch.float32).contiguous()
+        out = torch.empty((n, lay.out_channels, h, w), dtype=torch.float32, device=device)
+        plan.run(xin, timesteps, y, out)
+    return out.to(x.dtype)

@@ -40,7 +40,7 @@ def supports(sampler, x: Tensor) -> bool:
         and x.numel() > 0
         and not x.requires_grad
         and isinstance(den, Preconditioned)
-        and type(den).forward is Preconditioned.forward
+        and den.fusable()
         and get_module_dtype(den.backbone) in (None, *_F_DTYPES)
     )
 

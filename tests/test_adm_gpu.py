@@ -1,0 +1,136 @@
+"""GPU parity of the native ADM backbone (azula_b200.engine.adm, every launch through the C ABI)
+against the oracle's fp32 restatement of the reference forward (oracle/adm_unet.py), evaluated on
+the same device with TF32 off, and against the reference-generated fixtures in tests/golden/.
+
+Stated bf16 tolerance.  The native path keeps activations in bf16 (8 significand bits) with fp32
+accumulation, so outputs are compared relative to the output scale: relative L2 error <= 1e-2
+and 99.9th-percentile absolute error <= 3 % of the output standard deviation per forward (the
+reference's own low-precision bar is p99 < 1e-3 / max < 1e-2 for fp16 on O(1e-1) outputs,
+tests/test_nn_unet.py:78-91).  End to end (sampler output in [-1, 1]) the bar is a mean absolute
+error <= 2e-2.  The fp32 north-star tolerance (rtol 1e-3 / atol 1e-5) is what the step kernel
+meets bit-exactly given equal backbone outputs (tests/test_step_gpu.py).
+"""
+
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import adm_unet as AU
+from oracle import ref_math as RM
+from oracle.gen_golden_cfg import MID_ADM, TINY_ADM
+
+from azula_b200.plugins import adm
+from azula_b200.sample import DDIMSampler, DDPMSampler
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _exact_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        yield
+
+
+def _seeded(cfg, seed=1234):
+    den = adm.make_model(**cfg).eval()
+    sd = AU.seeded_state(den.backbone.state_dict(), seed=seed)
+    den.backbone.load_state_dict(sd)
+    return den.to(DEV), {k: v.to(DEV) for k, v in sd.items()}
+
+
+def _report(got, ref, what, rel_l2=1e-2, p999=3e-2):
+    err = (got.float() - ref.float()).abs().flatten()
+    scale = ref.float().std().item()
+    l2 = (err.square().sum().sqrt() / ref.float().square().sum().sqrt()).item()
+    q = err.kthvalue(max(1, int(0.999 * err.numel()))).values.item() / scale
+    print(f"{what}: rel_l2 {l2:.2e}  p99.9/std {q:.2e}  max/std {err.max().item() / scale:.2e}")
+    assert l2 <= rel_l2 and q <= p999, (what, l2, q)
+
+
+@pytest.mark.parametrize("tag,cfg", [("adm_tiny", TINY_ADM), ("adm_mid", MID_ADM)])
+def test_native_forward_vs_oracle_and_golden(tag, cfg):
+    g = load_golden(tag)
+    den, sd = _seeded(cfg)
+    tab = AU.block_table(**cfg)
+    x = g["x"].to(DEV)
+    for tstep in (3, 500, 999):
+        ts = torch.full((x.shape[0],), tstep, dtype=torch.int64, device=DEV)
+        got = den.backbone(x, ts)
+        assert got.dtype == torch.float32 and got.shape == g[f"unet_t{tstep}"].shape
+        _report(got, AU.forward(sd, tab, x, ts), f"{tag} t={tstep} vs oracle")
+        _report(got, g[f"unet_t{tstep}"].to(DEV), f"{tag} t={tstep} vs reference fixture")
+    # shared timestep (shape (1,)) == per-sample timesteps with equal values, bit for bit
+    a = den.backbone(x, torch.tensor([500], device=DEV))
+    b = den.backbone(x, torch.full((x.shape[0],), 500, device=DEV))
+    assert torch.equal(a, b)
+    # deterministic
+    assert torch.equal(a, den.backbone(x, torch.tensor([500], device=DEV)))
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 32, 32), (1, 3, 48, 16), (5, 3, 16, 16)])
+def test_native_forward_other_shapes(shape):
+    """Batch sizes that do not fill an M tile, non-square and non-power-of-two extents."""
+    den, sd = _seeded(TINY_ADM, seed=7)
+    tab = AU.block_table(**TINY_ADM)
+    x = torch.randn(shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    ts = torch.randint(0, 1000, (shape[0],), device=DEV)
+    _report(den.backbone(x, ts), AU.forward(sd, tab, x, ts), f"shape {shape}")
+
+
+def test_native_class_conditional_new_attention_order():
+    cfg = dict(TINY_ADM, num_classes=10, use_new_attention_order=True)
+    den, sd = _seeded(cfg, seed=9)
+    tab = AU.block_table(**cfg)
+    x = torch.randn(4, 3, 16, 16, device=DEV)
+    ts = torch.tensor([10, 200, 600, 999], device=DEV)
+    y = torch.tensor([1, 0, 9, 4], device=DEV)
+    _report(den.backbone(x, ts, y=y), AU.forward(sd, tab, x, ts, y), "class-conditional")
+    # the shared-timestep form used by the sampling loop
+    _report(den.backbone(x, ts[:1], y=y), AU.forward(sd, tab, x, ts[:1].expand(4), y), "class-conditional, shared t")
+
+
+def test_weights_are_repacked_after_an_update():
+    den, _ = _seeded(TINY_ADM)
+    x = torch.randn(2, 3, 16, 16, device=DEV)
+    ts = torch.tensor([5], device=DEV)
+    a = den.backbone(x, ts)
+    sd2 = {k: v.to(DEV) for k, v in AU.seeded_state(den.backbone.state_dict(), seed=99).items()}
+    den.backbone.load_state_dict(sd2)
+    b = den.backbone(x, ts)
+    assert not torch.equal(a, b)
+    _report(b, AU.forward(sd2, AU.block_table(**TINY_ADM), x, ts.expand(2)), "after load_state_dict")
+
+
+@pytest.mark.parametrize("tag,cfg,steps", [("adm_tiny", TINY_ADM, 4), ("adm_mid", MID_ADM, 2)])
+def test_denoiser_and_sampler_end_to_end(tag, cfg, steps):
+    g = load_golden(tag)
+    den, sd = _seeded(cfg)
+    x = g["x"].to(DEV)
+    q = den(x, torch.tensor(0.6, device=DEV))
+    err = (q.mean - g["den_mean_t06"].to(DEV)).abs().mean().item()
+    print(f"{tag} posterior mean: mean|d| {err:.2e}")
+    assert err <= 2e-2
+    for kind, S in (("ddim", DDIMSampler), ("ddpm", DDPMSampler)):
+        for graph in (False, True):
+            smp = S(den, steps=steps, silent=True, graph=graph)
+            x1 = g[f"{kind}_x1"].to(DEV)
+            # DDPM noise comes from the CUDA Philox stream, not the CPU generator of the fixture:
+            # compare against the oracle loop driven with torch.randn_like on the same device and seed
+            torch.manual_seed(0)
+            x0 = smp(x1)
+            tab = AU.block_table(**cfg)
+            sched = lambda t: RM.vp_alpha_sigma(t, 1e-2, 1e-2)  # noqa: E731
+            net = lambda xx, tt, y=None: AU.forward(sd, tab, xx, tt)  # noqa: E731
+            sig = RM.adm_sigmas().to(DEV)
+            mean = lambda xx, tt: RM.adm_mean_var(net, sched, sig, xx, tt)[0]  # noqa: E731
+            torch.manual_seed(0)
+            ref = RM.sample_loop(mean, sched, x1, steps=steps, eta=0.0 if kind == "ddim" else None)
+            err = (x0 - ref).abs().mean().item()
+            print(f"{tag} {kind} graph={graph}: mean|d| {err:.2e} max|d| {(x0 - ref).abs().max().item():.2e}")
+            assert err <= 2e-2, (tag, kind, graph, err)
+            if kind == "ddim":
+                fix = (x0 - g["ddim_x0"].to(DEV)).abs().mean().item()
+                assert fix <= 2e-2, (tag, "fixture", fix)
