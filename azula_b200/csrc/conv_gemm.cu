@@ -8,13 +8,19 @@
 // Data layout: activations NHWC bf16 (pixel stride `ld` elements), weights bf16 [C_out][taps][K_tap]
 // with K_tap = C_in rounded up to 64 (zero padded), accumulation fp32 in tensor memory.
 //
-// Per CTA: one 128-pixel x BLOCK_N output tile.  The 128 pixels are a (BN images x BH rows x BW
-// columns) patch, so the A operand of filter tap (kh, kw) is ONE 4-d TMA box load at spatial offset
-// (kh-1, kw-1); out-of-image coordinates are zero-filled by the TMA unit, which implements the
-// padding for free.  TMA writes both operands with the 128-byte swizzle the tensor core expects;
-// a single elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) into TMEM; mbarriers form a
-// STAGES-deep producer/consumer ring; the epilogue reads TMEM with tcgen05.ld, adds bias and the
-// residual, and stores bf16 NHWC (or fp32 NCHW for the network output).
+// Persistent, warp-specialised kernel, one CTA per SM, tiles handed out round-robin:
+//   warp 0      TMA producer.  One 128-pixel x BLOCK_N output tile = (BN images x BH rows x BW columns)
+//               of pixels, so the A operand of filter tap (kh, kw) is ONE 4-d TMA box load at spatial
+//               offset (kh-1, kw-1); out-of-image coordinates are zero-filled by the TMA unit, which
+//               implements the padding for free.  128-byte swizzle, STAGES-deep mbarrier ring.
+//   warp 1      MMA issuer: a single elected thread issues tcgen05.mma (M=128, N=BLOCK_N, K=16) into one
+//               of TWO accumulator stages in tensor memory, so the epilogue of tile i overlaps the main
+//               loop of tile i+1.  BLOCK_N = 256 keeps the shared-memory operand traffic of the SS-mode
+//               MMA at 96 B/clk (128 B/clk is the SM limit that a 128x128 tile sits on).
+//   warps 2..9  epilogue: tcgen05.ld (warp w reads TMEM lanes 32*(w%4)...), bias, residual, bf16 NHWC
+//               store (or fp32 NCHW for the network output); optionally per-channel sums / sums of
+//               squares of the stored values for the GroupNorm that consumes this tensor (see
+//               azb_gn_finalize_f32), which removes a full read pass over the activation.
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -24,12 +30,16 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 128 bytes of bf16 = one swizzle row
 constexpr int UMMA_K = 16;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int SMEM_BUDGET = 200 * 1024;
 
 struct ConvParams {
     int N, H, W;              // activation extent (pixels)
     int BW, BH, BN;           // patch shape of one M tile (BW*BH*BN == 128)
     int tiles_w, tiles_h;     // tiles per row / column of one image group
     int n_tiles;              // tiles along C_out
+    int total_tiles;
     int taps, ksize, pad;     // 9,3,1 or 1,1,0
     int kb_per_tap;           // K blocks (of 64) per tap
     int c_out;                // valid output channels
@@ -39,178 +49,274 @@ struct ConvParams {
     void* out;
     int64_t out_ld;           // NHWC pixel stride (mode 0)
     int out_mode;             // 0: bf16 NHWC, 1: fp32 NCHW
+    float2* colsum;           // [m_tiles * 4][c_out] per-(32-row slab, channel) {sum, sum of squares}, or null
 };
 
 template <int BLOCK_N>
-struct Smem {
+struct Cfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES > 8 ? 8 : SMEM_BUDGET / STAGE_BYTES;
+    static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;  // columns of one accumulator stage
+    static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+    static constexpr int COLS_PER_WARP = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;  // two warps share a lane quarter
+    static constexpr int CHUNK = COLS_PER_WARP < 32 ? 16 : 32;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;
 };
 
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(128) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                                                         const __grid_constant__ CUtensorMap tmap_b,
-                                                         const ConvParams p) {
-    using S = Smem<BLOCK_N>;
-    constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-    constexpr int CHUNK = BLOCK_N < 32 ? 16 : 32;
+__device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& n_tile, int& w0, int& h0, int& n0) {
+    // C_out tiles fastest so that CTAs working at the same time share the activation patch in L2
+    n_tile = tile % p.n_tiles;
+    int m_tile = tile / p.n_tiles;
+    const int tw = m_tile % p.tiles_w;
+    m_tile /= p.tiles_w;
+    const int th = m_tile % p.tiles_h;
+    const int tn = m_tile / p.tiles_h;
+    w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+}
+
+// Column sums over the 32 rows held by a warp: v[i] of lane l is element (row l, column i).  After the
+// butterfly, lane l holds the sum of column l.  31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = hi ? v[i] : v[i + n];
+            const float keep = hi ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                const __grid_constant__ CUtensorMap tmap_b,
+                                                                const ConvParams p) {
+    using C = Cfg<BLOCK_N>;
+    constexpr int STAGES = C::STAGES;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ __align__(8) uint64_t bar_full[STAGES];
     __shared__ __align__(8) uint64_t bar_empty[STAGES];
-    __shared__ __align__(8) uint64_t bar_acc;
+    __shared__ __align__(8) uint64_t bar_acc_full[2];
+    __shared__ __align__(8) uint64_t bar_acc_empty[2];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    // tile coordinates: C_out tiles fastest so that neighbouring CTAs share the activation patch in L2
-    const int n_tile = blockIdx.x % p.n_tiles;
-    int m_tile = blockIdx.x / p.n_tiles;
-    const int tw = m_tile % p.tiles_w;
-    m_tile /= p.tiles_w;
-    const int th = m_tile % p.tiles_h;
-    const int tn = m_tile / p.tiles_h;
-    const int w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
-
-    if (warp == 1 && lane == 0) {
+    if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             tc::mbar_init(tc::smem_u32(&bar_full[s]), 1);
             tc::mbar_init(tc::smem_u32(&bar_empty[s]), 1);
         }
-        tc::mbar_init(tc::smem_u32(&bar_acc), 1);
-        tc::fence_barrier_init();
-    }
-    if (warp == 0) {
-        if (lane == 0) {
-            tc::prefetch_tmap(&tmap_a);
-            tc::prefetch_tmap(&tmap_b);
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(tc::smem_u32(&bar_acc_full[s]), 1);
+            tc::mbar_init(tc::smem_u32(&bar_acc_empty[s]), EPI_WARPS);
         }
-        __syncwarp();
-        tc::tmem_alloc(tc::smem_u32(&tmem_slot), TMEM_COLS);
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tmap_a);
+        tc::prefetch_tmap(&tmap_b);
+    }
+    if (warp == 1) {
+        tc::tmem_alloc(tc::smem_u32(&tmem_slot), C::TMEM_COLS);
         tc::tmem_relinquish();
     }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tmem_acc = tmem_slot;
+    const uint32_t tmem_base = tmem_slot;
 
     const int num_kb = p.taps * p.kb_per_tap;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
         // ===== TMA producer =====
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t parity = ((kb / STAGES) & 1) ^ 1;
-            tc::mbar_wait(tc::smem_u32(&bar_empty[s]), parity);
-            const int tap = kb / p.kb_per_tap;
-            const int cb = kb - tap * p.kb_per_tap;
-            const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-            const uint32_t full = tc::smem_u32(&bar_full[s]);
-            const uint32_t a_dst = smem_base + s * S::STAGE_BYTES;
-            const uint32_t b_dst = a_dst + S::A_BYTES;
-            tc::mbar_expect_tx(full, S::STAGE_BYTES);
-            tc::tma_load_4d(a_dst, &tmap_a, full, cb * BLOCK_K, w0 + kw - p.pad, h0 + kh - p.pad, n0);
-            tc::tma_load_2d(b_dst, &tmap_b, full, kb * BLOCK_K, n_tile * BLOCK_N);
-        }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
-        constexpr uint32_t idesc = tc::idesc_bf16_f32(BLOCK_M, BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t parity = (kb / STAGES) & 1;
-            tc::mbar_wait(tc::smem_u32(&bar_full[s]), parity);
-            tc::fence_after_sync();
-            const uint32_t a_src = smem_base + s * S::STAGE_BYTES;
-            const uint64_t da = tc::smem_desc_sw128(a_src);
-            const uint64_t db = tc::smem_desc_sw128(a_src + S::A_BYTES);
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
-                tc::mma_f16_ss(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-            }
-            tc::mma_commit(tc::smem_u32(&bar_empty[s]));  // frees the smem slot when these MMAs retire
-        }
-        tc::mma_commit(tc::smem_u32(&bar_acc));  // accumulator complete
-    }
-    __syncwarp();
-
-    // ===== epilogue: all four warps, warp w owns TMEM lanes [32w, 32w+32) =====
-    tc::mbar_wait(tc::smem_u32(&bar_acc), 0);
-    tc::fence_after_sync();
-
-    const int row = warp * 32 + lane;  // row of the tile = TMEM lane
-    const int bw = row % p.BW;
-    const int bh = (row / p.BW) % p.BH;
-    const int bn = row / (p.BW * p.BH);
-    const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
-    const bool row_ok = (n < p.N) && (h < p.H) && (w < p.W);
-    const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
-    const int col_base = n_tile * BLOCK_N;
-
-#pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += CHUNK) {
-        uint32_t acc[CHUNK];
-        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
-        const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-        if constexpr (CHUNK == 32) {
-            tc::tmem_ld_32x32b_x32(taddr, acc);
-        } else {
-            tc::tmem_ld_32x32b_x16(taddr, acc);
-        }
-        tc::tmem_ld_wait();
-        const int col0 = col_base + c0;
-        if (!row_ok || col0 >= p.c_out) continue;
-
-        if (p.out_mode == 0) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + col0;
-            const __nv_bfloat16* rsd = p.res ? p.res + pix * p.res_ld + col0 : nullptr;
-#pragma unroll
-            for (int v = 0; v < CHUNK / 8; ++v) {
-                if (col0 + v * 8 >= p.c_out) break;
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(acc[v * 8 + j]);
-                if (p.bias) {
-                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + v * 8));
-                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + v * 8) + 1);
-                    f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
-                    f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
+        if (lane == 0) {
+            int it = 0;  // running k-block counter across tiles
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int n_tile, w0, h0, n0;
+                tile_coords(p, tile, n_tile, w0, h0, n0);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t parity = ((it / STAGES) & 1) ^ 1;
+                    tc::mbar_wait(tc::smem_u32(&bar_empty[s]), parity);
+                    const int tap = kb / p.kb_per_tap;
+                    const int cb = kb - tap * p.kb_per_tap;
+                    const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+                    const uint32_t full = tc::smem_u32(&bar_full[s]);
+                    const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
+                    const uint32_t b_dst = a_dst + C::A_BYTES;
+                    tc::mbar_expect_tx(full, C::STAGE_BYTES);
+                    tc::tma_load_4d(a_dst, &tmap_a, full, cb * BLOCK_K, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+                    tc::tma_load_2d(b_dst, &tmap_b, full, kb * BLOCK_K, n_tile * BLOCK_N);
                 }
-                if (rsd) {
-                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(rsd + v * 8));
-                    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::idesc_bf16_f32(BLOCK_M, BLOCK_N);
+            int it = 0, local = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+                const int as = local & 1;
+                // wait until the epilogue has drained this accumulator stage (first use passes immediately)
+                tc::mbar_wait(tc::smem_u32(&bar_acc_empty[as]), ((local >> 1) & 1) ^ 1);
+                tc::fence_after_sync();
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(as * C::ACC_COLS);
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t parity = (it / STAGES) & 1;
+                    tc::mbar_wait(tc::smem_u32(&bar_full[s]), parity);
+                    tc::fence_after_sync();
+                    const uint32_t a_src = smem_base + s * C::STAGE_BYTES;
+                    const uint64_t da = tc::smem_desc_sw128(a_src);
+                    const uint64_t db = tc::smem_desc_sw128(a_src + C::A_BYTES);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        f[2 * j] += bf16_bits_to_f32(rr[j] & 0xffffu);
-                        f[2 * j + 1] += bf16_bits_to_f32(rr[j] >> 16);
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
+                        tc::mma_f16_ss(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    }
+                    tc::mma_commit(tc::smem_u32(&bar_empty[s]));  // frees the smem slot when these MMAs retire
+                }
+                tc::mma_commit(tc::smem_u32(&bar_acc_full[as]));  // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue: warp e reads TMEM lanes [32*(warp%4), +32) and one half of the columns =====
+        const int e = warp - 2;
+        const int quarter = warp & 3;
+        const int half = (BLOCK_N >= 64) ? (e >> 2) : 0;
+        const bool active = (BLOCK_N >= 64) || (e < 4);
+        constexpr int CHUNK = C::CHUNK;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+            const int as = local & 1;
+            int n_tile, w0, h0, n0;
+            tile_coords(p, tile, n_tile, w0, h0, n0);
+            const int row = quarter * 32 + lane;  // row of the tile = TMEM lane
+            const int bw = row % p.BW;
+            const int bh = (row / p.BW) % p.BH;
+            const int bn = row / (p.BW * p.BH);
+            const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
+            const bool row_ok = (n < p.N) && (h < p.H) && (w < p.W);
+            const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
+            const int col_base = n_tile * BLOCK_N + half * C::COLS_PER_WARP;
+
+            tc::mbar_wait(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
+            tc::fence_after_sync();
+
+            if (active) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < C::COLS_PER_WARP; c0 += CHUNK) {
+                    uint32_t acc[CHUNK];
+                    __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                           (uint32_t)(as * C::ACC_COLS + half * C::COLS_PER_WARP + c0);
+                    if constexpr (CHUNK == 32) {
+                        tc::tmem_ld_32x32b_x32(taddr, acc);
+                    } else {
+                        tc::tmem_ld_32x32b_x16(taddr, acc);
+                    }
+                    const int col0 = col_base + c0;
+                    // residual loads are issued before the TMEM wait so both latencies overlap
+                    uint4 rsd[CHUNK / 8];
+                    const bool use_res = p.res != nullptr && row_ok && p.out_mode == 0;
+                    if (use_res) {
+                        const __nv_bfloat16* rp = p.res + pix * p.res_ld + col0;
+#pragma unroll
+                        for (int v = 0; v < CHUNK / 8; ++v)
+                            rsd[v] = (col0 + v * 8 < p.c_out) ? __ldg(reinterpret_cast<const uint4*>(rp + v * 8))
+                                                              : make_uint4(0, 0, 0, 0);
+                    }
+                    tc::tmem_ld_wait();
+                    if (col0 >= p.c_out) continue;
+
+                    if (p.out_mode == 0) {
+                        float f[CHUNK];
+#pragma unroll
+                        for (int j = 0; j < CHUNK; ++j) f[j] = __uint_as_float(acc[j]);
+                        if (p.bias) {
+#pragma unroll
+                            for (int v = 0; v < CHUNK / 4; ++v) {
+                                if (col0 + v * 4 < p.c_out) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + v * 4));
+                                    f[4 * v] += b.x, f[4 * v + 1] += b.y, f[4 * v + 2] += b.z, f[4 * v + 3] += b.w;
+                                }
+                            }
+                        }
+                        if (use_res) {
+#pragma unroll
+                            for (int v = 0; v < CHUNK / 8; ++v) {
+                                const uint32_t rr[4] = {rsd[v].x, rsd[v].y, rsd[v].z, rsd[v].w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    f[v * 8 + 2 * j] += bf16_bits_to_f32(rr[j] & 0xffffu);
+                                    f[v * 8 + 2 * j + 1] += bf16_bits_to_f32(rr[j] >> 16);
+                                }
+                            }
+                        }
+                        // round to the stored precision; statistics are taken of the STORED values
+                        uint32_t packed[CHUNK / 2];
+#pragma unroll
+                        for (int j = 0; j < CHUNK / 2; ++j) {
+                            __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                            packed[j] = *reinterpret_cast<uint32_t*>(&t);
+                        }
+                        if (row_ok) {
+                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + col0;
+#pragma unroll
+                            for (int v = 0; v < CHUNK / 8; ++v) {
+                                if (col0 + v * 8 < p.c_out)
+                                    *reinterpret_cast<uint4*>(dst + v * 8) =
+                                        make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+                            }
+                        }
+                        if constexpr (CHUNK == 32) {
+                            if (p.colsum) {
+                                float s1[32], s2[32];
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const float a = row_ok ? bf16_bits_to_f32(packed[j] & 0xffffu) : 0.f;
+                                    const float b = row_ok ? bf16_bits_to_f32(packed[j] >> 16) : 0.f;
+                                    s1[2 * j] = a, s1[2 * j + 1] = b;
+                                    s2[2 * j] = a * a, s2[2 * j + 1] = b * b;
+                                }
+                                const float cs = warp_transpose_sum32(s1, lane);
+                                const float cq = warp_transpose_sum32(s2, lane);
+                                const int m_tile = tile / p.n_tiles;
+                                if (col0 + lane < p.c_out)
+                                    p.colsum[((int64_t)m_tile * 4 + quarter) * p.c_out + col0 + lane] = make_float2(cs, cq);
+                            }
+                        }
+                    } else if (row_ok) {
+                        // fp32 NCHW: out[n][c][h][w]; consecutive lanes are consecutive w => coalesced per channel
+                        float* dst = reinterpret_cast<float*>(p.out);
+                        const int64_t plane = (int64_t)p.H * p.W;
+                        const int64_t base = (int64_t)n * p.c_out * plane + (int64_t)h * p.W + w;
+#pragma unroll
+                        for (int j = 0; j < CHUNK; ++j) {
+                            const int c = col0 + j;
+                            if (c < p.c_out)
+                                dst[base + c * plane] = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + c) : 0.0f);
+                        }
                     }
                 }
-                uint4 o;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
-                o.x = *reinterpret_cast<uint32_t*>(&t0), o.y = *reinterpret_cast<uint32_t*>(&t1);
-                o.z = *reinterpret_cast<uint32_t*>(&t2), o.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(dst + v * 8) = o;
             }
-        } else {
-            // fp32 NCHW: out[n][c][h][w]; consecutive lanes are consecutive w => coalesced per channel
-            float* dst = reinterpret_cast<float*>(p.out);
-            const int64_t plane = (int64_t)p.H * p.W;
-            const int64_t base = (int64_t)n * p.c_out * plane + (int64_t)h * p.W + w;
-#pragma unroll
-            for (int j = 0; j < CHUNK; ++j) {
-                const int c = col0 + j;
-                if (c < p.c_out) dst[base + c * plane] = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + c) : 0.0f);
-            }
+            // release the accumulator stage to the MMA warp
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[as]));
         }
     }
 
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_acc, TMEM_COLS);
+    if (warp == 1) tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------ host: tensor maps + launch
@@ -251,26 +357,42 @@ int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, c
     return r == CUDA_SUCCESS ? AZB_OK : AZB_E_SHAPE;
 }
 
-template <int BLOCK_N, int STAGES>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, int64_t grid, cudaStream_t s) {
-    constexpr int smem = STAGES * Smem<BLOCK_N>::STAGE_BYTES + 1024;
+int sm_count() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    return sms;
+}
+
+template <int BLOCK_N>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t s) {
+    constexpr int smem = Cfg<BLOCK_N>::SMEM;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, STAGES>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    conv_gemm_kernel<BLOCK_N, STAGES><<<(unsigned)grid, 128, smem, s>>>(ta, tb, p);
+    const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+    conv_gemm_kernel<BLOCK_N><<<(unsigned)grid, THREADS, smem, s>>>(ta, tb, p);
     return azb_launch_status();
 }
 
-}  // namespace
+void patch_shape(int64_t h, int64_t w, int& bw, int& bh, int& bn) {
+    // patch: as wide as the image up to 16 columns, then rows, then images
+    bw = 1;
+    while (bw < 16 && bw < w) bw <<= 1;
+    bh = 1;
+    while (bw * bh < BLOCK_M && bh < h) bh <<= 1;
+    bn = BLOCK_M / (bw * bh);
+}
 
-extern "C" int azb_conv_gemm_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld,
-                                  const void* wpack, int64_t c_out, int64_t c_out_rows, int taps, int64_t k_per_tap,
-                                  const float* bias, const void* residual, int64_t res_ld, void* out, int64_t out_ld,
-                                  int out_mode, void* stream) {
+int conv_impl(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld, const void* wpack,
+              int64_t c_out, int64_t c_out_rows, int taps, int64_t k_per_tap, const float* bias, const void* residual,
+              int64_t res_ld, void* out, int64_t out_ld, int out_mode, float* colsum, void* stream) {
     AZB_CHECK_PTR(act);
     AZB_CHECK_PTR(wpack);
     AZB_CHECK_PTR(out);
@@ -283,23 +405,31 @@ extern "C" int azb_conv_gemm_bf16(const void* act, int64_t n, int64_t h, int64_t
         return AZB_E_ALIGN;
     if (bias && !azb_aligned(bias, 16)) return AZB_E_ALIGN;
     if (out_mode != 0 && out_mode != 1) return AZB_E_SHAPE;
-
-    int block_n = c_out_rows >= 128 ? 128 : c_out_rows >= 64 ? 64 : c_out_rows >= 32 ? 32 : 16;
-    if (c_out_rows % block_n || c_out_rows < c_out) return AZB_E_SHAPE;
+    if (colsum && (out_mode != 0 || !azb_aligned(colsum, 8))) return AZB_E_SHAPE;
 
     ConvParams p{};
     p.N = (int)n, p.H = (int)h, p.W = (int)w;
-    // patch: as wide as the image up to 16 columns, then rows, then images
-    int bw = 1;
-    while (bw < 16 && bw < w) bw <<= 1;
-    int bh = 1;
-    while (bw * bh < BLOCK_M && bh < h) bh <<= 1;
-    int bn = BLOCK_M / (bw * bh);
-    p.BW = bw, p.BH = bh, p.BN = bn;
-    p.tiles_w = (int)((w + bw - 1) / bw);
-    p.tiles_h = (int)((h + bh - 1) / bh);
-    const int64_t tiles_n_img = (n + bn - 1) / bn;
+    patch_shape(h, w, p.BW, p.BH, p.BN);
+    p.tiles_w = (int)((w + p.BW - 1) / p.BW);
+    p.tiles_h = (int)((h + p.BH - 1) / p.BH);
+    const int64_t tiles_n_img = (n + p.BN - 1) / p.BN;
+    const int64_t m_tiles = (int64_t)p.tiles_w * p.tiles_h * tiles_n_img;
+
+    // N tile: the widest one that divides the (padded) row count and still gives every SM a tile
+    int block_n = 16;
+    const int sms = sm_count();
+    const int cand[5] = {256, 128, 64, 32, 16};
+    for (int i = 0; i < 5; ++i) {
+        if (c_out_rows % cand[i]) continue;
+        block_n = cand[i];
+        if (m_tiles * (c_out_rows / cand[i]) >= (sms * 3) / 4 || cand[i] <= 64) break;
+    }
+    if (colsum && block_n < 64) return AZB_E_SHAPE;
+    if (c_out_rows % block_n || c_out_rows < c_out) return AZB_E_SHAPE;
+
     p.n_tiles = (int)(c_out_rows / block_n);
+    if (m_tiles * p.n_tiles > 0x7fffffffLL) return AZB_E_SHAPE;
+    p.total_tiles = (int)(m_tiles * p.n_tiles);
     p.taps = taps, p.ksize = taps == 9 ? 3 : 1, p.pad = taps == 9 ? 1 : 0;
     p.kb_per_tap = (int)(k_per_tap / BLOCK_K);
     p.c_out = (int)c_out;
@@ -307,12 +437,13 @@ extern "C" int azb_conv_gemm_bf16(const void* act, int64_t n, int64_t h, int64_t
     p.res = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.res_ld = res_ld;
     p.out = out, p.out_ld = out_ld, p.out_mode = out_mode;
+    p.colsum = reinterpret_cast<float2*>(colsum);
 
     CUtensorMap ta, tb;
     {
         uint64_t dims[4] = {(uint64_t)c_in, (uint64_t)w, (uint64_t)h, (uint64_t)n};
         uint64_t str[3] = {(uint64_t)act_ld * 2, (uint64_t)act_ld * 2 * w, (uint64_t)act_ld * 2 * w * h};
-        uint32_t box[4] = {BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+        uint32_t box[4] = {BLOCK_K, (uint32_t)p.BW, (uint32_t)p.BH, (uint32_t)p.BN};
         int rc = make_map(&ta, act, 4, dims, str, box);
         if (rc) return rc;
     }
@@ -323,13 +454,42 @@ extern "C" int azb_conv_gemm_bf16(const void* act, int64_t n, int64_t h, int64_t
         int rc = make_map(&tb, wpack, 2, dims, str, box);
         if (rc) return rc;
     }
-    const int64_t grid = (int64_t)p.n_tiles * p.tiles_w * p.tiles_h * tiles_n_img;
-    if (grid > 0x7fffffffLL) return AZB_E_SHAPE;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     switch (block_n) {
-        case 128: return launch<128, 3>(ta, tb, p, grid, s);
-        case 64: return launch<64, 4>(ta, tb, p, grid, s);
-        case 32: return launch<32, 4>(ta, tb, p, grid, s);
-        default: return launch<16, 4>(ta, tb, p, grid, s);
+        case 256: return launch<256>(ta, tb, p, s);
+        case 128: return launch<128>(ta, tb, p, s);
+        case 64: return launch<64>(ta, tb, p, s);
+        case 32: return launch<32>(ta, tb, p, s);
+        default: return launch<16>(ta, tb, p, s);
     }
+}
+
+}  // namespace
+
+extern "C" int azb_conv_gemm_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld,
+                                  const void* wpack, int64_t c_out, int64_t c_out_rows, int taps, int64_t k_per_tap,
+                                  const float* bias, const void* residual, int64_t res_ld, void* out, int64_t out_ld,
+                                  int out_mode, void* stream) {
+    return conv_impl(act, n, h, w, c_in, act_ld, wpack, c_out, c_out_rows, taps, k_per_tap, bias, residual, res_ld, out,
+                     out_ld, out_mode, nullptr, stream);
+}
+
+extern "C" int azb_conv_colsum_rows(int64_t n, int64_t h, int64_t w, int64_t* rows, int64_t* rows_per_image) {
+    if (n <= 0 || h <= 0 || w <= 0 || !rows) return AZB_E_SHAPE;
+    int bw, bh, bn;
+    patch_shape(h, w, bw, bh, bn);
+    const int64_t tiles = ((w + bw - 1) / bw) * ((h + bh - 1) / bh) * ((n + bn - 1) / bn);
+    *rows = tiles * 4;
+    // a 32-row slab lies inside one image iff the per-image part of the patch is a multiple of 32 rows
+    if (rows_per_image) *rows_per_image = ((bw * bh) % 32 == 0) ? 1 : 0;
+    return AZB_OK;
+}
+
+extern "C" int azb_conv_gemm_stats_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld,
+                                        const void* wpack, int64_t c_out, int64_t c_out_rows, int taps,
+                                        int64_t k_per_tap, const float* bias, const void* residual, int64_t res_ld,
+                                        void* out, int64_t out_ld, float* colsum, void* stream) {
+    AZB_CHECK_PTR(colsum);
+    return conv_impl(act, n, h, w, c_in, act_ld, wpack, c_out, c_out_rows, taps, k_per_tap, bias, residual, res_ld, out,
+                     out_ld, 0, colsum, stream);
 }

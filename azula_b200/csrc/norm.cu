@@ -40,14 +40,21 @@ __global__ void __launch_bounds__(THREADS) gn_stats_kernel(const StatsParams p) 
     const int p1 = min(p0 + p.pix_per_chunk, p.hw);
     if (r < R) {
         const __nv_bfloat16* base = p.x + ((int64_t)n * p.hw) * p.ld + v * 8;
-        for (int pix = p0 + r; pix < p1; pix += R) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)pix * p.ld));
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        for (int pix = p0 + r; pix < p1; pix += 4 * R) {
+            uint4 u[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float a = bf16_bits_to_f32(w[j] & 0xffffu), b = bf16_bits_to_f32(w[j] >> 16);
-                s[2 * j] += a, q[2 * j] += a * a;
-                s[2 * j + 1] += b, q[2 * j + 1] += b * b;
+            for (int k = 0; k < 4; ++k)
+                u[k] = pix + k * R < p1 ? __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(pix + k * R) * p.ld))
+                                        : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float a = bf16_bits_to_f32(w[j] & 0xffffu), b = bf16_bits_to_f32(w[j] >> 16);
+                    s[2 * j] += a, q[2 * j] += a * a;
+                    s[2 * j + 1] += b, q[2 * j + 1] += b * b;
+                }
             }
         }
     }
@@ -89,13 +96,25 @@ __global__ void __launch_bounds__(THREADS) gn_stats_kernel(const StatsParams p) 
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // fixed-order two-level fold: SL slices of the chunk range per group, then the slices in order
+    const int SL = THREADS / p.groups;
+    double* fold = reinterpret_cast<double*>(sm);  // [SL][groups][2], reuses the (finished) staging area
+    {
+        const int g = threadIdx.x % p.groups, sl = threadIdx.x / p.groups;
+        if (sl < SL) {
+            double a = 0.0, b = 0.0;
+            for (int ch = sl; ch < p.chunks; ch += SL) {
+                const float* src = p.partial + (((int64_t)n * p.chunks + ch) * p.groups + g) * 2;
+                a += (double)__ldcg(src), b += (double)__ldcg(src + 1);
+            }
+            fold[(sl * p.groups + g) * 2] = a, fold[(sl * p.groups + g) * 2 + 1] = b;
+        }
+    }
+    __syncthreads();
     if (threadIdx.x < p.groups) {
         const int g = threadIdx.x;
         double a = 0.0, b = 0.0;
-        for (int ch = 0; ch < p.chunks; ++ch) {
-            const float* src = p.partial + (((int64_t)n * p.chunks + ch) * p.groups + g) * 2;
-            a += (double)__ldcg(src), b += (double)__ldcg(src + 1);
-        }
+        for (int sl = 0; sl < SL; ++sl) a += fold[(sl * p.groups + g) * 2], b += fold[(sl * p.groups + g) * 2 + 1];
         const double cnt = (double)p.hw * cg;
         const double mean = a / cnt;
         double var = b / cnt - mean * mean;
@@ -119,85 +138,199 @@ struct ApplyParams {
     const int32_t* ss_step;    // optional device step index selecting a row block of `ss_step_stride`
     int64_t ss_step_stride;
     int silu;
-    int mode;                // 0 same, 1 nearest x2 up, 2 2x2 average pool
     int pix_per_cta;         // output pixels per CTA
 };
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
-// y = act(A[c]*x + B[c]) with A = rstd*gamma*(1+scale), B = (beta - mean*rstd*gamma)*(1+scale) + shift
-// folded per (image, channel) into shared memory once per CTA; then a pure streaming pass.
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+    uint4 r;
+    // plain (coherent) streaming load: the apply pass may run in place (y == x)
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+
+template <bool SILU>
+__device__ __forceinline__ void affine8(const uint4 u, const float (&a)[8], const float (&b)[8], float (&acc)[8]) {
+    const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float f0 = fmaf(a[2 * j], bf16_bits_to_f32(wv[j] & 0xffffu), b[2 * j]);
+        float f1 = fmaf(a[2 * j + 1], bf16_bits_to_f32(wv[j] >> 16), b[2 * j + 1]);
+        if (SILU) f0 = silu_f(f0), f1 = silu_f(f1);
+        acc[2 * j] += f0, acc[2 * j + 1] += f1;
+    }
+}
+
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], float mul) {
+    __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0] * mul, f[1] * mul), t1 = __floats2bfloat162_rn(f[2] * mul, f[3] * mul);
+    __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4] * mul, f[5] * mul), t3 = __floats2bfloat162_rn(f[6] * mul, f[7] * mul);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&t0), o.y = *reinterpret_cast<uint32_t*>(&t1);
+    o.z = *reinterpret_cast<uint32_t*>(&t2), o.w = *reinterpret_cast<uint32_t*>(&t3);
+    return o;
+}
+
+// y = act(A[c]*x + B[c]) with A = rstd*gamma*(1+scale), B = (beta - mean*rstd*gamma)*(1+scale) + shift.
+// Thread (r, v) owns vector column v (8 channels, its A/B live in registers) and walks output pixels
+// r, r+R, ... of the CTA's pixel range with UNROLL independent 16-byte loads in flight.
+// MODE: 0 same size, 1 nearest x2 upsample, 2 2x2 average pool (of the activated values).
+template <int MODE, bool SILU>
 __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) {
-    extern __shared__ float sm[];  // A[C], B[C]
-    float* A = sm;
-    float* B = sm + p.c;
     const int n = blockIdx.y;
+    const int V = p.c >> 3;
+    const int VT = V < THREADS ? V : THREADS;  // vector columns handled per pass
+    const int R = THREADS / VT;
+    const int r = threadIdx.x / VT;
+    const int wo = MODE == 1 ? p.w * 2 : MODE == 2 ? p.w / 2 : p.w;
+    const int ho = MODE == 1 ? p.h * 2 : MODE == 2 ? p.h / 2 : p.h;
+    const int out_pix = ho * wo;
+    const int q0 = blockIdx.x * p.pix_per_cta;
+    const int q1 = min(q0 + p.pix_per_cta, out_pix);
+    const __nv_bfloat16* xin = p.x + (int64_t)n * p.h * p.w * p.x_ld;
+    __nv_bfloat16* yout = p.y + (int64_t)n * out_pix * p.y_ld;
     const int cg = p.c / p.groups;
     const float* ss = nullptr;
     if (p.scale_shift) {
         ss = p.scale_shift + (int64_t)n * p.ss_stride;
         if (p.ss_step) ss += (int64_t)(*p.ss_step) * p.ss_step_stride;
     }
-    for (int c = threadIdx.x; c < p.c; c += THREADS) {
-        float a = 1.f, b = 0.f;
-        if (p.stats) {
-            const int g = c / cg;
-            const float mean = p.stats[((int64_t)n * p.groups + g) * 2];
-            const float rstd = p.stats[((int64_t)n * p.groups + g) * 2 + 1];
-            a = rstd * __ldg(p.gamma + c);
-            b = __ldg(p.beta + c) - mean * a;
-        }
-        if (ss) {
-            const float sc = 1.0f + __ldg(ss + c);
-            a *= sc;
-            b = b * sc + __ldg(ss + p.c + c);
-        }
-        A[c] = a, B[c] = b;
-    }
-    __syncthreads();
+    if (r >= R) return;
 
-    const int V = p.c >> 3;
-    const int ho = p.mode == 1 ? p.h * 2 : p.mode == 2 ? p.h / 2 : p.h;
-    const int wo = p.mode == 1 ? p.w * 2 : p.mode == 2 ? p.w / 2 : p.w;
-    const int64_t out_pix = (int64_t)ho * wo;
-    const int64_t q0 = (int64_t)blockIdx.x * p.pix_per_cta;
-    const int64_t q1 = min(q0 + (int64_t)p.pix_per_cta, out_pix);
-    const __nv_bfloat16* xin = p.x + (int64_t)n * p.h * p.w * p.x_ld;
-    __nv_bfloat16* yout = p.y + (int64_t)n * out_pix * p.y_ld;
-
-    for (int64_t item = q0 * V + threadIdx.x; item < q1 * V; item += THREADS) {
-        const int64_t q = item / V;
-        const int v = (int)(item - q * V);
-        const int oh = (int)(q / wo), ow = (int)(q - (int64_t)oh * wo);
-        float a[8], b[8], acc[8];
+    for (int v = threadIdx.x % VT; v < V; v += VT) {
+        float a[8], b[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = A[v * 8 + j], b[j] = B[v * 8 + j], acc[j] = 0.f;
-        const int taps = p.mode == 2 ? 4 : 1;
-        for (int t = 0; t < taps; ++t) {
-            int ih, iw;
-            if (p.mode == 1) ih = oh >> 1, iw = ow >> 1;
-            else if (p.mode == 2) ih = oh * 2 + (t >> 1), iw = ow * 2 + (t & 1);
-            else ih = oh, iw = ow;
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(xin + ((int64_t)ih * p.w + iw) * p.x_ld + v * 8));
-            const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+        for (int j = 0; j < 8; ++j) {
+            const int c = v * 8 + j;
+            float aa = 1.f, bb = 0.f;
+            if (p.stats) {
+                const int g = c / cg;
+                const float mean = __ldg(p.stats + ((int64_t)n * p.groups + g) * 2);
+                const float rstd = __ldg(p.stats + ((int64_t)n * p.groups + g) * 2 + 1);
+                aa = rstd * __ldg(p.gamma + c);
+                bb = __ldg(p.beta + c) - mean * aa;
+            }
+            if (ss) {
+                const float sc = 1.0f + __ldg(ss + c);
+                aa *= sc;
+                bb = bb * sc + __ldg(ss + p.c + c);
+            }
+            a[j] = aa, b[j] = bb;
+        }
+        const __nv_bfloat16* xc = xin + v * 8;
+        __nv_bfloat16* yc = yout + v * 8;
+        constexpr int UNROLL = MODE == 2 ? 2 : 4;
+        for (int q = q0 + r; q < q1; q += UNROLL * R) {
+            if (MODE == 2) {
+                uint4 u[UNROLL][4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float f0 = fmaf(a[2 * j], bf16_bits_to_f32(wv[j] & 0xffffu), b[2 * j]);
-                float f1 = fmaf(a[2 * j + 1], bf16_bits_to_f32(wv[j] >> 16), b[2 * j + 1]);
-                if (p.silu) f0 = silu_f(f0), f1 = silu_f(f1);
-                acc[2 * j] += f0, acc[2 * j + 1] += f1;
+                for (int k = 0; k < UNROLL; ++k) {
+                    const int qq = q + k * R;
+                    if (qq < q1) {
+                        const int oh = qq / wo, ow = qq - oh * wo;
+                        const __nv_bfloat16* src = xc + ((int64_t)(2 * oh) * p.w + 2 * ow) * p.x_ld;
+                        u[k][0] = ldg_stream16(src);
+                        u[k][1] = ldg_stream16(src + p.x_ld);
+                        u[k][2] = ldg_stream16(src + (int64_t)p.w * p.x_ld);
+                        u[k][3] = ldg_stream16(src + (int64_t)(p.w + 1) * p.x_ld);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < UNROLL; ++k) {
+                    const int qq = q + k * R;
+                    if (qq < q1) {
+                        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) affine8<SILU>(u[k][t], a, b, acc);
+                        *reinterpret_cast<uint4*>(yc + (int64_t)qq * p.y_ld) = pack8(acc, 0.25f);
+                    }
+                }
+            } else {
+                uint4 u[UNROLL];
+#pragma unroll
+                for (int k = 0; k < UNROLL; ++k) {
+                    const int qq = q + k * R;
+                    if (qq < q1) {
+                        int src = qq;
+                        if (MODE == 1) {
+                            const int oh = qq / wo, ow = qq - oh * wo;
+                            src = (oh >> 1) * p.w + (ow >> 1);
+                        }
+                        u[k] = MODE == 1 ? __ldg(reinterpret_cast<const uint4*>(xc + (int64_t)src * p.x_ld))
+                                         : ldg_stream16(xc + (int64_t)src * p.x_ld);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < UNROLL; ++k) {
+                    const int qq = q + k * R;
+                    if (qq < q1) {
+                        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        affine8<SILU>(u[k], a, b, acc);
+                        *reinterpret_cast<uint4*>(yc + (int64_t)qq * p.y_ld) = pack8(acc, 1.0f);
+                    }
+                }
             }
         }
-        if (p.mode == 2) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] *= 0.25f;
+    }
+}
+
+template <int MODE>
+void launch_apply(const ApplyParams& p, dim3 grid, cudaStream_t s) {
+    if (p.silu)
+        gn_apply_kernel<MODE, true><<<grid, THREADS, 0, s>>>(p);
+    else
+        gn_apply_kernel<MODE, false><<<grid, THREADS, 0, s>>>(p);
+}
+
+struct FinalizeParams {
+    const float2* src[2];  // per-(32-row slab, channel) {sum, sum of squares} of up to two channel ranges
+    int c[2];
+    int n, hw, groups;
+    int tiles_per_image;   // M tiles that hold rows of one image
+    int images_per_tile;   // BN
+    int slabs_per_image;   // 32-row slabs of one tile that belong to one image
+    float eps;
+    float* stats;          // (N, groups, 2) mean / rstd
+};
+
+// One CTA per (image, group): folds the column sums written by the convolution epilogues in a fixed
+// order (thread-strided partials in double, then a shared-memory tree), so results are deterministic.
+__global__ void __launch_bounds__(THREADS) gn_finalize_kernel(const FinalizeParams p) {
+    __shared__ double red[2][THREADS];
+    const int g = blockIdx.x, n = blockIdx.y;
+    const int ctot = p.c[0] + p.c[1];
+    const int cg = ctot / p.groups;
+    const int tn = n / p.images_per_tile, bn = n - tn * p.images_per_tile;
+    const int slabs = p.tiles_per_image * p.slabs_per_image;
+    double a = 0.0, b = 0.0;
+    for (int item = threadIdx.x; item < slabs * cg; item += THREADS) {
+        const int sl = item / cg, cc = g * cg + (item - sl * cg);
+        const int t = sl / p.slabs_per_image, q = sl - t * p.slabs_per_image;
+        const int64_t row = ((int64_t)tn * p.tiles_per_image + t) * 4 + bn * p.slabs_per_image + q;
+        const int which = cc >= p.c[0];
+        const int ch = which ? cc - p.c[0] : cc;
+        const float2 v = __ldcg(p.src[which] + row * p.c[which] + ch);
+        a += (double)v.x, b += (double)v.y;
+    }
+    red[0][threadIdx.x] = a, red[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int off = THREADS / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            red[0][threadIdx.x] += red[0][threadIdx.x + off];
+            red[1][threadIdx.x] += red[1][threadIdx.x + off];
         }
-        uint4 o;
-        __nv_bfloat162 t0 = __floats2bfloat162_rn(acc[0], acc[1]), t1 = __floats2bfloat162_rn(acc[2], acc[3]);
-        __nv_bfloat162 t2 = __floats2bfloat162_rn(acc[4], acc[5]), t3 = __floats2bfloat162_rn(acc[6], acc[7]);
-        o.x = *reinterpret_cast<uint32_t*>(&t0), o.y = *reinterpret_cast<uint32_t*>(&t1);
-        o.z = *reinterpret_cast<uint32_t*>(&t2), o.w = *reinterpret_cast<uint32_t*>(&t3);
-        *reinterpret_cast<uint4*>(yout + q * p.y_ld + v * 8) = o;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double cnt = (double)p.hw * cg;
+        const double mean = red[0][0] / cnt;
+        double var = red[1][0] / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        p.stats[((int64_t)n * p.groups + g) * 2 + 0] = (float)mean;
+        p.stats[((int64_t)n * p.groups + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)p.eps));
     }
 }
 
@@ -205,7 +338,7 @@ __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) 
 
 extern "C" int azb_gn_stats_workspace(int64_t n, int64_t hw, int64_t c, int64_t groups, int64_t* partial_floats) {
     if (n <= 0 || hw <= 0 || c <= 0 || groups <= 0 || !partial_floats) return AZB_E_SHAPE;
-    int64_t chunks = (hw + 255) / 256;
+    int64_t chunks = (hw + 63) / 64;
     if (chunks > 1024) chunks = 1024;
     *partial_floats = n * chunks * groups * 2;
     return AZB_OK;
@@ -223,14 +356,16 @@ extern "C" int azb_gn_stats_bf16(const void* x, int64_t ld, int64_t n, int64_t h
     StatsParams p{};
     p.x = reinterpret_cast<const __nv_bfloat16*>(x);
     p.ld = ld, p.hw = (int)hw, p.c = (int)c, p.groups = (int)groups, p.eps = eps;
-    int64_t chunks = (hw + 255) / 256;
+    int64_t chunks = (hw + 63) / 64;
     if (chunks > 1024) chunks = 1024;
     p.chunks = (int)chunks;
     p.pix_per_chunk = (int)((hw + chunks - 1) / chunks);
     p.partial = partial, p.stats = stats, p.counters = counters;
     const int V = (int)(c >> 3);
     const int R = THREADS / V > 0 ? THREADS / V : 1;
-    const size_t smem = (size_t)(2 * R * c + 2 * c) * sizeof(float);
+    size_t smem = (size_t)(2 * R * c + 2 * c) * sizeof(float);
+    const size_t fold = (size_t)(THREADS / groups) * groups * 2 * sizeof(double);
+    if (smem < fold) smem = fold;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -258,15 +393,47 @@ extern "C" int azb_gn_apply_bf16(const void* x, int64_t x_ld, void* y, int64_t y
     p.n = (int)n, p.h = (int)h, p.w = (int)w, p.c = (int)c, p.groups = stats ? (int)groups : 1;
     p.stats = stats, p.gamma = gamma, p.beta = beta;
     p.scale_shift = scale_shift, p.ss_stride = ss_stride, p.ss_step = ss_step, p.ss_step_stride = ss_step_stride;
-    p.silu = silu, p.mode = mode;
+    p.silu = silu;
     const int64_t ho = mode == 1 ? h * 2 : mode == 2 ? h / 2 : h, wo = mode == 1 ? w * 2 : mode == 2 ? w / 2 : w;
     const int64_t out_pix = ho * wo;
-    // ~8 vectors per thread and CTA: pixels per CTA = 8*256 / V, at least 1
-    int64_t ppc = (8 * THREADS) / (c >> 3);
+    if (out_pix > 0x7fffffffLL || h * w > 0x7fffffffLL) return AZB_E_SHAPE;
+    // 16 vectors per thread and CTA (enough loads in flight, enough CTAs for every SM)
+    const int64_t V = c >> 3;
+    int64_t ppc = (16 * THREADS) / V;
     if (ppc < 1) ppc = 1;
+    // keep at least ~4 CTAs per SM when the tensor is large enough
+    while (ppc > 8 && ((out_pix + ppc - 1) / ppc) * n < 4 * 148) ppc >>= 1;
     p.pix_per_cta = (int)ppc;
     const int64_t ctas = (out_pix + ppc - 1) / ppc;
-    const size_t smem = (size_t)2 * c * sizeof(float);
-    gn_apply_kernel<<<dim3((unsigned)ctas, (unsigned)n), THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    const dim3 grid((unsigned)ctas, (unsigned)n);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (mode == 0) launch_apply<0>(p, grid, s);
+    else if (mode == 1) launch_apply<1>(p, grid, s);
+    else launch_apply<2>(p, grid, s);
+    return azb_launch_status();
+}
+
+extern "C" int azb_gn_finalize_f32(const float* colsum_a, int64_t c_a, const float* colsum_b, int64_t c_b, int64_t n,
+                                   int64_t h, int64_t w, int64_t groups, float eps, float* stats, void* stream) {
+    AZB_CHECK_PTR(colsum_a);
+    AZB_CHECK_PTR(stats);
+    if (n <= 0 || h <= 0 || w <= 0 || c_a <= 0 || c_b < 0 || groups <= 0 || (c_a + c_b) % groups) return AZB_E_SHAPE;
+    if (c_b > 0 && !colsum_b) return AZB_E_NULL;
+    // geometry of the convolution's M tiles (same rule as azb_conv_gemm_*: 128 = BN x BH x BW pixels)
+    int bw = 1;
+    while (bw < 16 && bw < w) bw <<= 1;
+    int bh = 1;
+    while (bw * bh < 128 && bh < h) bh <<= 1;
+    const int bn = 128 / (bw * bh);
+    if ((bw * bh) % 32) return AZB_E_SHAPE;  // a 32-row slab would straddle two images
+    FinalizeParams p{};
+    p.src[0] = reinterpret_cast<const float2*>(colsum_a), p.src[1] = reinterpret_cast<const float2*>(colsum_b);
+    p.c[0] = (int)c_a, p.c[1] = (int)c_b;
+    p.n = (int)n, p.hw = (int)(h * w), p.groups = (int)groups;
+    p.tiles_per_image = (int)(((w + bw - 1) / bw) * ((h + bh - 1) / bh));
+    p.images_per_tile = bn;
+    p.slabs_per_image = bn == 1 ? 4 : (bw * bh) / 32;
+    p.eps = eps, p.stats = stats;
+    gn_finalize_kernel<<<dim3((unsigned)groups, (unsigned)n), THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     return azb_launch_status();
 }

@@ -123,6 +123,8 @@ class Plan:
         self.lib = _lib.lib()
         self.ops: list[tuple] = []
         self.meta: list[tuple] = []
+        self.colsum_of: dict[tuple, tuple] = {}  # activation view -> (column sums of its producer, channels)
+        self.cat_parts: dict[tuple, list] = {}   # concatenation buffer -> [left view, right view]
         self.keep: list[Tensor] = []  # everything the launch list points into
         arena = self.arena = _Arena(device)
         f32 = dict(dtype=torch.float32, device=device)
@@ -154,7 +156,9 @@ class Plan:
         for j, block in enumerate(lay.decoder):
             sh, sw, sc = sizes[L - 1 - j]
             assert block[0].cin == carried + sc, (block[0], carried, sc)
-            self.cat.append((arena.take(n, sh, sw, carried + sc), carried))
+            buf = arena.take(n, sh, sw, carried + sc)
+            self.cat.append((buf, carried))
+            self.cat_parts[self._key(buf)] = [buf[..., :carried], buf[..., carried:]]
             carried = block[-1].cout
         for buf, _ in self.cat:  # concat buffers live for the whole forward
             arena.owner.pop(id(buf))
@@ -195,21 +199,59 @@ class Plan:
         self.ops.append((fn, args))
         self.meta.append((kind, flops, nbytes))
 
-    def _conv(self, x: Tensor, pc: ops.PackedConv, out: Tensor, residual: Tensor | None = None) -> None:
+    @staticmethod
+    def _key(t: Tensor) -> tuple:
+        return (t.data_ptr(), tuple(t.shape))
+
+    def _conv(self, x: Tensor, pc: ops.PackedConv, out: Tensor, residual: Tensor | None = None,
+              stats: bool = False) -> None:
+        r"""Queues a convolution; with ``stats`` its epilogue also emits the column sums from which the
+        GroupNorm consuming ``out`` gets its statistics (no separate read pass over ``out``)."""
         n, h, w, _ = x.shape
+        colsum = None
+        self.colsum_of.pop(self._key(out), None)  # the buffer may be a recycled one
+        if stats and pc.c_out_rows % 64 == 0:
+            rows, ok = ops.colsum_rows(n, h, w)
+            if ok:
+                colsum = torch.empty(rows, pc.c_out, 2, dtype=torch.float32, device=self.device)
+                self.colsum_of[self._key(out)] = (colsum, pc.c_out)
         self.keep += [x, out, pc.w] + ([residual] if residual is not None else []) + ([pc.bias] if pc.bias is not None else [])
         flops = 2.0 * n * h * w * pc.c_out * pc.taps * pc.c_in
         nbytes = 2.0 * (n * h * w * (pc.c_in + pc.c_out * (2 if residual is not None else 1)) + pc.c_out * pc.taps * pc.c_in)
+        kind = "conv3x3" if pc.taps == 9 else "conv1x1"
+        if colsum is not None:
+            self.keep.append(colsum)
+            self._emit(
+                kind, flops, nbytes + 4.0 * colsum.numel(),
+                self.lib.azb_conv_gemm_stats_bf16, x.data_ptr(), n, h, w, pc.c_in, ops._ld(x), pc.w.data_ptr(),
+                pc.c_out, pc.c_out_rows, pc.taps, pc.k_per_tap, _lib.ptr(pc.bias), _lib.ptr(residual),
+                0 if residual is None else ops._ld(residual), out.data_ptr(), ops._ld(out), colsum.data_ptr(),
+            )
+            return
         self._emit(
-            "conv3x3" if pc.taps == 9 else "conv1x1", flops, nbytes,
+            kind, flops, nbytes,
             self.lib.azb_conv_gemm_bf16, x.data_ptr(), n, h, w, pc.c_in, ops._ld(x), pc.w.data_ptr(), pc.c_out,
             pc.c_out_rows, pc.taps, pc.k_per_tap, _lib.ptr(pc.bias), _lib.ptr(residual),
             0 if residual is None else ops._ld(residual), out.data_ptr(), ops._ld(out), 0,
         )
 
     def _stats(self, x: Tensor) -> Tensor:
+        r"""GroupNorm statistics of ``x``: folded from the producers' column sums when every channel of
+        ``x`` has them (one tiny launch), else by the stand-alone reduction pass."""
         n, c = x.shape[0], x.shape[-1]
         hw = math.prod(x.shape[1:-1])
+        parts = self.cat_parts.get(self._key(x), [x])
+        sources = [self.colsum_of.get(self._key(t)) for t in parts]
+        if all(src is not None for src in sources):
+            stats = torch.empty(n, ops.GN_GROUPS, 2, dtype=torch.float32, device=self.device)
+            (a, ca), (b, cb) = sources[0], (sources[1] if len(sources) > 1 else (None, 0))
+            self.keep.append(stats)
+            self._emit(
+                "gn_finalize", 0.0, 4.0 * (a.numel() + (b.numel() if b is not None else 0)),
+                self.lib.azb_gn_finalize_f32, a.data_ptr(), ca, _lib.ptr(b), cb, n, x.shape[1], x.shape[2],
+                ops.GN_GROUPS, ops.GN_EPS, stats.data_ptr(),
+            )
+            return stats
         want = c_int64(0)
         _lib.check(self.lib.azb_gn_stats_workspace(n, hw, c, ops.GN_GROUPS, byref(want)), "azb_gn_stats_workspace")
         self.gn_partial_need = max(self.gn_partial_need, want.value)
@@ -230,6 +272,7 @@ class Plan:
                mode: int) -> None:
         n, h, w, c = x.shape
         gamma, beta = affine if affine is not None else (None, None)
+        self.colsum_of.pop(self._key(out), None)
         ss_ptr, ss_stride = None, 0
         if emb_offset is not None:
             ss_ptr = self.emb_all.data_ptr() + 4 * emb_offset
@@ -249,7 +292,7 @@ class Plan:
         for k, u in enumerate(block):
             last = k + 1 == len(block)
             if u.kind == "stem":
-                self._conv(self.patches, self.packed.unit[u.path]["conv"], dest)
+                self._conv(self.patches, self.packed.unit[u.path]["conv"], dest, stats=True)
                 return dest
             n, h, w, _ = x.shape
             ho, wo = (2 * h, 2 * w) if u.resample == 1 else (h // 2, w // 2) if u.resample == 2 else (h, w)
@@ -277,7 +320,7 @@ class Plan:
         else:
             xr = x
         h2 = arena.take(n, ho, wo, u.cout)
-        self._conv(h1, w_["conv1"], h2)
+        self._conv(h1, w_["conv1"], h2, stats=True)
         arena.give(h1)
         st2 = self._stats(h2)
         self._apply(h2, h2, st2, w_["gn2"], w_["emb_offset"], True, 0)  # SiLU(GN(h) (1 + scale) + shift), in place
@@ -286,7 +329,7 @@ class Plan:
             self._conv(xr, w_["skip"], sk)
         else:
             sk = xr
-        self._conv(h2, w_["conv2"], out, residual=sk)  # skip_connection(x) + h
+        self._conv(h2, w_["conv2"], out, residual=sk, stats=True)  # skip_connection(x) + h
         arena.give(h2)
         if sk is not xr:
             arena.give(sk)
@@ -310,7 +353,7 @@ class Plan:
         t = h * w
         self._emit("attention", 4.0 * n * u.heads * t * t * d, 2.0 * n * t * 4 * c, self.lib.azb_attention_bf16, qkv.data_ptr(), 3 * c, a.data_ptr(), c, n, h * w, u.heads, d, hs, kd, vd)
         arena.give(qkv)
-        self._conv(a, w_["proj"], out, residual=x)
+        self._conv(a, w_["proj"], out, residual=x, stats=True)
         arena.give(a)
 
     # ------------------------------------------------------------------------------ running

@@ -23,6 +23,16 @@ _lib.register({
         [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int64,
          c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p],
     ),
+    "azb_conv_gemm_stats_bf16": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int64,
+         c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p],
+    ),
+    "azb_conv_colsum_rows": (c_int, [c_int64, c_int64, c_int64, POINTER(c_int64), POINTER(c_int64)]),
+    "azb_gn_finalize_f32": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p],
+    ),
     "azb_gn_stats_workspace": (c_int, [c_int64, c_int64, c_int64, c_int64, POINTER(c_int64)]),
     "azb_gn_stats_bf16": (
         c_int,
@@ -87,7 +97,7 @@ def pack_conv(weight: Tensor, bias: Tensor | None) -> PackedConv:
     assert (kh, kw) in ((1, 1), (3, 3))
     taps = kh * kw
     k_pad = -(-c_in // 64) * 64
-    tile = 128 if c_out >= 128 else 64 if c_out >= 64 else 32 if c_out >= 32 else 16
+    tile = 128 if c_out >= 128 else 64 if c_out >= 64 else 32 if c_out >= 32 else 16  # row padding; the kernel picks the N tile
     rows = -(-c_out // tile) * tile
     w = torch.zeros(rows, taps, k_pad, dtype=torch.bfloat16, device=weight.device)
     w[:c_out, :, :c_in] = weight.permute(0, 2, 3, 1).reshape(c_out, taps, c_in).to(torch.bfloat16)
@@ -95,11 +105,36 @@ def pack_conv(weight: Tensor, bias: Tensor | None) -> PackedConv:
     return PackedConv(w=w.contiguous(), bias=b, c_in=c_in, c_out=c_out, taps=taps)
 
 
+def colsum_rows(n: int, h: int, w: int) -> tuple[int, bool]:
+    r"""(rows of the column-sum buffer of an (n, h, w) convolution output, whether it can feed
+    :func:`gn_finalize`)."""
+    rows, ok = c_int64(0), c_int64(0)
+    _lib.check(_lib.lib().azb_conv_colsum_rows(n, h, w, byref(rows), byref(ok)), "azb_conv_colsum_rows")
+    return rows.value, bool(ok.value)
+
+
+def gn_finalize(parts: list[tuple[Tensor, int]], n: int, h: int, w: int, stats: Tensor | None = None,
+                groups: int = 32, eps: float = 1e-5) -> Tensor:
+    r"""GroupNorm statistics (N, groups, 2) from the column sums of one or two convolutions
+    (``azb_gn_finalize_f32``); ``parts`` = [(colsum, channels), ...] in channel order."""
+    (a, ca), (b, cb) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
+    if stats is None:
+        stats = torch.empty(n, groups, 2, dtype=torch.float32, device=a.device)
+    _lib.check(
+        _lib.lib().azb_gn_finalize_f32(a.data_ptr(), ca, _lib.ptr(b), cb, n, h, w, groups, eps, stats.data_ptr(),
+                                       _lib.stream_ptr(a.device)),
+        "azb_gn_finalize_f32",
+    )
+    return stats
+
+
 def conv(x: Tensor, pc: PackedConv, out: Tensor | None = None, residual: Tensor | None = None,
-         nchw_f32: bool = False) -> Tensor:
+         nchw_f32: bool = False, colsum: Tensor | None = None) -> Tensor:
     r"""3x3 (pad 1) / 1x1 convolution or linear layer on tcgen05 (``azb_conv_gemm_bf16``).
 
     x: (N, H, W, C_in) or (rows, C_in) bf16.  Returns bf16 NHWC (or fp32 NCHW when ``nchw_f32``).
+    With ``colsum`` (fp32 (rows, C_out, 2), see :func:`colsum_rows`) the epilogue also emits the
+    per-channel sums the consuming GroupNorm needs (``azb_conv_gemm_stats_bf16``).
     """
     assert x.dtype == torch.bfloat16 and x.is_cuda
     if x.ndim == 2:
@@ -113,6 +148,17 @@ def conv(x: Tensor, pc: PackedConv, out: Tensor | None = None, residual: Tensor 
         else:
             out = torch.empty((*x.shape[:-1], pc.c_out), dtype=torch.bfloat16, device=x.device)
     out_ld = 0 if nchw_f32 else _ld(out)
+    if colsum is not None:
+        assert not nchw_f32 and colsum.dtype == torch.float32 and colsum.is_contiguous()
+        _lib.check(
+            _lib.lib().azb_conv_gemm_stats_bf16(
+                x.data_ptr(), n, h, w, pc.c_in, _ld(x), pc.w.data_ptr(), pc.c_out, pc.c_out_rows, pc.taps,
+                pc.k_per_tap, _lib.ptr(pc.bias), _lib.ptr(residual), 0 if residual is None else _ld(residual),
+                out.data_ptr(), out_ld, colsum.data_ptr(), _lib.stream_ptr(x.device),
+            ),
+            "azb_conv_gemm_stats_bf16",
+        )
+        return out
     _lib.check(
         _lib.lib().azb_conv_gemm_bf16(
             x.data_ptr(), n, h, w, pc.c_in, _ld(x), pc.w.data_ptr(), pc.c_out, pc.c_out_rows, pc.taps, pc.k_per_tap,

@@ -115,9 +115,60 @@ def test_linear_layer_rows():
         _check(got, F.linear(x.float(), wt.float(), b), (rows, ci, co))
 
 
+def _group_stats(t, groups=32, eps=1e-5):
+    """(N, groups, 2) = (mean, rstd) of an NHWC tensor, as torch.nn.GroupNorm defines them."""
+    n, c = t.shape[0], t.shape[-1]
+    grp = t.float().permute(0, 3, 1, 2).reshape(n, groups, -1)
+    return torch.stack((grp.mean(-1), torch.rsqrt(grp.var(-1, unbiased=False) + eps)), dim=-1)
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 16, 16, 64, 128, 3), (3, 8, 8, 128, 256, 3), (1, 64, 64, 64, 64, 3), (2, 32, 32, 256, 256, 3),
+    (2, 12, 12, 64, 128, 3), (1, 20, 24, 192, 128, 3), (2, 16, 16, 128, 384, 1), (5, 8, 8, 64, 512, 1),
+    (16, 8, 8, 256, 1024, 3),
+])
+def test_conv_epilogue_statistics(shape):
+    """azb_conv_gemm_stats_bf16 + azb_gn_finalize_f32 == GroupNorm statistics of the stored output,
+    and the output itself equals the plain convolution's bit for bit."""
+    n, h, w, ci, co, k = shape
+    x, wt, b = _mk(*shape, seed=7)
+    pc = ops.pack_conv(wt.float(), b)
+    res = torch.randn(n, h, w, co, device=DEV).to(torch.bfloat16)
+    rows, ok = ops.colsum_rows(n, h, w)
+    assert ok
+    colsum = torch.full((rows, co, 2), float("nan"), device=DEV)
+    plain = ops.conv(x, pc, residual=res)
+    got = ops.conv(x, pc, residual=res, colsum=colsum)
+    assert torch.equal(got, plain)
+    stats = ops.gn_finalize([(colsum, co)], n, h, w)
+    ref = _group_stats(got)
+    assert torch.allclose(stats[..., 0], ref[..., 0], atol=2e-5, rtol=1e-4), (stats[..., 0] - ref[..., 0]).abs().max()
+    assert torch.allclose(stats[..., 1], ref[..., 1], rtol=1e-4)
+    assert torch.equal(stats, ops.gn_finalize([(colsum, co)], n, h, w))  # deterministic
+
+
+def test_statistics_of_a_concatenation():
+    """Two producers write the halves of a decoder concat buffer; groups straddle the boundary
+    (1024 + 512 channels -> 48 channels per group)."""
+    n, h, w = 2, 16, 16
+    ca, cb = 1024, 512
+    wide = torch.empty(n, h, w, ca + cb, device=DEV, dtype=torch.bfloat16)
+    rows, _ = ops.colsum_rows(n, h, w)
+    xa, wa, ba = _mk(n, h, w, 128, ca, 1, seed=1)
+    xb, wb, bb = _mk(n, h, w, 64, cb, 3, seed=2)
+    sa, sb = torch.empty(rows, ca, 2, device=DEV), torch.empty(rows, cb, 2, device=DEV)
+    ops.conv(xa, ops.pack_conv(wa.float(), ba), out=wide[..., :ca], colsum=sa)
+    ops.conv(xb, ops.pack_conv(wb.float(), bb), out=wide[..., ca:], colsum=sb)
+    stats = ops.gn_finalize([(sa, ca), (sb, cb)], n, h, w)
+    ref = _group_stats(wide)
+    assert torch.allclose(stats[..., 0], ref[..., 0], atol=2e-5, rtol=1e-4)
+    assert torch.allclose(stats[..., 1], ref[..., 1], rtol=1e-4)
+
+
 def test_conv_throughput_report():
     """Not a pass/fail perf gate: prints achieved TFLOP/s of the heaviest ADM shapes."""
-    for (n, h, w, ci, co) in ((4, 256, 256, 256, 256), (16, 64, 64, 512, 512), (16, 16, 16, 1024, 1024)):
+    for (n, h, w, ci, co) in ((4, 256, 256, 256, 256), (16, 64, 64, 512, 512), (16, 32, 32, 512, 512),
+                              (16, 16, 16, 1024, 1024), (16, 8, 8, 1024, 1024)):
         x, wt, b = _mk(n, h, w, ci, co, 3)
         pc = ops.pack_conv(wt.float(), b)
         out = torch.empty(n, h, w, co, device=DEV, dtype=torch.bfloat16)
