@@ -32,7 +32,7 @@ constexpr int BLOCK_K = 64;  // 128 bytes of bf16 = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 193 * 1024;  // operand ring; + 32 KiB epilogue staging + alignment <= 227 KiB
 
 struct ConvParams {
     int N, H, W;              // activation extent (pixels)
@@ -49,7 +49,8 @@ struct ConvParams {
     void* out;
     int64_t out_ld;           // NHWC pixel stride (mode 0)
     int out_mode;             // 0: bf16 NHWC, 1: fp32 NCHW
-    float2* colsum;           // [m_tiles * 4][c_out] per-(32-row slab, channel) {sum, sum of squares}, or null
+    float2* colsum;           // [m_tiles * 4][c_out / stat_gran] per-(32-row slab, channel block) {sum, sum of squares}
+    int stat_gran;            // channels per colsum entry: 1 or 8
 };
 
 template <int BLOCK_N>
@@ -62,7 +63,8 @@ struct Cfg {
     static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
     static constexpr int COLS_PER_WARP = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;  // two warps share a lane quarter
     static constexpr int CHUNK = COLS_PER_WARP < 32 ? 16 : 32;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024;
+    static constexpr int STAGING_BYTES = EPI_WARPS * 32 * 128;  // per epilogue warp: 32 rows x 32 fp32, swizzled
+    static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + 1024;
 };
 
 __device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& n_tile, int& w0, int& h0, int& n0) {
@@ -74,22 +76,6 @@ __device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& 
     const int th = m_tile % p.tiles_h;
     const int tn = m_tile / p.tiles_h;
     w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
-}
-
-// Column sums over the 32 rows held by a warp: v[i] of lane l is element (row l, column i).  After the
-// butterfly, lane l holds the sum of column l.  31 shuffles instead of 32 x 5.
-__device__ __forceinline__ float warp_transpose_sum32(float (&v)[32], int lane) {
-#pragma unroll
-    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
-        const bool hi = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-            const float send = hi ? v[i] : v[i + n];
-            const float keep = hi ? v[i + n] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
-    }
-    return v[0];
 }
 
 template <int BLOCK_N>
@@ -188,33 +174,170 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
         }
     } else {
         // ===== epilogue: warp e reads TMEM lanes [32*(warp%4), +32) and one half of the columns =====
+        // Row domain (lane = tile row, as tcgen05.ld delivers it) -> swizzled fp32 staging in shared memory
+        // -> "coalesced domain": 4 lanes cover 32 consecutive channels of one pixel (64 contiguous bytes), a
+        // warp instruction covers 8 pixels.  Bias, residual, rounding, the store and the GroupNorm sums all
+        // happen in the coalesced domain (8x fewer memory wavefronts than one-row-per-lane stores).
         const int e = warp - 2;
         const int quarter = warp & 3;
         const int half = (BLOCK_N >= 64) ? (e >> 2) : 0;
         const bool active = (BLOCK_N >= 64) || (e < 4);
         constexpr int CHUNK = C::CHUNK;
+        const uint32_t stage_base = smem_base + STAGES * C::STAGE_BYTES + e * (32 * 128);
+        const int cg4 = lane & 3;       // which 8-channel group of the 32-column chunk
+        const int rl = lane >> 2;       // row within a group of 8 rows
         int local = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
             const int as = local & 1;
             int n_tile, w0, h0, n0;
             tile_coords(p, tile, n_tile, w0, h0, n0);
-            const int row = quarter * 32 + lane;  // row of the tile = TMEM lane
-            const int bw = row % p.BW;
-            const int bh = (row / p.BW) % p.BH;
-            const int bn = row / (p.BW * p.BH);
-            const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
-            const bool row_ok = (n < p.N) && (h < p.H) && (w < p.W);
-            const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
             const int col_base = n_tile * BLOCK_N + half * C::COLS_PER_WARP;
+            const int m_tile = tile / p.n_tiles;
 
             tc::mbar_wait(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
             tc::fence_after_sync();
 
-            if (active) {
+            if (active && p.out_mode == 0) {
+                {
+                    // pixels of the 4 rows this lane handles in the coalesced domain
+                    int64_t pixc[4];
+                    bool okc[4];
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int row = quarter * 32 + it * 8 + rl;
+                        const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
+                        const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
+                        okc[it] = (n < p.N) && (h < p.H) && (w < p.W);
+                        pixc[it] = ((int64_t)n * p.H + h) * p.W + w;
+                    }
+#pragma unroll 1
+                    for (int c0 = 0; c0 < C::COLS_PER_WARP; c0 += 32) {
+                        uint32_t acc[32];
+                        __syncwarp();  // staging buffer free again; tcgen05.ld is warp-collective
+                        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                               (uint32_t)(as * C::ACC_COLS + half * C::COLS_PER_WARP + c0);
+                        if constexpr (CHUNK == 32) {
+                            tc::tmem_ld_32x32b_x32(taddr, acc);
+                        } else {  // BLOCK_N = 16: the upper half of the chunk does not exist
+                            uint32_t lo[16];
+                            tc::tmem_ld_32x32b_x16(taddr, lo);
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) acc[j] = lo[j], acc[16 + j] = 0u;
+                        }
+                        const int col = col_base + c0 + cg4 * 8;
+                        const bool col_ok = col < p.c_out;
+                        // residual and bias loads are issued before the TMEM wait so the latencies overlap
+                        uint4 rsd[4];
+                        const bool use_res = p.res != nullptr && col_ok;
+                        if (use_res) {
+#pragma unroll
+                            for (int it = 0; it < 4; ++it)
+                                rsd[it] = okc[it] ? __ldg(reinterpret_cast<const uint4*>(p.res + pixc[it] * p.res_ld + col))
+                                                  : make_uint4(0, 0, 0, 0);
+                        }
+                        float bias8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (p.bias && col_ok) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 1);
+                            bias8[0] = b0.x, bias8[1] = b0.y, bias8[2] = b0.z, bias8[3] = b0.w;
+                            bias8[4] = b1.x, bias8[5] = b1.y, bias8[6] = b1.z, bias8[7] = b1.w;
+                        }
+                        tc::tmem_ld_wait();
+                        // row domain -> staging: 16-byte slot j of row `lane` lives at slot j ^ (lane & 7)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t addr = stage_base + lane * 128 + ((j ^ (lane & 7)) << 4);
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(acc[4 * j]),
+                                         "r"(acc[4 * j + 1]), "r"(acc[4 * j + 2]), "r"(acc[4 * j + 3])
+                                         : "memory");
+                        }
+                        __syncwarp();
+                        float s1[8], s2[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int r = it * 8 + rl;
+                            float f[8];
+#pragma unroll
+                            for (int hslot = 0; hslot < 2; ++hslot) {
+                                const uint32_t addr = stage_base + r * 128 + (((2 * cg4 + hslot) ^ (r & 7)) << 4);
+                                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                             : "=f"(f[4 * hslot]), "=f"(f[4 * hslot + 1]), "=f"(f[4 * hslot + 2]),
+                                               "=f"(f[4 * hslot + 3])
+                                             : "r"(addr)
+                                             : "memory");
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] += bias8[j];
+                            if (use_res) {
+                                const uint32_t rr[4] = {rsd[it].x, rsd[it].y, rsd[it].z, rsd[it].w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    f[2 * j] += bf16_bits_to_f32(rr[j] & 0xffffu);
+                                    f[2 * j + 1] += bf16_bits_to_f32(rr[j] >> 16);
+                                }
+                            }
+                            uint32_t packed[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                                packed[j] = *reinterpret_cast<uint32_t*>(&t);
+                            }
+                            if (okc[it] && col_ok) {
+                                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pixc[it] * p.out_ld + col) =
+                                    make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                                // statistics are taken of the STORED (rounded) values
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float a = bf16_bits_to_f32(packed[j] & 0xffffu), b = bf16_bits_to_f32(packed[j] >> 16);
+                                    s1[2 * j] += a, s2[2 * j] += a * a;
+                                    s1[2 * j + 1] += b, s2[2 * j + 1] += b * b;
+                                }
+                            }
+                        }
+                        if (p.colsum) {
+                            const int64_t slab = (int64_t)m_tile * 4 + quarter;
+                            if (p.stat_gran == 8) {
+                                // one {sum, sumsq} per 8-channel block: fold the lane's 8 channels, then the 8 row lanes
+                                float a = ((s1[0] + s1[1]) + (s1[2] + s1[3])) + ((s1[4] + s1[5]) + (s1[6] + s1[7]));
+                                float b = ((s2[0] + s2[1]) + (s2[2] + s2[3])) + ((s2[4] + s2[5]) + (s2[6] + s2[7]));
+#pragma unroll
+                                for (int off = 4; off <= 16; off <<= 1) {
+                                    a += __shfl_xor_sync(0xffffffffu, a, off);
+                                    b += __shfl_xor_sync(0xffffffffu, b, off);
+                                }
+                                if (rl == 0 && col_ok) p.colsum[slab * (p.c_out >> 3) + (col >> 3)] = make_float2(a, b);
+                            } else {
+                                // per channel: transpose-reduce 8 values over the 8 row lanes (bits 2..4 of the lane id);
+                                // afterwards the lane with row-lane id k holds channel col + k
+#pragma unroll
+                                for (int off = 16, nn = 4; off >= 4; off >>= 1, nn >>= 1) {
+                                    const bool hi = (lane & off) != 0;
+#pragma unroll
+                                    for (int i = 0; i < nn; ++i) {
+                                        const float send1 = hi ? s1[i] : s1[i + nn], keep1 = hi ? s1[i + nn] : s1[i];
+                                        const float send2 = hi ? s2[i] : s2[i + nn], keep2 = hi ? s2[i + nn] : s2[i];
+                                        s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+                                        s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+                                    }
+                                }
+                                const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                                if (col + k < p.c_out) p.colsum[slab * p.c_out + col + k] = make_float2(s1[0], s2[0]);
+                            }
+                        }
+                    }
+                }
+            } else if (active) {
+                // fp32 NCHW network output: out[n][c][h][w]; consecutive lanes are consecutive w => coalesced per channel
+                const int row = quarter * 32 + lane;
+                const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
+                const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
+                const bool row_ok = (n < p.N) && (h < p.H) && (w < p.W);
 #pragma unroll 1
                 for (int c0 = 0; c0 < C::COLS_PER_WARP; c0 += CHUNK) {
                     uint32_t acc[CHUNK];
-                    __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the divergent stores
+                    __syncwarp();
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                                            (uint32_t)(as * C::ACC_COLS + half * C::COLS_PER_WARP + c0);
                     if constexpr (CHUNK == 32) {
@@ -222,88 +345,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                     } else {
                         tc::tmem_ld_32x32b_x16(taddr, acc);
                     }
-                    const int col0 = col_base + c0;
-                    // residual loads are issued before the TMEM wait so both latencies overlap
-                    uint4 rsd[CHUNK / 8];
-                    const bool use_res = p.res != nullptr && row_ok && p.out_mode == 0;
-                    if (use_res) {
-                        const __nv_bfloat16* rp = p.res + pix * p.res_ld + col0;
-#pragma unroll
-                        for (int v = 0; v < CHUNK / 8; ++v)
-                            rsd[v] = (col0 + v * 8 < p.c_out) ? __ldg(reinterpret_cast<const uint4*>(rp + v * 8))
-                                                              : make_uint4(0, 0, 0, 0);
-                    }
                     tc::tmem_ld_wait();
-                    if (col0 >= p.c_out) continue;
-
-                    if (p.out_mode == 0) {
-                        float f[CHUNK];
+                    const int col0 = col_base + c0;
+                    if (!row_ok || col0 >= p.c_out) continue;
+                    float* dst = reinterpret_cast<float*>(p.out);
+                    const int64_t plane = (int64_t)p.H * p.W;
+                    const int64_t base = (int64_t)n * p.c_out * plane + (int64_t)h * p.W + w;
 #pragma unroll
-                        for (int j = 0; j < CHUNK; ++j) f[j] = __uint_as_float(acc[j]);
-                        if (p.bias) {
-#pragma unroll
-                            for (int v = 0; v < CHUNK / 4; ++v) {
-                                if (col0 + v * 4 < p.c_out) {
-                                    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + v * 4));
-                                    f[4 * v] += b.x, f[4 * v + 1] += b.y, f[4 * v + 2] += b.z, f[4 * v + 3] += b.w;
-                                }
-                            }
-                        }
-                        if (use_res) {
-#pragma unroll
-                            for (int v = 0; v < CHUNK / 8; ++v) {
-                                const uint32_t rr[4] = {rsd[v].x, rsd[v].y, rsd[v].z, rsd[v].w};
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    f[v * 8 + 2 * j] += bf16_bits_to_f32(rr[j] & 0xffffu);
-                                    f[v * 8 + 2 * j + 1] += bf16_bits_to_f32(rr[j] >> 16);
-                                }
-                            }
-                        }
-                        // round to the stored precision; statistics are taken of the STORED values
-                        uint32_t packed[CHUNK / 2];
-#pragma unroll
-                        for (int j = 0; j < CHUNK / 2; ++j) {
-                            __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                            packed[j] = *reinterpret_cast<uint32_t*>(&t);
-                        }
-                        if (row_ok) {
-                            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.out_ld + col0;
-#pragma unroll
-                            for (int v = 0; v < CHUNK / 8; ++v) {
-                                if (col0 + v * 8 < p.c_out)
-                                    *reinterpret_cast<uint4*>(dst + v * 8) =
-                                        make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
-                            }
-                        }
-                        if constexpr (CHUNK == 32) {
-                            if (p.colsum) {
-                                float s1[32], s2[32];
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const float a = row_ok ? bf16_bits_to_f32(packed[j] & 0xffffu) : 0.f;
-                                    const float b = row_ok ? bf16_bits_to_f32(packed[j] >> 16) : 0.f;
-                                    s1[2 * j] = a, s1[2 * j + 1] = b;
-                                    s2[2 * j] = a * a, s2[2 * j + 1] = b * b;
-                                }
-                                const float cs = warp_transpose_sum32(s1, lane);
-                                const float cq = warp_transpose_sum32(s2, lane);
-                                const int m_tile = tile / p.n_tiles;
-                                if (col0 + lane < p.c_out)
-                                    p.colsum[((int64_t)m_tile * 4 + quarter) * p.c_out + col0 + lane] = make_float2(cs, cq);
-                            }
-                        }
-                    } else if (row_ok) {
-                        // fp32 NCHW: out[n][c][h][w]; consecutive lanes are consecutive w => coalesced per channel
-                        float* dst = reinterpret_cast<float*>(p.out);
-                        const int64_t plane = (int64_t)p.H * p.W;
-                        const int64_t base = (int64_t)n * p.c_out * plane + (int64_t)h * p.W + w;
-#pragma unroll
-                        for (int j = 0; j < CHUNK; ++j) {
-                            const int c = col0 + j;
-                            if (c < p.c_out)
-                                dst[base + c * plane] = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + c) : 0.0f);
-                        }
+                    for (int j = 0; j < CHUNK; ++j) {
+                        const int c = col0 + j;
+                        if (c < p.c_out) dst[base + c * plane] = __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + c) : 0.0f);
                     }
                 }
             }
@@ -392,7 +443,7 @@ void patch_shape(int64_t h, int64_t w, int& bw, int& bh, int& bn) {
 
 int conv_impl(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld, const void* wpack,
               int64_t c_out, int64_t c_out_rows, int taps, int64_t k_per_tap, const float* bias, const void* residual,
-              int64_t res_ld, void* out, int64_t out_ld, int out_mode, float* colsum, void* stream) {
+              int64_t res_ld, void* out, int64_t out_ld, int out_mode, float* colsum, int stat_gran, void* stream) {
     AZB_CHECK_PTR(act);
     AZB_CHECK_PTR(wpack);
     AZB_CHECK_PTR(out);
@@ -405,7 +456,7 @@ int conv_impl(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, in
         return AZB_E_ALIGN;
     if (bias && !azb_aligned(bias, 16)) return AZB_E_ALIGN;
     if (out_mode != 0 && out_mode != 1) return AZB_E_SHAPE;
-    if (colsum && (out_mode != 0 || !azb_aligned(colsum, 8))) return AZB_E_SHAPE;
+    if (colsum && (out_mode != 0 || !azb_aligned(colsum, 8) || (stat_gran != 1 && stat_gran != 8))) return AZB_E_SHAPE;
 
     ConvParams p{};
     p.N = (int)n, p.H = (int)h, p.W = (int)w;
@@ -424,7 +475,6 @@ int conv_impl(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, in
         block_n = cand[i];
         if (m_tiles * (c_out_rows / cand[i]) >= (sms * 3) / 4 || cand[i] <= 64) break;
     }
-    if (colsum && block_n < 64) return AZB_E_SHAPE;
     if (c_out_rows % block_n || c_out_rows < c_out) return AZB_E_SHAPE;
 
     p.n_tiles = (int)(c_out_rows / block_n);
@@ -438,6 +488,7 @@ int conv_impl(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, in
     p.res_ld = res_ld;
     p.out = out, p.out_ld = out_ld, p.out_mode = out_mode;
     p.colsum = reinterpret_cast<float2*>(colsum);
+    p.stat_gran = stat_gran;
 
     CUtensorMap ta, tb;
     {
@@ -471,7 +522,7 @@ extern "C" int azb_conv_gemm_bf16(const void* act, int64_t n, int64_t h, int64_t
                                   const float* bias, const void* residual, int64_t res_ld, void* out, int64_t out_ld,
                                   int out_mode, void* stream) {
     return conv_impl(act, n, h, w, c_in, act_ld, wpack, c_out, c_out_rows, taps, k_per_tap, bias, residual, res_ld, out,
-                     out_ld, out_mode, nullptr, stream);
+                     out_ld, out_mode, nullptr, 1, stream);
 }
 
 extern "C" int azb_conv_colsum_rows(int64_t n, int64_t h, int64_t w, int64_t* rows, int64_t* rows_per_image) {
@@ -488,8 +539,8 @@ extern "C" int azb_conv_colsum_rows(int64_t n, int64_t h, int64_t w, int64_t* ro
 extern "C" int azb_conv_gemm_stats_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld,
                                         const void* wpack, int64_t c_out, int64_t c_out_rows, int taps,
                                         int64_t k_per_tap, const float* bias, const void* residual, int64_t res_ld,
-                                        void* out, int64_t out_ld, float* colsum, void* stream) {
+                                        void* out, int64_t out_ld, float* colsum, int stat_gran, void* stream) {
     AZB_CHECK_PTR(colsum);
     return conv_impl(act, n, h, w, c_in, act_ld, wpack, c_out, c_out_rows, taps, k_per_tap, bias, residual, res_ld, out,
-                     out_ld, 0, colsum, stream);
+                     out_ld, 0, colsum, stat_gran, stream);
 }

@@ -286,8 +286,9 @@ void launch_apply(const ApplyParams& p, dim3 grid, cudaStream_t s) {
 }
 
 struct FinalizeParams {
-    const float2* src[2];  // per-(32-row slab, channel) {sum, sum of squares} of up to two channel ranges
-    int c[2];
+    const float2* src[2];  // per-(32-row slab, channel block) {sum, sum of squares} of up to two channel ranges
+    int c[2];              // channels of each range
+    int gran[2];           // channels per entry of each range (1 or 8)
     int n, hw, groups;
     int tiles_per_image;   // M tiles that hold rows of one image
     int images_per_tile;   // BN
@@ -306,14 +307,21 @@ __global__ void __launch_bounds__(THREADS) gn_finalize_kernel(const FinalizePara
     const int tn = n / p.images_per_tile, bn = n - tn * p.images_per_tile;
     const int slabs = p.tiles_per_image * p.slabs_per_image;
     double a = 0.0, b = 0.0;
-    for (int item = threadIdx.x; item < slabs * cg; item += THREADS) {
-        const int sl = item / cg, cc = g * cg + (item - sl * cg);
-        const int t = sl / p.slabs_per_image, q = sl - t * p.slabs_per_image;
-        const int64_t row = ((int64_t)tn * p.tiles_per_image + t) * 4 + bn * p.slabs_per_image + q;
-        const int which = cc >= p.c[0];
-        const int ch = which ? cc - p.c[0] : cc;
-        const float2 v = __ldcg(p.src[which] + row * p.c[which] + ch);
-        a += (double)v.x, b += (double)v.y;
+    // the group's channels [g*cg, (g+1)*cg) split into the part inside range 0 and the part inside range 1
+    for (int which = 0; which < 2; ++which) {
+        const int lo = max(g * cg, which ? p.c[0] : 0) - (which ? p.c[0] : 0);
+        const int hi = min((g + 1) * cg, which ? ctot : p.c[0]) - (which ? p.c[0] : 0);
+        if (hi <= lo) continue;
+        const int gr = p.gran[which];
+        const int e0 = lo / gr, ne = (hi - lo) / gr;  // entries (host guarantees alignment)
+        const int epr = p.c[which] / gr;              // entries per slab row
+        for (int item = threadIdx.x; item < slabs * ne; item += THREADS) {
+            const int sl = item / ne, en = e0 + (item - sl * ne);
+            const int t = sl / p.slabs_per_image, q = sl - t * p.slabs_per_image;
+            const int64_t row = ((int64_t)tn * p.tiles_per_image + t) * 4 + bn * p.slabs_per_image + q;
+            const float2 v = __ldcg(p.src[which] + row * epr + en);
+            a += (double)v.x, b += (double)v.y;
+        }
     }
     red[0][threadIdx.x] = a, red[1][threadIdx.x] = b;
     __syncthreads();
@@ -413,12 +421,20 @@ extern "C" int azb_gn_apply_bf16(const void* x, int64_t x_ld, void* y, int64_t y
     return azb_launch_status();
 }
 
-extern "C" int azb_gn_finalize_f32(const float* colsum_a, int64_t c_a, const float* colsum_b, int64_t c_b, int64_t n,
-                                   int64_t h, int64_t w, int64_t groups, float eps, float* stats, void* stream) {
+extern "C" int azb_gn_finalize_f32(const float* colsum_a, int64_t c_a, int gran_a, const float* colsum_b, int64_t c_b,
+                                   int gran_b, int64_t n, int64_t h, int64_t w, int64_t groups, float eps, float* stats,
+                                   void* stream) {
     AZB_CHECK_PTR(colsum_a);
     AZB_CHECK_PTR(stats);
     if (n <= 0 || h <= 0 || w <= 0 || c_a <= 0 || c_b < 0 || groups <= 0 || (c_a + c_b) % groups) return AZB_E_SHAPE;
     if (c_b > 0 && !colsum_b) return AZB_E_NULL;
+    if ((gran_a != 1 && gran_a != 8) || (c_b > 0 && gran_b != 1 && gran_b != 8)) return AZB_E_SHAPE;
+    {
+        // group boundaries must fall on entry boundaries of both ranges
+        const int64_t cg = (c_a + c_b) / groups;
+        if (gran_a == 8 && (cg % 8 || c_a % 8)) return AZB_E_SHAPE;
+        if (c_b > 0 && gran_b == 8 && (cg % 8 || c_a % 8 || c_b % 8)) return AZB_E_SHAPE;
+    }
     // geometry of the convolution's M tiles (same rule as azb_conv_gemm_*: 128 = BN x BH x BW pixels)
     int bw = 1;
     while (bw < 16 && bw < w) bw <<= 1;
@@ -429,6 +445,7 @@ extern "C" int azb_gn_finalize_f32(const float* colsum_a, int64_t c_a, const flo
     FinalizeParams p{};
     p.src[0] = reinterpret_cast<const float2*>(colsum_a), p.src[1] = reinterpret_cast<const float2*>(colsum_b);
     p.c[0] = (int)c_a, p.c[1] = (int)c_b;
+    p.gran[0] = gran_a, p.gran[1] = c_b > 0 ? gran_b : 1;
     p.n = (int)n, p.hw = (int)(h * w), p.groups = (int)groups;
     p.tiles_per_image = (int)(((w + bw - 1) / bw) * ((h + bh - 1) / bh));
     p.images_per_tile = bn;

@@ -123,6 +123,9 @@ class Plan:
         self.lib = _lib.lib()
         self.ops: list[tuple] = []
         self.meta: list[tuple] = []
+        # every width of the network is a multiple of model_channels: with model_channels % 256 == 0 all GroupNorm
+        # groups (C / 32 channels) are multiples of 8 channels and the epilogues emit one sum per 8-channel block
+        self.stat_gran = 8 if lay.model_channels % 256 == 0 else 1
         self.colsum_of: dict[tuple, tuple] = {}  # activation view -> (column sums of its producer, channels)
         self.cat_parts: dict[tuple, list] = {}   # concatenation buffer -> [left view, right view]
         self.keep: list[Tensor] = []  # everything the launch list points into
@@ -194,10 +197,10 @@ class Plan:
         self.scratch_bytes = arena.bytes
 
     # ------------------------------------------------------------------------ plan building
-    def _emit(self, kind: str, flops: float, nbytes: float, fn, *args) -> None:
+    def _emit(self, kind: str, flops: float, nbytes: float, fn, *args, desc: str = "") -> None:
         r"""Queues one launch; ``flops`` / ``nbytes`` are its ALGORITHMIC work."""
         self.ops.append((fn, args))
-        self.meta.append((kind, flops, nbytes))
+        self.meta.append((kind, flops, nbytes, desc))
 
     @staticmethod
     def _key(t: Tensor) -> tuple:
@@ -210,15 +213,16 @@ class Plan:
         n, h, w, _ = x.shape
         colsum = None
         self.colsum_of.pop(self._key(out), None)  # the buffer may be a recycled one
-        if stats and pc.c_out_rows % 64 == 0:
+        if stats:
             rows, ok = ops.colsum_rows(n, h, w)
             if ok:
-                colsum = torch.empty(rows, pc.c_out, 2, dtype=torch.float32, device=self.device)
+                colsum = torch.empty(rows, pc.c_out // self.stat_gran, 2, dtype=torch.float32, device=self.device)
                 self.colsum_of[self._key(out)] = (colsum, pc.c_out)
         self.keep += [x, out, pc.w] + ([residual] if residual is not None else []) + ([pc.bias] if pc.bias is not None else [])
         flops = 2.0 * n * h * w * pc.c_out * pc.taps * pc.c_in
         nbytes = 2.0 * (n * h * w * (pc.c_in + pc.c_out * (2 if residual is not None else 1)) + pc.c_out * pc.taps * pc.c_in)
         kind = "conv3x3" if pc.taps == 9 else "conv1x1"
+        desc = f"{n}x{h}x{w} {pc.c_in}->{pc.c_out}" + (" +res" if residual is not None else "")
         if colsum is not None:
             self.keep.append(colsum)
             self._emit(
@@ -226,13 +230,14 @@ class Plan:
                 self.lib.azb_conv_gemm_stats_bf16, x.data_ptr(), n, h, w, pc.c_in, ops._ld(x), pc.w.data_ptr(),
                 pc.c_out, pc.c_out_rows, pc.taps, pc.k_per_tap, _lib.ptr(pc.bias), _lib.ptr(residual),
                 0 if residual is None else ops._ld(residual), out.data_ptr(), ops._ld(out), colsum.data_ptr(),
+                self.stat_gran, desc=desc + " +stats",
             )
             return
         self._emit(
             kind, flops, nbytes,
             self.lib.azb_conv_gemm_bf16, x.data_ptr(), n, h, w, pc.c_in, ops._ld(x), pc.w.data_ptr(), pc.c_out,
             pc.c_out_rows, pc.taps, pc.k_per_tap, _lib.ptr(pc.bias), _lib.ptr(residual),
-            0 if residual is None else ops._ld(residual), out.data_ptr(), ops._ld(out), 0,
+            0 if residual is None else ops._ld(residual), out.data_ptr(), ops._ld(out), 0, desc=desc,
         )
 
     def _stats(self, x: Tensor) -> Tensor:
@@ -248,8 +253,8 @@ class Plan:
             self.keep.append(stats)
             self._emit(
                 "gn_finalize", 0.0, 4.0 * (a.numel() + (b.numel() if b is not None else 0)),
-                self.lib.azb_gn_finalize_f32, a.data_ptr(), ca, _lib.ptr(b), cb, n, x.shape[1], x.shape[2],
-                ops.GN_GROUPS, ops.GN_EPS, stats.data_ptr(),
+                self.lib.azb_gn_finalize_f32, a.data_ptr(), ca, self.stat_gran, _lib.ptr(b), cb, self.stat_gran, n,
+                x.shape[1], x.shape[2], ops.GN_GROUPS, ops.GN_EPS, stats.data_ptr(),
             )
             return stats
         want = c_int64(0)
@@ -283,6 +288,7 @@ class Plan:
             "gn_apply", 0.0, 2.0 * c * (n * h * w + px_out),
             self.lib.azb_gn_apply_bf16, x.data_ptr(), ops._ld(x), out.data_ptr(), ops._ld(out), n, h, w, c,
             ops.GN_GROUPS, _lib.ptr(stats), _lib.ptr(gamma), _lib.ptr(beta), ss_ptr, ss_stride, None, 0, int(silu), mode,
+            desc=f"{n}x{h}x{w}x{c} mode{mode}",
         )
 
     def _block(self, block, x: Tensor | None, dest: Tensor) -> Tensor:
@@ -362,9 +368,10 @@ class Plan:
         r"""Kernels launched by one :meth:`run` (without the label lookup)."""
         return len(self.ops) + 6
 
-    def profile(self) -> dict[str, dict]:
+    def profile(self, detail: list | None = None) -> dict[str, dict]:
         r"""Times every queued launch with CUDA events on the current stream (buffers keep whatever
-        the last :meth:`run` left in them); returns per kernel kind: launches, ms, flops, bytes."""
+        the last :meth:`run` left in them); returns per kernel kind: launches, ms, flops, bytes.
+        ``detail`` (a list) receives one (kind, description, ms, flops, bytes) tuple per launch."""
         s = _lib.stream_ptr(self.device)
         events = [torch.cuda.Event(enable_timing=True) for _ in range(len(self.ops) + 1)]
         events[0].record()
@@ -373,10 +380,13 @@ class Plan:
             events[i + 1].record()
         torch.cuda.synchronize(self.device)
         table: dict[str, dict] = {}
-        for i, (kind, flops, nbytes) in enumerate(self.meta):
+        for i, (kind, flops, nbytes, desc) in enumerate(self.meta):
             row = table.setdefault(kind, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             row["launches"] += 1
-            row["ms"] += events[i].elapsed_time(events[i + 1])
+            ms = events[i].elapsed_time(events[i + 1])
+            row["ms"] += ms
+            if detail is not None:
+                detail.append((kind, desc, ms, flops, nbytes))
             row["flops"] += flops
             row["bytes"] += nbytes
         return table

@@ -26,12 +26,13 @@ _lib.register({
     "azb_conv_gemm_stats_bf16": (
         c_int,
         [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int64,
-         c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p],
+         c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p],
     ),
     "azb_conv_colsum_rows": (c_int, [c_int64, c_int64, c_int64, POINTER(c_int64), POINTER(c_int64)]),
     "azb_gn_finalize_f32": (
         c_int,
-        [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p],
+        [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p,
+         c_void_p],
     ),
     "azb_gn_stats_workspace": (c_int, [c_int64, c_int64, c_int64, c_int64, POINTER(c_int64)]),
     "azb_gn_stats_bf16": (
@@ -120,9 +121,10 @@ def gn_finalize(parts: list[tuple[Tensor, int]], n: int, h: int, w: int, stats: 
     (a, ca), (b, cb) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
     if stats is None:
         stats = torch.empty(n, groups, 2, dtype=torch.float32, device=a.device)
+    gran = lambda t, c: 1 if t is None else c // t.shape[1]  # noqa: E731  (channels per colsum entry)
     _lib.check(
-        _lib.lib().azb_gn_finalize_f32(a.data_ptr(), ca, _lib.ptr(b), cb, n, h, w, groups, eps, stats.data_ptr(),
-                                       _lib.stream_ptr(a.device)),
+        _lib.lib().azb_gn_finalize_f32(a.data_ptr(), ca, gran(a, ca), _lib.ptr(b), cb, gran(b, cb), n, h, w, groups, eps,
+                                       stats.data_ptr(), _lib.stream_ptr(a.device)),
         "azb_gn_finalize_f32",
     )
     return stats
@@ -133,8 +135,9 @@ def conv(x: Tensor, pc: PackedConv, out: Tensor | None = None, residual: Tensor 
     r"""3x3 (pad 1) / 1x1 convolution or linear layer on tcgen05 (``azb_conv_gemm_bf16``).
 
     x: (N, H, W, C_in) or (rows, C_in) bf16.  Returns bf16 NHWC (or fp32 NCHW when ``nchw_f32``).
-    With ``colsum`` (fp32 (rows, C_out, 2), see :func:`colsum_rows`) the epilogue also emits the
-    per-channel sums the consuming GroupNorm needs (``azb_conv_gemm_stats_bf16``).
+    With ``colsum`` (fp32 (rows, C_out, 2) or (rows, C_out / 8, 2), see :func:`colsum_rows`) the epilogue
+    also emits the per-channel (per-8-channel-block) sums the consuming GroupNorm needs
+    (``azb_conv_gemm_stats_bf16``).
     """
     assert x.dtype == torch.bfloat16 and x.is_cuda
     if x.ndim == 2:
@@ -154,7 +157,7 @@ def conv(x: Tensor, pc: PackedConv, out: Tensor | None = None, residual: Tensor 
             _lib.lib().azb_conv_gemm_stats_bf16(
                 x.data_ptr(), n, h, w, pc.c_in, _ld(x), pc.w.data_ptr(), pc.c_out, pc.c_out_rows, pc.taps,
                 pc.k_per_tap, _lib.ptr(pc.bias), _lib.ptr(residual), 0 if residual is None else _ld(residual),
-                out.data_ptr(), out_ld, colsum.data_ptr(), _lib.stream_ptr(x.device),
+                out.data_ptr(), out_ld, colsum.data_ptr(), pc.c_out // colsum.shape[1], _lib.stream_ptr(x.device),
             ),
             "azb_conv_gemm_stats_bf16",
         )

@@ -120,14 +120,16 @@ int azb_conv_gemm_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t
 /*
  * Same convolution, additionally writing what the GroupNorm that CONSUMES `out` needs: for every
  * 32-row slab of every 128-pixel M tile and every output channel, {sum, sum of squares} of the stored
- * (bf16-rounded) values: colsum float2[rows][c_out], rows from azb_conv_colsum_rows().  Fusing this
- * into the epilogue removes the separate statistics read pass (native_group_norm's first half,
- * azula/plugins/adm/_src/nn.py:80-87).  bf16 NHWC output only; c_out_rows must be a multiple of 64.
+ * (bf16-rounded) values: colsum float2[rows][c_out / stat_gran], rows from azb_conv_colsum_rows();
+ * stat_gran = 1 (one entry per channel) or 8 (one entry per block of 8 channels: enough whenever the
+ * consuming GroupNorm's groups are multiples of 8 channels, 8x less traffic).  Fusing this into the
+ * epilogue removes the separate statistics read pass (native_group_norm's first half,
+ * azula/plugins/adm/_src/nn.py:80-87).  bf16 NHWC output only.
  */
 int azb_conv_gemm_stats_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld,
                              const void* wpack, int64_t c_out, int64_t c_out_rows, int taps, int64_t k_per_tap,
                              const float* bias, const void* residual, int64_t res_ld, void* out, int64_t out_ld,
-                             float* colsum, void* stream);
+                             float* colsum, int stat_gran, void* stream);
 
 /* Rows of the colsum buffer for an (n, h, w) activation; *slab_in_image = 1 when every 32-row slab
  * lies inside one image (the condition for azb_gn_finalize_f32), else 0.  Host-side helper. */
@@ -136,8 +138,8 @@ int azb_conv_colsum_rows(int64_t n, int64_t h, int64_t w, int64_t* rows, int64_t
 /* stats[n][g] = {mean, rstd} from the column sums of one or two convolutions whose outputs form the
  * channel ranges [0, c_a) and [c_a, c_a + c_b) of the normalised tensor (a decoder concatenation,
  * azula/plugins/adm/_src/unet.py:631); colsum_b may be NULL with c_b = 0.  Deterministic. */
-int azb_gn_finalize_f32(const float* colsum_a, int64_t c_a, const float* colsum_b, int64_t c_b, int64_t n, int64_t h,
-                        int64_t w, int64_t groups, float eps, float* stats, void* stream);
+int azb_gn_finalize_f32(const float* colsum_a, int64_t c_a, int gran_a, const float* colsum_b, int64_t c_b, int gran_b,
+                        int64_t n, int64_t h, int64_t w, int64_t groups, float eps, float* stats, void* stream);
 
 /*
  * GroupNorm statistics over NHWC bf16 (N, HW, C), pixel stride ld: stats[n][g] = {mean, rstd}.

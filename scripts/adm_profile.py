@@ -44,7 +44,8 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.reps
         plan = next(v for k, v in den.backbone._native.items() if k != "packed")
-        table = plan.profile()
+        detail = []
+        table = plan.profile(detail)
     total = sum(r["ms"] for r in table.values())
     flops = sum(r["flops"] for r in table.values())
     print(f"forward {ms:.2f} ms eager ({plan.launches} launches), sum of kernels {total:.2f} ms, "
@@ -52,6 +53,13 @@ def main():
     for kind, r in sorted(table.items(), key=lambda kv: -kv[1]["ms"]):
         print(f"  {kind:10s} n={r['launches']:4d}  {r['ms']:8.2f} ms  {100 * r['ms'] / total:5.1f}%  "
               f"{r['flops'] / r['ms'] / 1e9:8.0f} TFLOP/s  {r['bytes'] / r['ms'] / 1e6:8.0f} GB/s")
+    groups = {}
+    for kind, desc, t, fl, by in detail:
+        g = groups.setdefault((kind, desc), [0, 0.0, 0.0, 0.0])
+        g[0] += 1; g[1] += t; g[2] += fl; g[3] += by
+    print("  -- by shape (top 30) --")
+    for (kind, desc), g in sorted(groups.items(), key=lambda kv: -kv[1][1])[:30]:
+        print(f"  {kind:10s} {desc:34s} n={g[0]:3d} {g[1]:7.3f} ms  {g[2] / g[1] / 1e9:6.0f} TFLOP/s {g[3] / g[1] / 1e6:6.0f} GB/s")
     print(json.dumps({"forward_ms": ms, "kernels": table}))
 
 

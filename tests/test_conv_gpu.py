@@ -52,6 +52,8 @@ SHAPES = [
     (2, 32, 32, 256, 256, 3),
     (1, 64, 64, 64, 64, 3),      # N tile 64
     (2, 16, 16, 32, 32, 3),      # C_in < 64: zero-padded K, N tile 32
+    (2, 16, 16, 64, 16, 3),      # N tile 16
+    (2, 16, 16, 64, 8, 1),       # fewer output channels than the narrowest tile
     (3, 4, 4, 64, 64, 3),
     (5, 2, 2, 128, 256, 3),
     (2, 12, 12, 64, 128, 3),     # extent not a multiple of the patch
@@ -125,18 +127,21 @@ def _group_stats(t, groups=32, eps=1e-5):
 @pytest.mark.parametrize("shape", [
     (2, 16, 16, 64, 128, 3), (3, 8, 8, 128, 256, 3), (1, 64, 64, 64, 64, 3), (2, 32, 32, 256, 256, 3),
     (2, 12, 12, 64, 128, 3), (1, 20, 24, 192, 128, 3), (2, 16, 16, 128, 384, 1), (5, 8, 8, 64, 512, 1),
-    (16, 8, 8, 256, 1024, 3),
+    (16, 8, 8, 256, 1024, 3), (2, 16, 16, 32, 32, 3),
 ])
-def test_conv_epilogue_statistics(shape):
+@pytest.mark.parametrize("gran", [1, 8])
+def test_conv_epilogue_statistics(shape, gran):
     """azb_conv_gemm_stats_bf16 + azb_gn_finalize_f32 == GroupNorm statistics of the stored output,
     and the output itself equals the plain convolution's bit for bit."""
     n, h, w, ci, co, k = shape
+    if gran == 8 and (co // 32) % 8:
+        pytest.skip("GroupNorm groups are not multiples of 8 channels")
     x, wt, b = _mk(*shape, seed=7)
     pc = ops.pack_conv(wt.float(), b)
     res = torch.randn(n, h, w, co, device=DEV).to(torch.bfloat16)
     rows, ok = ops.colsum_rows(n, h, w)
     assert ok
-    colsum = torch.full((rows, co, 2), float("nan"), device=DEV)
+    colsum = torch.full((rows, co // gran, 2), float("nan"), device=DEV)
     plain = ops.conv(x, pc, residual=res)
     got = ops.conv(x, pc, residual=res, colsum=colsum)
     assert torch.equal(got, plain)
@@ -156,13 +161,15 @@ def test_statistics_of_a_concatenation():
     rows, _ = ops.colsum_rows(n, h, w)
     xa, wa, ba = _mk(n, h, w, 128, ca, 1, seed=1)
     xb, wb, bb = _mk(n, h, w, 64, cb, 3, seed=2)
-    sa, sb = torch.empty(rows, ca, 2, device=DEV), torch.empty(rows, cb, 2, device=DEV)
-    ops.conv(xa, ops.pack_conv(wa.float(), ba), out=wide[..., :ca], colsum=sa)
-    ops.conv(xb, ops.pack_conv(wb.float(), bb), out=wide[..., ca:], colsum=sb)
-    stats = ops.gn_finalize([(sa, ca), (sb, cb)], n, h, w)
-    ref = _group_stats(wide)
-    assert torch.allclose(stats[..., 0], ref[..., 0], atol=2e-5, rtol=1e-4)
-    assert torch.allclose(stats[..., 1], ref[..., 1], rtol=1e-4)
+    ref = None
+    for ga, gb in ((1, 1), (8, 8), (8, 1)):
+        sa, sb = torch.empty(rows, ca // ga, 2, device=DEV), torch.empty(rows, cb // gb, 2, device=DEV)
+        ops.conv(xa, ops.pack_conv(wa.float(), ba), out=wide[..., :ca], colsum=sa)
+        ops.conv(xb, ops.pack_conv(wb.float(), bb), out=wide[..., ca:], colsum=sb)
+        stats = ops.gn_finalize([(sa, ca), (sb, cb)], n, h, w)
+        ref = _group_stats(wide) if ref is None else ref
+        assert torch.allclose(stats[..., 0], ref[..., 0], atol=2e-5, rtol=1e-4), (ga, gb)
+        assert torch.allclose(stats[..., 1], ref[..., 1], rtol=1e-4), (ga, gb)
 
 
 def test_conv_throughput_report():
