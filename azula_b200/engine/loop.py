@@ -77,7 +77,7 @@ class FusedLoop:
         self.time_in = self.table.time[0].clone()
         self.kwargs = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in kwargs.items()}
 
-        self.rng_threads, self.offset_inc = _lib.rng_policy(x.numel())
+        self.rng_threads, self.offset_inc, self.rng_first = sampler._rng_layout(x.numel())
 
         if unroll is None:
             unroll = self.steps if (x.numel() <= (1 << 16) and self.steps <= 1024) else 1
@@ -118,7 +118,7 @@ class FusedLoop:
                 self.x.data_ptr(), out.data_ptr(), _lib.DTYPE_CODE[out.dtype], stride, None,
                 self.x.data_ptr(), self.x_in.data_ptr(), _lib.DTYPE_CODE[self.in_dtype],
                 n_per, batch, tab.coef.data_ptr(), self.step_idx.data_ptr(),
-                0, self.philox.data_ptr(), 0, self.rng_threads, 0, stream,
+                0, self.philox.data_ptr(), 0, self.rng_threads, self.rng_first, stream,
             ),
             "azb_step_f32",
         )
@@ -183,7 +183,7 @@ def signature(sampler, x: Tensor, kwargs: dict):
     den = sampler.denoiser
     return (
         tuple(x.shape), x.device, sampler.start, sampler.stop, sampler.steps, sampler._eta(),
-        sampler.dtype, sampler.device, den.training, id(den.schedule), id(den.backbone),
+        sampler.dtype, sampler.device, sampler.shard, den.training, id(den.schedule), id(den.backbone),
         get_module_dtype(den.backbone),
         tuple(sorted((k, _freeze(v)) for k, v in kwargs.items())),
     )

@@ -46,6 +46,10 @@ class Sampler(abc.ABC):
         graph: Engine knob. :py:`None` captures the fused loop in a CUDA graph when possible,
             :py:`True` insists (errors surface), :py:`False` launches the fused step eagerly.
         unroll: Engine knob, number of steps captured per graph (:py:`None` = automatic).
+        shard: Engine knob for batch-sharded sampling, :py:`(rank, world)`: this process holds slice
+            :py:`rank` of :py:`world` equal slices (along the first dimension) of a global batch. Noise
+            is then addressed by GLOBAL element index, so the concatenation of the shards' results
+            equals the single-process result on the global batch bit for bit (CUDA tensors only).
     """
 
     denoiser: Denoiser
@@ -60,6 +64,7 @@ class Sampler(abc.ABC):
         device: torch.device | None = None,
         graph: bool | None = None,
         unroll: int | None = None,
+        shard: tuple[int, int] | None = None,
     ) -> None:
         self.start = start
         self.stop = stop
@@ -71,7 +76,14 @@ class Sampler(abc.ABC):
 
         self.graph = graph
         self.unroll = unroll
+        self.shard = shard
         self._loops: dict = {}
+
+    def _rng_layout(self, numel: int) -> tuple[int, int, int]:
+        r"""(threads, offset increment, first global element) of this process's noise draws."""
+        rank, world = self.shard if self.shard is not None else (0, 1)
+        threads, inc = _lib.rng_policy(numel * world)
+        return threads, inc, rank * numel
 
     @property
     def timesteps(self) -> Tensor:
@@ -110,11 +122,11 @@ class Sampler(abc.ABC):
             x = torch.empty(tuple(shape), dtype=torch.float32, device=alpha_T.device)
             with torch.cuda.device(x.device):
                 gen = _loop.default_generator(x.device)
-                threads, inc = _lib.rng_policy(numel)
+                threads, inc, first = self._rng_layout(numel)
                 seed, offset = gen.initial_seed(), gen.get_offset()
                 _lib.check(
                     _lib.lib().azb_init_noise_f32(
-                        x.data_ptr(), numel, float(mean_T), float(std_T), seed, offset, threads, 0,
+                        x.data_ptr(), numel, float(mean_T), float(std_T), seed, offset, threads, first,
                         _lib.stream_ptr(x.device),
                     ),
                     "azb_init_noise_f32",
@@ -192,7 +204,7 @@ class _Ancestral(Sampler):
         mean = self.denoiser(x_t, t, **kwargs).mean
 
         if _cuda_step_ok(x_t, mean, alpha_s):
-            return _cuda_step(x_t, mean, alpha_s, k, alpha_t, n)
+            return _cuda_step(x_t, mean, alpha_s, k, alpha_t, n, self._rng_layout(x_t.numel()))
 
         x_s = alpha_s * mean
         x_s = x_s + k * (x_t - alpha_t * mean)
@@ -242,7 +254,7 @@ def _cuda_step_ok(x_t: Tensor, mean: Tensor, alpha_s: Tensor) -> bool:
     )
 
 
-def _cuda_step(x_t: Tensor, mean: Tensor, alpha_s, k, alpha_t, n) -> Tensor:
+def _cuda_step(x_t: Tensor, mean: Tensor, alpha_s, k, alpha_t, n, layout=None) -> Tensor:
     r"""The affine update of one generic step as a single ``azb_step_f32`` launch
     (row = [0, 1, alpha_s, k, alpha_t, n, 1, inf] so that m = F = the posterior mean)."""
     with torch.cuda.device(x_t.device):
@@ -253,12 +265,12 @@ def _cuda_step(x_t: Tensor, mean: Tensor, alpha_s, k, alpha_t, n) -> Tensor:
         x_c, m_c = x_t.contiguous(), mean.contiguous()
         out = torch.empty_like(x_c)
         gen = _loop.default_generator(x_t.device)
-        threads, inc = _lib.rng_policy(x_c.numel())
+        threads, inc, first = layout if layout is not None else (*_lib.rng_policy(x_c.numel()), 0)
         seed, offset = gen.initial_seed(), gen.get_offset()
         _lib.check(
             _lib.lib().azb_step_f32(
                 x_c.data_ptr(), m_c.data_ptr(), _lib.F32, x_c.numel(), None, out.data_ptr(), None, _lib.F32,
-                x_c.numel(), 1, row.data_ptr(), idx.data_ptr(), seed, None, offset, threads, 0,
+                x_c.numel(), 1, row.data_ptr(), idx.data_ptr(), seed, None, offset, threads, first,
                 _lib.stream_ptr(x_t.device),
             ),
             "azb_step_f32",

@@ -121,13 +121,9 @@ def build_denoiser(device, rank: int, world: int):
     if rank == 0:
         adm.seed_parameters(den.backbone, seed=1234)
     if world > 1:  # the ONE collective of the path: weights from rank 0 at init (no per-step collective)
-        import torch.distributed as dist
+        from azula_b200 import parallel
 
-        flat = torch._utils._flatten_dense_tensors([p.data for p in den.backbone.parameters()])
-        dist.broadcast(flat, src=0)
-        for p, q in zip(den.backbone.parameters(), torch._utils._unflatten_dense_tensors(flat, list(den.backbone.parameters()))):
-            p.data.copy_(q)
-        del flat
+        parallel.broadcast_parameters(den.backbone, src=0)
     return den
 
 
@@ -250,9 +246,11 @@ def run_engine(args) -> None:
         return float(t.item())
 
     den = build_denoiser(device, rank, world)
-    sampler = DDIMSampler(den, steps=SAMPLER_STEPS, silent=True, graph=True)
+    # rank r owns samples [r*B, (r+1)*B) of the global batch; noise is addressed by global element index,
+    # so the N-GPU run reproduces the one-GPU run on the global batch bit for bit
+    sampler = DDIMSampler(den, steps=SAMPLER_STEPS, silent=True, graph=True, shard=(rank, world))
     shape = (args.batch, 3, SIZE, SIZE)
-    torch.manual_seed(1000 + rank)  # every rank draws its own slice of the global batch
+    torch.manual_seed(1000)
     x1 = sampler.init(shape, device=device)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # 2 x L2
 
