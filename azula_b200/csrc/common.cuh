@@ -39,6 +39,16 @@ __device__ __forceinline__ void stg_stream4(float* p, float4 v) {
                  : "memory");
 }
 
+__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
+    uint4 r;
+    // plain (coherent) streaming load: the apply pass may run in place (y == x)
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+
 __device__ __forceinline__ float bf16_bits_to_f32(uint32_t lo16) { return __uint_as_float(lo16 << 16); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -51,7 +51,21 @@ struct ConvParams {
     int out_mode;             // 0: bf16 NHWC, 1: fp32 NCHW
     float2* colsum;           // [m_tiles * 4][c_out / stat_gran] per-(32-row slab, channel block) {sum, sum of squares}
     int stat_gran;            // channels per colsum entry: 1 or 8
+    int stride;               // 1 or 2: input pixel = stride * output pixel + tap - pad
+    int act;                  // AZB_ACT_*: applied to acc + bias
+    const float* gate;        // per-(sample, channel) multiplier of act(acc + bias), or null
+    int64_t gate_ld;          // floats between the gate rows of consecutive samples (0 = one shared row)
+    int gate_rows;            // output pixels per sample (sample = pixel index / gate_rows)
 };
+
+__device__ __forceinline__ float activate(float v, int act) {
+    switch (act) {
+        case AZB_ACT_SILU: return __fdividef(v, 1.0f + __expf(-v));
+        case AZB_ACT_RELU: return fmaxf(v, 0.f);
+        case AZB_ACT_RELU2: v = fmaxf(v, 0.f); return v * v;
+    }
+    return v;
+}
 
 template <int BLOCK_N>
 struct Cfg {
@@ -138,7 +152,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                     const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
                     const uint32_t b_dst = a_dst + C::A_BYTES;
                     tc::mbar_expect_tx(full, C::STAGE_BYTES);
-                    tc::tma_load_4d(a_dst, &tmap_a, full, cb * BLOCK_K, w0 + kw - p.pad, h0 + kh - p.pad, n0);
+                    tc::tma_load_4d(a_dst, &tmap_a, full, cb * BLOCK_K, w0 * p.stride + kw - p.pad,
+                                    h0 * p.stride + kh - p.pad, n0);
                     tc::tma_load_2d(b_dst, &tmap_b, full, kb * BLOCK_K, n_tile * BLOCK_N);
                 }
             }
@@ -270,6 +285,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                             }
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] += bias8[j];
+                            if (p.act) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) f[j] = activate(f[j], p.act);
+                            }
+                            if (p.gate && col_ok && okc[it]) {
+                                const float* gp = p.gate + (pixc[it] / p.gate_rows) * p.gate_ld + col;
+                                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
+                                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp) + 1);
+                                f[0] *= g0.x, f[1] *= g0.y, f[2] *= g0.z, f[3] *= g0.w;
+                                f[4] *= g1.x, f[5] *= g1.y, f[6] *= g1.z, f[7] *= g1.w;
+                            }
                             if (use_res) {
                                 const uint32_t rr[4] = {rsd[it].x, rsd[it].y, rsd[it].z, rsd[it].w};
 #pragma unroll
@@ -391,7 +417,7 @@ EncodeTiledFn encode_fn() {
 }
 
 int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-             const uint32_t* box) {
+             const uint32_t* box, const uint32_t* elem_strides = nullptr) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return AZB_E_DRIVER;
     cuuint64_t gdim[5], gstr[4];
@@ -399,7 +425,7 @@ int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, c
     for (int i = 0; i < rank; ++i) {
         gdim[i] = dims[i];
         bx[i] = box[i];
-        es[i] = 1;
+        es[i] = elem_strides ? elem_strides[i] : 1;
         if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
     }
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
@@ -441,14 +467,26 @@ void patch_shape(int64_t h, int64_t w, int& bw, int& bh, int& bn) {
     bn = BLOCK_M / (bw * bh);
 }
 
-int conv_impl(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld, const void* wpack,
+struct ConvExtra {
+    int stride = 1;
+    int act = AZB_ACT_NONE;
+    const float* gate = nullptr;
+    int64_t gate_ld = 0;
+    int64_t gate_rows = 0;
+};
+
+// (h, w) are the INPUT extents; the output is ceil(h / stride) x ceil(w / stride).
+int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_in, int64_t act_ld, const void* wpack,
               int64_t c_out, int64_t c_out_rows, int taps, int64_t k_per_tap, const float* bias, const void* residual,
-              int64_t res_ld, void* out, int64_t out_ld, int out_mode, float* colsum, int stat_gran, void* stream) {
+              int64_t res_ld, void* out, int64_t out_ld, int out_mode, float* colsum, int stat_gran, void* stream,
+              const ConvExtra& ex = ConvExtra()) {
     AZB_CHECK_PTR(act);
     AZB_CHECK_PTR(wpack);
     AZB_CHECK_PTR(out);
-    if (n <= 0 || h <= 0 || w <= 0 || c_in <= 0 || c_out <= 0) return AZB_E_SHAPE;
+    if (n <= 0 || h_in <= 0 || w_in <= 0 || c_in <= 0 || c_out <= 0) return AZB_E_SHAPE;
     if (taps != 1 && taps != 9) return AZB_E_SHAPE;
+    if (ex.stride != 1 && ex.stride != 2) return AZB_E_SHAPE;
+    if (ex.act < AZB_ACT_NONE || ex.act > AZB_ACT_RELU2) return AZB_E_SHAPE;
     if (k_per_tap % BLOCK_K || k_per_tap < c_in) return AZB_E_SHAPE;
     if (c_in % 8 || act_ld % 8 || act_ld < c_in) return AZB_E_ALIGN;
     if (!azb_aligned(act, 16) || !azb_aligned(wpack, 16) || !azb_aligned(out, 16)) return AZB_E_ALIGN;
@@ -457,6 +495,9 @@ int conv_impl(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, in
     if (bias && !azb_aligned(bias, 16)) return AZB_E_ALIGN;
     if (out_mode != 0 && out_mode != 1) return AZB_E_SHAPE;
     if (colsum && (out_mode != 0 || !azb_aligned(colsum, 8) || (stat_gran != 1 && stat_gran != 8))) return AZB_E_SHAPE;
+    if (ex.gate && (out_mode != 0 || ex.gate_rows <= 0 || ex.gate_ld % 4 || !azb_aligned(ex.gate, 16))) return AZB_E_ALIGN;
+    if (out_mode == 1 && ex.act != AZB_ACT_NONE) return AZB_E_UNSUPPORTED;
+    const int64_t h = (h_in + ex.stride - 1) / ex.stride, w = (w_in + ex.stride - 1) / ex.stride;
 
     ConvParams p{};
     p.N = (int)n, p.H = (int)h, p.W = (int)w;
@@ -489,13 +530,20 @@ int conv_impl(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, in
     p.out = out, p.out_ld = out_ld, p.out_mode = out_mode;
     p.colsum = reinterpret_cast<float2*>(colsum);
     p.stat_gran = stat_gran;
+    p.stride = ex.stride, p.act = ex.act;
+    p.gate = ex.gate, p.gate_ld = ex.gate_ld, p.gate_rows = (int)ex.gate_rows;
 
     CUtensorMap ta, tb;
     {
-        uint64_t dims[4] = {(uint64_t)c_in, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-        uint64_t str[3] = {(uint64_t)act_ld * 2, (uint64_t)act_ld * 2 * w, (uint64_t)act_ld * 2 * w * h};
-        uint32_t box[4] = {BLOCK_K, (uint32_t)p.BW, (uint32_t)p.BH, (uint32_t)p.BN};
-        int rc = make_map(&ta, act, 4, dims, str, box);
+        // strided convolutions traverse the input with element strides (2, 2): the box spans stride * B pixels
+        // of the input and delivers B of them; coordinates stay in input pixels
+        const uint32_t st = (uint32_t)ex.stride;
+        uint64_t dims[4] = {(uint64_t)c_in, (uint64_t)w_in, (uint64_t)h_in, (uint64_t)n};
+        uint64_t str[3] = {(uint64_t)act_ld * 2, (uint64_t)act_ld * 2 * w_in, (uint64_t)act_ld * 2 * w_in * h_in};
+        uint32_t box[4] = {BLOCK_K, (uint32_t)p.BW * st, (uint32_t)p.BH * st, (uint32_t)p.BN};
+        uint32_t es[4] = {1, st, st, 1};
+        if (box[1] > 256 || box[2] > 256) return AZB_E_SHAPE;
+        int rc = make_map(&ta, act, 4, dims, str, box, es);
         if (rc) return rc;
     }
     {
@@ -543,4 +591,15 @@ extern "C" int azb_conv_gemm_stats_bf16(const void* act, int64_t n, int64_t h, i
     AZB_CHECK_PTR(colsum);
     return conv_impl(act, n, h, w, c_in, act_ld, wpack, c_out, c_out_rows, taps, k_per_tap, bias, residual, res_ld, out,
                      out_ld, 0, colsum, stat_gran, stream);
+}
+
+extern "C" int azb_conv2d_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld,
+                               const void* wpack, int64_t c_out, int64_t c_out_rows, int taps, int64_t k_per_tap,
+                               int stride, const float* bias, int act_fn, const float* gate, int64_t gate_ld,
+                               int64_t gate_rows, const void* residual, int64_t res_ld, void* out, int64_t out_ld,
+                               int out_mode, float* colsum, int stat_gran, void* stream) {
+    ConvExtra ex;
+    ex.stride = stride, ex.act = act_fn, ex.gate = gate, ex.gate_ld = gate_ld, ex.gate_rows = gate_rows;
+    return conv_impl(act, n, h, w, c_in, act_ld, wpack, c_out, c_out_rows, taps, k_per_tap, bias, residual, res_ld, out,
+                     out_ld, out_mode, colsum, colsum ? stat_gran : 1, stream, ex);
 }

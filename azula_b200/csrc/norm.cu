@@ -143,16 +143,6 @@ struct ApplyParams {
 
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
-__device__ __forceinline__ uint4 ldg_stream16(const void* p) {
-    uint4 r;
-    // plain (coherent) streaming load: the apply pass may run in place (y == x)
-    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p)
-                 : "memory");
-    return r;
-}
-
 template <bool SILU>
 __device__ __forceinline__ void affine8(const uint4 u, const float (&a)[8], const float (&b)[8], float (&acc)[8]) {
     const uint32_t wv[4] = {u.x, u.y, u.z, u.w};

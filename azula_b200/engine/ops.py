@@ -53,7 +53,26 @@ _lib.register({
     "azb_timestep_features_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_float, c_void_p, c_void_p]),
     "azb_linear_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     "azb_add_rows_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+    "azb_conv2d_bf16": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int64,
+         c_int, c_void_p, c_int, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p,
+         c_int, c_void_p],
+    ),
+    "azb_rownorm_mod_bf16": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_float, c_void_p, c_int64, c_int64, c_void_p],
+    ),
+    "azb_segment_rmsnorm_bf16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p]),
+    "azb_patchify_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "azb_unpatchify_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "azb_linear_gather_f32": (
+        c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p],
+    ),
 })
+
+ACT = {None: 0, "none": 0, "silu": 1, "relu": 2, "relu2": 3}
+NORM = {"layer": 0, "rms": 1}
 
 
 def _ld(t: Tensor) -> int:
@@ -314,3 +333,132 @@ def add_rows(y: Tensor, table: Tensor, idx: Tensor) -> Tensor:
         "azb_add_rows_f32",
     )
     return y
+
+
+# ------------------------------------------------------------------ in-repo backbones (nn.unet / nn.dit)
+
+
+def token_grid(rows: int) -> tuple[int, int, int]:
+    r"""(n, h, w) under which a (rows, C) token matrix is handed to the convolution entry so that an M tile is
+    128 consecutive rows."""
+    w = math.gcd(rows, 16)
+    return 1, rows // w, w
+
+
+def conv2d(x: Tensor, pc: PackedConv, out: Tensor | None = None, stride: int = 1, act: str | None = None,
+           gate: Tensor | None = None, gate_rows: int = 0, residual: Tensor | None = None, nchw_f32: bool = False) -> Tensor:
+    r"""``out = residual + gate[sample] * act(conv(x) + bias)`` (``azb_conv2d_bf16``).
+
+    x: (N, H, W, C_in) bf16 NHWC, or (rows, C_in) tokens.  ``gate``: fp32 (C_out,) shared or (samples, >= C_out)
+    rows (a slice of a wider matrix is fine: its row stride is used); ``gate_rows`` = output pixels (tokens) per
+    sample, default one image.
+    """
+    assert x.dtype == torch.bfloat16 and x.is_cuda
+    tokens = x.ndim == 2
+    n, h, w = token_grid(x.shape[0]) if tokens else x.shape[:3]
+    ho, wo = -(-h // stride), -(-w // stride)
+    if out is None:
+        if nchw_f32:
+            out = torch.empty((n, pc.c_out, ho, wo), dtype=torch.float32, device=x.device)
+        elif tokens:
+            out = torch.empty((x.shape[0], pc.c_out), dtype=torch.bfloat16, device=x.device)
+        else:
+            out = torch.empty((n, ho, wo, pc.c_out), dtype=torch.bfloat16, device=x.device)
+    gate_ld = 0
+    if gate is not None:
+        assert gate.dtype == torch.float32 and gate.stride(-1) == 1
+        if gate.ndim == 2 and gate.shape[0] > 1:
+            gate_ld = gate.stride(0)
+        gate_rows = gate_rows or ho * wo
+    _lib.check(
+        _lib.lib().azb_conv2d_bf16(
+            x.data_ptr(), n, h, w, pc.c_in, _ld(x), pc.w.data_ptr(), pc.c_out, pc.c_out_rows, pc.taps, pc.k_per_tap,
+            stride, _lib.ptr(pc.bias), ACT[act], _lib.ptr(gate), gate_ld, gate_rows, _lib.ptr(residual),
+            0 if residual is None else _ld(residual), out.data_ptr(), 0 if nchw_f32 else _ld(out),
+            1 if nchw_f32 else 0, None, 1, _lib.stream_ptr(x.device),
+        ),
+        "azb_conv2d_bf16",
+    )
+    return out
+
+
+def rownorm_mod(x: Tensor, kind: str = "layer", mod: Tensor | None = None, rows_per_sample: int = 0,
+                out: Tensor | None = None, eps: float = 1e-5) -> Tensor:
+    r"""``(1 + a) * norm(x) + b`` over the last dimension of a bf16 NHWC / token tensor
+    (``azb_rownorm_mod_bf16``); ``mod``: fp32 (>= 2C,) or (samples, >= 2C) = [a | b | ...]."""
+    c = x.shape[-1]
+    rows = x.numel() // c if x.is_contiguous() else math.prod(x.shape[:-1])
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    mod_ld = 0
+    if mod is not None:
+        assert mod.dtype == torch.float32 and mod.stride(-1) == 1 and mod.shape[-1] >= 2 * c
+        if mod.ndim == 2 and mod.shape[0] > 1:
+            mod_ld = mod.stride(0)
+            rows_per_sample = rows_per_sample or rows // mod.shape[0]
+        else:
+            rows_per_sample = rows
+    _lib.check(
+        _lib.lib().azb_rownorm_mod_bf16(
+            x.data_ptr(), _ld(x) if x.ndim in (2, 4) else x.stride(-2), out.data_ptr(),
+            _ld(out) if out.ndim in (2, 4) else out.stride(-2), rows, c, NORM[kind], eps, _lib.ptr(mod), mod_ld,
+            rows_per_sample, _lib.stream_ptr(x.device),
+        ),
+        "azb_rownorm_mod_bf16",
+    )
+    return out
+
+
+def segment_rmsnorm_(x: Tensor, segs: int, d: int, eps: float = 1e-5) -> Tensor:
+    r"""In-place RMS normalisation of the first ``segs`` d-wide channel segments of every row of a
+    (rows, ld) bf16 matrix (``azb_segment_rmsnorm_bf16``)."""
+    assert x.ndim == 2 and x.dtype == torch.bfloat16
+    _lib.check(
+        _lib.lib().azb_segment_rmsnorm_bf16(x.data_ptr(), x.stride(0), x.shape[0], segs, d, eps, _lib.stream_ptr(x.device)),
+        "azb_segment_rmsnorm_bf16",
+    )
+    return x
+
+
+def patchify(x: Tensor, p: int, q: int, k_pad: int, out: Tensor | None = None) -> Tensor:
+    r"""fp32 NCHW -> bf16 tokens (N * H/p * W/q, k_pad) (``azb_patchify_f32``)."""
+    n, c, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and h % p == 0 and w % q == 0
+    hp, wp = h // p, w // q
+    if out is None:
+        out = torch.empty(n * hp * wp, k_pad, dtype=torch.bfloat16, device=x.device)
+    _lib.check(
+        _lib.lib().azb_patchify_f32(x.data_ptr(), out.data_ptr(), n, c, hp, wp, p, q, k_pad, _lib.stream_ptr(x.device)),
+        "azb_patchify_f32",
+    )
+    return out
+
+
+def unpatchify(yt: Tensor, n: int, c: int, hp: int, wp: int, p: int, q: int, out: Tensor | None = None) -> Tensor:
+    r"""Channel-major fp32 GEMM output (c*p*q, tokens) -> fp32 NCHW (``azb_unpatchify_f32``)."""
+    assert yt.dtype == torch.float32 and yt.is_contiguous()
+    if out is None:
+        out = torch.empty(n, c, hp * p, wp * q, dtype=torch.float32, device=yt.device)
+    _lib.check(
+        _lib.lib().azb_unpatchify_f32(yt.data_ptr(), out.data_ptr(), n, c, hp, wp, p, q, _lib.stream_ptr(yt.device)),
+        "azb_unpatchify_f32",
+    )
+    return out
+
+
+def linear_gather(x: Tensor, xoff: Tensor | None, weight: Tensor, bias: Tensor | None, silu_in: bool = False,
+                  out: Tensor | None = None) -> Tensor:
+    r"""``y[:, j] = b[j] + act(x[:, xoff[j] : xoff[j] + K]) @ w[j]`` in fp32 (``azb_linear_gather_f32``)."""
+    m = x.shape[0]
+    nn_, k = weight.shape
+    assert x.dtype == torch.float32 and weight.dtype == torch.float32 and weight.is_contiguous() and x.stride(1) == 1
+    if out is None:
+        out = torch.empty(m, nn_, dtype=torch.float32, device=x.device)
+    _lib.check(
+        _lib.lib().azb_linear_gather_f32(
+            x.data_ptr(), x.stride(0), _lib.ptr(xoff), weight.data_ptr(), _lib.ptr(bias), out.data_ptr(), m, nn_, k,
+            int(silu_in), _lib.stream_ptr(x.device),
+        ),
+        "azb_linear_gather_f32",
+    )
+    return out

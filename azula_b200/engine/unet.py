@@ -1,0 +1,301 @@
+r"""Native sm_100a executor of :class:`azula_b200.nn.unet.UNet` (2-d, 3x3 kernels, stride 2).
+
+Replaces ``UNet.forward`` of the reference (``azula/nn/unet.py:207-259`` and ``UNetBlock._forward``
+``:97-107``: per block a normalisation, two broadcast multiplies/adds, two cuDNN convolutions, a
+SiLU and a gated residual -- 8 ATen launches and as many HBM round trips in fp32 NCHW) by a launch
+plan over NHWC bf16 buffers:
+
+    per block   azb_rownorm_mod_bf16   y = (1 + a) * LayerNorm_C(x) + b           (one pass)
+                azb_conv2d_bf16        h = SiLU(conv3x3(y) + bias)                 (tcgen05, epilogue act)
+                azb_conv2d_bf16        out = x + c * (conv3x3(h) + bias)           (tcgen05, epilogue gate + residual)
+    down        azb_conv2d_bf16 stride 2 (TMA element strides: no im2col, no gather pass)
+    up          azb_gn_apply_bf16 mode 1 (nearest x2) writing straight into the concatenation buffer
+    (a, b, c)   all blocks' Ada-Norm-Zero MLPs in two fp32 launches (:class:`ModulationBank`)
+
+``torch.cat((skip, x), dim=1)`` (``:257``) costs nothing: the last module of descent level *i* and the
+upsampling of ascent level *i + 1* write the two channel slices of one buffer.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from torch import Tensor
+
+from .. import _lib
+from . import ops
+from .plan import LaunchPlan, ModulationBank, fingerprint
+
+_MAX_PLANS = 2
+_NORM_KIND = {"layer": 0, "rms": 1}
+
+
+def _is_block(m) -> bool:
+    from ..nn.unet import UNetBlock
+
+    return isinstance(m, UNetBlock)
+
+
+def _conv_ok(conv: nn.Module, stride: int) -> bool:
+    return (
+        isinstance(conv, nn.Conv2d)
+        and conv.kernel_size == (3, 3)
+        and conv.padding == (1, 1)
+        and conv.padding_mode == "zeros"
+        and conv.stride == (stride, stride)
+        and conv.dilation == (1, 1)
+        and conv.groups == 1
+    )
+
+
+def structure_ok(model) -> bool:
+    r"""Whether every module of the network has a native counterpart (checked once per model)."""
+    cached = model._native.get("structure_ok")
+    if cached is not None:
+        return cached
+    ok = not hasattr(model, "bottleneck")
+    mod_features = set()
+    for levels, ascending in ((model.descent, False), (model.ascent, True)):
+        depth = len(levels)
+        for pos, level in enumerate(levels):
+            i = depth - 1 - pos if ascending else pos
+            for k, m in enumerate(level):
+                if _is_block(m):
+                    ok &= m.norm_kind in ("layer", "rms", "group")
+                    ok &= m.channels % 8 == 0 and m.channels <= 2048
+                    ok &= _conv_ok(m.ffn[0], 1) and _conv_ok(m.ffn[3], 1)
+                    ok &= not (isinstance(m.ffn[2], nn.Dropout) and m.training and m.ffn[2].p > 0)
+                    ok &= m.ffn[0].out_channels % 8 == 0
+                    if m.norm_kind == "group":
+                        ok &= m.channels <= 2048 and m.norm.num_groups <= 256
+                    mod_features.add(0 if torch.is_tensor(m.ada_zero) else m.ada_zero[0].in_features)
+                elif isinstance(m, nn.Upsample):
+                    ok &= m.mode == "nearest" and tuple(m.scale_factor) == (2.0, 2.0)
+                elif isinstance(m, nn.Conv2d):
+                    strided = (not ascending) and k == 0 and i > 0
+                    ok &= _conv_ok(m, 2 if strided else 1)
+                    first = (not ascending) and i == 0 and k == 0
+                    last = ascending and i == 0 and k == len(level) - 1
+                    ok &= first or m.in_channels % 8 == 0
+                    ok &= last or m.out_channels % 8 == 0
+                else:
+                    ok = False
+    ok &= len(mod_features) <= 1
+    model._native["structure_ok"] = bool(ok)
+    return bool(ok)
+
+
+def supports(model, x: Tensor, mod: Tensor | None) -> bool:
+    if x.ndim != 4 or not x.is_floating_point() or x.numel() == 0:
+        return False
+    if not structure_ok(model):
+        return False
+    if any(isinstance(m, nn.Dropout) and m.training and m.p > 0 for m in model.modules()):
+        return False
+    depth = len(model.descent)
+    if x.shape[2] % (1 << (depth - 1)) or x.shape[3] % (1 << (depth - 1)):
+        return False  # odd sizes need the crop of azula/nn/unet.py:253-255
+    if mod is not None and (mod.ndim not in (1, 2) or (mod.ndim == 2 and mod.shape[0] not in (1, x.shape[0]))):
+        return False
+    return True
+
+
+class Packed:
+    r"""Kernel-layout copy of the parameters on one device."""
+
+    def __init__(self, model, device: torch.device) -> None:
+        self.fingerprint = fingerprint(model)
+        self.device = device
+        first = model.descent[0][0]
+        self.k_pad = -(-9 * first.in_channels // 64) * 64
+        self.conv: dict[int, ops.PackedConv] = {}
+        blocks = []
+        for level in (*model.descent, *model.ascent):
+            for m in level:
+                if _is_block(m):
+                    blocks.append(m)
+                    for c in (m.ffn[0], m.ffn[3]):
+                        self.conv[id(c)] = ops.pack_conv(c.weight.detach().to(device), None if c.bias is None else c.bias.detach().to(device))
+                elif isinstance(m, nn.Conv2d):
+                    w = m.weight.detach().to(device)
+                    b = None if m.bias is None else m.bias.detach().to(device)
+                    if m is first:
+                        self.conv[id(m)] = ops.pack_first_conv(w.float(), b, self.k_pad)
+                    else:
+                        self.conv[id(m)] = ops.pack_conv(w, b)
+        self.bank = ModulationBank(blocks, device)
+        self.ones = torch.ones(2048, dtype=torch.float32, device=device)   # affine-free GroupNorm through gn_apply
+        self.zeros = torch.zeros(2048, dtype=torch.float32, device=device)
+
+
+class Plan(LaunchPlan):
+    r"""The launch list of one (batch, height, width, modulation rows) signature."""
+
+    def __init__(self, model, packed: Packed, n: int, h: int, w: int, rows: int, device: torch.device) -> None:
+        super().__init__(device)
+        self.packed = packed
+        self.n, self.h, self.w, self.rows = n, h, w, rows
+        arena = self.arena
+        bank = packed.bank
+        self.hid, self.abc = bank.buffers(rows, device)
+        self.mod_ld = self.abc.stride(0) if (rows == n and n > 1) else 0
+        self.gn_partial_need = 0
+        self.counters = torch.zeros(max(n, 1), dtype=torch.int32, device=device)
+
+        depth = len(model.descent)
+        first = model.descent[0][0]
+        widths = [level[0].out_channels for level in model.descent]
+        self.patches = arena.pin(arena.take(n, h, w, packed.k_pad))
+        self.in_channels = first.in_channels
+        # concatenation buffer of level i: [output of descent level i | upsampled output of ascent level i + 1]
+        self.cat = [arena.pin(arena.take(n, h >> i, w >> i, widths[i] + widths[i + 1])) for i in range(depth - 1)]
+
+        # ---- descent
+        cur = None
+        for i, level in enumerate(model.descent):
+            hi, wi = h >> i, w >> i
+            for k, m in enumerate(level):
+                last = k + 1 == len(level)
+                if last and i + 1 < depth:
+                    out = self.cat[i][..., : widths[i]]
+                else:
+                    out = arena.take(n, hi, wi, widths[i])
+                if _is_block(m):
+                    self._block(m, cur, out)
+                elif m is first:
+                    self.conv(self.patches, packed.conv[id(m)], out, kind="gemm")
+                else:
+                    self.conv(cur, packed.conv[id(m)], out, stride=2)
+                self._release(cur)
+                cur = out
+        # ---- ascent
+        self.out_conv = None
+        for pos, level in enumerate(model.ascent):
+            i = depth - 1 - pos
+            hi, wi = h >> i, w >> i
+            if i + 1 < depth:
+                self._release(cur)
+                cur = self.cat[i]
+            for m in level:
+                if _is_block(m):
+                    out = arena.take(n, hi, wi, widths[i])
+                    self._block(m, cur, out)
+                elif isinstance(m, nn.Upsample):
+                    out = self.cat[i - 1][..., widths[i - 1] :]
+                    self._upsample(cur, out)
+                elif i == 0 and m is level[-1]:
+                    self.out_conv = packed.conv[id(m)]  # bound per call (output tensor)
+                    self.final = cur
+                    arena.owner.pop(id(cur), None)
+                    break
+                else:
+                    out = arena.take(n, hi, wi, m.out_channels)
+                    self.conv(cur, packed.conv[id(m)], out)
+                self._release(cur)
+                cur = out
+        assert self.out_conv is not None
+
+        self.gn_partial = torch.empty(max(self.gn_partial_need, 1), dtype=torch.float32, device=device)
+        ptr = self.gn_partial.data_ptr()
+        self.ops = [(fn, tuple(ptr if isinstance(a, str) else a for a in args)) for fn, args in self.ops]
+        self.scratch_bytes = arena.bytes
+
+    def _release(self, t: Tensor | None) -> None:
+        if t is not None and id(t) in self.arena.owner:
+            self.arena.give(t)
+
+    def _block(self, m, x: Tensor, out: Tensor) -> None:
+        r"""``UNetBlock._forward`` (``azula/nn/unet.py:97-107``)."""
+        arena, pk = self.arena, self.packed
+        n, h, w, c = x.shape
+        off = pk.bank.offset[id(m)]
+        abc = self.abc.data_ptr() + 4 * off
+        y = arena.take(n, h, w, c)
+        if m.norm_kind == "group":
+            self._group_norm(m, x, y, abc)
+        else:
+            self.rownorm(x, y, _NORM_KIND[m.norm_kind], abc, self.mod_ld, h * w, eps=m.norm.eps)
+        c1, c2 = pk.conv[id(m.ffn[0])], pk.conv[id(m.ffn[3])]
+        hbuf = arena.take(n, h, w, c1.c_out)
+        self.conv(y, c1, hbuf, act=ops.ACT["silu"])
+        arena.give(y)
+        self.conv(hbuf, c2, out, gate=abc + 4 * 2 * c, gate_ld=self.mod_ld, gate_rows=h * w, residual=x)
+        arena.give(hbuf)
+
+    def _group_norm(self, m, x: Tensor, y: Tensor, abc: int) -> None:
+        from ctypes import byref, c_int64
+
+        n, h, w, c = x.shape
+        groups = m.norm.num_groups
+        want = c_int64(0)
+        _lib.check(self.lib.azb_gn_stats_workspace(n, h * w, c, groups, byref(want)), "azb_gn_stats_workspace")
+        self.gn_partial_need = max(self.gn_partial_need, want.value)
+        stats = torch.empty(n, groups, 2, dtype=torch.float32, device=self.device)
+        self.keep += [x, y, stats]
+        self._emit("gn_stats", 0.0, 2.0 * n * h * w * c, self.lib.azb_gn_stats_bf16, x.data_ptr(), x.stride(-2), n, h * w,
+                   c, groups, m.norm.eps, "partial", stats.data_ptr(), self.counters.data_ptr())
+        pk = self.packed
+        self._emit("gn_apply", 0.0, 4.0 * n * h * w * c, self.lib.azb_gn_apply_bf16, x.data_ptr(), x.stride(-2),
+                   y.data_ptr(), y.stride(-2), n, h, w, c, groups, stats.data_ptr(), pk.ones.data_ptr(),
+                   pk.zeros.data_ptr(), abc, self.mod_ld, None, 0, 0, 0)
+
+    def _upsample(self, x: Tensor, out: Tensor) -> None:
+        n, h, w, c = x.shape
+        self.keep += [x, out]
+        self._emit("upsample", 0.0, 2.0 * n * h * w * c * 5, self.lib.azb_gn_apply_bf16, x.data_ptr(), x.stride(-2),
+                   out.data_ptr(), out.stride(-2), n, h, w, c, 1, None, None, None, None, 0, None, 0, 0, 1,
+                   desc=f"{n}x{h}x{w}x{c} x2")
+
+    @property
+    def launches(self) -> int:
+        return len(self.ops) + 2 + (2 if self.packed.bank.hidden else 0)
+
+    def run(self, x: Tensor, mod: Tensor | None, out: Tensor) -> Tensor:
+        lib, pk = self.lib, self.packed
+        s = _lib.stream_ptr(self.device)
+        n, c, h, w = x.shape
+        _lib.check(lib.azb_im2col3x3_f32(x.data_ptr(), self.patches.data_ptr(), n, c, h, w, pk.k_pad, s), "azb_im2col3x3_f32")
+        if pk.bank.hidden:
+            pk.bank.run(lib, mod, self.hid, self.abc, s)
+        self.replay()
+        oc = self.out_conv
+        f = self.final
+        _lib.check(lib.azb_conv2d_bf16(f.data_ptr(), n, h, w, oc.c_in, f.stride(-2), oc.w.data_ptr(), oc.c_out,
+                                       oc.c_out_rows, oc.taps, oc.k_per_tap, 1, _lib.ptr(oc.bias), 0, None, 0, 0, None, 0,
+                                       out.data_ptr(), 0, 1, None, 1, s), "azb_conv2d_bf16")
+        return out
+
+
+def forward(model, x: Tensor, mod: Tensor | None = None) -> Tensor:
+    r"""``UNet.forward`` on a CUDA device: (N, C_i, H, W) any float dtype -> (N, C_o, H, W) same dtype."""
+    device = x.device
+    n, _, h, w = x.shape
+    with torch.cuda.device(device):
+        cache = model._native
+        packed = cache.get("packed")
+        if packed is None or packed.fingerprint != fingerprint(model) or packed.device != device:
+            ok = cache.get("structure_ok")
+            cache.clear()
+            cache["structure_ok"] = ok
+            packed = cache["packed"] = Packed(model, device)
+
+        rows = 1
+        if packed.bank.hidden:
+            if mod is None:
+                raise ValueError("this network needs a modulation vector `mod`")
+            mod = mod.to(device=device, dtype=torch.float32).reshape(-1, packed.bank.features).contiguous()
+            rows = mod.shape[0]
+
+        key = (n, h, w, rows)
+        plan = cache.get(key)
+        if plan is None:
+            plans = [k for k in cache if isinstance(k, tuple)]
+            while len(plans) >= _MAX_PLANS:
+                del cache[plans.pop(0)]
+            plan = cache[key] = Plan(model, packed, n, h, w, rows, device)
+
+        xin = x.to(torch.float32).contiguous()
+        out = torch.empty((n, plan.out_conv.c_out, h, w), dtype=torch.float32, device=device)
+        plan.run(xin, mod, out)
+    return out.to(x.dtype)

@@ -2,10 +2,12 @@ r"""Module helpers used by the denoisers (interface of ``azula/nn/utils.py:24-42
 
 from __future__ import annotations
 
-__all__ = ["get_module_dtype", "get_module_device", "skip_init"]
+__all__ = ["checkpoint", "get_module_dtype", "get_module_device", "promote_dtype", "skip_init"]
 
+import functools
 import itertools
 import torch
+import torch.utils.checkpoint
 
 
 def _first(module: torch.nn.Module, attr: str, only_float: bool):
@@ -44,3 +46,36 @@ class skip_init(torch.overrides.TorchFunctionMode):
         if getattr(func, "__module__", None) == "torch.nn.init":
             return kwargs["tensor"] if "tensor" in kwargs else args[0]
         return func(*args, **kwargs)
+
+
+def checkpoint(f, reentrant: bool = False):
+    r"""Activation checkpointing of a function (interface of ``azula/nn/utils.py:109-161``).
+
+    Training-side utility, outside the generation path: without autograd the function is simply
+    called; with autograd the inputs are stored and the graph recomputed during the backward pass
+    (:func:`torch.utils.checkpoint.checkpoint`, non-reentrant, so that implicit inputs such as module
+    parameters receive gradients in both modes).
+    """
+
+    @functools.wraps(f)
+    def g(*args, **kwargs):
+        if not torch.is_grad_enabled():
+            return f(*args, **kwargs)
+        return torch.utils.checkpoint.checkpoint(f, *args, use_reentrant=False, **kwargs)
+
+    return g
+
+
+def promote_dtype(f, min_dtype: torch.dtype = torch.float32):
+    r"""Runs a function of tensors in at least ``min_dtype`` and casts the result(s) back to the
+    promoted input dtype (interface of ``azula/nn/utils.py:191-221``)."""
+
+    @functools.wraps(f)
+    def g(*args, **kwargs):
+        dtype = functools.reduce(torch.promote_types, [a.dtype for a in args])
+        outs = f(*(a.to(torch.promote_types(a.dtype, min_dtype)) for a in args), **kwargs)
+        if torch.is_tensor(outs):
+            return outs.to(dtype)
+        return tuple(o.to(dtype) for o in outs)
+
+    return g

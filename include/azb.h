@@ -41,6 +41,12 @@ enum {
 /* dtype codes */
 enum { AZB_F32 = 0, AZB_BF16 = 1, AZB_F16 = 2, AZB_I64 = 3 };
 
+/* activation codes of the GEMM epilogue */
+enum { AZB_ACT_NONE = 0, AZB_ACT_SILU = 1, AZB_ACT_RELU = 2, AZB_ACT_RELU2 = 3 };
+
+/* row normalisations of azb_rownorm_mod_bf16 */
+enum { AZB_NORM_LAYER = 0, AZB_NORM_RMS = 1 };
+
 /* Columns of one row of the per-step coefficient table (float32[steps][AZB_COEF_COLS]).
  * The row is built once per sampler from the schedule itself (azula_b200/engine/table.py)
  * with the reference's own scalar operation order, see DESIGN.md "coefficient table". */
@@ -131,6 +137,25 @@ int azb_conv_gemm_stats_bf16(const void* act, int64_t n, int64_t h, int64_t w, i
                              const float* bias, const void* residual, int64_t res_ld, void* out, int64_t out_ld,
                              float* colsum, int stat_gran, void* stream);
 
+/*
+ * The general form of the convolution / linear entry, for the in-repo backbones
+ * (azula/nn/unet.py:75-81,87-95,168-205 ConvNd + SiLU + gated residual; azula/nn/dit.py:86-91,
+ * 104-107 and azula/nn/attention.py:101,116-118 linears):
+ *
+ *     out = residual + gate[sample] * act_fn(conv(act) + bias)
+ *
+ *   stride      1 or 2 (3x3 pad 1 only): (h, w) are INPUT extents, output = ceil(h/stride) x ceil(w/stride)
+ *   act_fn      AZB_ACT_*
+ *   gate        fp32, channel c of sample s at gate[s*gate_ld + c] (gate_ld = 0: one shared row);
+ *               sample = output pixel index / gate_rows.  NULL = no gate.  bf16 NHWC output only.
+ *   colsum      as in azb_conv_gemm_stats_bf16, or NULL.
+ */
+int azb_conv2d_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld,
+                    const void* wpack, int64_t c_out, int64_t c_out_rows, int taps, int64_t k_per_tap,
+                    int stride, const float* bias, int act_fn, const float* gate, int64_t gate_ld,
+                    int64_t gate_rows, const void* residual, int64_t res_ld, void* out, int64_t out_ld,
+                    int out_mode, float* colsum, int stat_gran, void* stream);
+
 /* Rows of the colsum buffer for an (n, h, w) activation; *slab_in_image = 1 when every 32-row slab
  * lies inside one image (the condition for azb_gn_finalize_f32), else 0.  Host-side helper. */
 int azb_conv_colsum_rows(int64_t n, int64_t h, int64_t w, int64_t* rows, int64_t* slab_in_image);
@@ -192,6 +217,39 @@ int azb_linear_f32(const float* x, const float* w, const float* b, float* y, int
 
 /* y[r][:] += table[idx[r]][:] (class-label embedding, _src/unet.py:621-623). */
 int azb_add_rows_f32(float* y, const float* table, const int64_t* idx, int64_t rows, int64_t dim, void* stream);
+
+/*
+ * y[r][c] = (1 + a[s][c]) * norm(x[r])[c] + b[s][c] over rows of C contiguous bf16 channels (row stride
+ * x_ld / y_ld elements), fp32 arithmetic: the Ada-Norm-Zero prologue of UNetBlock (azula/nn/unet.py:
+ * 99-104 with azula/nn/layers.py:152-155: standardisation over the channel dimension with the UNBIASED
+ * variance of torch.var_mean, no affine) and of DiTBlock (azula/nn/dit.py:102-103 with
+ * torch.nn.RMSNorm(elementwise_affine=False)).  mod is fp32 with [a(C) | b(C) | ...] per sample,
+ * sample s = r / rows_per_sample at mod + s*mod_ld (mod_ld = 0: shared); mod NULL = plain normalisation.
+ */
+int azb_rownorm_mod_bf16(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t rows, int64_t c, int kind,
+                         float eps, const float* mod, int64_t mod_ld, int64_t rows_per_sample, void* stream);
+
+/* In-place RMS normalisation (no affine) of `segs` contiguous segments of d channels per row, starting at
+ * channel 0 of x (rows x ld, bf16): the query-key normalisation of MultiheadSelfAttention
+ * (azula/nn/attention.py:103 on the q and k thirds of the qkv projection: segs = 2 * heads). */
+int azb_segment_rmsnorm_bf16(void* x, int64_t ld, int64_t rows, int64_t segs, int64_t d, float eps, void* stream);
+
+/* Patchify(channel_last) of azula/nn/vit.py:97 (azula/nn/layers.py:198-222): fp32 NCHW (n, c, hp*p, wp*q)
+ * -> bf16 tokens (n*hp*wp, k_pad), token (i, j) channel (z*p + a)*q + b = x[n][z][i*p + a][j*q + b], zero
+ * padded to k_pad channels. */
+int azb_patchify_f32(const float* x, void* tokens, int64_t n, int64_t c, int64_t hp, int64_t wp, int64_t p,
+                     int64_t q, int64_t k_pad, void* stream);
+
+/* Unpatchify(channel_last) of azula/nn/vit.py:105 from the channel-major fp32 GEMM output
+ * yt[(z*p + a)*q + b][token] (out_mode 1 of the convolution entry) -> fp32 NCHW (n, c, hp*p, wp*q). */
+int azb_unpatchify_f32(const float* yt, float* out, int64_t n, int64_t c, int64_t hp, int64_t wp, int64_t p,
+                       int64_t q, void* stream);
+
+/* y[m][j] = b[j] + sum_k act(x[m][xoff[j] + k]) w[j][k]: azb_linear_f32 whose output column j reads its K
+ * inputs at column offset xoff[j] of a row of x (row stride x_ld): every block's second Ada-Norm-Zero
+ * linear in ONE launch (azula/nn/unet.py:65-70, azula/nn/dit.py:57-63).  xoff NULL = 0. */
+int azb_linear_gather_f32(const float* x, int64_t x_ld, const int32_t* xoff, const float* w, const float* b,
+                          float* y, int64_t m, int64_t n, int64_t k, int silu_in, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,3 +39,40 @@ IMAGENET_256 = dict(
     resblock_updown=True,
     use_scale_shift_norm=True,
 )
+
+# ---- in-repo backbones (azula/nn/unet.py, azula/nn/vit.py): small CPU-friendly fixtures
+UNET_CASES = {
+    # tag: (constructor kwargs, input (B, C, H, W), modulation rows: None | 1 | B, cond channels)
+    "layer": (dict(in_channels=3, out_channels=3, hid_channels=(16, 32, 64), hid_blocks=(2, 2, 1), mod_features=32), (2, 3, 16, 16)),
+    "rms_free": (dict(in_channels=2, out_channels=5, hid_channels=(16, 32), hid_blocks=(1, 2), norm="rms", ffn_factor=2), (3, 2, 8, 12)),
+    "group_cond": (dict(in_channels=3, out_channels=3, cond_channels=1, hid_channels=(32, 64), hid_blocks=(1, 1), mod_features=16,
+                        norm="group", groups=4), (2, 3, 8, 8)),
+}
+
+VIT_CASES = {
+    "dit_b2_small": (dict(in_channels=4, out_channels=4, mod_features=64, hid_channels=128, hid_blocks=2, attention_heads=2,
+                          patch_size=2), (2, 4, 8, 8)),
+    "relu2_free": (dict(in_channels=3, out_channels=2, hid_channels=64, hid_blocks=1, attention_heads=2, patch_size=(2, 1),
+                        ffn_activation="relu2", qk_norm=False, ffn_factor=2), (2, 3, 4, 6)),
+}
+
+DIT_CASE = (dict(in_channels=6, out_channels=3, mod_features=32, hid_channels=64, hid_blocks=2, attention_heads=4), (2, 10, 6))
+
+
+def time_wrapper(net_cls, features: int, **kwargs):
+    """The tutorial pattern around an in-repo backbone (reference docs/tutorials/mnist.ipynb cell 8, minus the
+    label embedding): mod = MLP(log_snr[..., None]); BASELINE configs 2 and 4 use it."""
+    import torch
+
+    class Wrapper(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.net = net_cls(mod_features=features, **kwargs)
+            self.time_embedding = torch.nn.Sequential(
+                torch.nn.Linear(1, features), torch.nn.SiLU(), torch.nn.Linear(features, features)
+            )
+
+        def forward(self, x_t, log_snr_t):
+            return self.net(x_t, self.time_embedding(log_snr_t[..., None]))
+
+    return Wrapper()
