@@ -56,6 +56,7 @@ struct ConvParams {
     const float* gate;        // per-(sample, channel) multiplier of act(acc + bias), or null
     int64_t gate_ld;          // floats between the gate rows of consecutive samples (0 = one shared row)
     int gate_rows;            // output pixels per sample (sample = pixel index / gate_rows)
+    int kb_extra;             // K blocks of the second (1x1, same resolution) operand appended after the taps
 };
 
 __device__ __forceinline__ float activate(float v, int act) {
@@ -95,6 +96,7 @@ __device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                 const __grid_constant__ CUtensorMap tmap_b,
+                                                                const __grid_constant__ CUtensorMap tmap_a2,
                                                                 const ConvParams p) {
     using C = Cfg<BLOCK_N>;
     constexpr int STAGES = C::STAGES;
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tmap_a);
         tc::prefetch_tmap(&tmap_b);
+        if (p.kb_extra) tc::prefetch_tmap(&tmap_a2);
     }
     if (warp == 1) {
         tc::tmem_alloc(tc::smem_u32(&tmem_slot), C::TMEM_COLS);
@@ -132,7 +135,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
 
-    const int num_kb = p.taps * p.kb_per_tap;
+    const int num_kb_taps = p.taps * p.kb_per_tap;
+    const int num_kb = num_kb_taps + p.kb_extra;
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -145,15 +149,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                     const int s = it % STAGES;
                     const uint32_t parity = ((it / STAGES) & 1) ^ 1;
                     tc::mbar_wait(tc::smem_u32(&bar_empty[s]), parity);
-                    const int tap = kb / p.kb_per_tap;
-                    const int cb = kb - tap * p.kb_per_tap;
-                    const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
                     const uint32_t full = tc::smem_u32(&bar_full[s]);
                     const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
                     const uint32_t b_dst = a_dst + C::A_BYTES;
                     tc::mbar_expect_tx(full, C::STAGE_BYTES);
-                    tc::tma_load_4d(a_dst, &tmap_a, full, cb * BLOCK_K, w0 * p.stride + kw - p.pad,
-                                    h0 * p.stride + kh - p.pad, n0);
+                    if (kb < num_kb_taps) {
+                        const int tap = kb / p.kb_per_tap;
+                        const int cb = kb - tap * p.kb_per_tap;
+                        const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+                        tc::tma_load_4d(a_dst, &tmap_a, full, cb * BLOCK_K, w0 * p.stride + kw - p.pad,
+                                        h0 * p.stride + kh - p.pad, n0);
+                    } else {  // the fused 1x1 operand (ResBlock skip connection): same pixels, no offset
+                        tc::tma_load_4d(a_dst, &tmap_a2, full, (kb - num_kb_taps) * BLOCK_K, w0, h0, n0);
+                    }
                     tc::tma_load_2d(b_dst, &tmap_b, full, kb * BLOCK_K, n_tile * BLOCK_N);
                 }
             }
@@ -445,7 +453,7 @@ int sm_count() {
 }
 
 template <int BLOCK_N>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cudaStream_t s) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const ConvParams& p, cudaStream_t s) {
     constexpr int smem = Cfg<BLOCK_N>::SMEM;
     static bool configured = false;
     if (!configured) {
@@ -454,7 +462,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const ConvParams& p, cu
         configured = true;
     }
     const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-    conv_gemm_kernel<BLOCK_N><<<(unsigned)grid, THREADS, smem, s>>>(ta, tb, p);
+    conv_gemm_kernel<BLOCK_N><<<(unsigned)grid, THREADS, smem, s>>>(ta, tb, ta2, p);
     return azb_launch_status();
 }
 
@@ -473,6 +481,8 @@ struct ConvExtra {
     const float* gate = nullptr;
     int64_t gate_ld = 0;
     int64_t gate_rows = 0;
+    const void* act2 = nullptr;  // second operand: NHWC bf16 at the OUTPUT resolution, 1x1, weights appended along K
+    int64_t c_in2 = 0, act2_ld = 0, k2 = 0;
 };
 
 // (h, w) are the INPUT extents; the output is ceil(h / stride) x ceil(w / stride).
@@ -497,6 +507,9 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     if (colsum && (out_mode != 0 || !azb_aligned(colsum, 8) || (stat_gran != 1 && stat_gran != 8))) return AZB_E_SHAPE;
     if (ex.gate && (out_mode != 0 || ex.gate_rows <= 0 || ex.gate_ld % 4 || !azb_aligned(ex.gate, 16))) return AZB_E_ALIGN;
     if (out_mode == 1 && ex.act != AZB_ACT_NONE) return AZB_E_UNSUPPORTED;
+    if (ex.act2 && (ex.c_in2 <= 0 || ex.c_in2 % 8 || ex.act2_ld % 8 || ex.act2_ld < ex.c_in2 || ex.k2 % BLOCK_K ||
+                    ex.k2 < ex.c_in2 || !azb_aligned(ex.act2, 16)))
+        return AZB_E_ALIGN;
     const int64_t h = (h_in + ex.stride - 1) / ex.stride, w = (w_in + ex.stride - 1) / ex.stride;
 
     ConvParams p{};
@@ -532,8 +545,10 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     p.stat_gran = stat_gran;
     p.stride = ex.stride, p.act = ex.act;
     p.gate = ex.gate, p.gate_ld = ex.gate_ld, p.gate_rows = (int)ex.gate_rows;
+    p.kb_extra = ex.act2 ? (int)(ex.k2 / BLOCK_K) : 0;
+    const int64_t k_total = taps * k_per_tap + (ex.act2 ? ex.k2 : 0);
 
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, ta2;
     {
         // strided convolutions traverse the input with element strides (2, 2): the box spans stride * B pixels
         // of the input and delivers B of them; coordinates stay in input pixels
@@ -547,19 +562,28 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
         if (rc) return rc;
     }
     {
-        uint64_t dims[2] = {(uint64_t)(taps * k_per_tap), (uint64_t)c_out_rows};
-        uint64_t str[1] = {(uint64_t)(taps * k_per_tap) * 2};
+        uint64_t dims[2] = {(uint64_t)k_total, (uint64_t)c_out_rows};
+        uint64_t str[1] = {(uint64_t)k_total * 2};
         uint32_t box[2] = {BLOCK_K, (uint32_t)block_n};
         int rc = make_map(&tb, wpack, 2, dims, str, box);
         if (rc) return rc;
     }
+    if (ex.act2) {
+        uint64_t dims[4] = {(uint64_t)ex.c_in2, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        uint64_t str[3] = {(uint64_t)ex.act2_ld * 2, (uint64_t)ex.act2_ld * 2 * w, (uint64_t)ex.act2_ld * 2 * w * h};
+        uint32_t box[4] = {BLOCK_K, (uint32_t)p.BW, (uint32_t)p.BH, (uint32_t)p.BN};
+        int rc = make_map(&ta2, ex.act2, 4, dims, str, box);
+        if (rc) return rc;
+    } else {
+        ta2 = ta;
+    }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     switch (block_n) {
-        case 256: return launch<256>(ta, tb, p, s);
-        case 128: return launch<128>(ta, tb, p, s);
-        case 64: return launch<64>(ta, tb, p, s);
-        case 32: return launch<32>(ta, tb, p, s);
-        default: return launch<16>(ta, tb, p, s);
+        case 256: return launch<256>(ta, tb, ta2, p, s);
+        case 128: return launch<128>(ta, tb, ta2, p, s);
+        case 64: return launch<64>(ta, tb, ta2, p, s);
+        case 32: return launch<32>(ta, tb, ta2, p, s);
+        default: return launch<16>(ta, tb, ta2, p, s);
     }
 }
 
@@ -602,4 +626,16 @@ extern "C" int azb_conv2d_bf16(const void* act, int64_t n, int64_t h, int64_t w,
     ex.stride = stride, ex.act = act_fn, ex.gate = gate, ex.gate_ld = gate_ld, ex.gate_rows = gate_rows;
     return conv_impl(act, n, h, w, c_in, act_ld, wpack, c_out, c_out_rows, taps, k_per_tap, bias, residual, res_ld, out,
                      out_ld, out_mode, colsum, colsum ? stat_gran : 1, stream, ex);
+}
+
+extern "C" int azb_conv_skip_stats_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld,
+                                        const void* act2, int64_t c_in2, int64_t act2_ld, const void* wpack,
+                                        int64_t c_out, int64_t c_out_rows, int64_t k_per_tap, int64_t k2,
+                                        const float* bias, void* out, int64_t out_ld, float* colsum, int stat_gran,
+                                        void* stream) {
+    AZB_CHECK_PTR(act2);
+    ConvExtra ex;
+    ex.act2 = act2, ex.c_in2 = c_in2, ex.act2_ld = act2_ld, ex.k2 = k2;
+    return conv_impl(act, n, h, w, c_in, act_ld, wpack, c_out, c_out_rows, 9, k_per_tap, bias, nullptr, 0, out, out_ld, 0,
+                     colsum, colsum ? stat_gran : 1, stream, ex);
 }

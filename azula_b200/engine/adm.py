@@ -57,13 +57,17 @@ class Packed:
                 w = ops.pack_first_conv(p[u.path + ".weight"].float(), p[u.path + ".bias"], self.k_pad)
                 self.unit[u.path] = {"conv": w}
             elif u.kind == "res":
+                conv2 = ops.pack_conv(p[u.path + ".out_layers.3.weight"], p[u.path + ".out_layers.3.bias"])
+                skip = (ops.pack_conv(p[u.path + ".skip_connection.weight"], p[u.path + ".skip_connection.bias"])
+                        if u.cin != u.cout else None)
+                if skip is not None and skip.taps == 1:
+                    conv2, skip = ops.pack_conv_skip(conv2, skip), None  # one GEMM: K = [9 taps | skip channels]
                 self.unit[u.path] = {
                     "gn1": (f32(u.path + ".in_layers.0.weight"), f32(u.path + ".in_layers.0.bias")),
                     "conv1": ops.pack_conv(p[u.path + ".in_layers.2.weight"], p[u.path + ".in_layers.2.bias"]),
                     "gn2": (f32(u.path + ".out_layers.0.weight"), f32(u.path + ".out_layers.0.bias")),
-                    "conv2": ops.pack_conv(p[u.path + ".out_layers.3.weight"], p[u.path + ".out_layers.3.bias"]),
-                    "skip": ops.pack_conv(p[u.path + ".skip_connection.weight"], p[u.path + ".skip_connection.bias"])
-                    if u.cin != u.cout else None,
+                    "conv2": conv2,
+                    "skip": skip,
                     "emb_offset": offset,
                 }
                 emb_w.append(f32(u.path + ".emb_layers.1.weight"))
@@ -240,6 +244,27 @@ class Plan:
             0 if residual is None else ops._ld(residual), out.data_ptr(), ops._ld(out), 0, desc=desc,
         )
 
+    def _conv_skip(self, x: Tensor, x2: Tensor, pc: ops.PackedConvSkip, out: Tensor) -> None:
+        r"""Queues ``conv3x3(x) + conv1x1(x2) + bias`` with the GroupNorm column sums of ``out``."""
+        n, h, w, _ = x.shape
+        self.colsum_of.pop(self._key(out), None)
+        rows, ok = ops.colsum_rows(n, h, w)
+        colsum = None
+        if ok:
+            colsum = torch.empty(rows, pc.c_out // self.stat_gran, 2, dtype=torch.float32, device=self.device)
+            self.colsum_of[self._key(out)] = (colsum, pc.c_out)
+            self.keep.append(colsum)
+        self.keep += [x, x2, out, pc.w, pc.bias]
+        flops = 2.0 * n * h * w * pc.c_out * (9 * pc.c_in + pc.c_in2)
+        nbytes = 2.0 * (n * h * w * (pc.c_in + pc.c_in2 + pc.c_out) + pc.c_out * (9 * pc.c_in + pc.c_in2))
+        self._emit(
+            "conv3x3", flops, nbytes + (4.0 * colsum.numel() if colsum is not None else 0.0),
+            self.lib.azb_conv_skip_stats_bf16, x.data_ptr(), n, h, w, pc.c_in, ops._ld(x), x2.data_ptr(), pc.c_in2,
+            ops._ld(x2), pc.w.data_ptr(), pc.c_out, pc.c_out_rows, pc.k_per_tap, pc.k2, pc.bias.data_ptr(),
+            out.data_ptr(), ops._ld(out), _lib.ptr(colsum), self.stat_gran,
+            desc=f"{n}x{h}x{w} {pc.c_in}->{pc.c_out} +skip1x1({pc.c_in2}) +stats",
+        )
+
     def _stats(self, x: Tensor) -> Tensor:
         r"""GroupNorm statistics of ``x``: folded from the producers' column sums when every channel of
         ``x`` has them (one tiny launch), else by the stand-alone reduction pass."""
@@ -330,12 +355,16 @@ class Plan:
         arena.give(h1)
         st2 = self._stats(h2)
         self._apply(h2, h2, st2, w_["gn2"], w_["emb_offset"], True, 0)  # SiLU(GN(h) (1 + scale) + shift), in place
-        if w_["skip"] is not None:
+        if isinstance(w_["conv2"], ops.PackedConvSkip):
+            self._conv_skip(h2, xr, w_["conv2"], out)  # skip_connection(x) + h, the 1x1 folded into the GEMM's K
+            sk = xr
+        elif w_["skip"] is not None:
             sk = arena.take(n, ho, wo, u.cout)
             self._conv(xr, w_["skip"], sk)
+            self._conv(h2, w_["conv2"], out, residual=sk, stats=True)
         else:
             sk = xr
-        self._conv(h2, w_["conv2"], out, residual=sk, stats=True)  # skip_connection(x) + h
+            self._conv(h2, w_["conv2"], out, residual=sk, stats=True)  # x + h
         arena.give(h2)
         if sk is not xr:
             arena.give(sk)

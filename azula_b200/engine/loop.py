@@ -33,9 +33,12 @@ def supports(sampler, x: Tensor) -> bool:
     r"""Whether :class:`FusedLoop` can run this (sampler, input) pair."""
     from ..denoise import Preconditioned
 
+    from . import native_enabled
+
     den = sampler.denoiser
     return (
         x.is_cuda
+        and native_enabled()
         and x.dtype == torch.float32
         and x.numel() > 0
         and not x.requires_grad

@@ -28,6 +28,11 @@ _lib.register({
         [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int64,
          c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p],
     ),
+    "azb_conv_skip_stats_bf16": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
+         c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p],
+    ),
     "azb_conv_colsum_rows": (c_int, [c_int64, c_int64, c_int64, POINTER(c_int64), POINTER(c_int64)]),
     "azb_gn_finalize_f32": (
         c_int,
@@ -123,6 +128,48 @@ def pack_conv(weight: Tensor, bias: Tensor | None) -> PackedConv:
     w[:c_out, :, :c_in] = weight.permute(0, 2, 3, 1).reshape(c_out, taps, c_in).to(torch.bfloat16)
     b = None if bias is None else bias.detach().to(torch.float32).contiguous()
     return PackedConv(w=w.contiguous(), bias=b, c_in=c_in, c_out=c_out, taps=taps)
+
+
+@dataclass
+class PackedConvSkip:
+    r"""conv3x3 and the 1x1 skip connection of a ResBlock as one GEMM: weights [rows][9 * k_per_tap + k2]."""
+
+    w: Tensor
+    bias: Tensor
+    c_in: int
+    c_in2: int
+    c_out: int
+    k_per_tap: int
+    k2: int
+
+    @property
+    def c_out_rows(self) -> int:
+        return self.w.shape[0]
+
+
+def pack_conv_skip(conv: PackedConv, skip: PackedConv) -> PackedConvSkip:
+    assert conv.taps == 9 and skip.taps == 1 and conv.c_out == skip.c_out and conv.c_out_rows == skip.c_out_rows
+    rows = conv.c_out_rows
+    w = torch.cat((conv.w.reshape(rows, -1), skip.w.reshape(rows, -1)), dim=1).contiguous()
+    return PackedConvSkip(w=w, bias=(conv.bias + skip.bias).contiguous(), c_in=conv.c_in, c_in2=skip.c_in, c_out=conv.c_out,
+                          k_per_tap=conv.k_per_tap, k2=skip.k_per_tap)
+
+
+def conv_skip(x: Tensor, x2: Tensor, pc: PackedConvSkip, out: Tensor | None = None, colsum: Tensor | None = None) -> Tensor:
+    r"""``conv3x3(x) + conv1x1(x2) + bias`` in one launch (``azb_conv_skip_stats_bf16``); both NHWC bf16."""
+    n, h, w, _ = x.shape
+    assert x2.shape[:3] == x.shape[:3] and x.shape[-1] == pc.c_in and x2.shape[-1] == pc.c_in2
+    if out is None:
+        out = torch.empty(n, h, w, pc.c_out, dtype=torch.bfloat16, device=x.device)
+    _lib.check(
+        _lib.lib().azb_conv_skip_stats_bf16(
+            x.data_ptr(), n, h, w, pc.c_in, _ld(x), x2.data_ptr(), pc.c_in2, _ld(x2), pc.w.data_ptr(), pc.c_out,
+            pc.c_out_rows, pc.k_per_tap, pc.k2, pc.bias.data_ptr(), out.data_ptr(), _ld(out), _lib.ptr(colsum),
+            1 if colsum is None else pc.c_out // colsum.shape[1], _lib.stream_ptr(x.device),
+        ),
+        "azb_conv_skip_stats_bf16",
+    )
+    return out
 
 
 def colsum_rows(n: int, h: int, w: int) -> tuple[int, bool]:

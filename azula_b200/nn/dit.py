@@ -22,7 +22,7 @@ from typing import Literal
 
 from .attention import MultiheadSelfAttention
 from .layers import ReLU2, RMSNorm, SineEncoding, SwiGLU
-from .utils import checkpoint
+from .utils import NativeCache, checkpoint
 
 
 class _SplitTokenMod(nn.Module):
@@ -121,7 +121,7 @@ class DiTBlock(nn.Module):
         return self._forward(x, mod, pos, mask)
 
 
-class DiT(nn.Module):
+class DiT(NativeCache, nn.Module):
     r"""Modulated DiT-like network over tokens (``azula/nn/dit.py:135-218``).
 
     Arguments:
@@ -181,9 +181,10 @@ class DiT(nn.Module):
 
         if pos is None:
             if x.is_cuda and not torch.is_grad_enabled():
+                from .. import engine
                 from ..engine import dit as _engine
 
-                if _engine.supports(self, x, mod, "arange"):
+                if engine.native_enabled() and _engine.supports(self, x, mod, "arange"):
                     return _engine.forward(self, x, mod, "arange")
 
             pos = torch.arange(x.shape[-2], dtype=x.dtype, device=x.device)[..., None]

@@ -18,7 +18,7 @@ from collections.abc import Sequence
 from torch import Tensor
 
 from .layers import ConvNd, LayerNorm, RMSNorm
-from .utils import checkpoint
+from .utils import NativeCache, checkpoint
 
 
 class _SplitMod(nn.Module):
@@ -117,7 +117,7 @@ class UNetBlock(nn.Module):
         return self._forward(x, mod)
 
 
-class UNet(nn.Module):
+class UNet(NativeCache, nn.Module):
     r"""Modulated U-Net (``azula/nn/unet.py:125-259``).
 
     Arguments:
@@ -205,9 +205,10 @@ class UNet(nn.Module):
             x = torch.cat((x, cond), dim=1)
 
         if x.is_cuda and not torch.is_grad_enabled():
+            from .. import engine
             from ..engine import unet as _engine
 
-            if _engine.supports(self, x, mod):
+            if engine.native_enabled() and _engine.supports(self, x, mod):
                 return _engine.forward(self, x, mod)
 
         return self._torch_forward(x, mod)

@@ -2,7 +2,7 @@ r"""Module helpers used by the denoisers (interface of ``azula/nn/utils.py:24-42
 
 from __future__ import annotations
 
-__all__ = ["checkpoint", "get_module_dtype", "get_module_device", "promote_dtype", "skip_init"]
+__all__ = ["NativeCache", "checkpoint", "get_module_dtype", "get_module_device", "promote_dtype", "skip_init"]
 
 import functools
 import itertools
@@ -79,3 +79,17 @@ def promote_dtype(f, min_dtype: torch.dtype = torch.float32):
         return tuple(o.to(dtype) for o in outs)
 
     return g
+
+
+class NativeCache:
+    r"""Mixin of the backbones that own a native launch-plan cache (``self._native``): the cache is
+    dropped when the module moves / changes dtype and is never copied or pickled with the module."""
+
+    def _apply(self, fn, *args, **kwargs):
+        self._native.clear()  # packed weights and plans belong to the old device / dtype
+        return super()._apply(fn, *args, **kwargs)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_native"] = {}
+        return state

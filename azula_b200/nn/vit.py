@@ -84,9 +84,10 @@ class ViT(DiT):
             The output tensor, with shape :math:`(B, C_o, L_1, ..., L_N)`.
         """
         if x.is_cuda and not torch.is_grad_enabled():
+            from .. import engine
             from ..engine import dit as _engine
 
-            if _engine.supports_image(self, x, mod, cond):
+            if engine.native_enabled() and _engine.supports_image(self, x, mod, cond):
                 return _engine.forward_image(self, x, mod, cond)
 
         x = self.patch(x)

@@ -273,15 +273,22 @@ class UNetModel(nn.Module):
         if (y is not None) != (self.num_classes is not None):
             raise ValueError("must specify y if and only if the model is class-conditional")
         if x.is_cuda and not torch.is_grad_enabled() and not (self.training and self.layout.dropout > 0):
+            from ... import engine as _engine
             from ...engine import adm as engine
 
-            return engine.forward(self, x, timesteps, y)
+            if _engine.native_enabled():
+                return engine.forward(self, x, timesteps, y)
         state = dict(self.named_parameters())
         return forward_torch(self.layout, state, x, timesteps, y, dropout=self.layout.dropout if self.training else 0.0)
 
     def _apply(self, fn, *args, **kwargs):
         self._native.clear()  # packed weights and plans belong to the old device / dtype
         return super()._apply(fn, *args, **kwargs)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_native"] = {}  # launch plans hold device pointers: never copied or pickled
+        return state
 
 
 # ----------------------------------------------------------------- plain torch executor (fp32)

@@ -243,8 +243,11 @@ class DDIMSampler(_Ancestral):
 
 
 def _cuda_step_ok(x_t: Tensor, mean: Tensor, alpha_s: Tensor) -> bool:
+    from . import engine
+
     return (
         x_t.is_cuda
+        and engine.native_enabled()
         and x_t.dtype == torch.float32
         and mean.dtype == torch.float32
         and mean.shape == x_t.shape

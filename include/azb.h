@@ -156,6 +156,18 @@ int azb_conv2d_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_
                     int64_t gate_rows, const void* residual, int64_t res_ld, void* out, int64_t out_ld,
                     int out_mode, float* colsum, int stat_gran, void* stream);
 
+/*
+ * The tail of an ADM ResBlock whose skip connection is a 1x1 convolution (azula/plugins/adm/_src/unet.py:
+ * 213-215,243-247):  out = conv3x3(act) + conv1x1(act2) + bias  as ONE implicit GEMM whose K dimension is
+ * [9 taps x k_per_tap | k2]: wpack is bf16 [c_out_rows][9*k_per_tap + k2] (the 1x1 weights appended, k2 = c_in2
+ * rounded up to 64), bias = the sum of both biases.  act2 is NHWC bf16 at the same resolution.  Removes the
+ * write + read of the skip tensor and one launch.  colsum as in azb_conv_gemm_stats_bf16 (may be NULL).
+ */
+int azb_conv_skip_stats_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld,
+                             const void* act2, int64_t c_in2, int64_t act2_ld, const void* wpack, int64_t c_out,
+                             int64_t c_out_rows, int64_t k_per_tap, int64_t k2, const float* bias, void* out,
+                             int64_t out_ld, float* colsum, int stat_gran, void* stream);
+
 /* Rows of the colsum buffer for an (n, h, w) activation; *slab_in_image = 1 when every 32-row slab
  * lies inside one image (the condition for azb_gn_finalize_f32), else 0.  Host-side helper. */
 int azb_conv_colsum_rows(int64_t n, int64_t h, int64_t w, int64_t* rows, int64_t* slab_in_image);

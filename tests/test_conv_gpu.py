@@ -191,3 +191,28 @@ def test_conv_throughput_report():
         ms = e0.elapsed_time(e1) / 10
         tf = 2.0 * n * h * w * co * ci * 9 / (ms * 1e-3) / 1e12
         print(f"conv3x3 {n}x{h}x{w} {ci}->{co}: {ms:.3f} ms, {tf:.0f} TFLOP/s")
+
+
+@pytest.mark.parametrize("n,h,w,ci,ci2,co", [(2, 16, 16, 64, 128, 64), (1, 32, 32, 256, 512, 256), (3, 8, 8, 128, 192, 128),
+                                            (2, 16, 16, 32, 64, 32)])
+def test_conv_with_fused_1x1_skip(n, h, w, ci, ci2, co):
+    """out = conv3x3(h) + conv1x1(x) + biases as one GEMM (the ResBlock tail, _src/unet.py:243-247), with the
+    GroupNorm column sums of the result."""
+    g = torch.Generator(device=DEV).manual_seed(21)
+    x, wt, b = _mk(n, h, w, ci, co, 3, seed=5)
+    x2 = torch.randn(n, h, w, ci2, device=DEV, generator=g).to(torch.bfloat16)
+    w2 = (torch.randn(co, ci2, 1, 1, device=DEV, generator=g) / ci2**0.5).to(torch.bfloat16)
+    b2 = torch.randn(co, device=DEV, generator=g)
+    pc = ops.pack_conv_skip(ops.pack_conv(wt.float(), b), ops.pack_conv(w2.float(), b2))
+    ref = _ref(x, wt, b) + _ref(x2, w2, b2)
+    got = ops.conv_skip(x, x2, pc)
+    _check(got, ref, "conv + skip")
+    rows, ok = ops.colsum_rows(n, h, w)
+    if ok:
+        colsum = torch.zeros(rows, co, 2, device=DEV)
+        got2 = ops.conv_skip(x, x2, pc, colsum=colsum)
+        assert torch.equal(got, got2)
+        tot = colsum.sum(0)
+        gf = got.float().reshape(-1, co)
+        assert torch.allclose(tot[:, 0], gf.sum(0), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(tot[:, 1], gf.square().sum(0), rtol=1e-4, atol=1e-2)
