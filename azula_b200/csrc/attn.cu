@@ -222,9 +222,24 @@ int launch_attn(const AttnParams& p, int n, cudaStream_t s) {
 
 }  // namespace
 
+int azb_attention_tc_launch(const void* qkv, int64_t ld, void* out, int64_t out_ld, int64_t n, int64_t t, int64_t heads,
+                            int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta, void* stream);  // attn_tc.cu
+
 extern "C" int azb_attention_bf16(const void* qkv, int64_t ld, void* out, int64_t out_ld, int64_t n, int64_t t,
                                   int64_t heads, int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta,
                                   void* stream) {
+    AZB_CHECK_PTR(qkv);
+    AZB_CHECK_PTR(out);
+    if (n <= 0 || t <= 0 || heads <= 0 || n > 65535 || heads > 65535) return AZB_E_SHAPE;
+    // head width 64 (every ADM card, DiT-B): tcgen05 kernel; other widths: the mma.sync kernel below
+    const int rc = azb_attention_tc_launch(qkv, ld, out, out_ld, n, t, heads, d, head_stride, k_delta, v_delta, stream);
+    if (rc != AZB_E_UNSUPPORTED) return rc;
+    return azb_attention_mma_bf16(qkv, ld, out, out_ld, n, t, heads, d, head_stride, k_delta, v_delta, stream);
+}
+
+extern "C" int azb_attention_mma_bf16(const void* qkv, int64_t ld, void* out, int64_t out_ld, int64_t n, int64_t t,
+                                      int64_t heads, int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta,
+                                      void* stream) {
     AZB_CHECK_PTR(qkv);
     AZB_CHECK_PTR(out);
     if (n <= 0 || t <= 0 || heads <= 0 || n > 65535 || heads > 65535) return AZB_E_SHAPE;

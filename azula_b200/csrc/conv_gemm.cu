@@ -406,40 +406,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
 
 // ------------------------------------------------------------------ host: tensor maps + launch
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(ptr);
-    }
-    return fn;
-}
-
 int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
              const uint32_t* box, const uint32_t* elem_strides = nullptr) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return AZB_E_DRIVER;
-    cuuint64_t gdim[5], gstr[4];
-    cuuint32_t bx[5], es[5];
-    for (int i = 0; i < rank; ++i) {
-        gdim[i] = dims[i];
-        bx[i] = box[i];
-        es[i] = elem_strides ? elem_strides[i] : 1;
-        if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
-    }
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? AZB_OK : AZB_E_SHAPE;
+    const int rc = tc::make_map_bf16(m, base, rank, dims, strides_bytes, box, elem_strides);
+    return rc == 0 ? AZB_OK : rc == -1 ? AZB_E_DRIVER : AZB_E_SHAPE;
 }
 
 int sm_count() {

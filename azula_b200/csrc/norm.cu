@@ -141,47 +141,27 @@ struct ApplyParams {
     int pix_per_cta;         // output pixels per CTA
 };
 
-__device__ __forceinline__ float ex2_approx(float v) {
+__device__ __forceinline__ float tanh_approx(float v) {
     float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-__device__ __forceinline__ float rcp_approx(float v) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
 
-// SiLU of four values with ONE reciprocal: 1 / d_i = (prod_{j != i} d_j) / (d_0 d_1 d_2 d_3), d = 1 + exp(-v).
-// The SFU (ex2 + rcp per element) co-limited this HBM-bound pass; this is 1.25 SFU operations per element.
-// exp(-v) is clamped to 2^30 so that the product stays finite; below v = -20.8 the result is |v| * 2^-30 ~ 0.
-__device__ __forceinline__ void silu4(float& v0, float& v1, float& v2, float& v3) {
-    constexpr float NLOG2E = -1.4426950408889634f;
-    const float d0 = 1.0f + ex2_approx(fminf(v0 * NLOG2E, 30.0f));
-    const float d1 = 1.0f + ex2_approx(fminf(v1 * NLOG2E, 30.0f));
-    const float d2 = 1.0f + ex2_approx(fminf(v2 * NLOG2E, 30.0f));
-    const float d3 = 1.0f + ex2_approx(fminf(v3 * NLOG2E, 30.0f));
-    const float p01 = d0 * d1, p23 = d2 * d3;
-    const float r = rcp_approx(p01 * p23);
-    const float r01 = r * p23, r23 = r * p01;
-    v0 *= r01 * d1, v1 *= r01 * d0, v2 *= r23 * d3, v3 *= r23 * d2;
-}
-
-template <bool SILU>
+// With SILU the caller passes HALVED coefficients, h = (A x + B) / 2, and SiLU(2h) = h + h tanh(h): one FMA, one
+// SFU operation (tanh.approx, absolute error ~2^-11 on tanh, i.e. <= |h| 2^-11 on the result: a tenth of the bf16
+// rounding that follows) and one FMA per element.  The exp + reciprocal form (2 SFU operations and ~10 issue slots
+// per element) kept this HBM-bound pass at 65 % of the DRAM rate (ncu: issue 69 %, XU 48 %).
+template <bool SILU, bool ADD = true>
 __device__ __forceinline__ void affine8(const uint4 u, const float (&a)[8], const float (&b)[8], float (&acc)[8]) {
     const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
-    float f[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        f[2 * j] = fmaf(a[2 * j], bf16_bits_to_f32(wv[j] & 0xffffu), b[2 * j]);
-        f[2 * j + 1] = fmaf(a[2 * j + 1], bf16_bits_to_f32(wv[j] >> 16), b[2 * j + 1]);
+        float f0 = fmaf(a[2 * j], bf16_bits_to_f32(wv[j] & 0xffffu), b[2 * j]);
+        float f1 = fmaf(a[2 * j + 1], __uint_as_float(wv[j] & 0xffff0000u), b[2 * j + 1]);
+        if (SILU) f0 = fmaf(f0, tanh_approx(f0), f0), f1 = fmaf(f1, tanh_approx(f1), f1);
+        if (ADD) acc[2 * j] += f0, acc[2 * j + 1] += f1;
+        else acc[2 * j] = f0, acc[2 * j + 1] = f1;
     }
-    if (SILU) {
-        silu4(f[0], f[1], f[2], f[3]);
-        silu4(f[4], f[5], f[6], f[7]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += f[j];
 }
 
 __device__ __forceinline__ uint4 pack8(const float (&f)[8], float mul) {
@@ -237,7 +217,7 @@ __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) 
                 aa *= sc;
                 bb = bb * sc + __ldg(ss + p.c + c);
             }
-            a[j] = aa, b[j] = bb;
+            a[j] = SILU ? 0.5f * aa : aa, b[j] = SILU ? 0.5f * bb : bb;
         }
         const __nv_bfloat16* xc = xin + v * 8;
         __nv_bfloat16* yc = yout + v * 8;
@@ -286,8 +266,8 @@ __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) 
                 for (int k = 0; k < UNROLL; ++k) {
                     const int qq = q + k * R;
                     if (qq < q1) {
-                        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        affine8<SILU>(u[k], a, b, acc);
+                        float acc[8];
+                        affine8<SILU, false>(u[k], a, b, acc);
                         *reinterpret_cast<uint4*>(yc + (int64_t)qq * p.y_ld) = pack8(acc, 1.0f);
                     }
                 }

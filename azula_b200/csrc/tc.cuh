@@ -146,5 +146,46 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Same with an MN-major B operand (bit 16): B is stored [K][N] with N contiguous, e.g. V (keys x channels) in P V.
+__host__ __device__ constexpr uint32_t idesc_bf16_f32_b_mn(int M, int N) { return idesc_bf16_f32(M, N) | (1u << 16); }
+
+// ------------------------------------------------------------------ host: tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// bf16 tensor map with 128-byte swizzle and zero fill of out-of-bounds elements; returns 0, -1 (no driver entry
+// point) or -2 (rejected by the driver).
+inline int make_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box, const uint32_t* elem_strides = nullptr) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return -1;
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = elem_strides ? elem_strides[i] : 1;
+        if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+    }
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
 
 }  // namespace tc

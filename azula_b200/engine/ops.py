@@ -54,6 +54,11 @@ _lib.register({
         [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
          c_void_p],
     ),
+    "azb_attention_mma_bf16": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+         c_void_p],
+    ),
     "azb_im2col3x3_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "azb_timestep_features_f32": (c_int, [c_void_p, c_int, c_int64, c_int64, c_float, c_void_p, c_void_p]),
     "azb_linear_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
@@ -303,19 +308,19 @@ def gn_apply(x: Tensor, out: Tensor | None = None, stats: Tensor | None = None, 
     return out
 
 
-def attention(qkv: Tensor, heads: int, new_order: bool = False, out: Tensor | None = None) -> Tensor:
-    r"""(N, T, 3C) bf16 -> (N, T, C) bf16, legacy (per-head q|k|v) or new (q|k|v blocks) channel order."""
+def attention(qkv: Tensor, heads: int, new_order: bool = False, out: Tensor | None = None, kernel: str = "auto") -> Tensor:
+    r"""(N, T, 3C) bf16 -> (N, T, C) bf16, legacy (per-head q|k|v) or new (q|k|v blocks) channel order.
+    ``kernel="mma"`` forces the warp-level kernel (``"auto"``: tcgen05 for head width 64)."""
     n, t, c3 = qkv.shape
     c = c3 // 3
     d = c // heads
     if out is None:
         out = torch.empty(n, t, c, dtype=torch.bfloat16, device=qkv.device)
     hs, kd, vd = (d, c, 2 * c) if new_order else (3 * d, d, 2 * d)
+    fn = _lib.lib().azb_attention_mma_bf16 if kernel == "mma" else _lib.lib().azb_attention_bf16
     _lib.check(
-        _lib.lib().azb_attention_bf16(
-            qkv.data_ptr(), qkv.stride(1), out.data_ptr(), out.stride(1), n, t, heads, d, hs, kd, vd,
-            _lib.stream_ptr(qkv.device),
-        ),
+        fn(qkv.data_ptr(), qkv.stride(1), out.data_ptr(), out.stride(1), n, t, heads, d, hs, kd, vd,
+           _lib.stream_ptr(qkv.device)),
         "azb_attention_bf16",
     )
     return out

@@ -212,6 +212,11 @@ int azb_gn_apply_bf16(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_
 int azb_attention_bf16(const void* qkv, int64_t ld, void* out, int64_t out_ld, int64_t n, int64_t t,
                        int64_t heads, int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta,
                        void* stream);
+/* The same contract served by the warp-level mma.sync kernel only (azb_attention_bf16 uses the tcgen05 / TMEM
+ * kernel for d = 64 and this one for the other widths); exported so that tests can compare the two. */
+int azb_attention_mma_bf16(const void* qkv, int64_t ld, void* out, int64_t out_ld, int64_t n, int64_t t,
+                           int64_t heads, int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta,
+                           void* stream);
 
 /* im2col of the fp32 NCHW network input for the first 3x3 conv (_src/unet.py:471):
  * out[n][h][w][k] bf16, k = (kh*3+kw)*c + ch for k < 9c, zero up to k_pad. */

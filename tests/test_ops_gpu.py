@@ -103,7 +103,7 @@ def test_per_step_scale_shift_table(scratch):
 
 
 @pytest.mark.parametrize("case", [(2, 64, 4, 16), (1, 256, 8, 64), (2, 1024, 8, 64), (3, 16, 16, 64), (2, 4, 2, 32),
-                                  (1, 100, 2, 128)])
+                                  (1, 100, 2, 128), (2, 300, 3, 64), (1, 129, 1, 64), (5, 640, 2, 64), (1, 4096, 2, 64)])
 @pytest.mark.parametrize("new_order", [False, True])
 def test_attention_matches_reference_formula(case, new_order):
     n, t, heads, d = case
@@ -121,6 +121,11 @@ def test_attention_matches_reference_formula(case, new_order):
     wgt = torch.softmax(torch.einsum("bct,bcs->bts", q * s, k * s), dim=-1)
     ref = torch.einsum("bts,bcs->bct", wgt, v).reshape(n, c, t).permute(0, 2, 1)
     _close(got, ref, (case, new_order), rel=2.0**-6)
+    if d == 64:  # the tcgen05 kernel ran above; the warp-level kernel must agree with the same formula
+        _close(ops.attention(qkv, heads, new_order, kernel="mma"), ref, (case, new_order, "mma"), rel=2.0**-6)
+    # large logits: the softmax must stay finite and exact about its maximum
+    big = (qkv.float() * 6).to(torch.bfloat16)
+    assert torch.isfinite(ops.attention(big, heads, new_order).float()).all()
 
 
 def test_first_conv_via_im2col():
