@@ -133,6 +133,13 @@ extern "C" int azb_linear_f32(const float* x, const float* w, const float* b, fl
     return azb_launch_status();
 }
 
+extern "C" int azb_zero_bytes(void* ptr, int64_t bytes, void* stream) {
+    AZB_CHECK_PTR(ptr);
+    if (bytes <= 0) return AZB_E_SHAPE;
+    cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, reinterpret_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? AZB_OK : (int)e;
+}
+
 extern "C" int azb_add_rows_f32(float* y, const float* table, const int64_t* idx, int64_t rows, int64_t dim,
                                 void* stream) {
     AZB_CHECK_PTR(y);

@@ -139,6 +139,11 @@ struct ApplyParams {
     int64_t ss_step_stride;
     int silu;
     int pix_per_cta;         // output pixels per CTA
+    const long long* acc[2];  // exact fixed-point sums (azb_conv_bf16 gn_acc) of channel ranges [0, c_a), [c_a, c): (N, c_x / gran, 4)
+    int acc_c[2];
+    int acc_gran;
+    float eps;
+    double acc_scale;  // 2^-40 / (h * w * channels per group)
 };
 
 __device__ __forceinline__ float tanh_approx(float v) {
@@ -197,6 +202,30 @@ __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) 
         ss = p.scale_shift + (int64_t)n * p.ss_stride;
         if (p.ss_step) ss += (int64_t)(*p.ss_step) * p.ss_step_stride;
     }
+    // (mean, rstd) of every group of image n, once per CTA: copied from `stats`, or folded from the producers' exact
+    // accumulators (integer fold, then a handful of double-precision operations by <= 256 threads)
+    __shared__ float2 s_stat[THREADS];
+    if ((p.stats || p.acc[0]) && threadIdx.x < p.groups) {
+        const int g = threadIdx.x;
+        if (p.stats) {
+            s_stat[g] = make_float2(__ldg(p.stats + ((int64_t)n * p.groups + g) * 2),
+                                    __ldg(p.stats + ((int64_t)n * p.groups + g) * 2 + 1));
+        } else {
+            long long s_hi = 0, s_lo = 0, q_hi = 0, q_lo = 0;
+            for (int ch = g * cg; ch < (g + 1) * cg; ch += p.acc_gran) {
+                const int which = ch >= p.acc_c[0];
+                const int local = which ? ch - p.acc_c[0] : ch;
+                const long long* src = p.acc[which] + ((int64_t)n * (p.acc_c[which] / p.acc_gran) + local / p.acc_gran) * 4;
+                s_hi += __ldg(src), s_lo += __ldg(src + 1), q_hi += __ldg(src + 2), q_lo += __ldg(src + 3);
+            }
+            // double precision only where the cancellation is (E[x^2] - mean^2); the slow DP pipe never sees a
+            // division or a square root (acc_scale = 2^-40 / count comes from the host)
+            const double m = ((double)s_hi * 4294967296.0 + (double)s_lo) * p.acc_scale;
+            const double var = fma(-m, m, ((double)q_hi * 4294967296.0 + (double)q_lo) * p.acc_scale);
+            s_stat[g] = make_float2((float)m, rsqrtf(fmaxf((float)var, 0.f) + p.eps));
+        }
+    }
+    __syncthreads();
     if (r >= R) return;
 
     for (int v = threadIdx.x % VT; v < V; v += VT) {
@@ -205,12 +234,10 @@ __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) 
         for (int j = 0; j < 8; ++j) {
             const int c = v * 8 + j;
             float aa = 1.f, bb = 0.f;
-            if (p.stats) {
-                const int g = c / cg;
-                const float mean = __ldg(p.stats + ((int64_t)n * p.groups + g) * 2);
-                const float rstd = __ldg(p.stats + ((int64_t)n * p.groups + g) * 2 + 1);
-                aa = rstd * __ldg(p.gamma + c);
-                bb = __ldg(p.beta + c) - mean * aa;
+            if (p.stats || p.acc[0]) {
+                const float2 st = s_stat[c / cg];
+                aa = st.y * __ldg(p.gamma + c);
+                bb = __ldg(p.beta + c) - st.x * aa;
             }
             if (ss) {
                 const float sc = 1.0f + __ldg(ss + c);
@@ -384,21 +411,30 @@ extern "C" int azb_gn_stats_bf16(const void* x, int64_t ld, int64_t n, int64_t h
     return azb_launch_status();
 }
 
-extern "C" int azb_gn_apply_bf16(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t n, int64_t h, int64_t w,
-                                 int64_t c, int64_t groups, const float* stats, const float* gamma, const float* beta,
-                                 const float* scale_shift, int64_t ss_stride, const int32_t* ss_step,
-                                 int64_t ss_step_stride, int silu, int mode, void* stream) {
+static int gn_apply_impl(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t n, int64_t h, int64_t w, int64_t c,
+                         int64_t groups, const float* stats, const int64_t* acc, int64_t c_a, const int64_t* acc_b,
+                         int64_t c_b, int64_t gran, float eps, const float* gamma,
+                         const float* beta, const float* scale_shift, int64_t ss_stride, const int32_t* ss_step,
+                         int64_t ss_step_stride, int silu, int mode, void* stream) {
     AZB_CHECK_PTR(x);
     AZB_CHECK_PTR(y);
     if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 8 || c > MAX_C) return AZB_E_SHAPE;
-    if (stats && (!gamma || !beta || groups <= 0 || c % groups)) return AZB_E_NULL;
+    if ((stats || acc) && (!gamma || !beta || groups <= 0 || c % groups)) return AZB_E_NULL;
+    if ((stats || acc) && groups > THREADS) return AZB_E_SHAPE;
     if (mode < 0 || mode > 2 || (mode == 2 && ((h | w) & 1))) return AZB_E_SHAPE;
     if (x_ld % 8 || y_ld % 8 || x_ld < c || y_ld < c || !azb_aligned(x, 16) || !azb_aligned(y, 16)) return AZB_E_ALIGN;
     ApplyParams p{};
     p.x = reinterpret_cast<const __nv_bfloat16*>(x), p.x_ld = x_ld;
     p.y = reinterpret_cast<__nv_bfloat16*>(y), p.y_ld = y_ld;
-    p.n = (int)n, p.h = (int)h, p.w = (int)w, p.c = (int)c, p.groups = stats ? (int)groups : 1;
+    p.n = (int)n, p.h = (int)h, p.w = (int)w, p.c = (int)c, p.groups = (stats || acc) ? (int)groups : 1;
     p.stats = stats, p.gamma = gamma, p.beta = beta;
+    if (acc) {
+        if (c_a <= 0 || c_b < 0 || c_a + c_b != c || (c_b > 0 && !acc_b) || (gran != 1 && gran != 8)) return AZB_E_SHAPE;
+        if (c_a % gran || c_b % gran || (c / groups) % gran) return AZB_E_SHAPE;
+    }
+    p.acc[0] = reinterpret_cast<const long long*>(acc), p.acc[1] = reinterpret_cast<const long long*>(acc_b);
+    p.acc_c[0] = (int)c_a, p.acc_c[1] = (int)c_b, p.acc_gran = (int)gran, p.eps = eps;
+    p.acc_scale = acc ? 1.0 / (1099511627776.0 * (double)h * (double)w * (double)(c / groups)) : 0.0;
     p.scale_shift = scale_shift, p.ss_stride = ss_stride, p.ss_step = ss_step, p.ss_step_stride = ss_step_stride;
     p.silu = silu;
     const int64_t ho = mode == 1 ? h * 2 : mode == 2 ? h / 2 : h, wo = mode == 1 ? w * 2 : mode == 2 ? w / 2 : w;
@@ -418,6 +454,23 @@ extern "C" int azb_gn_apply_bf16(const void* x, int64_t x_ld, void* y, int64_t y
     else if (mode == 1) launch_apply<1>(p, grid, s);
     else launch_apply<2>(p, grid, s);
     return azb_launch_status();
+}
+
+extern "C" int azb_gn_apply_bf16(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t n, int64_t h, int64_t w,
+                                 int64_t c, int64_t groups, const float* stats, const float* gamma, const float* beta,
+                                 const float* scale_shift, int64_t ss_stride, const int32_t* ss_step,
+                                 int64_t ss_step_stride, int silu, int mode, void* stream) {
+    return gn_apply_impl(x, x_ld, y, y_ld, n, h, w, c, groups, stats, nullptr, 0, nullptr, 0, 1, 0.f, gamma, beta,
+                         scale_shift, ss_stride, ss_step, ss_step_stride, silu, mode, stream);
+}
+
+extern "C" int azb_gn_apply_acc_bf16(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t n, int64_t h, int64_t w,
+                                     int64_t c, int64_t groups, const int64_t* acc_a, int64_t c_a, const int64_t* acc_b,
+                                     int64_t c_b, int64_t gran, float eps, const float* gamma, const float* beta,
+                                     const float* scale_shift, int64_t ss_stride, int silu, int mode, void* stream) {
+    AZB_CHECK_PTR(acc_a);
+    return gn_apply_impl(x, x_ld, y, y_ld, n, h, w, c, groups, nullptr, acc_a, c_a, acc_b, c_b, gran, eps, gamma, beta,
+                         scale_shift, ss_stride, nullptr, 0, silu, mode, stream);
 }
 
 extern "C" int azb_gn_finalize_f32(const float* colsum_a, int64_t c_a, int gran_a, const float* colsum_b, int64_t c_b,

@@ -130,7 +130,7 @@ class Plan:
         # every width of the network is a multiple of model_channels: with model_channels % 256 == 0 all GroupNorm
         # groups (C / 32 channels) are multiples of 8 channels and the epilogues emit one sum per 8-channel block
         self.stat_gran = 8 if lay.model_channels % 256 == 0 else 1
-        self.colsum_of: dict[tuple, tuple] = {}  # activation view -> (column sums of its producer, channels)
+        self.acc_of: dict[tuple, tuple] = {}  # activation view -> (exact GroupNorm accumulators of its producer, channels)
         self.cat_parts: dict[tuple, list] = {}   # concatenation buffer -> [left view, right view]
         self.keep: list[Tensor] = []  # everything the launch list points into
         arena = self.arena = _Arena(device)
@@ -143,7 +143,16 @@ class Plan:
         self.emb = torch.empty(rows, D, **f32)
         self.emb_all = torch.empty(rows, packed.emb_total, **f32)
 
-        # ---- GroupNorm workspace sized for the largest site
+        # ---- GroupNorm: one pool of exact accumulators (int64 {sum, sumsq} x {hi, lo} per image and channel block),
+        # one slice per convolution output, cleared by ONE memset at the start of a forward
+        widths = [u.cout for u in lay.units() if u.kind != "attn"] + [u.cout for u in lay.units() if u.kind == "res"] + [
+            u.cin for u in lay.units() if u.kind == "attn"]
+        self.acc_pool = torch.zeros(max(4 * n * sum(-(-c // self.stat_gran) for c in widths), 4), dtype=torch.int64,
+                                    device=device)
+        self.acc_used = 0
+        self._emit("zero", 0.0, 8.0 * self.acc_pool.numel(), self.lib.azb_zero_bytes, self.acc_pool.data_ptr(),
+                   8 * self.acc_pool.numel())
+        # ---- GroupNorm fallback workspace (feature maps too small for the fused sums)
         self.gn_partial_need = 0
         self.counters = torch.zeros(max(n, 1), dtype=torch.int32, device=device)
 
@@ -210,78 +219,53 @@ class Plan:
     def _key(t: Tensor) -> tuple:
         return (t.data_ptr(), tuple(t.shape))
 
-    def _conv(self, x: Tensor, pc: ops.PackedConv, out: Tensor, residual: Tensor | None = None,
-              stats: bool = False) -> None:
-        r"""Queues a convolution; with ``stats`` its epilogue also emits the column sums from which the
-        GroupNorm consuming ``out`` gets its statistics (no separate read pass over ``out``)."""
+    def _acc_for(self, out: Tensor, c_out: int) -> Tensor | None:
+        r"""A zeroed-per-forward slice of the accumulator pool for the GroupNorm sums of ``out``, or ``None``
+        when a 32-row slab of the convolution's M tiles would straddle two images (tiny feature maps)."""
+        n, h, w = out.shape[:3]
+        self.acc_of.pop(self._key(out), None)  # the buffer may be a recycled one
+        if not ops.colsum_rows(n, h, w)[1]:
+            return None
+        count = n * (c_out // self.stat_gran) * 4
+        if self.acc_used + count > self.acc_pool.numel():
+            raise RuntimeError("GroupNorm accumulator pool exhausted")
+        acc = self.acc_pool[self.acc_used : self.acc_used + count].view(n, c_out // self.stat_gran, 4)
+        self.acc_used += count
+        self.acc_of[self._key(out)] = (acc, c_out)
+        return acc
+
+    def _conv(self, x: Tensor, pc, out: Tensor, residual: Tensor | None = None, stats: bool = False,
+              x2: Tensor | None = None) -> None:
+        r"""Queues a convolution (``azb_conv_bf16``); with ``stats`` its epilogue also adds the exact sums from
+        which the GroupNorm(s) consuming ``out`` derive their statistics (no read pass over ``out``, no reduction
+        launch).  With ``x2`` the ResBlock's 1x1 skip connection is part of the same GEMM."""
         n, h, w, _ = x.shape
-        colsum = None
-        self.colsum_of.pop(self._key(out), None)  # the buffer may be a recycled one
-        if stats:
-            rows, ok = ops.colsum_rows(n, h, w)
-            if ok:
-                colsum = torch.empty(rows, pc.c_out // self.stat_gran, 2, dtype=torch.float32, device=self.device)
-                self.colsum_of[self._key(out)] = (colsum, pc.c_out)
-        self.keep += [x, out, pc.w] + ([residual] if residual is not None else []) + ([pc.bias] if pc.bias is not None else [])
-        flops = 2.0 * n * h * w * pc.c_out * pc.taps * pc.c_in
-        nbytes = 2.0 * (n * h * w * (pc.c_in + pc.c_out * (2 if residual is not None else 1)) + pc.c_out * pc.taps * pc.c_in)
-        kind = "conv3x3" if pc.taps == 9 else "conv1x1"
-        desc = f"{n}x{h}x{w} {pc.c_in}->{pc.c_out}" + (" +res" if residual is not None else "")
-        if colsum is not None:
-            self.keep.append(colsum)
-            self._emit(
-                kind, flops, nbytes + 4.0 * colsum.numel(),
-                self.lib.azb_conv_gemm_stats_bf16, x.data_ptr(), n, h, w, pc.c_in, ops._ld(x), pc.w.data_ptr(),
-                pc.c_out, pc.c_out_rows, pc.taps, pc.k_per_tap, _lib.ptr(pc.bias), _lib.ptr(residual),
-                0 if residual is None else ops._ld(residual), out.data_ptr(), ops._ld(out), colsum.data_ptr(),
-                self.stat_gran, desc=desc + " +stats",
-            )
-            return
-        self._emit(
-            kind, flops, nbytes,
-            self.lib.azb_conv_gemm_bf16, x.data_ptr(), n, h, w, pc.c_in, ops._ld(x), pc.w.data_ptr(), pc.c_out,
-            pc.c_out_rows, pc.taps, pc.k_per_tap, _lib.ptr(pc.bias), _lib.ptr(residual),
-            0 if residual is None else ops._ld(residual), out.data_ptr(), ops._ld(out), 0, desc=desc,
-        )
+        acc = self._acc_for(out, pc.c_out) if stats else None
+        if not stats:
+            self.acc_of.pop(self._key(out), None)
+        d = ops.conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=self.stat_gran)
+        self.keep += [d, x, out, pc.w] + [t for t in (residual, pc.bias, x2) if t is not None]
+        taps = 9 if x2 is not None else pc.taps
+        k_extra = pc.c_in2 if x2 is not None else 0
+        flops = 2.0 * n * h * w * pc.c_out * (taps * pc.c_in + k_extra)
+        nbytes = 2.0 * (n * h * w * (pc.c_in + k_extra + pc.c_out * (2 if residual is not None else 1))
+                        + pc.c_out * (taps * pc.c_in + k_extra))
+        desc = f"{n}x{h}x{w} {pc.c_in}->{pc.c_out}" + (" +res" if residual is not None else "") + (
+            f" +skip1x1({pc.c_in2})" if x2 is not None else "") + (" +stats" if acc is not None else "")
+        self._emit("conv3x3" if taps == 9 else "conv1x1", flops, nbytes, self.lib.azb_conv_bf16, byref(d), desc=desc)
 
     def _conv_skip(self, x: Tensor, x2: Tensor, pc: ops.PackedConvSkip, out: Tensor) -> None:
-        r"""Queues ``conv3x3(x) + conv1x1(x2) + bias`` with the GroupNorm column sums of ``out``."""
-        n, h, w, _ = x.shape
-        self.colsum_of.pop(self._key(out), None)
-        rows, ok = ops.colsum_rows(n, h, w)
-        colsum = None
-        if ok:
-            colsum = torch.empty(rows, pc.c_out // self.stat_gran, 2, dtype=torch.float32, device=self.device)
-            self.colsum_of[self._key(out)] = (colsum, pc.c_out)
-            self.keep.append(colsum)
-        self.keep += [x, x2, out, pc.w, pc.bias]
-        flops = 2.0 * n * h * w * pc.c_out * (9 * pc.c_in + pc.c_in2)
-        nbytes = 2.0 * (n * h * w * (pc.c_in + pc.c_in2 + pc.c_out) + pc.c_out * (9 * pc.c_in + pc.c_in2))
-        self._emit(
-            "conv3x3", flops, nbytes + (4.0 * colsum.numel() if colsum is not None else 0.0),
-            self.lib.azb_conv_skip_stats_bf16, x.data_ptr(), n, h, w, pc.c_in, ops._ld(x), x2.data_ptr(), pc.c_in2,
-            ops._ld(x2), pc.w.data_ptr(), pc.c_out, pc.c_out_rows, pc.k_per_tap, pc.k2, pc.bias.data_ptr(),
-            out.data_ptr(), ops._ld(out), _lib.ptr(colsum), self.stat_gran,
-            desc=f"{n}x{h}x{w} {pc.c_in}->{pc.c_out} +skip1x1({pc.c_in2}) +stats",
-        )
+        self._conv(x, pc, out, stats=True, x2=x2)
 
-    def _stats(self, x: Tensor) -> Tensor:
-        r"""GroupNorm statistics of ``x``: folded from the producers' column sums when every channel of
-        ``x`` has them (one tiny launch), else by the stand-alone reduction pass."""
+    def _stats(self, x: Tensor):
+        r"""Where the GroupNorm over ``x`` finds its statistics: ``("acc", parts)`` -- the exact accumulators of
+        the one or two producers of ``x`` -- or ``("stats", tensor)`` from the stand-alone reduction pass."""
         n, c = x.shape[0], x.shape[-1]
         hw = math.prod(x.shape[1:-1])
         parts = self.cat_parts.get(self._key(x), [x])
-        sources = [self.colsum_of.get(self._key(t)) for t in parts]
-        if all(src is not None for src in sources):
-            stats = torch.empty(n, ops.GN_GROUPS, 2, dtype=torch.float32, device=self.device)
-            (a, ca), (b, cb) = sources[0], (sources[1] if len(sources) > 1 else (None, 0))
-            self.keep.append(stats)
-            self._emit(
-                "gn_finalize", 0.0, 4.0 * (a.numel() + (b.numel() if b is not None else 0)),
-                self.lib.azb_gn_finalize_f32, a.data_ptr(), ca, self.stat_gran, _lib.ptr(b), cb, self.stat_gran, n,
-                x.shape[1], x.shape[2], ops.GN_GROUPS, ops.GN_EPS, stats.data_ptr(),
-            )
-            return stats
+        sources = [self.acc_of.get(self._key(t)) for t in parts]
+        if all(src is not None for src in sources) and (c // ops.GN_GROUPS) % self.stat_gran == 0:
+            return ("acc", sources)
         want = c_int64(0)
         _lib.check(self.lib.azb_gn_stats_workspace(n, hw, c, ops.GN_GROUPS, byref(want)), "azb_gn_stats_workspace")
         self.gn_partial_need = max(self.gn_partial_need, want.value)
@@ -292,28 +276,41 @@ class Plan:
             self.lib.azb_gn_stats_bf16, x.data_ptr(), ops._ld(x), n, hw, c, ops.GN_GROUPS, ops.GN_EPS, "partial",
             stats.data_ptr(), self.counters.data_ptr(),
         )
-        return stats
+        return ("stats", stats)
 
     def _bind_partial(self) -> None:
         ptr = self.gn_partial.data_ptr()
         self.ops = [(fn, tuple(ptr if isinstance(a, str) else a for a in args)) for fn, args in self.ops]
 
-    def _apply(self, x: Tensor, out: Tensor, stats: Tensor | None, affine, emb_offset: int | None, silu: bool,
-               mode: int) -> None:
+    def _apply(self, x: Tensor, out: Tensor, stats, affine, emb_offset: int | None, silu: bool, mode: int) -> None:
         n, h, w, c = x.shape
         gamma, beta = affine if affine is not None else (None, None)
-        self.colsum_of.pop(self._key(out), None)
+        self.acc_of.pop(self._key(out), None)
         ss_ptr, ss_stride = None, 0
         if emb_offset is not None:
             ss_ptr = self.emb_all.data_ptr() + 4 * emb_offset
             ss_stride = self.packed.emb_total if (self.rows == n and n > 1) else 0
-        self.keep += [x, out] + ([stats] if stats is not None else []) + ([gamma, beta] if gamma is not None else [])
+        self.keep += [x, out] + ([gamma, beta] if gamma is not None else [])
         px_out = n * h * w * (4 if mode == 1 else 1) // (4 if mode == 2 else 1)
+        desc = f"{n}x{h}x{w}x{c} mode{mode}"
+        if stats is not None and stats[0] == "acc":
+            (a, ca), (b, cb) = stats[1][0], (stats[1][1] if len(stats[1]) > 1 else (None, 0))
+            self.keep += [a] + ([b] if b is not None else [])
+            self._emit(
+                "gn_apply", 0.0, 2.0 * c * (n * h * w + px_out),
+                self.lib.azb_gn_apply_acc_bf16, x.data_ptr(), ops._ld(x), out.data_ptr(), ops._ld(out), n, h, w, c,
+                ops.GN_GROUPS, a.data_ptr(), ca, _lib.ptr(b), cb, self.stat_gran, ops.GN_EPS, _lib.ptr(gamma),
+                _lib.ptr(beta), ss_ptr, ss_stride, int(silu), mode, desc=desc,
+            )
+            return
+        st = stats[1] if stats is not None else None
+        if st is not None:
+            self.keep.append(st)
         self._emit(
             "gn_apply", 0.0, 2.0 * c * (n * h * w + px_out),
             self.lib.azb_gn_apply_bf16, x.data_ptr(), ops._ld(x), out.data_ptr(), ops._ld(out), n, h, w, c,
-            ops.GN_GROUPS, _lib.ptr(stats), _lib.ptr(gamma), _lib.ptr(beta), ss_ptr, ss_stride, None, 0, int(silu), mode,
-            desc=f"{n}x{h}x{w}x{c} mode{mode}",
+            ops.GN_GROUPS, _lib.ptr(st), _lib.ptr(gamma), _lib.ptr(beta), ss_ptr, ss_stride, None, 0, int(silu), mode,
+            desc=desc,
         )
 
     def _block(self, block, x: Tensor | None, dest: Tensor) -> Tensor:

@@ -11,13 +11,36 @@ from __future__ import annotations
 import math
 import torch
 
-from ctypes import POINTER, byref, c_float, c_int, c_int64, c_void_p
+import ctypes
+
+from ctypes import POINTER, byref, c_float, c_int, c_int32, c_int64, c_void_p
 from dataclasses import dataclass
 from torch import Tensor
 
 from .. import _lib
 
+class AzbConv(ctypes.Structure):
+    r"""``AzbConv`` of ``include/azb.h``: every option of the convolution / linear kernel (zero = not used)."""
+
+    _fields_ = [
+        ("act", c_void_p), ("n", c_int64), ("h", c_int64), ("w", c_int64), ("c_in", c_int64), ("act_ld", c_int64),
+        ("wpack", c_void_p), ("c_out", c_int64), ("c_out_rows", c_int64), ("k_per_tap", c_int64),
+        ("taps", c_int32), ("stride", c_int32), ("act_fn", c_int32), ("out_mode", c_int32), ("stat_gran", c_int32),
+        ("reserved", c_int32),
+        ("bias", c_void_p), ("gate", c_void_p), ("gate_ld", c_int64), ("gate_rows", c_int64),
+        ("residual", c_void_p), ("res_ld", c_int64), ("out", c_void_p), ("out_ld", c_int64), ("colsum", c_void_p),
+        ("act2", c_void_p), ("c_in2", c_int64), ("act2_ld", c_int64), ("k2", c_int64), ("gn_acc", c_void_p),
+    ]
+
+
 _lib.register({
+    "azb_conv_bf16": (c_int, [POINTER(AzbConv), c_void_p]),
+    "azb_zero_bytes": (c_int, [c_void_p, c_int64, c_void_p]),
+    "azb_gn_apply_acc_bf16": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p,
+         c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p],
+    ),
     "azb_conv_gemm_bf16": (
         c_int,
         [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int64,
@@ -512,5 +535,64 @@ def linear_gather(x: Tensor, xoff: Tensor | None, weight: Tensor, bias: Tensor |
             int(silu_in), _lib.stream_ptr(x.device),
         ),
         "azb_linear_gather_f32",
+    )
+    return out
+
+
+def conv_desc(x: Tensor, pc, out: Tensor, *, grid: tuple[int, int, int] | None = None, stride: int = 1, act: int = 0,
+              gate: int | None = None, gate_ld: int = 0, gate_rows: int = 0, residual: Tensor | None = None,
+              nchw_f32: bool = False, x2: Tensor | None = None, gn_acc: Tensor | None = None, gran: int = 8) -> AzbConv:
+    r"""Fills an :class:`AzbConv` for ``azb_conv_bf16``; ``pc`` is a :class:`PackedConv` or, with ``x2``, a
+    :class:`PackedConvSkip``.  ``gn_acc``: int64 (N, C_out / gran, 4) exact GroupNorm accumulators (zeroed by the
+    caller)."""
+    n, h, w = grid if grid is not None else x.shape[:3]
+    d = AzbConv()
+    d.act, d.n, d.h, d.w, d.c_in, d.act_ld = x.data_ptr(), n, h, w, pc.c_in, x.stride(-2)
+    d.wpack, d.c_out, d.c_out_rows, d.k_per_tap = pc.w.data_ptr(), pc.c_out, pc.c_out_rows, pc.k_per_tap
+    d.taps, d.stride, d.act_fn, d.out_mode, d.stat_gran = (9 if x2 is not None else pc.taps), stride, act, int(nchw_f32), gran
+    d.bias = _lib.ptr(pc.bias)
+    d.gate, d.gate_ld, d.gate_rows = gate, gate_ld, gate_rows
+    d.residual, d.res_ld = _lib.ptr(residual), (0 if residual is None else residual.stride(-2))
+    d.out, d.out_ld = out.data_ptr(), (0 if nchw_f32 else out.stride(-2))
+    if x2 is not None:
+        d.act2, d.c_in2, d.act2_ld, d.k2 = x2.data_ptr(), pc.c_in2, x2.stride(-2), pc.k2
+    if gn_acc is not None:
+        assert gn_acc.dtype == torch.int64 and gn_acc.is_contiguous() and gn_acc.numel() == n * (pc.c_out // gran) * 4
+        d.gn_acc = gn_acc.data_ptr()
+    return d
+
+
+def conv_acc(x: Tensor, pc, out: Tensor | None = None, residual: Tensor | None = None, x2: Tensor | None = None,
+             gran: int = 8) -> tuple[Tensor, Tensor]:
+    r"""Convolution that also returns the exact GroupNorm accumulators of its output: (out, int64 (N, C_out / gran, 4))."""
+    n, h, w, _ = x.shape
+    if out is None:
+        out = torch.empty(n, h, w, pc.c_out, dtype=torch.bfloat16, device=x.device)
+    acc = torch.zeros(n, pc.c_out // gran, 4, dtype=torch.int64, device=x.device)
+    d = conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=gran)
+    _lib.check(_lib.lib().azb_conv_bf16(byref(d), _lib.stream_ptr(x.device)), "azb_conv_bf16")
+    return out, acc
+
+
+def gn_apply_acc(x: Tensor, parts: list[tuple[Tensor, int]], gamma: Tensor, beta: Tensor, out: Tensor | None = None,
+                 scale_shift: Tensor | None = None, silu: bool = True, mode: int = 0, gran: int = 8,
+                 groups: int = GN_GROUPS, eps: float = GN_EPS) -> Tensor:
+    r"""GroupNorm + modulation + SiLU + resampling with statistics from exact accumulators
+    (``azb_gn_apply_acc_bf16``); ``parts`` = [(acc, channels), ...] of the one or two producers of ``x``."""
+    n, h, w, c = x.shape
+    ho, wo = (h * 2, w * 2) if mode == 1 else (h // 2, w // 2) if mode == 2 else (h, w)
+    if out is None:
+        out = torch.empty(n, ho, wo, c, dtype=torch.bfloat16, device=x.device)
+    (a, ca), (b, cb) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
+    ss_stride = 0
+    if scale_shift is not None and scale_shift.ndim == 2 and scale_shift.shape[0] == n and n > 1:
+        ss_stride = scale_shift.stride(0)
+    _lib.check(
+        _lib.lib().azb_gn_apply_acc_bf16(
+            x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), n, h, w, c, groups, a.data_ptr(), ca, _lib.ptr(b), cb, gran,
+            eps, gamma.data_ptr(), beta.data_ptr(), _lib.ptr(scale_shift), ss_stride, int(silu), mode,
+            _lib.stream_ptr(x.device),
+        ),
+        "azb_gn_apply_acc_bf16",
     )
     return out

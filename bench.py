@@ -262,6 +262,8 @@ def run_engine(args) -> None:
     # ---- timed region: K full samplings, inputs resident in HBM
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.profile_range:  # ncu --profile-from-start off: only the timed region is captured
+        torch.cuda.profiler.start()
     with ClockSampler(local) as clocks:
         e0.record()
         for _ in range(args.steps):
@@ -269,6 +271,8 @@ def run_engine(args) -> None:
             x0 = sampler(x1)
         e1.record()
         barrier()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     ms = max_over_ranks(e0.elapsed_time(e1))
     images = world * args.batch * args.steps
     value = images / (ms / 1e3)
@@ -341,6 +345,8 @@ def main() -> None:
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed region (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

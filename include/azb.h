@@ -168,6 +168,40 @@ int azb_conv_skip_stats_bf16(const void* act, int64_t n, int64_t h, int64_t w, i
                              int64_t c_out_rows, int64_t k_per_tap, int64_t k2, const float* bias, void* out,
                              int64_t out_ld, float* colsum, int stat_gran, void* stream);
 
+/*
+ * Every option of the convolution / linear kernel in one descriptor (plain C struct, zero = "not used"):
+ *
+ *     out = residual + gate[sample] * act_fn(conv(act) [+ conv1x1(act2)] + bias)
+ *
+ * Fields as in the flat entry points above, plus the exact GroupNorm accumulators: when gn_acc is given, the
+ * epilogue adds {sum, sum of squares} of the stored (bf16-rounded) values of every (image, block of stat_gran
+ * channels) of `out` into  int64 gn_acc[n][c_out / stat_gran][4] = {sum hi, sum lo, sumsq hi, sumsq lo}
+ * (value * 2^40 = hi * 2^32 + lo) with integer atomics: exact, hence independent of the order in which tiles
+ * finish (bit reproducible), and no reduction pass or launch is needed before azb_gn_apply_acc_bf16, which folds
+ * the blocks of each group -- of one tensor or of a concatenation of two -- in its prologue.  The caller zeroes
+ * gn_acc before the producer runs.  Needs every 32-row slab of an M tile inside one image (azb_conv_colsum_rows).
+ */
+typedef struct AzbConv {
+    const void* act;
+    int64_t n, h, w, c_in, act_ld;
+    const void* wpack;
+    int64_t c_out, c_out_rows, k_per_tap;
+    int32_t taps, stride, act_fn, out_mode, stat_gran, reserved;
+    const float* bias;
+    const float* gate;
+    int64_t gate_ld, gate_rows;
+    const void* residual;
+    int64_t res_ld;
+    void* out;
+    int64_t out_ld;
+    float* colsum;
+    const void* act2;
+    int64_t c_in2, act2_ld, k2;
+    int64_t* gn_acc;
+} AzbConv;
+
+int azb_conv_bf16(const AzbConv* desc, void* stream);
+
 /* Rows of the colsum buffer for an (n, h, w) activation; *slab_in_image = 1 when every 32-row slab
  * lies inside one image (the condition for azb_gn_finalize_f32), else 0.  Host-side helper. */
 int azb_conv_colsum_rows(int64_t n, int64_t h, int64_t w, int64_t* rows, int64_t* slab_in_image);
@@ -203,6 +237,16 @@ int azb_gn_apply_bf16(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_
                       const float* scale_shift, int64_t ss_stride, const int32_t* ss_step, int64_t ss_step_stride,
                       int silu, int mode, void* stream);
 
+/* azb_gn_apply_bf16 with the statistics taken from the exact accumulators written by azb_conv_bf16 (gn_acc, see
+ * AzbConv): x is the concatenation of channel ranges [0, c_a) and [c_a, c_a + c_b) whose producers accumulated
+ * into acc_a and acc_b (acc_b NULL, c_b = 0 for a single tensor), `gran` channels per accumulator entry.  Mean and
+ * rstd of every group are derived in the kernel's prologue in double precision: GroupNorm without a statistics
+ * pass and without a reduction launch (azula/plugins/adm/_src/nn.py:80-87). */
+int azb_gn_apply_acc_bf16(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t n, int64_t h, int64_t w,
+                          int64_t c, int64_t groups, const int64_t* acc_a, int64_t c_a, const int64_t* acc_b,
+                          int64_t c_b, int64_t gran, float eps, const float* gamma, const float* beta,
+                          const float* scale_shift, int64_t ss_stride, int silu, int mode, void* stream);
+
 /*
  * softmax(q k^T / sqrt(d)) v per (image, head) without materialising the T x T logits
  * (QKVAttentionLegacy / QKVAttention, azula/plugins/adm/_src/unet.py:328-345,361-381).
@@ -231,6 +275,10 @@ int azb_timestep_features_f32(const void* t, int t_dtype, int64_t rows, int64_t 
  * MLP and the per-block emb_layers (_src/unet.py:458-462,198-204). */
 int azb_linear_f32(const float* x, const float* w, const float* b, float* y, int64_t m, int64_t n, int64_t k,
                    int silu_in, void* stream);
+
+/* Zeroes `bytes` bytes on the stream (a memset node when captured): clears the GroupNorm accumulators of a
+ * forward pass before its first producer runs. */
+int azb_zero_bytes(void* ptr, int64_t bytes, void* stream);
 
 /* y[r][:] += table[idx[r]][:] (class-label embedding, _src/unet.py:621-623). */
 int azb_add_rows_f32(float* y, const float* table, const int64_t* idx, int64_t rows, int64_t dim, void* stream);

@@ -57,8 +57,8 @@ def main():
     for kind, desc, t, fl, by in detail:
         g = groups.setdefault((kind, desc), [0, 0.0, 0.0, 0.0])
         g[0] += 1; g[1] += t; g[2] += fl; g[3] += by
-    print("  -- by shape (top 30) --")
-    for (kind, desc), g in sorted(groups.items(), key=lambda kv: -kv[1][1])[:30]:
+    print("  -- by shape --")
+    for (kind, desc), g in sorted(groups.items(), key=lambda kv: -kv[1][1])[:90]:
         print(f"  {kind:10s} {desc:34s} n={g[0]:3d} {g[1]:7.3f} ms  {g[2] / g[1] / 1e9:6.0f} TFLOP/s {g[3] / g[1] / 1e6:6.0f} GB/s")
     print(json.dumps({"forward_ms": ms, "kernels": table}))
 

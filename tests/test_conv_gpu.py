@@ -216,3 +216,48 @@ def test_conv_with_fused_1x1_skip(n, h, w, ci, ci2, co):
         gf = got.float().reshape(-1, co)
         assert torch.allclose(tot[:, 0], gf.sum(0), rtol=1e-4, atol=1e-2)
         assert torch.allclose(tot[:, 1], gf.square().sum(0), rtol=1e-4, atol=1e-2)
+
+
+def _acc_to_sums(acc):
+    """int64 (N, blocks, 4) fixed point -> float64 (N, blocks, 2) = (sum, sum of squares)."""
+    a = acc.to(torch.float64)
+    return torch.stack(((a[..., 0] * 2.0**32 + a[..., 1]) / 2.0**40, (a[..., 2] * 2.0**32 + a[..., 3]) / 2.0**40), dim=-1)
+
+
+@pytest.mark.parametrize("n,h,w,ci,co,gran", [(2, 16, 16, 64, 128, 8), (3, 32, 32, 128, 256, 8), (2, 8, 8, 32, 32, 1),
+                                             (16, 8, 8, 256, 512, 8), (1, 64, 64, 64, 64, 8)])
+def test_conv_exact_groupnorm_accumulators(n, h, w, ci, co, gran):
+    """The epilogue's integer-atomic {sum, sumsq} per (image, channel block): equal to the sums of the stored
+    values, and bit-identical from run to run (integer additions commute)."""
+    x, wt, b = _mk(n, h, w, ci, co, 3, seed=9)
+    res = torch.randn(n, h, w, co, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2)).to(torch.bfloat16)
+    pc = ops.pack_conv(wt.float(), b)
+    out, acc = ops.conv_acc(x, pc, residual=res, gran=gran)
+    _check(out, _ref(x, wt, b, res), "conv with accumulators")
+    got = _acc_to_sums(acc)
+    o = out.double().reshape(n, h * w, co // gran, gran)
+    want = torch.stack((o.sum(dim=(1, 3)), o.square().sum(dim=(1, 3))), dim=-1)
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-3), (got - want).abs().max()
+    for _ in range(3):
+        out2, acc2 = ops.conv_acc(x, pc, residual=res, gran=gran)
+        assert torch.equal(acc, acc2) and torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("split", [None, 512, 256])
+def test_gn_apply_from_accumulators(split):
+    """GroupNorm(32) + SiLU with statistics folded from one or two producers' accumulators == torch group_norm
+    (768 channels: groups of 24, so with the 512 | 256 split group 21 straddles the two producers)."""
+    n, h, w, c = 3, 16, 16, 768
+    g = torch.Generator(device=DEV).manual_seed(4)
+    parts, outs = [], []
+    for cc in ([c] if split is None else [split, c - split]):
+        x, wt, b = _mk(n, h, w, 64, cc, 3, seed=cc)
+        out, acc = ops.conv_acc(x, ops.pack_conv(wt.float() * 3, b))
+        parts.append((acc, cc)), outs.append(out)
+    t = torch.cat(outs, dim=-1).contiguous()
+    gamma, beta = 1 + 0.1 * torch.randn(c, device=DEV, generator=g), 0.1 * torch.randn(c, device=DEV, generator=g)
+    ss = 0.2 * torch.randn(n, 2 * c, device=DEV, generator=g)
+    got = ops.gn_apply_acc(t, parts, gamma, beta, scale_shift=ss)
+    ref = F.group_norm(t.float().permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5)
+    ref = F.silu(ref * (1 + ss[:, :c, None, None]) + ss[:, c:, None, None]).permute(0, 2, 3, 1)
+    _check(got, ref, f"gn_apply_acc split={split}")
