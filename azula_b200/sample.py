@@ -17,7 +17,20 @@ tensors when ``libazb.so`` is missing (the call raises).
 
 from __future__ import annotations
 
-__all__ = ["Sampler", "DDPMSampler", "DDIMSampler"]
+__all__ = [
+    "Sampler",
+    "DDPMSampler",
+    "DDIMSampler",
+    "EulerSampler",
+    "HeunSampler",
+    "ItoSampler",
+    "zABSampler",
+    "vABSampler",
+    "zEABSampler",
+    "xEABSampler",
+    "REABSampler",
+    "PCSampler",
+]
 
 import abc
 import math
@@ -237,6 +250,367 @@ class DDIMSampler(_Ancestral):
 
     def _eta(self) -> float | None:
         return self.eta
+
+
+# ------------------------------------------------------------------------- one-step ODE / SDE samplers
+
+
+def _affine(x_t: Tensor, mean: Tensor, a, k, b, n, sampler: Sampler | None = None) -> Tensor | None:
+    r""":math:`x_s = a \mu + k (x_t - b \mu) + n \varepsilon` as ONE ``azb_step_f32`` launch when the tensors
+    live on a CUDA device (scalars are 0-d tensors); :py:`None` when the caller must use torch arithmetic."""
+    if _cuda_step_ok(x_t, mean, a):
+        layout = None if sampler is None else sampler._rng_layout(x_t.numel())  # noise addressed by global index
+        return _cuda_step(x_t, mean, a, k, b, n, layout)
+    return None
+
+
+class EulerSampler(Sampler):
+    r"""Explicit Euler (1st order) sampler of the probability-flow ODE (``azula/sample.py:264-304``).
+
+    With :math:`z(x_t) = (x_t - \alpha_t \mu) / \sigma_t`,
+
+    .. math:: x_s = \frac{\alpha_s}{\alpha_t} x_t + \alpha_s \left( \frac{\sigma_s}{\alpha_s} -
+        \frac{\sigma_t}{\alpha_t} \right) z(x_t)
+
+    Arguments:
+        denoiser: A denoiser :math:`q_\phi(X \mid X_t)`.
+        kwargs: Keyword arguments passed to :class:`Sampler`.
+    """
+
+    def __init__(self, denoiser: Denoiser, **kwargs) -> None:
+        super().__init__(**kwargs)
+
+        self.denoiser = denoiser
+
+    def step(self, x_t: Tensor, t: Tensor, s: Tensor, **kwargs) -> Tensor:
+        alpha_s, sigma_s = self.denoiser.schedule(s)
+        alpha_t, sigma_t = self.denoiser.schedule(t)
+
+        mean = self.denoiser(x_t, t, **kwargs).mean
+        slope = alpha_s * (sigma_s / alpha_s - sigma_t / alpha_t)
+
+        # a mu + k (x - alpha_t mu) with k = alpha_s / alpha_t + slope / sigma_t and a = alpha_s
+        fused = _affine(x_t, mean, alpha_s, alpha_s / alpha_t + slope / sigma_t, alpha_t, torch.zeros_like(alpha_s))
+        if fused is not None:
+            return fused
+
+        z_t = (x_t - alpha_t * mean) / sigma_t
+        return alpha_s / alpha_t * x_t + slope * z_t
+
+
+class HeunSampler(Sampler):
+    r"""Explicit Heun (2nd order) sampler: an Euler predictor, then the same step with the average of the
+    slopes at both ends; two denoiser evaluations per step (``azula/sample.py:306-352``).
+
+    Arguments:
+        denoiser: A denoiser :math:`q_\phi(X \mid X_t)`.
+        kwargs: Keyword arguments passed to :class:`Sampler`.
+    """
+
+    def __init__(self, denoiser: Denoiser, **kwargs) -> None:
+        super().__init__(**kwargs)
+
+        self.denoiser = denoiser
+
+    def step(self, x_t: Tensor, t: Tensor, s: Tensor, **kwargs) -> Tensor:
+        alpha_s, sigma_s = self.denoiser.schedule(s)
+        alpha_t, sigma_t = self.denoiser.schedule(t)
+        slope = alpha_s * (sigma_s / alpha_s - sigma_t / alpha_t)
+
+        z_t = (x_t - alpha_t * self.denoiser(x_t, t, **kwargs).mean) / sigma_t
+        x_s = alpha_s / alpha_t * x_t + slope * z_t
+
+        z_s = (x_s - alpha_s * self.denoiser(x_s, s, **kwargs).mean) / sigma_s
+        return alpha_s / alpha_t * x_t + slope * ((z_t + z_s) / 2)
+
+
+class ItoSampler(Sampler):
+    r"""First-order sampler of the Ito SDE with stochasticity :math:`\eta` and temperature :math:`\tau`
+    (``azula/sample.py:355-431``):
+
+    .. math:: x_s = \frac{\alpha_s}{\alpha_t} x_t + \frac{1 + \eta^2}{\tau} \left( \frac{\sigma_s}{\sigma_t}
+        - \frac{\alpha_s}{\alpha_t} \right) (x_t - \alpha_t \mu) + \eta \, \alpha_s \sqrt{\left|
+        \frac{\sigma_t^2}{\alpha_t^2} - \frac{\sigma_s^2}{\alpha_s^2} \right|} \, \varepsilon
+
+    Arguments:
+        denoiser: A denoiser :math:`q_\phi(X \mid X_t)`.
+        eta: The stochasticity parameter :math:`\eta \geq 0`.
+        temperature: The temperature parameter :math:`\tau \geq 0`.
+        kwargs: Keyword arguments passed to :class:`Sampler`.
+    """
+
+    def __init__(self, denoiser: Denoiser, eta: float = 1.0, temperature: float = 1.0, **kwargs) -> None:
+        super().__init__(**kwargs)
+
+        self.denoiser = denoiser
+        self.eta = eta
+        self.temperature = temperature
+
+    def step(self, x_t: Tensor, t: Tensor, s: Tensor, **kwargs) -> Tensor:
+        alpha_s, sigma_s = self.denoiser.schedule(s)
+        alpha_t, sigma_t = self.denoiser.schedule(t)
+
+        mean = self.denoiser(x_t, t, **kwargs).mean
+
+        ratio = alpha_s / alpha_t
+        drift = (1 + self.eta**2) / self.temperature * (sigma_s / sigma_t - ratio)
+        noise = self.eta * alpha_s * torch.sqrt(torch.abs((sigma_t / alpha_t) ** 2 - (sigma_s / alpha_s) ** 2))
+
+        # ratio x + drift (x - alpha_t mu) + noise eps = alpha_s mu + (ratio + drift) (x - alpha_t mu) + noise eps
+        fused = _affine(x_t, mean, alpha_s, ratio + drift, alpha_t, noise, self)
+        if fused is not None:
+            return fused
+
+        x_s = ratio * x_t
+        x_s = x_s + drift * (x_t - alpha_t * mean)
+        return x_s + noise * torch.randn_like(x_s)
+
+
+class PCSampler(Sampler):
+    r"""Predictor-corrector sampler: ``corrections`` Langevin-like corrector steps of amplitude
+    :math:`\delta` at time :math:`t`, then a deterministic (DDIM) predictor to :math:`s`
+    (``azula/sample.py:953-999``).
+
+    Arguments:
+        denoiser: A denoiser :math:`q_\phi(X \mid X_t)`.
+        corrections: The number of corrector steps for each predictor step.
+        delta: The amplitude of corrector steps :math:`\delta \in [0,1]`.
+        kwargs: Keyword arguments passed to :class:`Sampler`.
+    """
+
+    def __init__(self, denoiser: Denoiser, corrections: int = 1, delta: float = 0.01, **kwargs) -> None:
+        super().__init__(**kwargs)
+
+        self.denoiser = denoiser
+        self.corrections = corrections
+        self.delta = delta
+
+    def step(self, x_t: Tensor, t: Tensor, s: Tensor, **kwargs) -> Tensor:
+        alpha_s, sigma_s = self.denoiser.schedule(s)
+        alpha_t, sigma_t = self.denoiser.schedule(t)
+        keep, kick = math.sqrt(1 - self.delta), math.sqrt(self.delta)
+
+        for _ in range(self.corrections):
+            mean = self.denoiser(x_t, t, **kwargs).mean
+            fused = _affine(x_t, mean, alpha_t, keep * torch.ones_like(alpha_t), alpha_t, kick * sigma_t, self)
+            if fused is not None:
+                x_t = fused
+            else:
+                x_t = alpha_t * mean + keep * (x_t - alpha_t * mean) + kick * sigma_t * torch.randn_like(x_t)
+
+        mean = self.denoiser(x_t, t, **kwargs).mean
+        fused = _affine(x_t, mean, alpha_s, sigma_s / sigma_t, alpha_t, torch.zeros_like(alpha_s))
+        if fused is not None:
+            return fused
+        return alpha_s * mean + sigma_s / sigma_t * (x_t - alpha_t * mean)
+
+
+# ----------------------------------------------------------------------------------- multi-step samplers
+
+
+class _Multistep(Sampler):
+    r"""Adams-Bashforth-type samplers: in a variable :math:`u(t)` in which the probability-flow ODE is (semi-)
+    linear, the integral of the last :math:`n` evaluations' Lagrange interpolant is added at every step,
+
+    .. math:: x_s = r_i \, x_t + g_i \sum_{j=1}^{n} w_{ij} \, h_{t_j}
+
+    where the weights solve the Vandermonde system :math:`V w = b` with :math:`V_{kj} = u_j^k` and
+    :math:`b_k = \int_{u_t}^{u_s} \omega(v) \, v^k \, dv` in float64 (``azula/sample.py:485-508``).
+    Subclasses define :math:`u`, the moments :math:`b`, the stored quantity :math:`h` and :math:`(r_i, g_i)`.
+    """
+
+    def __init__(self, denoiser: Denoiser, order: int = 2, **kwargs) -> None:
+        super().__init__(**kwargs)
+
+        self.denoiser = denoiser
+        self.order = order
+
+    # -- to be provided
+    def _variable(self, alpha: Tensor, sigma: Tensor) -> Tensor:
+        raise NotImplementedError()
+
+    @staticmethod
+    def _moments(u: Tensor, i: int, k: Tensor) -> Tensor:
+        raise NotImplementedError()
+
+    def _stored(self, x_t: Tensor, mean: Tensor, alpha: Tensor, sigma: Tensor, i: int) -> Tensor:
+        raise NotImplementedError()
+
+    def _update(self, x_t: Tensor, integral: Tensor, alpha: Tensor, sigma: Tensor, i: int) -> Tensor:
+        raise NotImplementedError()
+
+    # -- shared
+    @classmethod
+    def _weights(cls, u: Tensor, i: int, n: int) -> Tensor:
+        r"""The :math:`\min(n, i + 1)` weights of step :math:`i`, computed in float64, returned in :py:`u.dtype`."""
+        wide = u.to(torch.promote_types(u.dtype, torch.float64))
+        n = min(n, i + 1)
+        k = torch.arange(n, device=u.device)
+        vandermonde = wide[i + 1 - n : i + 1] ** k[:, None]
+        return torch.linalg.solve(vandermonde, cls._moments(wide, i, k)).to(u.dtype)
+
+    @torch.no_grad()
+    def __call__(self, x: Tensor, **kwargs) -> Tensor:
+        time = self.timesteps.to(device=x.device)
+        alpha, sigma = self.denoiser.schedule(time)
+        u = self._variable(alpha, sigma)
+
+        x_t, history = x, []
+        for i, t in enumerate(self.progress_bar(time[:-1])):
+            mean = self.denoiser(x_t, t, **kwargs).mean
+            history.append(self._stored(x_t, mean, alpha, sigma, i))
+            del history[: -self.order]
+
+            weights = self._weights(u, i, self.order)
+            integral = sum(h * w for h, w in zip(history, weights, strict=True))
+            x_t = self._update(x_t, integral, alpha, sigma, i)
+
+        return x_t
+
+
+class zABSampler(_Multistep):
+    r"""Adams-Bashforth sampler with noise (:math:`z`) prediction in :math:`u = \sigma / \alpha`
+    (``azula/sample.py:434-537``; the LMS sampler of k-diffusion).
+
+    Arguments:
+        denoiser: A denoiser :math:`q_\phi(X \mid X_t)`.
+        order: The order :math:`n` of the multi-step method.
+        kwargs: Keyword arguments passed to :class:`Sampler`.
+    """
+
+    def _variable(self, alpha: Tensor, sigma: Tensor) -> Tensor:
+        return sigma / alpha
+
+    @staticmethod
+    def _moments(u: Tensor, i: int, k: Tensor) -> Tensor:
+        return u[i + 1] ** (k + 1) / (k + 1) - u[i] ** (k + 1) / (k + 1)
+
+    _adams_bashforth = classmethod(lambda cls, t, i, n: cls._weights(t, i, n))
+
+    def _stored(self, x_t, mean, alpha, sigma, i):
+        return (x_t - alpha[i] * mean) / sigma[i]
+
+    def _update(self, x_t, integral, alpha, sigma, i):
+        return alpha[i + 1] / alpha[i] * x_t + alpha[i + 1] * integral
+
+
+class vABSampler(zABSampler):
+    r"""Adams-Bashforth sampler with velocity (:math:`v`) prediction in :math:`u = \sigma / (\alpha +
+    \sigma)` (``azula/sample.py:540-593``).
+
+    Arguments:
+        denoiser: A denoiser :math:`q_\phi(X \mid X_t)`.
+        order: The order :math:`n` of the multi-step method.
+        kwargs: Keyword arguments passed to :class:`Sampler`.
+    """
+
+    def _variable(self, alpha: Tensor, sigma: Tensor) -> Tensor:
+        return sigma / (alpha + sigma)
+
+    def _stored(self, x_t, mean, alpha, sigma, i):
+        return 1 / sigma[i] * x_t - (1 + alpha[i] / sigma[i]) * mean
+
+    def _update(self, x_t, integral, alpha, sigma, i):
+        total_s, total_t = alpha[i + 1] + sigma[i + 1], alpha[i] + sigma[i]
+        return total_s / total_t * x_t + total_s * integral
+
+
+def _factorials(k: Tensor) -> Tensor:
+    return torch.cumprod(torch.clip(k, min=1), dim=0)
+
+
+class zEABSampler(_Multistep):
+    r"""Exponential Adams-Bashforth sampler with noise prediction in :math:`u = \log(\sigma / \alpha)`: a
+    multi-step DPM-Solver (``azula/sample.py:596-699``); moments :math:`\int e^v v^k dv`.
+
+    Arguments:
+        denoiser: A denoiser :math:`q_\phi(X \mid X_t)`.
+        order: The order :math:`n` of the multi-step method.
+        kwargs: Keyword arguments passed to :class:`Sampler`.
+    """
+
+    def _variable(self, alpha: Tensor, sigma: Tensor) -> Tensor:
+        return sigma.log() - alpha.log()
+
+    @staticmethod
+    def _moments(u: Tensor, i: int, k: Tensor) -> Tensor:
+        fact = _factorials(k)
+        hi = torch.exp(u[i + 1]) * torch.cumsum((-u[i + 1]) ** k / fact, dim=0)
+        lo = torch.exp(u[i]) * torch.cumsum((-u[i]) ** k / fact, dim=0)
+        return (-1) ** k * fact * (hi - lo)
+
+    _exponential_adams_bashforth = classmethod(lambda cls, t, i, n: cls._weights(t, i, n))
+
+    def _stored(self, x_t, mean, alpha, sigma, i):
+        return (x_t - alpha[i] * mean) / sigma[i]
+
+    def _update(self, x_t, integral, alpha, sigma, i):
+        return alpha[i + 1] / alpha[i] * x_t + alpha[i + 1] * integral
+
+
+class xEABSampler(_Multistep):
+    r"""Exponential Adams-Bashforth sampler with data (:math:`x`) prediction: a multi-step DPM-Solver++
+    (``azula/sample.py:702-801``); moments :math:`\int e^{-v} v^k dv`.
+
+    Arguments:
+        denoiser: A denoiser :math:`q_\phi(X \mid X_t)`.
+        order: The order :math:`n` of the multi-step method.
+        kwargs: Keyword arguments passed to :class:`Sampler`.
+    """
+
+    def _variable(self, alpha: Tensor, sigma: Tensor) -> Tensor:
+        return sigma.log() - alpha.log()
+
+    @staticmethod
+    def _moments(u: Tensor, i: int, k: Tensor) -> Tensor:
+        fact = _factorials(k)
+        hi = torch.exp(-u[i + 1]) * torch.cumsum(u[i + 1] ** k / fact, dim=0)
+        lo = torch.exp(-u[i]) * torch.cumsum(u[i] ** k / fact, dim=0)
+        return -fact * (hi - lo)
+
+    _exponential_adams_bashforth = classmethod(lambda cls, t, i, n: cls._weights(t, i, n))
+
+    def _stored(self, x_t, mean, alpha, sigma, i):
+        return mean
+
+    def _update(self, x_t, integral, alpha, sigma, i):
+        return sigma[i + 1] / sigma[i] * x_t - sigma[i + 1] * integral
+
+
+class REABSampler(_Multistep):
+    r"""Rosenbrock-type exponential Adams-Bashforth sampler: a multi-step DPM-Solver-v3
+    (``azula/sample.py:804-950``); moments :math:`\int \frac{e^v}{1 + e^{2v}} v^k dv` by the trapezoidal
+    rule on 257 points.
+
+    Arguments:
+        denoiser: A denoiser :math:`q_\phi(X \mid X_t)`.
+        order: The order :math:`n` of the multi-step method.
+        kwargs: Keyword arguments passed to :class:`Sampler`.
+    """
+
+    def _variable(self, alpha: Tensor, sigma: Tensor) -> Tensor:
+        return sigma.log() - alpha.log()
+
+    @staticmethod
+    def _moments(u: Tensor, i: int, k: Tensor) -> Tensor:
+        v = torch.linspace(u[i], u[i + 1], steps=256 + 1, dtype=u.dtype, device=u.device)
+        y = torch.exp(v) / (1 + torch.exp(2 * v)) * (v ** k[:, None])
+        return torch.trapezoid(y, v, dim=-1)
+
+    _exponential_adams_bashforth = classmethod(lambda cls, t, i, n: cls._weights(t, i, n))
+
+    def _stored(self, x_t, mean, alpha, sigma, i):
+        a_t = sigma[i] ** 2 / (alpha[i] ** 2 + sigma[i] ** 2)
+        b_t = sigma[i] * torch.rsqrt(alpha[i] ** 2 + sigma[i] ** 2)
+        return (1 - a_t) / b_t / alpha[i] * x_t - 1 / b_t * mean
+
+    def _update(self, x_t, integral, alpha, sigma, i):
+        alpha_t, sigma_t, alpha_s, sigma_s = alpha[i], sigma[i], alpha[i + 1], sigma[i + 1]
+        # the reference mixes alpha_s with sigma_t in the second square root (azula/sample.py:944); kept as is
+        return (
+            torch.sqrt((alpha_s**2 + sigma_s**2) / (alpha_t**2 + sigma_t**2)) * x_t
+            + torch.sqrt(alpha_s**2 + sigma_t**2) * integral
+        )
 
 
 # ---------------------------------------------------------------- eager step on a CUDA device

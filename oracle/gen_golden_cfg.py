@@ -76,3 +76,36 @@ def time_wrapper(net_cls, features: int, **kwargs):
             return self.net(x_t, self.time_embedding(log_snr_t[..., None]))
 
     return Wrapper()
+
+
+# ---- every sampler of azula/sample.py on the README-style MLP denoiser: tag -> (class name, kwargs)
+SAMPLER_CASES = {
+    "euler": ("EulerSampler", dict(steps=16)),
+    "heun": ("HeunSampler", dict(steps=8)),
+    "ito": ("ItoSampler", dict(steps=16, eta=0.7, temperature=0.9)),
+    "ito_ode": ("ItoSampler", dict(steps=16, eta=0.0)),
+    "pc": ("PCSampler", dict(steps=8, corrections=2, delta=0.05)),
+    "zab2": ("zABSampler", dict(steps=12, order=2)),
+    "zab3": ("zABSampler", dict(steps=12, order=3)),
+    "vab": ("vABSampler", dict(steps=12, order=2)),
+    "zeab": ("zEABSampler", dict(steps=12, order=3)),
+    "xeab": ("xEABSampler", dict(steps=12, order=2)),
+    "reab": ("REABSampler", dict(steps=12, order=2, stop=0.02)),
+}
+
+
+def LabelMlp(module_cls, torch):
+    """A tiny label-conditional backbone b(x, t, label) for the classifier-free-guidance fixtures."""
+
+    class Net(module_cls):
+        def __init__(self):
+            super().__init__()
+            self.l1 = torch.nn.Linear(5 + 1, 32)
+            self.l2 = torch.nn.Linear(32, 5)
+            self.emb = torch.nn.Embedding(3, 32)
+
+        def forward(self, x, t, label):
+            h = self.l1(torch.cat((x, t.expand(x.shape[:-1])[..., None]), dim=-1)) + self.emb(label)
+            return self.l2(torch.tanh(h))
+
+    return Net()
