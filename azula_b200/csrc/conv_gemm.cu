@@ -59,6 +59,11 @@ struct ConvParams {
     int kb_extra;             // K blocks of the second (1x1, same resolution) operand appended after the taps
     unsigned long long* gn_acc;  // [N][c_out / stat_gran][4] exact fixed-point {sum hi, sum lo, sumsq hi, sumsq lo}
     int chunked;              // 1: CTA b owns the contiguous tile range [b * per, (b + 1) * per) instead of b, b + grid, ...
+    int splits;               // split-K factor S (1 = off): tile t = split * tiles_out + output tile, single wave only
+    int tiles_out;            // output tiles (= total_tiles / splits)
+    float* ws_partial;        // [(S - 1) * tiles_out][128][BLOCK_N] fp32 partial accumulators of splits 1 .. S-1
+    int* ws_flags;            // [tiles_out][EPI_WARPS] arrival counters, zero between launches
+    int prefetch_kb;          // > 0: the producer pulls the weight tile of k-block kb + prefetch_kb into L2
 };
 
 // Adds v * 2^40 to a 96-bit fixed-point accumulator held as two int64 words (value = hi * 2^32 + lo, 0 <= lo < 2^32):
@@ -166,6 +171,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
 
     const int num_kb_taps = p.taps * p.kb_per_tap;
     const int num_kb = num_kb_taps + p.kb_extra;
+    const int kb_per_split = num_kb / p.splits;  // the host guarantees divisibility
 
     // this CTA's tiles: round robin, or (chunked) a contiguous range -- then consecutive tiles lie in the same image
     // and the GroupNorm sums can be carried across tiles instead of hitting the accumulators once per tile
@@ -186,8 +192,11 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
             for (int local = 0; local < tile_count; ++local) {
                 const int tile = tile_first + local * tile_step;
                 int n_tile, w0, h0, n0;
-                tile_coords(p, tile, n_tile, w0, h0, n0);
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                tile_coords(p, tile % p.tiles_out, n_tile, w0, h0, n0);
+                const int kb0 = (tile / p.tiles_out) * kb_per_split;
+                for (int j = 0; j < p.prefetch_kb && j < kb_per_split; ++j)
+                    tc::tma_prefetch_l2_2d(&tmap_b, (kb0 + j) * BLOCK_K, n_tile * BLOCK_N);
+                for (int kb = kb0; kb < kb0 + kb_per_split; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t parity = ((it / STAGES) & 1) ^ 1;
                     tc::mbar_wait(tc::smem_u32(&bar_empty[s]), parity);
@@ -205,6 +214,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                         tc::tma_load_4d(a_dst, &tmap_a2, full, (kb - num_kb_taps) * BLOCK_K, w0, h0, n0);
                     }
                     tc::tma_load_2d(b_dst, &tmap_b, full, kb * BLOCK_K, n_tile * BLOCK_N);
+                    if (p.prefetch_kb && kb + p.prefetch_kb < kb0 + kb_per_split)
+                        tc::tma_prefetch_l2_2d(&tmap_b, (kb + p.prefetch_kb) * BLOCK_K, n_tile * BLOCK_N);
                 }
             }
         }
@@ -219,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                 tc::mbar_wait(tc::smem_u32(&bar_acc_empty[as]), ((local >> 1) & 1) ^ 1);
                 tc::fence_after_sync();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(as * C::ACC_COLS);
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                for (int kb = 0; kb < kb_per_split; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t parity = (it / STAGES) & 1;
                     tc::mbar_wait(tc::smem_u32(&bar_full[s]), parity);
@@ -274,9 +285,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
             const int tile = tile_first + local * tile_step;
             const int as = local & 1;
             int n_tile, w0, h0, n0;
-            tile_coords(p, tile, n_tile, w0, h0, n0);
+            const int out_tile = tile % p.tiles_out, split = tile / p.tiles_out;
+            tile_coords(p, out_tile, n_tile, w0, h0, n0);
             const int col_base = n_tile * BLOCK_N + half * C::COLS_PER_WARP;
-            const int m_tile = tile / p.n_tiles;
+            const int m_tile = out_tile / p.n_tiles;
             if (p.chunked && n0 != carry_img) {  // a new image begins: hand the finished one to the accumulators
                 flush_carry(carry_img);
                 carry_img = n0;
@@ -285,7 +297,38 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
             tc::mbar_wait(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
             tc::fence_after_sync();
 
-            if (active && p.out_mode == 0) {
+            if (active && split > 0) {
+                // split-K helper: this CTA accumulated K range `split`; its raw fp32 accumulator goes to the workspace
+                // (lane = tile row: 128 contiguous bytes per lane and chunk), then the owner (split 0) is signalled
+                float* dst = p.ws_partial + ((int64_t)(split - 1) * p.tiles_out + out_tile) * (BLOCK_M * BLOCK_N) +
+                             (int64_t)(quarter * 32 + lane) * BLOCK_N + half * C::COLS_PER_WARP;
+#pragma unroll 1
+                for (int c0 = 0; c0 < C::COLS_PER_WARP; c0 += CHUNK) {
+                    uint32_t acc[CHUNK];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                                           (uint32_t)(as * C::ACC_COLS + half * C::COLS_PER_WARP + c0);
+                    if constexpr (CHUNK == 32) tc::tmem_ld_32x32b_x32(taddr, acc);
+                    else tc::tmem_ld_32x32b_x16(taddr, acc);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < CHUNK; j += 4)
+                        __stcg(reinterpret_cast<uint4*>(dst + c0 + j), make_uint4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(p.ws_flags + out_tile * EPI_WARPS + e, 1);
+            } else if (active && p.out_mode == 0) {
+                if (p.splits > 1) {  // owner: wait for the S - 1 helpers of this warp's part of the tile
+                    int* flag = p.ws_flags + out_tile * EPI_WARPS + e;
+                    if (lane == 0) {
+                        int seen;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+                        } while (seen < p.splits - 1);
+                        *flag = 0;  // clean for the next launch (stream order)
+                    }
+                    __syncwarp();
+                }
                 {
                     // pixels of the 4 rows this lane handles in the coalesced domain
                     int64_t pixc[4];
@@ -331,6 +374,20 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                             bias8[4] = b1.x, bias8[5] = b1.y, bias8[6] = b1.z, bias8[7] = b1.w;
                         }
                         tc::tmem_ld_wait();
+                        if (p.splits > 1) {  // fold the helpers' partial accumulators (row domain, L2-resident)
+                            for (int sp = 1; sp < p.splits; ++sp) {
+                                const float* src = p.ws_partial + ((int64_t)(sp - 1) * p.tiles_out + out_tile) * (BLOCK_M * BLOCK_N) +
+                                                   (int64_t)(quarter * 32 + lane) * BLOCK_N + half * C::COLS_PER_WARP + c0;
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    const float4 v = __ldcg(reinterpret_cast<const float4*>(src + j));
+                                    acc[j] = __float_as_uint(__uint_as_float(acc[j]) + v.x);
+                                    acc[j + 1] = __float_as_uint(__uint_as_float(acc[j + 1]) + v.y);
+                                    acc[j + 2] = __float_as_uint(__uint_as_float(acc[j + 2]) + v.z);
+                                    acc[j + 3] = __float_as_uint(__uint_as_float(acc[j + 3]) + v.w);
+                                }
+                            }
+                        }
                         // row domain -> staging: 16-byte slot j of row `lane` lives at slot j ^ (lane & 7)
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -547,6 +604,8 @@ struct ConvExtra {
     const void* act2 = nullptr;  // second operand: NHWC bf16 at the OUTPUT resolution, 1x1, weights appended along K
     int64_t c_in2 = 0, act2_ld = 0, k2 = 0;
     int64_t* gn_acc = nullptr;   // exact per-(image, channel block) sums of `out` for the GroupNorms that consume it
+    void* workspace = nullptr;   // split-K scratch: flags (zero between launches) + fp32 partial tiles
+    int64_t workspace_bytes = 0;
 };
 
 // (h, w) are the INPUT extents; the output is ceil(h / stride) x ceil(w / stride).
@@ -597,9 +656,36 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     }
     if (c_out_rows % block_n || c_out_rows < c_out) return AZB_E_SHAPE;
 
+    // Split-K for small feature maps with long reductions (8 x 8 layers: 8 M tiles, K = 9216 .. 18432): a wide N tile
+    // alone leaves most SMs idle and the narrow one (N = 64) re-reads the A operand at half MMA rate.  S CTAs share an
+    // output tile, each reduces 1/S of K; the helpers park their fp32 accumulators in the workspace and the owner
+    // folds them before its epilogue.  Single wave only (all CTAs co-resident), so the owner's wait cannot deadlock.
+    int splits = 1;
+    const int64_t num_kb_total = (int64_t)taps * (k_per_tap / BLOCK_K) + (ex.act2 ? ex.k2 / BLOCK_K : 0);
+    if (ex.workspace && out_mode == 0 && m_tiles * (c_out_rows / block_n) <= sms && (block_n <= 64 || m_tiles * (c_out_rows / block_n) < sms / 2)) {
+        const int try_n[2] = {128, 256}, try_s[2] = {2, 4};
+        for (int i = 0; i < 2 && splits == 1; ++i) {
+            const int bn = try_n[i], sp = try_s[i];
+            if (c_out_rows % bn || num_kb_total % sp || num_kb_total / sp < 16) continue;
+            const int64_t tiles = m_tiles * (c_out_rows / bn);
+            if (tiles * sp > sms || tiles * sp < sms / 2) continue;
+            const int64_t need = 256 + ((tiles * EPI_WARPS * 4 + 255) / 256) * 256 + (int64_t)(sp - 1) * tiles * BLOCK_M * bn * 4;
+            if (need > ex.workspace_bytes) continue;
+            block_n = bn, splits = sp;
+        }
+    }
+
     p.n_tiles = (int)(c_out_rows / block_n);
-    if (m_tiles * p.n_tiles > 0x7fffffffLL) return AZB_E_SHAPE;
-    p.total_tiles = (int)(m_tiles * p.n_tiles);
+    if (m_tiles * p.n_tiles * splits > 0x7fffffffLL) return AZB_E_SHAPE;
+    p.tiles_out = (int)(m_tiles * p.n_tiles);
+    p.total_tiles = p.tiles_out * splits;
+    p.splits = splits;
+    if (splits > 1) {
+        if (!azb_aligned(ex.workspace, 256)) return AZB_E_ALIGN;
+        p.ws_flags = reinterpret_cast<int*>(ex.workspace);
+        p.ws_partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ex.workspace) +
+                                                 (((int64_t)p.tiles_out * EPI_WARPS * 4 + 255) / 256) * 256);
+    }
     p.taps = taps, p.ksize = taps == 9 ? 3 : 1, p.pad = taps == 9 ? 1 : 0;
     p.kb_per_tap = (int)(k_per_tap / BLOCK_K);
     p.c_out = (int)c_out;
@@ -617,7 +703,10 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     // Large feature maps (one image per M tile, at most two N tiles): contiguous tile ranges per CTA, sums carried
     // across the tiles of an image.  With round-robin tiles every CTA works on the same image at the same time and the ~4 M
     // same-address atomics of a 256 x 256 layer serialise in L2 (measured: +15 % on the K = 2304 layers).
-    p.chunked = (ex.gn_acc && p.n_tiles <= 2 && p.BN == 1 && stat_gran == 8 && block_n >= 64) ? 1 : 0;
+    // few M tiles => every weight tile is used by a handful of CTAs right after its first (HBM) read: with only
+    // STAGES loads in flight the main loop would run at HBM latency; prefetch the weight stream into L2 ahead of use
+    p.prefetch_kb = m_tiles <= 32 ? 24 : 0;
+    p.chunked = (ex.gn_acc && p.n_tiles <= 2 && p.BN == 1 && stat_gran == 8 && block_n >= 64 && splits == 1) ? 1 : 0;
     const int64_t k_total = taps * k_per_tap + (ex.act2 ? ex.k2 : 0);
 
     CUtensorMap ta, tb, ta2;
@@ -719,6 +808,7 @@ extern "C" int azb_conv_bf16(const AzbConv* d, void* stream) {
     ex.gate = d->gate, ex.gate_ld = d->gate_ld, ex.gate_rows = d->gate_rows;
     ex.act2 = d->act2, ex.c_in2 = d->c_in2, ex.act2_ld = d->act2_ld, ex.k2 = d->k2;
     ex.gn_acc = d->gn_acc;
+    ex.workspace = d->workspace, ex.workspace_bytes = d->workspace_bytes;
     return conv_impl(d->act, d->n, d->h, d->w, d->c_in, d->act_ld, d->wpack, d->c_out, d->c_out_rows, d->taps, d->k_per_tap,
                      d->bias, d->residual, d->res_ld, d->out, d->out_ld, d->out_mode, d->colsum,
                      (d->colsum || d->gn_acc) ? d->stat_gran : 1, stream, ex);

@@ -152,6 +152,7 @@ class Plan:
         self.acc_used = 0
         self._emit("zero", 0.0, 8.0 * self.acc_pool.numel(), self.lib.azb_zero_bytes, self.acc_pool.data_ptr(),
                    8 * self.acc_pool.numel())
+        self.splitk_ws = ops.splitk_workspace(device)
         # ---- GroupNorm fallback workspace (feature maps too small for the fused sums)
         self.gn_partial_need = 0
         self.counters = torch.zeros(max(n, 1), dtype=torch.int32, device=device)
@@ -243,7 +244,7 @@ class Plan:
         acc = self._acc_for(out, pc.c_out) if stats else None
         if not stats:
             self.acc_of.pop(self._key(out), None)
-        d = ops.conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=self.stat_gran)
+        d = ops.conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=self.stat_gran, workspace=self.splitk_ws)
         self.keep += [d, x, out, pc.w] + [t for t in (residual, pc.bias, x2) if t is not None]
         taps = 9 if x2 is not None else pc.taps
         k_extra = pc.c_in2 if x2 is not None else 0

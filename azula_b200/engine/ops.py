@@ -30,6 +30,7 @@ class AzbConv(ctypes.Structure):
         ("bias", c_void_p), ("gate", c_void_p), ("gate_ld", c_int64), ("gate_rows", c_int64),
         ("residual", c_void_p), ("res_ld", c_int64), ("out", c_void_p), ("out_ld", c_int64), ("colsum", c_void_p),
         ("act2", c_void_p), ("c_in2", c_int64), ("act2_ld", c_int64), ("k2", c_int64), ("gn_acc", c_void_p),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64),
     ]
 
 
@@ -541,7 +542,8 @@ def linear_gather(x: Tensor, xoff: Tensor | None, weight: Tensor, bias: Tensor |
 
 def conv_desc(x: Tensor, pc, out: Tensor, *, grid: tuple[int, int, int] | None = None, stride: int = 1, act: int = 0,
               gate: int | None = None, gate_ld: int = 0, gate_rows: int = 0, residual: Tensor | None = None,
-              nchw_f32: bool = False, x2: Tensor | None = None, gn_acc: Tensor | None = None, gran: int = 8) -> AzbConv:
+              nchw_f32: bool = False, x2: Tensor | None = None, gn_acc: Tensor | None = None, gran: int = 8,
+              workspace: Tensor | None = None) -> AzbConv:
     r"""Fills an :class:`AzbConv` for ``azb_conv_bf16``; ``pc`` is a :class:`PackedConv` or, with ``x2``, a
     :class:`PackedConvSkip``.  ``gn_acc``: int64 (N, C_out / gran, 4) exact GroupNorm accumulators (zeroed by the
     caller)."""
@@ -559,19 +561,29 @@ def conv_desc(x: Tensor, pc, out: Tensor, *, grid: tuple[int, int, int] | None =
     if gn_acc is not None:
         assert gn_acc.dtype == torch.int64 and gn_acc.is_contiguous() and gn_acc.numel() == n * (pc.c_out // gran) * 4
         d.gn_acc = gn_acc.data_ptr()
+    if workspace is not None:  # zero-initialised uint8 scratch for split-K (flags stay zero between launches)
+        d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     return d
 
 
 def conv_acc(x: Tensor, pc, out: Tensor | None = None, residual: Tensor | None = None, x2: Tensor | None = None,
-             gran: int = 8) -> tuple[Tensor, Tensor]:
+             gran: int = 8, workspace: Tensor | None = None) -> tuple[Tensor, Tensor]:
     r"""Convolution that also returns the exact GroupNorm accumulators of its output: (out, int64 (N, C_out / gran, 4))."""
     n, h, w, _ = x.shape
     if out is None:
         out = torch.empty(n, h, w, pc.c_out, dtype=torch.bfloat16, device=x.device)
     acc = torch.zeros(n, pc.c_out // gran, 4, dtype=torch.int64, device=x.device)
-    d = conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=gran)
+    d = conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=gran, workspace=workspace)
     _lib.check(_lib.lib().azb_conv_bf16(byref(d), _lib.stream_ptr(x.device)), "azb_conv_bf16")
     return out, acc
+
+
+SPLITK_WORKSPACE_BYTES = 16 << 20
+
+
+def splitk_workspace(device) -> Tensor:
+    r"""Zeroed scratch that lets ``azb_conv_bf16`` split the reduction of small-map / long-K layers over CTAs."""
+    return torch.zeros(SPLITK_WORKSPACE_BYTES, dtype=torch.uint8, device=device)
 
 
 def gn_apply_acc(x: Tensor, parts: list[tuple[Tensor, int]], gamma: Tensor, beta: Tensor, out: Tensor | None = None,

@@ -13,8 +13,12 @@ __all__ = ["get_hub_dir", "set_hub_dir", "download"]
 import hashlib
 import os
 import re
+import shutil
 import sys
+import tarfile
+import tempfile
 import torch
+import zipfile
 
 _HUB = os.path.expanduser("~/.cache/azula/hub")
 
@@ -33,9 +37,11 @@ def cache_path(url: str) -> str:
     return os.path.join(get_hub_dir(), re.sub(r"[^a-zA-Z0-9_]+", ".", url))
 
 
-def download(url: str, filename: str | None = None, hash_prefix: str | None = None, quiet: bool = False) -> str:
+def download(url: str, filename: str | None = None, hash_prefix: str | None = None, extract: bool = False,
+             quiet: bool = False) -> str:
     r"""Returns the local path of a (cached) file, fetching it with :mod:`torch.hub` if absent;
-    verifies an ``"alg:prefix"`` hash when given."""
+    verifies an ``"alg:prefix"`` hash when given.  With :py:`extract=True` the file is a tar or zip
+    archive and the directory ``<file>+x`` holding its contents is returned (``azula/hub.py:40-125``)."""
     path = cache_path(url) if filename is None else os.path.abspath(os.path.expanduser(filename))
     os.makedirs(os.path.dirname(path), exist_ok=True)
     if not os.path.exists(path):
@@ -52,4 +58,22 @@ def download(url: str, filename: str | None = None, hash_prefix: str | None = No
                 digest.update(block)
         if not digest.hexdigest().startswith(prefix):
             raise AssertionError(f"hash of {path} ({alg}:{digest.hexdigest()}) does not start with {alg}:{prefix}")
+    if extract:
+        xd = f"{path}+x"
+        if os.path.exists(xd):
+            return xd
+        if not quiet:
+            print(f"Extracting to {xd}", file=sys.stderr)
+        with tempfile.TemporaryDirectory() as td:
+            if tarfile.is_tarfile(path):
+                with tarfile.open(path, "r") as f:
+                    f.extractall(td)
+            elif zipfile.is_zipfile(path):
+                with zipfile.ZipFile(path, "r") as f:
+                    f.extractall(td)
+            else:
+                raise ValueError("Unknown archive format.")
+            shutil.move(td, xd)
+            os.makedirs(td, exist_ok=True)  # TemporaryDirectory cleans up the (now empty) original path
+        return xd
     return path

@@ -290,7 +290,7 @@ class EulerSampler(Sampler):
         slope = alpha_s * (sigma_s / alpha_s - sigma_t / alpha_t)
 
         # a mu + k (x - alpha_t mu) with k = alpha_s / alpha_t + slope / sigma_t and a = alpha_s
-        fused = _affine(x_t, mean, alpha_s, alpha_s / alpha_t + slope / sigma_t, alpha_t, torch.zeros_like(alpha_s))
+        fused = _affine(x_t, mean, alpha_s, alpha_s / alpha_t + slope / sigma_t, alpha_t, None)
         if fused is not None:
             return fused
 
@@ -399,7 +399,7 @@ class PCSampler(Sampler):
                 x_t = alpha_t * mean + keep * (x_t - alpha_t * mean) + kick * sigma_t * torch.randn_like(x_t)
 
         mean = self.denoiser(x_t, t, **kwargs).mean
-        fused = _affine(x_t, mean, alpha_s, sigma_s / sigma_t, alpha_t, torch.zeros_like(alpha_s))
+        fused = _affine(x_t, mean, alpha_s, sigma_s / sigma_t, alpha_t, None)
         if fused is not None:
             return fused
         return alpha_s * mean + sigma_s / sigma_t * (x_t - alpha_t * mean)
@@ -633,9 +633,12 @@ def _cuda_step_ok(x_t: Tensor, mean: Tensor, alpha_s: Tensor) -> bool:
 
 def _cuda_step(x_t: Tensor, mean: Tensor, alpha_s, k, alpha_t, n, layout=None) -> Tensor:
     r"""The affine update of one generic step as a single ``azb_step_f32`` launch
-    (row = [0, 1, alpha_s, k, alpha_t, n, 1, inf] so that m = F = the posterior mean)."""
+    (row = [0, 1, alpha_s, k, alpha_t, n, 1, inf] so that m = F = the posterior mean).  :py:`n=None`: the
+    transition has no noise term, nothing is drawn and the generator does not advance."""
     with torch.cuda.device(x_t.device):
         zero = torch.zeros((), dtype=torch.float32, device=x_t.device)
+        draws = n is not None
+        n = zero if n is None else n
         cols = [zero, zero + 1, alpha_s, k, alpha_t, n, zero + 1, zero + float("inf")]
         row = torch.stack([c.to(device=x_t.device, dtype=torch.float32).reshape(()) for c in cols])
         idx = torch.zeros((), dtype=torch.int32, device=x_t.device)
@@ -652,5 +655,6 @@ def _cuda_step(x_t: Tensor, mean: Tensor, alpha_s, k, alpha_t, n, layout=None) -
             ),
             "azb_step_f32",
         )
-        gen.set_offset(offset + inc)
+        if draws:
+            gen.set_offset(offset + inc)
     return out.reshape(x_t.shape)

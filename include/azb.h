@@ -180,6 +180,10 @@ int azb_conv_skip_stats_bf16(const void* act, int64_t n, int64_t h, int64_t w, i
  * finish (bit reproducible), and no reduction pass or launch is needed before azb_gn_apply_acc_bf16, which folds
  * the blocks of each group -- of one tensor or of a concatenation of two -- in its prologue.  The caller zeroes
  * gn_acc before the producer runs.  Needs every 32-row slab of an M tile inside one image (azb_conv_colsum_rows).
+ *
+ * With a workspace the kernel may split the K dimension over 2 or 4 CTAs per output tile when the feature map is
+ * small and the reduction long (ADM's 8 x 8 layers, K = 9216 .. 18432): helpers park fp32 partial accumulators in
+ * the workspace, the owner folds them in a fixed order before its epilogue (deterministic).
  */
 typedef struct AzbConv {
     const void* act;
@@ -198,6 +202,8 @@ typedef struct AzbConv {
     const void* act2;
     int64_t c_in2, act2_ld, k2;
     int64_t* gn_acc;
+    void* workspace;          /* optional split-K scratch, 256-byte aligned, ZERO-initialised once by the caller (the */
+    int64_t workspace_bytes;  /* kernel leaves its flags zeroed); 16 MiB covers every shape.  NULL = never split K    */
 } AzbConv;
 
 int azb_conv_bf16(const AzbConv* desc, void* stream);

@@ -109,3 +109,52 @@ def LabelMlp(module_cls, torch):
             return self.l2(torch.tanh(h))
 
     return Net()
+
+
+# ---- preconditioners of the other plugins: tag -> (plugin module, class, ctor kwargs, call kwargs)
+def precond_backbone(kind: str, torch):
+    """Tiny image backbones with the call conventions of the vdm / edm / jit / sd plugins."""
+    nn = torch.nn
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(3, 8, 3, padding=1)
+            self.conv2 = nn.Conv2d(8, 3, 3, padding=1)
+            self.time = nn.Linear(1, 8)
+            self.cond = nn.Linear(4, 8) if kind in ("edm", "sd") else nn.Embedding(5, 8)
+
+        def body(self, x, t, c):
+            t = t.to(x.dtype).reshape(-1, 1).expand(x.shape[0], 1)
+            h = self.conv1(x) + (self.time(t) + c)[:, :, None, None]
+            return self.conv2(torch.tanh(h))
+
+        def forward(self, *args, **kwargs):
+            if kind == "vdm":
+                x, t = args
+                return self.body(x, t, 0.0)
+            if kind == "edm":
+                x, t = args
+                return self.body(x, t, self.cond(kwargs["class_labels"]))
+            if kind == "jit":
+                x, t = args
+                return self.body(x, t, self.cond(kwargs["y"]))
+            from types import SimpleNamespace
+
+            c = self.cond(kwargs["encoder_hidden_states"]).mean(dim=1)
+            return SimpleNamespace(sample=self.body(kwargs["sample"], kwargs["timestep"] / 1000.0, c))
+
+    return Net()
+
+
+def precond_cases(torch):
+    sig = torch.linspace(0.03, 0.995, 1000)
+    return {
+        "vdm": ("vdm", "VelocityDenoiser", {}, {}),
+        "edm": ("edm", "ElucidatedDenoiser", {}, {"label": torch.eye(4)[[0, 2, 1, 3]]}),
+        "jit": ("jit", "JITDenoiser", {"num_classes": 4}, {"label": torch.tensor([1, 0, 3, 2])}),
+        "jit_null": ("jit", "JITDenoiser", {"num_classes": 4}, {}),
+        "sd_eps": ("sd", "StableDenoiser", {"sigmas": sig}, {"prompt_embeds": torch.linspace(-1, 1, 24).reshape(1, 6, 4)}),
+        "sd_v": ("sd", "StableDenoiser", {"sigmas": sig, "prediction": "velocity"},
+                 {"prompt_embeds": torch.linspace(-1, 1, 96).reshape(4, 6, 4)}),
+    }

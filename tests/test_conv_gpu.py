@@ -261,3 +261,34 @@ def test_gn_apply_from_accumulators(split):
     ref = F.group_norm(t.float().permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5)
     ref = F.silu(ref * (1 + ss[:, :c, None, None]) + ss[:, c:, None, None]).permute(0, 2, 3, 1)
     _check(got, ref, f"gn_apply_acc split={split}")
+
+
+@pytest.mark.parametrize("n,h,w,ci,co,skip", [(16, 8, 8, 1024, 1024, 0), (16, 8, 8, 2048, 1024, 0), (4, 8, 8, 512, 512, 0),
+                                             (16, 8, 8, 1024, 1024, 1536), (2, 16, 16, 1024, 1024, 0)])
+def test_conv_split_k(n, h, w, ci, co, skip):
+    """Small maps with long reductions: with a workspace the kernel splits K over CTAs; same result as the unsplit
+    kernel up to fp32 summation order, accumulators included, and reproducible."""
+    x, wt, b = _mk(n, h, w, ci, co, 3, seed=31)
+    res = torch.randn(n, h, w, co, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3)).to(torch.bfloat16)
+    pc = ops.pack_conv(wt.float(), b)
+    x2 = None
+    ref = _ref(x, wt, b, None if skip else res)
+    if skip:
+        g = torch.Generator(device=DEV).manual_seed(5)
+        x2 = torch.randn(n, h, w, skip, device=DEV, generator=g).to(torch.bfloat16)
+        w2 = (torch.randn(co, skip, 1, 1, device=DEV, generator=g) / skip**0.5).to(torch.bfloat16)
+        b2 = torch.randn(co, device=DEV, generator=g)
+        pc = ops.pack_conv_skip(pc, ops.pack_conv(w2.float(), b2))
+        ref = ref + _ref(x2, w2, b2)
+    ws = ops.splitk_workspace(DEV)
+    kw = dict(residual=None if skip else res, x2=x2)
+    plain, acc0 = ops.conv_acc(x, pc, **kw)
+    split, acc1 = ops.conv_acc(x, pc, workspace=ws, **kw)
+    _check(plain, ref, "unsplit")
+    _check(split, ref, "split-K")
+    assert not ws[:256].any(), "flags must be left zeroed"
+    s0, s1 = _acc_to_sums(acc0), _acc_to_sums(acc1)
+    assert torch.allclose(s0, s1, rtol=2e-2, atol=2.0)
+    for _ in range(3):
+        again, acc2 = ops.conv_acc(x, pc, workspace=ws, **kw)
+        assert torch.equal(again, split) and torch.equal(acc1, acc2)
