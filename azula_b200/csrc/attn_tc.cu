@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(THREADS, Cfg<BK>::CTAS_PER_SM)
     const uint32_t tmem_base = tmem_slot;
 
     if (warp == SOFTMAX_WARPS) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer (one ELECTED lane: operands go straight to uniform registers) =====
+        if (tc::elect_one()) {
             tc::mbar_expect_tx(tc::smem_u32(&bar_q), Q_BYTES);
             tc::tma_load_3d(q_smem, &tmap_q, tc::smem_u32(&bar_q), ch_q, q0, img);
             for (int it = 0; it < 2 * n_tiles; ++it) {
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(THREADS, Cfg<BK>::CTAS_PER_SM)
         }
     } else if (warp == SOFTMAX_WARPS + 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (tc::elect_one()) {
             constexpr uint32_t idesc_s = tc::idesc_bf16_f32(BQ, BK);
             constexpr uint32_t idesc_o = tc::idesc_bf16_f32_b_mn(BQ, D);
             const uint64_t desc_q = tc::smem_desc_sw128(q_smem);

@@ -21,6 +21,13 @@
 //               store (or fp32 NCHW for the network output); optionally per-channel sums / sums of
 //               squares of the stored values for the GroupNorm that consumes this tensor (see
 //               azb_gn_finalize_f32), which removes a full read pass over the activation.
+//
+// CTA pairs (PAIR = true, large layers): two CTAs on the two SMs of a TPC form a cluster and share one
+// 256-pixel x BLOCK_N tile through tcgen05.mma.cta_group::2.  Each CTA loads ITS 128 pixels of A and HALF of
+// the weight tile (BLOCK_N / 2 rows); the leader's MMA thread drives both tensor cores, each of which reads the
+// other half of B from the peer's shared memory.  Per CTA and k-block that is 32 KiB from L2 instead of 48
+// (N = 256) -- the L2 -> SM path (~ 15 TB/s chip-wide at the single-CTA rate) is what caps the tensor pipe of
+// the single-CTA kernel at ~ 75 % -- and 6 pipeline stages instead of 4 in the same shared memory.
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -102,10 +109,11 @@ __device__ __forceinline__ float activate(float v, int act) {
     return v;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR = false>
 struct Cfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;  // weight rows this CTA stages per k-block
+    static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES > 8 ? 8 : SMEM_BUDGET / STAGE_BYTES;
     static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;  // columns of one accumulator stage
@@ -127,13 +135,14 @@ __device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& 
     w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                 const __grid_constant__ CUtensorMap tmap_b,
                                                                 const __grid_constant__ CUtensorMap tmap_a2,
                                                                 const ConvParams p) {
-    using C = Cfg<BLOCK_N>;
+    using C = Cfg<BLOCK_N, PAIR>;
     constexpr int STAGES = C::STAGES;
+    static_assert(!PAIR || BLOCK_N >= 128, "a CTA pair splits the weight tile in two halves of >= 64 rows");
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -145,6 +154,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // CTA pair: rank 0 (the leader) issues the MMAs and owns the `full` and `accumulator drained` barriers
+    const uint32_t cta_rank = PAIR ? (blockIdx.x & 1u) : 0u;  // cluster (2, 1, 1): rank in the pair = parity of the block index
+    const bool leader = cta_rank == 0;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -153,7 +165,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
         }
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(tc::smem_u32(&bar_acc_full[s]), 1);
-            tc::mbar_init(tc::smem_u32(&bar_acc_empty[s]), EPI_WARPS);
+            tc::mbar_init(tc::smem_u32(&bar_acc_empty[s]), PAIR ? 2 * EPI_WARPS : EPI_WARPS);
         }
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tmap_a);
@@ -161,11 +173,17 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
         if (p.kb_extra) tc::prefetch_tmap(&tmap_a2);
     }
     if (warp == 1) {
-        tc::tmem_alloc(tc::smem_u32(&tmem_slot), C::TMEM_COLS);
-        tc::tmem_relinquish();
+        if constexpr (PAIR) {
+            tc::tmem_alloc_pair(tc::smem_u32(&tmem_slot), C::TMEM_COLS);
+            tc::tmem_relinquish_pair();
+        } else {
+            tc::tmem_alloc(tc::smem_u32(&tmem_slot), C::TMEM_COLS);
+            tc::tmem_relinquish();
+        }
     }
     tc::fence_before_sync();
     __syncthreads();
+    if constexpr (PAIR) tc::cluster_sync();  // the peer's barriers are initialised before anything is sent to them
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
 
@@ -175,64 +193,89 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
 
     // this CTA's tiles: round robin, or (chunked) a contiguous range -- then consecutive tiles lie in the same image
     // and the GroupNorm sums can be carried across tiles instead of hitting the accumulators once per tile
+    // A pair schedules like one CTA: unit u = (pair of M tiles 2 mp, 2 mp + 1) x N tile; this CTA works on M tile
+    // 2 mp + rank.  p.total_tiles counts units.
+    const int sched_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int sched_n = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     int tile_first, tile_step, tile_count;
     if (p.chunked) {
-        const int per = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
-        tile_first = (int)blockIdx.x * per, tile_step = 1;
+        const int per = (p.total_tiles + sched_n - 1) / sched_n;
+        tile_first = sched_id * per, tile_step = 1;
         tile_count = max(0, min(per, p.total_tiles - tile_first));
     } else {
-        tile_first = (int)blockIdx.x, tile_step = (int)gridDim.x;
-        tile_count = (int)blockIdx.x < p.total_tiles ? (p.total_tiles - (int)blockIdx.x + tile_step - 1) / tile_step : 0;
+        tile_first = sched_id, tile_step = sched_n;
+        tile_count = sched_id < p.total_tiles ? (p.total_tiles - sched_id + tile_step - 1) / tile_step : 0;
     }
+    auto unit_to_tile = [&](int unit) -> int {
+        if constexpr (PAIR) return (2 * (unit / p.n_tiles) + (int)cta_rank) * p.n_tiles + unit % p.n_tiles;
+        else return unit;
+    };
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
-            int it = 0;  // running k-block counter across tiles
+        // One ELECTED lane (elect.sync tells ptxas that exactly one lane is active, so descriptor and coordinate
+        // operands go straight to uniform registers instead of through per-value waterfall loops).  The loop is the
+        // pacemaker of the whole kernel -- one k-block must be issued every 512 cycles -- so it carries its ring slot,
+        // parity and (tap, channel block) position incrementally: no division, no modulo.
+        if (tc::elect_one()) {
+            int s = 0;
+            uint32_t parity = 1;  // of the `empty` barriers: the first pass over the ring finds every slot free
+            const uint32_t full0 = PAIR ? tc::mapa(tc::smem_u32(&bar_full[0]), 0) : tc::smem_u32(&bar_full[0]);
             for (int local = 0; local < tile_count; ++local) {
-                const int tile = tile_first + local * tile_step;
+                const int tile = unit_to_tile(tile_first + local * tile_step);
                 int n_tile, w0, h0, n0;
                 tile_coords(p, tile % p.tiles_out, n_tile, w0, h0, n0);
                 const int kb0 = (tile / p.tiles_out) * kb_per_split;
+                const int b_row0 = n_tile * BLOCK_N + (int)cta_rank * C::B_ROWS;
                 for (int j = 0; j < p.prefetch_kb && j < kb_per_split; ++j)
                     tc::tma_prefetch_l2_2d(&tmap_b, (kb0 + j) * BLOCK_K, n_tile * BLOCK_N);
-                for (int kb = kb0; kb < kb0 + kb_per_split; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t parity = ((it / STAGES) & 1) ^ 1;
+                // position of k-block kb0 inside the taps: (kh, kw, channel block); one division per tile
+                int tap = kb0 / p.kb_per_tap, cb = kb0 - tap * p.kb_per_tap;
+                int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+                const int wbase = w0 * p.stride - p.pad, hbase = h0 * p.stride - p.pad;
+                for (int kb = kb0; kb < kb0 + kb_per_split; ++kb) {
                     tc::mbar_wait(tc::smem_u32(&bar_empty[s]), parity);
-                    const uint32_t full = tc::smem_u32(&bar_full[s]);
                     const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
                     const uint32_t b_dst = a_dst + C::A_BYTES;
-                    tc::mbar_expect_tx(full, C::STAGE_BYTES);
-                    if (kb < num_kb_taps) {
-                        const int tap = kb / p.kb_per_tap;
-                        const int cb = kb - tap * p.kb_per_tap;
-                        const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-                        tc::tma_load_4d(a_dst, &tmap_a, full, cb * BLOCK_K, w0 * p.stride + kw - p.pad,
-                                        h0 * p.stride + kh - p.pad, n0);
-                    } else {  // the fused 1x1 operand (ResBlock skip connection): same pixels, no offset
-                        tc::tma_load_4d(a_dst, &tmap_a2, full, (kb - num_kb_taps) * BLOCK_K, w0, h0, n0);
+                    const uint32_t full = full0 + 8u * (uint32_t)s;
+                    const bool in_taps = kb < num_kb_taps;
+                    // the fused 1x1 operand (ResBlock skip connection) follows the taps: same pixels, no offset
+                    const CUtensorMap* ma = in_taps ? &tmap_a : &tmap_a2;
+                    const int c0 = (in_taps ? cb : kb - num_kb_taps) * BLOCK_K;
+                    const int cw = in_taps ? wbase + kw : w0, ch = in_taps ? hbase + kh : h0;
+                    if constexpr (PAIR) {
+                        // both CTAs' bytes are credited to the LEADER's barrier, which its producer arms for the pair
+                        if (leader) tc::mbar_expect_tx(tc::smem_u32(&bar_full[s]), 2 * C::STAGE_BYTES);
+                        tc::tma_load_4d_pair(a_dst, ma, full, c0, cw, ch, n0);
+                        tc::tma_load_2d_pair(b_dst, &tmap_b, full, kb * BLOCK_K, b_row0);
+                    } else {
+                        tc::mbar_expect_tx(full, C::STAGE_BYTES);
+                        tc::tma_load_4d(a_dst, ma, full, c0, cw, ch, n0);
+                        tc::tma_load_2d(b_dst, &tmap_b, full, kb * BLOCK_K, b_row0);
                     }
-                    tc::tma_load_2d(b_dst, &tmap_b, full, kb * BLOCK_K, n_tile * BLOCK_N);
                     if (p.prefetch_kb && kb + p.prefetch_kb < kb0 + kb_per_split)
                         tc::tma_prefetch_l2_2d(&tmap_b, (kb + p.prefetch_kb) * BLOCK_K, n_tile * BLOCK_N);
+                    if (++cb == p.kb_per_tap) {
+                        cb = 0;
+                        if (++kw == p.ksize) kw = 0, ++kh;
+                    }
+                    if (++s == STAGES) s = 0, parity ^= 1u;
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::idesc_bf16_f32(BLOCK_M, BLOCK_N);
-            int it = 0;
+        if (leader && tc::elect_one()) {
+            constexpr uint32_t idesc = tc::idesc_bf16_f32(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+            int s = 0;
+            uint32_t parity = 0;
             for (int local = 0; local < tile_count; ++local) {
                 const int as = local & 1;
                 // wait until the epilogue has drained this accumulator stage (first use passes immediately)
                 tc::mbar_wait(tc::smem_u32(&bar_acc_empty[as]), ((local >> 1) & 1) ^ 1);
                 tc::fence_after_sync();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(as * C::ACC_COLS);
-                for (int kb = 0; kb < kb_per_split; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t parity = (it / STAGES) & 1;
+                for (int kb = 0; kb < kb_per_split; ++kb) {
                     tc::mbar_wait(tc::smem_u32(&bar_full[s]), parity);
                     tc::fence_after_sync();
                     const uint32_t a_src = smem_base + s * C::STAGE_BYTES;
@@ -241,11 +284,19 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
-                        tc::mma_f16_ss(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        if constexpr (PAIR)
+                            tc::mma_f16_ss_pair(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        else
+                            tc::mma_f16_ss(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                     }
-                    tc::mma_commit(tc::smem_u32(&bar_empty[s]));  // frees the smem slot when these MMAs retire
+                    // frees the smem slot (of both CTAs) when these MMAs retire
+                    if constexpr (PAIR) tc::mma_commit_pair(tc::smem_u32(&bar_empty[s]), 0b11);
+                    else tc::mma_commit(tc::smem_u32(&bar_empty[s]));
+                    if (++s == STAGES) s = 0, parity ^= 1u;
                 }
-                tc::mma_commit(tc::smem_u32(&bar_acc_full[as]));  // accumulator complete
+                // accumulator complete (in both CTAs' tensor memory)
+                if constexpr (PAIR) tc::mma_commit_pair(tc::smem_u32(&bar_acc_full[as]), 0b11);
+                else tc::mma_commit(tc::smem_u32(&bar_acc_full[as]));
             }
         }
     } else {
@@ -282,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
             }
         };
         for (int local = 0; local < tile_count; ++local) {
-            const int tile = tile_first + local * tile_step;
+            const int tile = unit_to_tile(tile_first + local * tile_step);
             const int as = local & 1;
             int n_tile, w0, h0, n0;
             const int out_tile = tile % p.tiles_out, split = tile / p.tiles_out;
@@ -294,7 +345,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                 carry_img = n0;
             }
 
-            tc::mbar_wait(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
+            // the epilogue is ahead of the main loop most of the time: wait with back-off instead of a hot spin that
+            // would take issue slots (and power) from the producer and MMA lanes
+            tc::mbar_wait_backoff(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
             tc::fence_after_sync();
 
             if (active && split > 0) {
@@ -544,14 +597,22 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
             // release the accumulator stage to the MMA warp
             tc::fence_before_sync();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[as]));
+            if (lane == 0) {
+                if (PAIR && !leader) tc::mbar_arrive_cluster(tc::mapa(tc::smem_u32(&bar_acc_empty[as]), 0));
+                else tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[as]));
+            }
         }
         if (p.chunked) flush_carry(carry_img);
     }
 
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (PAIR) {
+        tc::cluster_sync();  // neither CTA retires (shared memory, barriers, tensor memory) while its peer still works
+        if (warp == 1) tc::tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    } else {
+        if (warp == 1) tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
 }
 
 // ------------------------------------------------------------------ host: tensor maps + launch
@@ -572,17 +633,42 @@ int sm_count() {
     return sms;
 }
 
-template <int BLOCK_N>
+// Tuning knobs (azb_conv_tuning): -1 = automatic.
+int g_knob[AZB_CONV_KNOBS] = {-1, -1, -1};
+
+template <int BLOCK_N, bool PAIR = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const ConvParams& p, cudaStream_t s) {
-    constexpr int smem = Cfg<BLOCK_N>::SMEM;
+    constexpr int smem = Cfg<BLOCK_N, PAIR>::SMEM;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e =
+            cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-    conv_gemm_kernel<BLOCK_N><<<(unsigned)grid, THREADS, smem, s>>>(ta, tb, ta2, p);
+    if constexpr (PAIR) {
+        // one cluster of two CTAs (the two SMs of a TPC) per scheduling unit, at most one cluster per TPC
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)sm_count() & ~1u), cfg.blockDim = dim3(THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        static int resident = 0;  // clusters that fit on the device at once: the persistent grid is one wave of them
+        if (!resident) {
+            if (cudaOccupancyMaxActiveClusters(&resident, conv_gemm_kernel<BLOCK_N, PAIR>, &cfg) != cudaSuccess || resident < 1) {
+                cudaGetLastError();
+                resident = sm_count() / 2;
+            }
+        }
+        const int pairs = p.total_tiles < resident ? p.total_tiles : resident;
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, PAIR>, ta, tb, ta2, p);
+        if (e != cudaSuccess) return (int)e;
+    } else {
+        const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+        conv_gemm_kernel<BLOCK_N, PAIR><<<(unsigned)grid, THREADS, smem, s>>>(ta, tb, ta2, p);
+    }
     return azb_launch_status();
 }
 
@@ -654,6 +740,8 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
         block_n = cand[i];
         if (m_tiles * (c_out_rows / cand[i]) >= (sms * 3) / 4 || cand[i] <= 64) break;
     }
+    // forced CTA pairs (tuning knob): take the wide tile even when it leaves SMs idle
+    if (g_knob[AZB_CONV_KNOB_PAIR] == 1 && m_tiles % 2 == 0 && c_out_rows % 128 == 0) block_n = c_out_rows % 256 ? 128 : 256;
     if (c_out_rows % block_n || c_out_rows < c_out) return AZB_E_SHAPE;
 
     // Split-K for small feature maps with long reductions (8 x 8 layers: 8 M tiles, K = 9216 .. 18432): a wide N tile
@@ -662,7 +750,7 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     // folds them before its epilogue.  Single wave only (all CTAs co-resident), so the owner's wait cannot deadlock.
     int splits = 1;
     const int64_t num_kb_total = (int64_t)taps * (k_per_tap / BLOCK_K) + (ex.act2 ? ex.k2 / BLOCK_K : 0);
-    if (ex.workspace && out_mode == 0 && m_tiles * (c_out_rows / block_n) <= sms && (block_n <= 64 || m_tiles * (c_out_rows / block_n) < sms / 2)) {
+    if (g_knob[AZB_CONV_KNOB_SPLITK] != 0 && ex.workspace && out_mode == 0 && m_tiles * (c_out_rows / block_n) <= sms && (block_n <= 64 || m_tiles * (c_out_rows / block_n) < sms / 2)) {
         const int try_n[2] = {128, 256}, try_s[2] = {2, 4};
         for (int i = 0; i < 2 && splits == 1; ++i) {
             const int bn = try_n[i], sp = try_s[i];
@@ -678,7 +766,12 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     p.n_tiles = (int)(c_out_rows / block_n);
     if (m_tiles * p.n_tiles * splits > 0x7fffffffLL) return AZB_E_SHAPE;
     p.tiles_out = (int)(m_tiles * p.n_tiles);
-    p.total_tiles = p.tiles_out * splits;
+    // CTA pairs: wide tiles, an even number of M tiles, and enough of them that every TPC gets several units
+    bool pair = block_n >= 128 && splits == 1 && m_tiles % 2 == 0 && g_knob[AZB_CONV_KNOB_PAIR] != 0;
+    // measured on the ADM shapes (scripts/conv_ab.py): pairs win 5 - 20 % whenever the reduction is at least 16 k-blocks;
+    // with short reductions (1x1 layers, K <= 512) the epilogue dominates and the pair's extra handshakes cost 5 - 8 %
+    if (pair && g_knob[AZB_CONV_KNOB_PAIR] < 0) pair = num_kb_total >= 16;
+    p.total_tiles = pair ? p.tiles_out / 2 : p.tiles_out * splits;
     p.splits = splits;
     if (splits > 1) {
         if (!azb_aligned(ex.workspace, 256)) return AZB_E_ALIGN;
@@ -705,7 +798,7 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     // same-address atomics of a 256 x 256 layer serialise in L2 (measured: +15 % on the K = 2304 layers).
     // few M tiles => every weight tile is used by a handful of CTAs right after its first (HBM) read: with only
     // STAGES loads in flight the main loop would run at HBM latency; prefetch the weight stream into L2 ahead of use
-    p.prefetch_kb = m_tiles <= 32 ? 24 : 0;
+    p.prefetch_kb = g_knob[AZB_CONV_KNOB_PREFETCH] >= 0 ? g_knob[AZB_CONV_KNOB_PREFETCH] : (m_tiles <= 32 ? 24 : 0);
     p.chunked = (ex.gn_acc && p.n_tiles <= 2 && p.BN == 1 && stat_gran == 8 && block_n >= 64 && splits == 1) ? 1 : 0;
     const int64_t k_total = taps * k_per_tap + (ex.act2 ? ex.k2 : 0);
 
@@ -725,7 +818,7 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     {
         uint64_t dims[2] = {(uint64_t)k_total, (uint64_t)c_out_rows};
         uint64_t str[1] = {(uint64_t)k_total * 2};
-        uint32_t box[2] = {BLOCK_K, (uint32_t)block_n};
+        uint32_t box[2] = {BLOCK_K, (uint32_t)(pair ? block_n / 2 : block_n)};  // a pair member stages half the rows
         int rc = make_map(&tb, wpack, 2, dims, str, box);
         if (rc) return rc;
     }
@@ -739,6 +832,7 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
         ta2 = ta;
     }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (pair) return block_n == 256 ? launch<256, true>(ta, tb, ta2, p, s) : launch<128, true>(ta, tb, ta2, p, s);
     switch (block_n) {
         case 256: return launch<256>(ta, tb, ta2, p, s);
         case 128: return launch<128>(ta, tb, ta2, p, s);
@@ -799,6 +893,12 @@ extern "C" int azb_conv_skip_stats_bf16(const void* act, int64_t n, int64_t h, i
     ex.act2 = act2, ex.c_in2 = c_in2, ex.act2_ld = act2_ld, ex.k2 = k2;
     return conv_impl(act, n, h, w, c_in, act_ld, wpack, c_out, c_out_rows, 9, k_per_tap, bias, nullptr, 0, out, out_ld, 0,
                      colsum, colsum ? stat_gran : 1, stream, ex);
+}
+
+extern "C" int azb_conv_tuning(int knob, int value) {
+    if (knob < 0 || knob >= AZB_CONV_KNOBS) return AZB_E_SHAPE;
+    g_knob[knob] = value;
+    return AZB_OK;
 }
 
 extern "C" int azb_conv_bf16(const AzbConv* d, void* stream) {

@@ -36,6 +36,7 @@ class AzbConv(ctypes.Structure):
 
 _lib.register({
     "azb_conv_bf16": (c_int, [POINTER(AzbConv), c_void_p]),
+    "azb_conv_tuning": (c_int, [c_int, c_int]),
     "azb_zero_bytes": (c_int, [c_void_p, c_int64, c_void_p]),
     "azb_gn_apply_acc_bf16": (
         c_int,
@@ -576,6 +577,14 @@ def conv_acc(x: Tensor, pc, out: Tensor | None = None, residual: Tensor | None =
     d = conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=gran, workspace=workspace)
     _lib.check(_lib.lib().azb_conv_bf16(byref(d), _lib.stream_ptr(x.device)), "azb_conv_bf16")
     return out, acc
+
+
+KNOB_PAIR, KNOB_PREFETCH, KNOB_SPLITK = 0, 1, 2
+
+
+def conv_tuning(knob: int, value: int) -> None:
+    r"""``azb_conv_tuning``: overrides an automatic choice of the convolution launcher (-1 restores it)."""
+    _lib.check(_lib.lib().azb_conv_tuning(knob, value), "azb_conv_tuning")
 
 
 SPLITK_WORKSPACE_BYTES = 16 << 20

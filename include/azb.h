@@ -208,6 +208,18 @@ typedef struct AzbConv {
 
 int azb_conv_bf16(const AzbConv* desc, void* stream);
 
+/* Tuning hooks of the convolution kernels (process-wide, not thread-safe; meant for A/B measurements).
+ * value -1 restores the automatic choice.
+ *   AZB_CONV_KNOB_PAIR      0: never use CTA pairs, 1: whenever the shape allows (even number of 128-pixel tiles,
+ *                           N tile >= 128, no split-K), -1: large layers only
+ *   AZB_CONV_KNOB_PREFETCH  k-blocks of weight prefetch into L2 (0 = off)
+ *   AZB_CONV_KNOB_SPLITK    0: never split K even when a workspace is given */
+#define AZB_CONV_KNOB_PAIR 0
+#define AZB_CONV_KNOB_PREFETCH 1
+#define AZB_CONV_KNOB_SPLITK 2
+#define AZB_CONV_KNOBS 3
+int azb_conv_tuning(int knob, int value);
+
 /* Rows of the colsum buffer for an (n, h, w) activation; *slab_in_image = 1 when every 32-row slab
  * lies inside one image (the condition for azb_gn_finalize_f32), else 0.  Host-side helper. */
 int azb_conv_colsum_rows(int64_t n, int64_t h, int64_t w, int64_t* rows, int64_t* slab_in_image);

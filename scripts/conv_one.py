@@ -1,0 +1,41 @@
+"""One convolution shape under a chosen launcher configuration (for ncu captures).
+
+    ncu --set full -k regex:conv_gemm -c 2 python scripts/conv_one.py --hw 256 --ci 512 --co 256 --pair 1
+"""
+
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from azula_b200.engine import ops  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--hw", type=int, default=256)
+    ap.add_argument("--ci", type=int, default=256)
+    ap.add_argument("--co", type=int, default=256)
+    ap.add_argument("--k", type=int, default=3)
+    ap.add_argument("--pair", type=int, default=-1)
+    ap.add_argument("--reps", type=int, default=2)
+    a = ap.parse_args()
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(a.batch, a.hw, a.hw, a.ci, device=dev, generator=g).to(torch.bfloat16)
+    pc = ops.pack_conv(torch.randn(a.co, a.ci, a.k, a.k, device=dev, generator=g) / (a.ci * a.k * a.k) ** 0.5,
+                       torch.randn(a.co, device=dev, generator=g))
+    out = torch.empty(a.batch, a.hw, a.hw, a.co, dtype=torch.bfloat16, device=dev)
+    ops.conv_tuning(ops.KNOB_PAIR, a.pair)
+    for _ in range(a.reps):
+        ops.conv_acc(x, pc, out=out)
+    torch.cuda.synchronize()
+    print("ok", float(out.float().abs().mean()))
+
+
+if __name__ == "__main__":
+    main()

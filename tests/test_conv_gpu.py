@@ -292,3 +292,58 @@ def test_conv_split_k(n, h, w, ci, co, skip):
     for _ in range(3):
         again, acc2 = ops.conv_acc(x, pc, workspace=ws, **kw)
         assert torch.equal(again, split) and torch.equal(acc1, acc2)
+
+
+@pytest.fixture
+def force_pairs():
+    ops.conv_tuning(ops.KNOB_PAIR, 1)
+    yield
+    ops.conv_tuning(ops.KNOB_PAIR, -1)
+
+
+PAIR_SHAPES = [
+    # n, h, w, c_in, c_out, k: an even number of 128-pixel tiles and C_out a multiple of 128
+    (2, 16, 16, 64, 128, 3),     # 4 M tiles, one pair-unit per N tile: the smallest case
+    (1, 32, 32, 128, 256, 3),    # N = 256 across the pair
+    (2, 32, 32, 256, 256, 3),
+    (4, 8, 8, 128, 128, 3),      # patch spans 2 images
+    (1, 64, 64, 320, 512, 3),    # 2 N tiles of 256, many units per pair (persistent loop, both accumulator stages)
+    (1, 32, 32, 512, 384, 1),    # 1x1, N tile 128
+    (3, 48, 40, 192, 256, 3),    # extents not multiples of the patch: out-of-bounds rows in both CTAs
+]
+
+
+@pytest.mark.parametrize("shape", PAIR_SHAPES)
+def test_conv_cta_pairs_match_single_cta(shape, force_pairs):
+    """tcgen05.mma.cta_group::2 path: same accumulation order per output element as the single-CTA kernel (K is
+    traversed identically), so the two must agree BIT FOR BIT -- output, residual add and GroupNorm accumulators."""
+    n, h, w, ci, co, k = shape
+    x, wt, b = _mk(*shape, seed=41)
+    res = torch.randn(n, h, w, co, device=DEV, generator=torch.Generator(device=DEV).manual_seed(9)).to(torch.bfloat16)
+    pc = ops.pack_conv(wt.float(), b)
+    pair, acc_p = ops.conv_acc(x, pc, residual=res, gran=1)
+    ops.conv_tuning(ops.KNOB_PAIR, 0)
+    single, acc_s = ops.conv_acc(x, pc, residual=res, gran=1)
+    torch.cuda.synchronize()
+    _check(single, _ref(x, wt, b, res), ("single", shape))
+    _check(pair, _ref(x, wt, b, res), ("pair", shape))
+    assert torch.equal(pair, single)
+    assert torch.equal(acc_p, acc_s)
+
+
+def test_conv_cta_pairs_with_fused_skip_and_chunked_stats(force_pairs):
+    """The ADM decoder shape class: 3x3 + fused 1x1 skip operand, 8-channel-block sums carried across tiles."""
+    n, h, w, ci, co, skip = 2, 64, 64, 256, 256, 512
+    x, wt, b = _mk(n, h, w, ci, co, 3, seed=43)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x2 = torch.randn(n, h, w, skip, device=DEV, generator=g).to(torch.bfloat16)
+    w2 = (torch.randn(co, skip, 1, 1, device=DEV, generator=g) / skip**0.5).to(torch.bfloat16)
+    b2 = torch.randn(co, device=DEV, generator=g)
+    pc = ops.pack_conv_skip(ops.pack_conv(wt.float(), b), ops.pack_conv(w2.float(), b2))
+    pair, acc_p = ops.conv_acc(x, pc, x2=x2)
+    ops.conv_tuning(ops.KNOB_PAIR, 0)
+    single, acc_s = ops.conv_acc(x, pc, x2=x2)
+    _check(pair, _ref(x, wt, b) + _ref(x2, w2, b2), "pair + skip")
+    assert torch.equal(pair, single)
+    # carried fp32 partial sums depend on which tiles a CTA owns: equal up to fp32 rounding of the partial sums
+    assert torch.allclose(_acc_to_sums(acc_p), _acc_to_sums(acc_s), rtol=1e-4, atol=1e-2)
