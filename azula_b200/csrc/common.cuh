@@ -13,6 +13,8 @@
         if ((p) == nullptr) return AZB_E_NULL; \
     } while (0)
 
+extern int azb_knob[AZB_CONV_KNOBS];  // api.cu
+
 static inline int azb_launch_status() {
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? AZB_OK : (int)e;

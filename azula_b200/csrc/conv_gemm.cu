@@ -633,8 +633,7 @@ int sm_count() {
     return sms;
 }
 
-// Tuning knobs (azb_conv_tuning): -1 = automatic.
-int g_knob[AZB_CONV_KNOBS] = {-1, -1, -1};
+#define g_knob azb_knob
 
 template <int BLOCK_N, bool PAIR = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const ConvParams& p, cudaStream_t s) {
@@ -742,6 +741,7 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     }
     // forced CTA pairs (tuning knob): take the wide tile even when it leaves SMs idle
     if (g_knob[AZB_CONV_KNOB_PAIR] == 1 && m_tiles % 2 == 0 && c_out_rows % 128 == 0) block_n = c_out_rows % 256 ? 128 : 256;
+    if (g_knob[AZB_CONV_KNOB_BLOCKN] >= 16 && c_out_rows % g_knob[AZB_CONV_KNOB_BLOCKN] == 0) block_n = g_knob[AZB_CONV_KNOB_BLOCKN];
     if (c_out_rows % block_n || c_out_rows < c_out) return AZB_E_SHAPE;
 
     // Split-K for small feature maps with long reductions (8 x 8 layers: 8 M tiles, K = 9216 .. 18432): a wide N tile
@@ -893,12 +893,6 @@ extern "C" int azb_conv_skip_stats_bf16(const void* act, int64_t n, int64_t h, i
     ex.act2 = act2, ex.c_in2 = c_in2, ex.act2_ld = act2_ld, ex.k2 = k2;
     return conv_impl(act, n, h, w, c_in, act_ld, wpack, c_out, c_out_rows, 9, k_per_tap, bias, nullptr, 0, out, out_ld, 0,
                      colsum, colsum ? stat_gran : 1, stream, ex);
-}
-
-extern "C" int azb_conv_tuning(int knob, int value) {
-    if (knob < 0 || knob >= AZB_CONV_KNOBS) return AZB_E_SHAPE;
-    g_knob[knob] = value;
-    return AZB_OK;
 }
 
 extern "C" int azb_conv_bf16(const AzbConv* d, void* stream) {

@@ -446,6 +446,23 @@ static int gn_apply_impl(const void* x, int64_t x_ld, void* y, int64_t y_ld, int
     if (ppc < 1) ppc = 1;
     // keep at least ~4 CTAs per SM when the tensor is large enough
     while (ppc > 8 && ((out_pix + ppc - 1) / ppc) * n < 4 * 148) ppc >>= 1;
+    // Large tensors: ONE wave of long-lived CTAs (`wave` per SM, all resident at once) instead of thousands of short
+    // ones.  Every CTA pays two dependent global round trips (group statistics, then per-channel coefficients) before
+    // its first data load; with 128-pixel CTAs that prologue was 10 - 15 % of a CTA's life and of the kernel's time.
+    // Measured (scripts/gn_ab.py, B200): 15 - 30 % faster for 8 .. 270 MB inputs (13 vs 19 us at 32 x 32 x 512, 27 vs 32
+    // at 64 x 64 x 512, 167 vs 196 for the 128 -> 256 upsample); the 0.5 - 1 GB tensors already stream at 5.7 - 5.9 TB/s
+    // with short CTAs and lose 3 % to the imbalance of a single wave, and the pooling mode is indifferent.
+    const bool mid = mode != 2 && (double)n * h * w * c * 2.0 <= 3.0e8;
+    const int wave = azb_knob[AZB_GN_KNOB_WAVE] >= 0 ? azb_knob[AZB_GN_KNOB_WAVE] : (mid ? 4 : 0);
+    if (wave > 0) {
+        const int64_t per_image = (148 * (int64_t)wave) / n;
+        if (per_image >= 1) {
+            const int64_t VT = V < THREADS ? V : THREADS, step = 4 * (THREADS / VT);  // pixels per unrolled iteration
+            int64_t big = (out_pix + per_image - 1) / per_image;
+            big = ((big + step - 1) / step) * step;
+            if (big > ppc) ppc = big;
+        }
+    }
     p.pix_per_cta = (int)ppc;
     const int64_t ctas = (out_pix + ppc - 1) / ppc;
     const dim3 grid((unsigned)ctas, (unsigned)n);

@@ -208,16 +208,21 @@ typedef struct AzbConv {
 
 int azb_conv_bf16(const AzbConv* desc, void* stream);
 
-/* Tuning hooks of the convolution kernels (process-wide, not thread-safe; meant for A/B measurements).
+/* Tuning hooks of the launchers (process-wide, not thread-safe; meant for A/B measurements).
  * value -1 restores the automatic choice.
  *   AZB_CONV_KNOB_PAIR      0: never use CTA pairs, 1: whenever the shape allows (even number of 128-pixel tiles,
- *                           N tile >= 128, no split-K), -1: large layers only
+ *                           N tile >= 128, no split-K), -1: when the reduction is long enough to pay
  *   AZB_CONV_KNOB_PREFETCH  k-blocks of weight prefetch into L2 (0 = off)
- *   AZB_CONV_KNOB_SPLITK    0: never split K even when a workspace is given */
+ *   AZB_CONV_KNOB_SPLITK    0: never split K even when a workspace is given
+ *   AZB_GN_KNOB_WAVE        GroupNorm apply: resident CTAs per SM of the single-wave grid (0 = short CTAs of 16
+ *                           vectors per thread, the pre-wave policy)
+ *   AZB_CONV_KNOB_BLOCKN    force the N tile (16 .. 256; ignored unless it divides the padded C_out) */
 #define AZB_CONV_KNOB_PAIR 0
 #define AZB_CONV_KNOB_PREFETCH 1
 #define AZB_CONV_KNOB_SPLITK 2
-#define AZB_CONV_KNOBS 3
+#define AZB_GN_KNOB_WAVE 3
+#define AZB_CONV_KNOB_BLOCKN 4
+#define AZB_CONV_KNOBS 5
 int azb_conv_tuning(int knob, int value);
 
 /* Rows of the colsum buffer for an (n, h, w) activation; *slab_in_image = 1 when every 32-row slab

@@ -23,6 +23,8 @@ SHAPES = [
     (32, 512, 512, 9, 0), (32, 1024, 1024, 9, 0), (32, 512, 1536, 1, 0),
     (16, 1024, 1024, 9, 0), (16, 2048, 1024, 9, 0), (16, 1024, 3072, 1, 0),
     (8, 1024, 1024, 9, 0), (8, 2048, 1024, 9, 0),
+    (64, 256, 256, 9, 0), (32, 1024, 512, 9, 0), (32, 512, 512, 9, 1024), (16, 1024, 1024, 9, 2048), (16, 512, 1024, 9, 0),
+    (16, 1024, 1024, 1, 0), (32, 512, 512, 1, 0), (8, 1024, 3072, 1, 0), (8, 1024, 1024, 1, 0),
 ]
 
 
@@ -31,6 +33,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--configs", default="single,pair")
+    ap.add_argument("--max-hw", type=int, default=256)
     args = ap.parse_args()
     dev = "cuda"
     configs = {
@@ -39,6 +42,11 @@ def main():
         "auto": {},
         "noprefetch": {ops.KNOB_PREFETCH: 0},
         "nosplit": {ops.KNOB_SPLITK: 0},
+        "p256": {ops.KNOB_PAIR: 1, ops.KNOB_BLOCKN: 256, ops.KNOB_SPLITK: 0},
+        "p128": {ops.KNOB_PAIR: 1, ops.KNOB_BLOCKN: 128, ops.KNOB_SPLITK: 0},
+        "s256": {ops.KNOB_PAIR: 0, ops.KNOB_BLOCKN: 256, ops.KNOB_SPLITK: 0},
+        "s128": {ops.KNOB_PAIR: 0, ops.KNOB_BLOCKN: 128, ops.KNOB_SPLITK: 0},
+        "s64": {ops.KNOB_PAIR: 0, ops.KNOB_BLOCKN: 64, ops.KNOB_SPLITK: 0},
     }
     names = args.configs.split(",")
     ws = ops.splitk_workspace(dev)
@@ -46,6 +54,8 @@ def main():
     g = torch.Generator(device=dev).manual_seed(0)
     out_rows = []
     for hw, ci, co, taps, skip in SHAPES:
+        if hw > args.max_hw:
+            continue
         n = args.batch
         x = torch.randn(n, hw, hw, ci, device=dev, generator=g).to(torch.bfloat16)
         k = 3 if taps == 9 else 1
@@ -62,7 +72,7 @@ def main():
         ref = None
         for rep in range(args.reps + 1):
             for c in names:
-                for kn in (ops.KNOB_PAIR, ops.KNOB_PREFETCH, ops.KNOB_SPLITK):
+                for kn in (ops.KNOB_PAIR, ops.KNOB_PREFETCH, ops.KNOB_SPLITK, ops.KNOB_BLOCKN):
                     ops.conv_tuning(kn, configs[c].get(kn, -1))
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -76,15 +86,14 @@ def main():
                 elif ref is None:
                     ref = out.clone()
                 else:
-                    assert torch.equal(ref, out) or c in ("nosplit", "auto", "single", "pair") and torch.allclose(
-                        ref.float(), out.float(), rtol=2e-2, atol=2e-2), (c, hw, ci, co)
+                    assert torch.allclose(ref.float(), out.float(), rtol=2e-2, atol=2e-2), (c, hw, ci, co)
         row = {"shape": f"{n}x{hw}x{hw} {ci}->{co} k{k}" + (f" +skip{skip}" if skip else ""), "gflop": flop / 1e9}
         row.update({c: round(best[c], 4) for c in names})
         row.update({f"{c}_tflops": round(flop / best[c] / 1e9, 1) for c in names})
         out_rows.append(row)
         print("  ".join(f"{k}={v}" for k, v in row.items()), flush=True)
         del x, x2, out, pc
-    for kn in (ops.KNOB_PAIR, ops.KNOB_PREFETCH, ops.KNOB_SPLITK):
+    for kn in (ops.KNOB_PAIR, ops.KNOB_PREFETCH, ops.KNOB_SPLITK, ops.KNOB_BLOCKN):
         ops.conv_tuning(kn, -1)
     print(json.dumps(out_rows))
 
