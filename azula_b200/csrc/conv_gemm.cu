@@ -135,7 +135,9 @@ __device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& 
     w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
 }
 
-template <int BLOCK_N, bool PAIR>
+// LEAN: the epilogue of the common case -- bf16 NHWC output, no activation, no gate, no split-K, GroupNorm sums (if
+// any) as exact accumulators per 8-channel block -- with those switches resolved at compile time.
+template <int BLOCK_N, bool PAIR, bool LEAN>
 __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                 const __grid_constant__ CUtensorMap tmap_b,
                                                                 const __grid_constant__ CUtensorMap tmap_a2,
@@ -307,6 +309,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
         // happen in the coalesced domain (8x fewer memory wavefronts than one-row-per-lane stores).
         const int e = warp - 2;
         const int quarter = warp & 3;
+        const int act = LEAN ? 0 : p.act;
+        const float* const gate = LEAN ? nullptr : p.gate;
+        float2* const colsum = LEAN ? nullptr : p.colsum;
+        const int stat_gran = LEAN ? 8 : p.stat_gran;
+        const int out_mode = LEAN ? 0 : p.out_mode;
+        const int splits = LEAN ? 1 : p.splits;
         const int half = (BLOCK_N >= 64) ? (e >> 2) : 0;
         const bool active = (BLOCK_N >= 64) || (e < 4);
         constexpr int CHUNK = C::CHUNK;
@@ -350,7 +358,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
             tc::mbar_wait_backoff(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
             tc::fence_after_sync();
 
-            if (active && split > 0) {
+            if (!LEAN && active && split > 0) {
                 // split-K helper: this CTA accumulated K range `split`; its raw fp32 accumulator goes to the workspace
                 // (lane = tile row: 128 contiguous bytes per lane and chunk), then the owner (split 0) is signalled
                 float* dst = p.ws_partial + ((int64_t)(split - 1) * p.tiles_out + out_tile) * (BLOCK_M * BLOCK_N) +
@@ -370,22 +378,25 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) atomicAdd(p.ws_flags + out_tile * EPI_WARPS + e, 1);
-            } else if (active && p.out_mode == 0) {
-                if (p.splits > 1) {  // owner: wait for the S - 1 helpers of this warp's part of the tile
+            } else if (active && out_mode == 0) {
+                if (splits > 1) {  // owner: wait for the S - 1 helpers of this warp's part of the tile
                     int* flag = p.ws_flags + out_tile * EPI_WARPS + e;
                     if (lane == 0) {
                         int seen;
                         do {
                             asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-                        } while (seen < p.splits - 1);
+                        } while (seen < splits - 1);
                         *flag = 0;  // clean for the next launch (stream order)
                     }
                     __syncwarp();
                 }
                 {
-                    // pixels of the 4 rows this lane handles in the coalesced domain
+                    // pixels of the 4 rows this lane handles in the coalesced domain; their output / residual addresses
+                    // at this lane's first channel are computed once per tile, a chunk only adds its column offset
                     int64_t pixc[4];
                     bool okc[4];
+                    __nv_bfloat16* outp[4];
+                    const __nv_bfloat16* resp[4];
 #pragma unroll
                     for (int it = 0; it < 4; ++it) {
                         const int row = quarter * 32 + it * 8 + rl;
@@ -393,6 +404,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                         const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
                         okc[it] = (n < p.N) && (h < p.H) && (w < p.W);
                         pixc[it] = ((int64_t)n * p.H + h) * p.W + w;
+                        outp[it] = reinterpret_cast<__nv_bfloat16*>(p.out) + pixc[it] * p.out_ld + col_base + cg4 * 8;
+                        resp[it] = p.res + pixc[it] * p.res_ld + col_base + cg4 * 8;
                     }
 #pragma unroll 1
                     for (int c0 = 0; c0 < C::COLS_PER_WARP; c0 += 32) {
@@ -416,8 +429,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                         if (use_res) {
 #pragma unroll
                             for (int it = 0; it < 4; ++it)
-                                rsd[it] = okc[it] ? __ldg(reinterpret_cast<const uint4*>(p.res + pixc[it] * p.res_ld + col))
-                                                  : make_uint4(0, 0, 0, 0);
+                                rsd[it] = okc[it] ? __ldg(reinterpret_cast<const uint4*>(resp[it] + c0)) : make_uint4(0, 0, 0, 0);
                         }
                         float bias8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                         if (p.bias && col_ok) {
@@ -427,8 +439,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                             bias8[4] = b1.x, bias8[5] = b1.y, bias8[6] = b1.z, bias8[7] = b1.w;
                         }
                         tc::tmem_ld_wait();
-                        if (p.splits > 1) {  // fold the helpers' partial accumulators (row domain, L2-resident)
-                            for (int sp = 1; sp < p.splits; ++sp) {
+                        if (splits > 1) {  // fold the helpers' partial accumulators (row domain, L2-resident)
+                            for (int sp = 1; sp < splits; ++sp) {
                                 const float* src = p.ws_partial + ((int64_t)(sp - 1) * p.tiles_out + out_tile) * (BLOCK_M * BLOCK_N) +
                                                    (int64_t)(quarter * 32 + lane) * BLOCK_N + half * C::COLS_PER_WARP + c0;
 #pragma unroll
@@ -468,12 +480,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                             }
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] += bias8[j];
-                            if (p.act) {
+                            if (act) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) f[j] = activate(f[j], p.act);
+                                for (int j = 0; j < 8; ++j) f[j] = activate(f[j], act);
                             }
-                            if (p.gate && col_ok && okc[it]) {
-                                const float* gp = p.gate + (pixc[it] / p.gate_rows) * p.gate_ld + col;
+                            if (gate && col_ok && okc[it]) {
+                                const float* gp = gate + (pixc[it] / p.gate_rows) * p.gate_ld + col;
                                 const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
                                 const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp) + 1);
                                 f[0] *= g0.x, f[1] *= g0.y, f[2] *= g0.z, f[3] *= g0.w;
@@ -494,8 +506,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                                 packed[j] = *reinterpret_cast<uint32_t*>(&t);
                             }
                             if (okc[it] && col_ok) {
-                                *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pixc[it] * p.out_ld + col) =
-                                    make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                                *reinterpret_cast<uint4*>(outp[it] + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
                                 // statistics are taken of the STORED (rounded) values
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
@@ -505,10 +516,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                                 }
                             }
                         }
-                        if (p.colsum || p.gn_acc) {
+                        if (colsum || p.gn_acc) {
                             const int64_t slab = (int64_t)m_tile * 4 + quarter;
                             const int img = n0 + (quarter * 32) / (p.BW * p.BH);  // the image this 32-row slab lies in
-                            if (p.stat_gran == 8) {
+                            if (stat_gran == 8) {
                                 // one {sum, sumsq} per 8-channel block: fold the lane's 8 channels, then the 8 row lanes
                                 float a = ((s1[0] + s1[1]) + (s1[2] + s1[3])) + ((s1[4] + s1[5]) + (s1[6] + s1[7]));
                                 float b = ((s2[0] + s2[1]) + (s2[2] + s2[3])) + ((s2[4] + s2[5]) + (s2[6] + s2[7]));
@@ -531,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                                             fixed_add(dst + 2, b);
                                         }
                                     } else {
-                                        p.colsum[slab * (p.c_out >> 3) + (col >> 3)] = make_float2(a, b);
+                                        colsum[slab * (p.c_out >> 3) + (col >> 3)] = make_float2(a, b);
                                     }
                                 }
                             } else {
@@ -557,14 +568,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
                                             fixed_add(dst + 2, s2[0]);
                                         }
                                     } else {
-                                        p.colsum[slab * p.c_out + col + k] = make_float2(s1[0], s2[0]);
+                                        colsum[slab * p.c_out + col + k] = make_float2(s1[0], s2[0]);
                                     }
                                 }
                             }
                         }
                     }
                 }
-            } else if (active) {
+            } else if (!LEAN && active) {
                 // fp32 NCHW network output: out[n][c][h][w]; consecutive lanes are consecutive w => coalesced per channel
                 const int row = quarter * 32 + lane;
                 const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
@@ -635,13 +646,13 @@ int sm_count() {
 
 #define g_knob azb_knob
 
-template <int BLOCK_N, bool PAIR = false>
+template <int BLOCK_N, bool PAIR = false, bool LEAN = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const ConvParams& p, cudaStream_t s) {
     constexpr int smem = Cfg<BLOCK_N, PAIR>::SMEM;
     static bool configured = false;
     if (!configured) {
         cudaError_t e =
-            cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, PAIR, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
@@ -655,18 +666,18 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2,
         cfg.attrs = attr, cfg.numAttrs = 1;
         static int resident = 0;  // clusters that fit on the device at once: the persistent grid is one wave of them
         if (!resident) {
-            if (cudaOccupancyMaxActiveClusters(&resident, conv_gemm_kernel<BLOCK_N, PAIR>, &cfg) != cudaSuccess || resident < 1) {
+            if (cudaOccupancyMaxActiveClusters(&resident, conv_gemm_kernel<BLOCK_N, PAIR, LEAN>, &cfg) != cudaSuccess || resident < 1) {
                 cudaGetLastError();
                 resident = sm_count() / 2;
             }
         }
         const int pairs = p.total_tiles < resident ? p.total_tiles : resident;
         cfg.gridDim = dim3((unsigned)(2 * pairs));
-        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, PAIR>, ta, tb, ta2, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, PAIR, LEAN>, ta, tb, ta2, p);
         if (e != cudaSuccess) return (int)e;
     } else {
         const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-        conv_gemm_kernel<BLOCK_N, PAIR><<<(unsigned)grid, THREADS, smem, s>>>(ta, tb, ta2, p);
+        conv_gemm_kernel<BLOCK_N, PAIR, LEAN><<<(unsigned)grid, THREADS, smem, s>>>(ta, tb, ta2, p);
     }
     return azb_launch_status();
 }
@@ -832,7 +843,11 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
         ta2 = ta;
     }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const bool lean = g_knob[AZB_CONV_KNOB_LEAN] != 0 && out_mode == 0 && ex.act == AZB_ACT_NONE && !ex.gate && !colsum &&
+                      splits == 1 && (!ex.gn_acc || stat_gran == 8) && block_n >= 128;
+    if (pair && lean) return block_n == 256 ? launch<256, true, true>(ta, tb, ta2, p, s) : launch<128, true, true>(ta, tb, ta2, p, s);
     if (pair) return block_n == 256 ? launch<256, true>(ta, tb, ta2, p, s) : launch<128, true>(ta, tb, ta2, p, s);
+    if (lean) return block_n == 256 ? launch<256, false, true>(ta, tb, ta2, p, s) : launch<128, false, true>(ta, tb, ta2, p, s);
     switch (block_n) {
         case 256: return launch<256>(ta, tb, ta2, p, s);
         case 128: return launch<128>(ta, tb, ta2, p, s);

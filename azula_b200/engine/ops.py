@@ -579,7 +579,7 @@ def conv_acc(x: Tensor, pc, out: Tensor | None = None, residual: Tensor | None =
     return out, acc
 
 
-KNOB_PAIR, KNOB_PREFETCH, KNOB_SPLITK, KNOB_GN_WAVE, KNOB_BLOCKN = 0, 1, 2, 3, 4
+KNOB_PAIR, KNOB_PREFETCH, KNOB_SPLITK, KNOB_GN_WAVE, KNOB_BLOCKN, KNOB_LEAN = 0, 1, 2, 3, 4, 5
 
 
 def conv_tuning(knob: int, value: int) -> None:

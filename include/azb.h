@@ -216,13 +216,15 @@ int azb_conv_bf16(const AzbConv* desc, void* stream);
  *   AZB_CONV_KNOB_SPLITK    0: never split K even when a workspace is given
  *   AZB_GN_KNOB_WAVE        GroupNorm apply: resident CTAs per SM of the single-wave grid (0 = short CTAs of 16
  *                           vectors per thread, the pre-wave policy)
- *   AZB_CONV_KNOB_BLOCKN    force the N tile (16 .. 256; ignored unless it divides the padded C_out) */
+ *   AZB_CONV_KNOB_BLOCKN    force the N tile (16 .. 256; ignored unless it divides the padded C_out)
+ *   AZB_CONV_KNOB_LEAN      0: always the generic epilogue (all switches at run time) */
 #define AZB_CONV_KNOB_PAIR 0
 #define AZB_CONV_KNOB_PREFETCH 1
 #define AZB_CONV_KNOB_SPLITK 2
 #define AZB_GN_KNOB_WAVE 3
 #define AZB_CONV_KNOB_BLOCKN 4
-#define AZB_CONV_KNOBS 5
+#define AZB_CONV_KNOB_LEAN 5
+#define AZB_CONV_KNOBS 6
 int azb_conv_tuning(int knob, int value);
 
 /* Rows of the colsum buffer for an (n, h, w) activation; *slab_in_image = 1 when every 32-row slab

@@ -47,6 +47,7 @@ def main():
         "s256": {ops.KNOB_PAIR: 0, ops.KNOB_BLOCKN: 256, ops.KNOB_SPLITK: 0},
         "s128": {ops.KNOB_PAIR: 0, ops.KNOB_BLOCKN: 128, ops.KNOB_SPLITK: 0},
         "s64": {ops.KNOB_PAIR: 0, ops.KNOB_BLOCKN: 64, ops.KNOB_SPLITK: 0},
+        "generic": {ops.KNOB_LEAN: 0},
     }
     names = args.configs.split(",")
     ws = ops.splitk_workspace(dev)
@@ -72,7 +73,7 @@ def main():
         ref = None
         for rep in range(args.reps + 1):
             for c in names:
-                for kn in (ops.KNOB_PAIR, ops.KNOB_PREFETCH, ops.KNOB_SPLITK, ops.KNOB_BLOCKN):
+                for kn in (ops.KNOB_PAIR, ops.KNOB_PREFETCH, ops.KNOB_SPLITK, ops.KNOB_BLOCKN, ops.KNOB_LEAN):
                     ops.conv_tuning(kn, configs[c].get(kn, -1))
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -93,7 +94,7 @@ def main():
         out_rows.append(row)
         print("  ".join(f"{k}={v}" for k, v in row.items()), flush=True)
         del x, x2, out, pc
-    for kn in (ops.KNOB_PAIR, ops.KNOB_PREFETCH, ops.KNOB_SPLITK, ops.KNOB_BLOCKN):
+    for kn in (ops.KNOB_PAIR, ops.KNOB_PREFETCH, ops.KNOB_SPLITK, ops.KNOB_BLOCKN, ops.KNOB_LEAN):
         ops.conv_tuning(kn, -1)
     print(json.dumps(out_rows))
 
