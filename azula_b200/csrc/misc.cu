@@ -11,33 +11,42 @@
 namespace {
 
 // out[n][h][w][k], k = (kh*3+kw)*C + c for k < 9C, zero up to K (=64); input zero padded by 1.
+// CT > 0: channel count known at compile time (the divisions by c and by 3 become multiplications; the RGB stem is
+// CT = 3), 0: generic.
+template <int CT>
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                                                        int n, int c, int h, int w, int K) {
-    const int64_t total = (int64_t)n * h * w * (K / 8);
+                                                        int n, int c_rt, int h, int w, int K) {
+    const int c = CT > 0 ? CT : c_rt;
+    const int vecs = K / 8;
+    const int live = (9 * c + 7) / 8;  // vectors that hold at least one tap; the rest of a row is zero padding
+    const int64_t total = (int64_t)n * h * w * vecs;
     for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < total;
          item += (int64_t)gridDim.x * blockDim.x) {
-        const int v = (int)(item % (K / 8));
-        const int64_t pix = item / (K / 8);
-        const int ow = (int)(pix % w);
-        const int oh = (int)((pix / w) % h);
-        const int on = (int)(pix / ((int64_t)w * h));
-        float f[8];
+        const int v = (int)(item % vecs);
+        const int64_t pix = item / vecs;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (v < live) {
+            const int ow = (int)(pix % w);
+            const int oh = (int)((pix / w) % h);
+            const int on = (int)(pix / ((int64_t)w * h));
+            const float* img = x + (int64_t)on * c * h * w;
+            float f[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int k = v * 8 + j;
-            float val = 0.f;
-            if (k < 9 * c) {
-                const int tap = k / c, ch = k - tap * c;
-                const int ih = oh + tap / 3 - 1, iw = ow + tap % 3 - 1;
-                if (ih >= 0 && ih < h && iw >= 0 && iw < w) val = __ldg(x + (((int64_t)on * c + ch) * h + ih) * w + iw);
+            for (int j = 0; j < 8; ++j) {
+                const int k = v * 8 + j;
+                float val = 0.f;
+                if (k < 9 * c) {
+                    const int tap = k / c, ch = k - tap * c;
+                    const int ih = oh + tap / 3 - 1, iw = ow + tap % 3 - 1;
+                    if (ih >= 0 && ih < h && iw >= 0 && iw < w) val = __ldg(img + ((int64_t)ch * h + ih) * w + iw);
+                }
+                f[j] = val;
             }
-            f[j] = val;
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
+            o.x = *reinterpret_cast<uint32_t*>(&t0), o.y = *reinterpret_cast<uint32_t*>(&t1);
+            o.z = *reinterpret_cast<uint32_t*>(&t2), o.w = *reinterpret_cast<uint32_t*>(&t3);
         }
-        uint4 o;
-        __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
-        __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
-        o.x = *reinterpret_cast<uint32_t*>(&t0), o.y = *reinterpret_cast<uint32_t*>(&t1);
-        o.z = *reinterpret_cast<uint32_t*>(&t2), o.w = *reinterpret_cast<uint32_t*>(&t3);
         *reinterpret_cast<uint4*>(out + pix * K + v * 8) = o;
     }
 }
@@ -102,8 +111,11 @@ extern "C" int azb_im2col3x3_f32(const float* x, void* out, int64_t n, int64_t c
     const int64_t total = n * h * w * (k_pad / 8);
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    im2col3x3_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        x, reinterpret_cast<__nv_bfloat16*>(out), (int)n, (int)c, (int)h, (int)w, (int)k_pad);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    if (c == 3) im2col3x3_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(x, o, (int)n, 3, (int)h, (int)w, (int)k_pad);
+    else if (c == 4) im2col3x3_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, o, (int)n, 4, (int)h, (int)w, (int)k_pad);
+    else im2col3x3_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(x, o, (int)n, (int)c, (int)h, (int)w, (int)k_pad);
     return azb_launch_status();
 }
 

@@ -92,6 +92,7 @@ def main() -> None:
     ap.add_argument("--configs", default="2,4")
     ap.add_argument("--eager", action="store_true", help="also time the plain torch eager execution model")
     ap.add_argument("--eager-steps", type=int, default=0, help="sampler steps of the eager run (0 = the config's)")
+    ap.add_argument("--no-tf32", action="store_true", help="eager run with TF32 off (strict fp32 convolutions / matmuls)")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "nn_bench.jsonl"))
     args = ap.parse_args()
@@ -128,6 +129,9 @@ def main() -> None:
             }
             if args.eager:
                 steps = args.eager_steps or cfg["steps"]
+                if args.no_tf32:
+                    torch.backends.cudnn.allow_tf32 = False
+                    torch.backends.cuda.matmul.allow_tf32 = False
                 with engine.eager_torch():
                     esmp = cfg["sampler"](cfg["den"], steps=steps, silent=True)
                     esmp(x1)  # warm-up (cuDNN autotune, lazy init)
