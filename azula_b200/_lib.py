@@ -14,7 +14,7 @@ from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libazb.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 F32, BF16, F16, I64 = 0, 1, 2, 3
 DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16, torch.int64: I64}

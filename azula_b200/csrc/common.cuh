@@ -52,6 +52,11 @@ __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
 }
 
 __device__ __forceinline__ float bf16_bits_to_f32(uint32_t lo16) { return __uint_as_float(lo16 << 16); }
+__device__ __forceinline__ float tanh_approx(float v) {
+    float r;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

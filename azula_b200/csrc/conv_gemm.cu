@@ -29,6 +29,17 @@
 // (N = 256) -- the L2 -> SM path (~ 15 TB/s chip-wide at the single-CTA rate) is what caps the tensor pipe of
 // the single-CTA kernel at ~ 75 % -- and 6 pipeline stages instead of 4 in the same shared memory.
 
+//
+// Halo tiles (HALO = true, 3 x 3 stride-1 layers on feature maps of at least 16 x 8 pixels with C_in % 64 == 0): an M tile
+// is an 8-wide x 16-tall patch of ONE image and the A operand of a 64-channel block is ONE TMA box of (16 + 2) x (8 + 2)
+// pixels.  The nine taps are shifted views of that tile (descriptor start + (kh * 10 + kw) * 128 bytes, 1280 bytes
+// between 8-pixel row groups; the swizzle is a function of the absolute address, see tc::smem_desc_sw128_sbo), so the
+// activation crosses the L2 -> SM path 1.4 times instead of 9 times.  Four extra warps sit between the TMA unit and
+// the tensor core: they rewrite each landed halo tile in place as  bf16(act(a[n, c] * x + b[n, c]))  -- the GroupNorm
+// (+ scale / shift + SiLU) that precedes the convolution in the reference (_src/unet.py:177-181,203-207,238-243), with
+// the per-(image, channel) coefficients of azb_gn_coef_f32 -- and leave out-of-image pixels at the zero the TMA unit
+// filled in (padding applies to the NORMALISED tensor).  The separate normalisation pass over HBM disappears.
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -39,6 +50,12 @@ constexpr int BLOCK_K = 64;  // 128 bytes of bf16 = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int XF_WARPS = 4;                          // halo kernels: warps that transform the A tiles in place
+constexpr int THREADS_HALO = THREADS + 32 * XF_WARPS;
+constexpr int HALO_W = 8, HALO_H = 16;               // patch of one M tile (pixels)
+constexpr int HALO_PITCH = HALO_W + 2;               // pixels per halo row
+constexpr int HALO_ROWS = (HALO_H + 2) * HALO_PITCH; // 128-byte rows of one halo tile
+constexpr int HALO_BYTES = HALO_ROWS * 128;
 constexpr int SMEM_BUDGET = 193 * 1024;  // operand ring; + 32 KiB epilogue staging + alignment <= 227 KiB
 
 struct ConvParams {
@@ -71,6 +88,11 @@ struct ConvParams {
     float* ws_partial;        // [(S - 1) * tiles_out][128][BLOCK_N] fp32 partial accumulators of splits 1 .. S-1
     int* ws_flags;            // [tiles_out][EPI_WARPS] arrival counters, zero between launches
     int prefetch_kb;          // > 0: the producer pulls the weight tile of k-block kb + prefetch_kb into L2
+    const float2* in_coef;    // halo kernels: [N][c_in] {a, b} of the input transform act(a x + b), or null (identity)
+    int in_silu;              // the transform ends in SiLU (coefficients are halved, see azb_gn_coef_f32)
+    int c_in;                 // row length of in_coef
+    int sa, sb;               // halo kernels: A slots and weight stages in the shared-memory budget
+    int a_ahead;              // halo kernels: 1 = load A items into every free slot as early as possible
 };
 
 // Adds v * 2^40 to a 96-bit fixed-point accumulator held as two int64 words (value = hi * 2^32 + lo, 0 <= lo < 2^32):
@@ -109,19 +131,30 @@ __device__ __forceinline__ float activate(float v, int act) {
     return v;
 }
 
-template <int BLOCK_N, bool PAIR = false>
+template <int BLOCK_N, bool PAIR = false, bool HALO = false>
 struct Cfg {
     static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
     static constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;  // weight rows this CTA stages per k-block
     static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    // halo kernels: SA slots of one halo tile each (also used for the plain tiles of the fused 1x1 operand) and a
+    // separate ring of weight tiles; otherwise one ring of {A tap tile, weight tile} stages
+    static constexpr int A_SLOT = (HALO_BYTES + 1023) / 1024 * 1024;
+    static constexpr int SA_MAX = 4;
+    static constexpr int B_SLOT = B_BYTES < 1024 ? 1024 : B_BYTES;
+    static constexpr int STAGE_BYTES = HALO ? B_SLOT : A_BYTES + B_BYTES;
+    // halo kernels split the budget at run time (ConvParams::sa A slots, ::sb weight stages); STAGES is the most the
+    // barrier arrays must hold
     static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES > 8 ? 8 : SMEM_BUDGET / STAGE_BYTES;
+    static constexpr int RING_BYTES = HALO ? SMEM_BUDGET : STAGES * STAGE_BYTES;
+    static constexpr int weight_stages(int sa) {
+        return (SMEM_BUDGET - sa * A_SLOT) / STAGE_BYTES > 8 ? 8 : (SMEM_BUDGET - sa * A_SLOT) / STAGE_BYTES;
+    }
     static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;  // columns of one accumulator stage
     static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
     static constexpr int COLS_PER_WARP = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;  // two warps share a lane quarter
     static constexpr int CHUNK = COLS_PER_WARP < 32 ? 16 : 32;
     static constexpr int STAGING_BYTES = EPI_WARPS * 32 * 128;  // per epilogue warp: 32 rows x 32 fp32, swizzled
-    static constexpr int SMEM = STAGES * STAGE_BYTES + STAGING_BYTES + 1024;
+    static constexpr int SMEM = RING_BYTES + STAGING_BYTES + 1024;
 };
 
 __device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& n_tile, int& w0, int& h0, int& n0) {
@@ -137,12 +170,11 @@ __device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& 
 
 // LEAN: the epilogue of the common case -- bf16 NHWC output, no activation, no gate, no split-K, GroupNorm sums (if
 // any) as exact accumulators per 8-channel block -- with those switches resolved at compile time.
-template <int BLOCK_N, bool PAIR, bool LEAN>
-__global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                                                                const __grid_constant__ CUtensorMap tmap_b,
-                                                                const __grid_constant__ CUtensorMap tmap_a2,
-                                                                const ConvParams p) {
-    using C = Cfg<BLOCK_N, PAIR>;
+template <int BLOCK_N, bool PAIR, bool LEAN, bool HALO>
+__global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
+    conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ CUtensorMap tmap_a2, const ConvParams p) {
+    using C = Cfg<BLOCK_N, PAIR, HALO>;
     constexpr int STAGES = C::STAGES;
     static_assert(!PAIR || BLOCK_N >= 128, "a CTA pair splits the weight tile in two halves of >= 64 rows");
 
@@ -152,6 +184,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
     __shared__ __align__(8) uint64_t bar_empty[STAGES];
     __shared__ __align__(8) uint64_t bar_acc_full[2];
     __shared__ __align__(8) uint64_t bar_acc_empty[2];
+    // halo kernels: A slot landed (TMA) -> transformed (XF_WARPS warps, of both CTAs of a pair) -> consumed (MMA commit)
+    __shared__ __align__(8) uint64_t bar_a_full[C::SA_MAX];
+    __shared__ __align__(8) uint64_t bar_a_ready[C::SA_MAX];
+    __shared__ __align__(8) uint64_t bar_a_empty[C::SA_MAX];
     __shared__ uint32_t tmem_slot;
 
     const int warp = threadIdx.x >> 5;
@@ -168,6 +204,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(tc::smem_u32(&bar_acc_full[s]), 1);
             tc::mbar_init(tc::smem_u32(&bar_acc_empty[s]), PAIR ? 2 * EPI_WARPS : EPI_WARPS);
+        }
+        if constexpr (HALO) {
+            for (int s = 0; s < C::SA_MAX; ++s) {
+                tc::mbar_init(tc::smem_u32(&bar_a_full[s]), 1);
+                tc::mbar_init(tc::smem_u32(&bar_a_ready[s]), PAIR ? 2 * XF_WARPS : XF_WARPS);
+                tc::mbar_init(tc::smem_u32(&bar_a_empty[s]), 1);
+            }
         }
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tmap_a);
@@ -213,7 +256,179 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
         else return unit;
     };
 
-    if (warp == 0) {
+    // halo kernels: A items per tile = 64-channel blocks of the 3 x 3 operand (one halo tile, nine weight tiles each)
+    // followed by the 64-channel blocks of the fused 1 x 1 operand (one plain 128-pixel tile, one weight tile each)
+    const int items = p.kb_per_tap + p.kb_extra;
+    const int SA = p.sa, SB = p.sb;
+    const uint32_t b_ring = smem_base + (uint32_t)(SA * C::A_SLOT);
+
+    if (HALO && warp == 0) {
+        // ===== TMA producer (halo) =====
+        // Two rings: A slots (one halo tile per 64-channel block, issued one item AHEAD of the weight stream so that the
+        // transform warps have a full item -- nine k-blocks of MMA time -- for their pass) and weight tiles.
+        if (tc::elect_one()) {
+            const int total_items = tile_count * items;
+            int sb = 0, sa = 0;
+            uint32_t pb = 1, pa = 1;  // parities of the `empty` barriers: the first pass finds every slot free
+            int ai = 0, a_local = 0, a_it = 0;  // next A item to issue
+            const uint32_t full_b0 = PAIR ? tc::mapa(tc::smem_u32(&bar_full[0]), 0) : tc::smem_u32(&bar_full[0]);
+            // Issues the load of A item `ai` into its slot; `must` = the weight stream is about to need it (block until
+            // the slot is free), otherwise only if the slot is free right now.  Returns false when nothing was issued.
+            auto issue_a = [&](bool must) -> bool {
+                if (!must && !tc::mbar_test(tc::smem_u32(&bar_a_empty[sa]), pa)) return false;
+                const int a_tile = unit_to_tile(tile_first + a_local * tile_step);
+                int n_tile, w0, h0, n0;
+                tile_coords(p, a_tile, n_tile, w0, h0, n0);
+                tc::mbar_wait(tc::smem_u32(&bar_a_empty[sa]), pa);
+                const uint32_t dst = smem_base + sa * C::A_SLOT;
+                const uint32_t full = tc::smem_u32(&bar_a_full[sa]);
+                if (a_it < p.kb_per_tap) {
+                    tc::mbar_expect_tx(full, HALO_BYTES);
+                    tc::tma_load_4d(dst, &tmap_a, full, a_it * BLOCK_K, w0 - 1, h0 - 1, n0);
+                } else {
+                    tc::mbar_expect_tx(full, C::A_BYTES);
+                    tc::tma_load_4d(dst, &tmap_a2, full, (a_it - p.kb_per_tap) * BLOCK_K, w0, h0, n0);
+                }
+                if (++a_it == items) a_it = 0, ++a_local;
+                ++ai;
+                if (++sa == SA) sa = 0, pa ^= 1u;
+                return true;
+            };
+            int bi = 0;
+            for (int local = 0; local < tile_count; ++local) {
+                const int tile = unit_to_tile(tile_first + local * tile_step);
+                const int b_row0 = (tile % p.n_tiles) * BLOCK_N + (int)cta_rank * C::B_ROWS;
+                for (int it = 0; it < items; ++it, ++bi) {
+                    while (ai < total_items && ai <= bi + (p.a_ahead ? 0 : 1)) issue_a(true);
+                    const bool halo = it < p.kb_per_tap;
+                    const int nb = halo ? 9 : 1;
+                    // weights are packed [tap][channel block]: tap t of channel block `it` is k-block t * kb_per_tap + it
+                    int kbx = halo ? it : num_kb_taps + (it - p.kb_per_tap);
+                    for (int t = 0; t < nb; ++t, kbx += p.kb_per_tap) {
+                        // keep every free A slot loading: the transform warps need a landed tile well before the MMA does
+                        if (p.a_ahead) {
+                            while (ai < total_items && issue_a(false)) {
+                            }
+                        }
+                        tc::mbar_wait(tc::smem_u32(&bar_empty[sb]), pb);
+                        const uint32_t b_dst = b_ring + sb * C::STAGE_BYTES;
+                        const uint32_t full = full_b0 + 8u * (uint32_t)sb;
+                        if constexpr (PAIR) {
+                            if (leader) tc::mbar_expect_tx(tc::smem_u32(&bar_full[sb]), 2 * C::B_BYTES);
+                            tc::tma_load_2d_pair(b_dst, &tmap_b, full, kbx * BLOCK_K, b_row0);
+                        } else {
+                            tc::mbar_expect_tx(full, C::B_BYTES);
+                            tc::tma_load_2d(b_dst, &tmap_b, full, kbx * BLOCK_K, b_row0);
+                        }
+                        if (++sb == SB) sb = 0, pb ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (HALO && warp == 1) {
+        // ===== MMA issuer (halo) =====
+        if (leader && tc::elect_one()) {
+            constexpr uint32_t idesc = tc::idesc_bf16_f32(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+            int sb = 0, sa = 0;
+            uint32_t pb = 0, pa = 0;
+            for (int local = 0; local < tile_count; ++local) {
+                const int as = local & 1;
+                tc::mbar_wait(tc::smem_u32(&bar_acc_empty[as]), ((local >> 1) & 1) ^ 1);
+                tc::fence_after_sync();
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(as * C::ACC_COLS);
+                for (int it = 0; it < items; ++it) {
+                    // the A slot has landed AND been transformed (by the transform warps of both CTAs of a pair)
+                    if constexpr (PAIR) tc::mbar_wait_cluster(tc::smem_u32(&bar_a_ready[sa]), pa);
+                    else tc::mbar_wait(tc::smem_u32(&bar_a_ready[sa]), pa);
+                    tc::fence_after_sync();
+                    const bool halo = it < p.kb_per_tap;
+                    const int nb = halo ? 9 : 1;
+                    const uint32_t sbo = halo ? HALO_PITCH * 128u : 1024u;
+                    uint32_t a_src = smem_base + sa * C::A_SLOT;  // tap (0, 0): the view that starts at halo pixel (0, 0)
+                    for (int t = 0, kw = 0; t < nb; ++t) {
+                        tc::mbar_wait(tc::smem_u32(&bar_full[sb]), pb);
+                        tc::fence_after_sync();
+                        const uint64_t da = tc::smem_desc_sw128_sbo(a_src, sbo);
+                        const uint64_t db = tc::smem_desc_sw128(b_ring + sb * C::STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            if constexpr (PAIR)
+                                tc::mma_f16_ss_pair(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | t | k) != 0);
+                            else
+                                tc::mma_f16_ss(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | t | k) != 0);
+                        }
+                        if constexpr (PAIR) tc::mma_commit_pair(tc::smem_u32(&bar_empty[sb]), 0b11);
+                        else tc::mma_commit(tc::smem_u32(&bar_empty[sb]));
+                        if (++sb == SB) sb = 0, pb ^= 1u;
+                        // next tap: one pixel to the right, or back to column 0 of the next halo row
+                        if (++kw == 3) kw = 0, a_src += (HALO_PITCH - 2) * 128u;
+                        else a_src += 128u;
+                    }
+                    if constexpr (PAIR) tc::mma_commit_pair(tc::smem_u32(&bar_a_empty[sa]), 0b11);
+                    else tc::mma_commit(tc::smem_u32(&bar_a_empty[sa]));
+                    if (++sa == SA) sa = 0, pa ^= 1u;
+                }
+                if constexpr (PAIR) tc::mma_commit_pair(tc::smem_u32(&bar_acc_full[as]), 0b11);
+                else tc::mma_commit(tc::smem_u32(&bar_acc_full[as]));
+            }
+        }
+    } else if (HALO && warp >= 2 + EPI_WARPS) {
+        // ===== input transform (halo) =====
+        // Thread (rg, chunk) owns the 16-byte chunk `chunk` (8 channels) of halo rows rg, rg + 16, ...: a warp
+        // instruction touches 4 full 128-byte rows (conflict free for any swizzle phase).  Same arithmetic as
+        // gn_apply_kernel: f = fma(a, x, b), SiLU as f + f tanh(f) on halved coefficients, round to bf16.
+        const int tx = (int)threadIdx.x - 32 * (2 + EPI_WARPS);
+        const int chunk = tx & 7, rg = tx >> 3;
+        int sa = 0;
+        uint32_t pa = 0;
+        const uint32_t ready0 = PAIR ? tc::mapa(tc::smem_u32(&bar_a_ready[0]), 0) : tc::smem_u32(&bar_a_ready[0]);
+        for (int local = 0; local < tile_count; ++local) {
+            const int tile = unit_to_tile(tile_first + local * tile_step);
+            int n_tile, w0, h0, n0;
+            tile_coords(p, tile, n_tile, w0, h0, n0);
+            for (int it = 0; it < items; ++it) {
+                const bool xf = p.in_coef != nullptr && it < p.kb_per_tap;
+                float a[8], b[8];
+                if (xf) {
+                    const float4* cp = reinterpret_cast<const float4*>(p.in_coef + (int64_t)n0 * p.c_in + it * BLOCK_K + chunk * 8);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 v = __ldg(cp + j);
+                        a[2 * j] = v.x, b[2 * j] = v.y, a[2 * j + 1] = v.z, b[2 * j + 1] = v.w;
+                    }
+                }
+                tc::mbar_wait(tc::smem_u32(&bar_a_full[sa]), pa);
+                if (xf) {
+                    const uint32_t slot = smem_base + sa * C::A_SLOT;
+#pragma unroll 4
+                    for (int i = rg; i < HALO_ROWS; i += 4 * XF_WARPS) {
+                        const int y = i / HALO_PITCH, x = i - y * HALO_PITCH;
+                        // out-of-image pixels stay at the zero the TMA unit wrote: the convolution pads the NORMALISED tensor
+                        if ((unsigned)(h0 - 1 + y) >= (unsigned)p.H || (unsigned)(w0 - 1 + x) >= (unsigned)p.W) continue;
+                        const uint32_t addr = slot + (uint32_t)i * 128u + ((uint32_t)(chunk ^ (i & 7)) << 4);
+                        uint32_t v[4];
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory");
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float f0 = fmaf(a[2 * j], bf16_bits_to_f32(v[j] & 0xffffu), b[2 * j]);
+                            float f1 = fmaf(a[2 * j + 1], __uint_as_float(v[j] & 0xffff0000u), b[2 * j + 1]);
+                            if (p.in_silu) f0 = fmaf(f0, tanh_approx(f0), f0), f1 = fmaf(f1, tanh_approx(f1), f1);
+                            __nv_bfloat162 r = __floats2bfloat162_rn(f0, f1);
+                            v[j] = *reinterpret_cast<uint32_t*>(&r);
+                        }
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+                    }
+                    tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    if (PAIR && !leader) tc::mbar_arrive_cluster(ready0 + 8u * (uint32_t)sa);
+                    else tc::mbar_arrive(tc::smem_u32(&bar_a_ready[sa]));
+                }
+                if (++sa == SA) sa = 0, pa ^= 1u;
+            }
+        }
+    } else if (warp == 0) {
         // ===== TMA producer =====
         // One ELECTED lane (elect.sync tells ptxas that exactly one lane is active, so descriptor and coordinate
         // operands go straight to uniform registers instead of through per-value waterfall loops).  The loop is the
@@ -318,7 +533,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const __grid_cons
         const int half = (BLOCK_N >= 64) ? (e >> 2) : 0;
         const bool active = (BLOCK_N >= 64) || (e < 4);
         constexpr int CHUNK = C::CHUNK;
-        const uint32_t stage_base = smem_base + STAGES * C::STAGE_BYTES + e * (32 * 128);
+        const uint32_t stage_base = smem_base + C::RING_BYTES + e * (32 * 128);
         const int cg4 = lane & 3;       // which 8-channel group of the 32-column chunk
         const int rl = lane >> 2;       // row within a group of 8 rows
         // chunked mode: the lanes that own an 8-channel block (rl == 0) carry its GroupNorm sums across the tiles of
@@ -646,38 +861,39 @@ int sm_count() {
 
 #define g_knob azb_knob
 
-template <int BLOCK_N, bool PAIR = false, bool LEAN = false>
+template <int BLOCK_N, bool PAIR = false, bool LEAN = false, bool HALO = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const ConvParams& p, cudaStream_t s) {
-    constexpr int smem = Cfg<BLOCK_N, PAIR>::SMEM;
+    constexpr int smem = Cfg<BLOCK_N, PAIR, HALO>::SMEM;
+    constexpr int threads = HALO ? THREADS_HALO : THREADS;
+    auto kernel = conv_gemm_kernel<BLOCK_N, PAIR, LEAN, HALO>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e =
-            cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, PAIR, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
     if constexpr (PAIR) {
         // one cluster of two CTAs (the two SMs of a TPC) per scheduling unit, at most one cluster per TPC
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)sm_count() & ~1u), cfg.blockDim = dim3(THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = s;
+        cfg.gridDim = dim3((unsigned)sm_count() & ~1u), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr, cfg.numAttrs = 1;
         static int resident = 0;  // clusters that fit on the device at once: the persistent grid is one wave of them
         if (!resident) {
-            if (cudaOccupancyMaxActiveClusters(&resident, conv_gemm_kernel<BLOCK_N, PAIR, LEAN>, &cfg) != cudaSuccess || resident < 1) {
+            if (cudaOccupancyMaxActiveClusters(&resident, kernel, &cfg) != cudaSuccess || resident < 1) {
                 cudaGetLastError();
                 resident = sm_count() / 2;
             }
         }
         const int pairs = p.total_tiles < resident ? p.total_tiles : resident;
         cfg.gridDim = dim3((unsigned)(2 * pairs));
-        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BLOCK_N, PAIR, LEAN>, ta, tb, ta2, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb, ta2, p);
         if (e != cudaSuccess) return (int)e;
     } else {
         const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-        conv_gemm_kernel<BLOCK_N, PAIR, LEAN><<<(unsigned)grid, THREADS, smem, s>>>(ta, tb, ta2, p);
+        kernel<<<(unsigned)grid, threads, smem, s>>>(ta, tb, ta2, p);
     }
     return azb_launch_status();
 }
@@ -691,6 +907,14 @@ void patch_shape(int64_t h, int64_t w, int& bw, int& bh, int& bn) {
     bn = BLOCK_M / (bw * bh);
 }
 
+// Temporarily forces the tap-wise kernel (restores the knob on scope exit)
+struct ExtraGuard {
+    int& slot;
+    int saved;
+    explicit ExtraGuard(int& k) : slot(k), saved(k) { slot = 0; }
+    ~ExtraGuard() { slot = saved; }
+};
+
 struct ConvExtra {
     int stride = 1;
     int act = AZB_ACT_NONE;
@@ -702,6 +926,9 @@ struct ConvExtra {
     int64_t* gn_acc = nullptr;   // exact per-(image, channel block) sums of `out` for the GroupNorms that consume it
     void* workspace = nullptr;   // split-K scratch: flags (zero between launches) + fp32 partial tiles
     int64_t workspace_bytes = 0;
+    const float* in_coef = nullptr;  // [N][c_in] {a, b}: the input is act(a x + b), applied on the fly (halo kernels only)
+    int in_silu = 0;
+    AzbConvChoice* choice = nullptr;  // dry run: report the launcher's choice instead of launching
 };
 
 // (h, w) are the INPUT extents; the output is ceil(h / stride) x ceil(w / stride).
@@ -733,9 +960,16 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
         return AZB_E_ALIGN;
     const int64_t h = (h_in + ex.stride - 1) / ex.stride, w = (w_in + ex.stride - 1) / ex.stride;
 
+    // Halo tiles: 3 x 3, stride 1, maps of at least one 8 x 16 patch, whole 64-channel blocks (see the kernel's header)
+    bool halo = g_knob[AZB_CONV_KNOB_HALO] != 0 && taps == 9 && ex.stride == 1 && h >= HALO_H && w >= HALO_W &&
+                c_in % BLOCK_K == 0 && k_per_tap == c_in && (!ex.act2 || (ex.c_in2 % BLOCK_K == 0 && ex.k2 == ex.c_in2)) &&
+                !colsum && ex.act == AZB_ACT_NONE && !ex.gate && (!ex.gn_acc || stat_gran == 8);
+    if (ex.in_coef && !azb_aligned(ex.in_coef, 16)) return AZB_E_ALIGN;
+
     ConvParams p{};
     p.N = (int)n, p.H = (int)h, p.W = (int)w;
-    patch_shape(h, w, p.BW, p.BH, p.BN);
+    if (halo) p.BW = HALO_W, p.BH = HALO_H, p.BN = 1;
+    else patch_shape(h, w, p.BW, p.BH, p.BN);
     p.tiles_w = (int)((w + p.BW - 1) / p.BW);
     p.tiles_h = (int)((h + p.BH - 1) / p.BH);
     const int64_t tiles_n_img = (n + p.BN - 1) / p.BN;
@@ -761,7 +995,16 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     // folds them before its epilogue.  Single wave only (all CTAs co-resident), so the owner's wait cannot deadlock.
     int splits = 1;
     const int64_t num_kb_total = (int64_t)taps * (k_per_tap / BLOCK_K) + (ex.act2 ? ex.k2 / BLOCK_K : 0);
-    if (g_knob[AZB_CONV_KNOB_SPLITK] != 0 && ex.workspace && out_mode == 0 && m_tiles * (c_out_rows / block_n) <= sms && (block_n <= 64 || m_tiles * (c_out_rows / block_n) < sms / 2)) {
+    // halo kernels exist for the wide lean tiles and for the narrowest generic one (the network's output convolution)
+    if (halo && !((out_mode == 0 && block_n >= 128) || (out_mode == 1 && block_n == 16))) {
+        if (ex.in_coef) return AZB_E_UNSUPPORTED;
+        // recompute the tiling for the tap-wise kernel
+        ExtraGuard guard(g_knob[AZB_CONV_KNOB_HALO]);
+        return conv_impl(act, n, h_in, w_in, c_in, act_ld, wpack, c_out, c_out_rows, taps, k_per_tap, bias, residual, res_ld,
+                         out, out_ld, out_mode, colsum, stat_gran, stream, ex);
+    }
+    if (!halo && ex.in_coef) return AZB_E_UNSUPPORTED;
+    if (!halo && g_knob[AZB_CONV_KNOB_SPLITK] != 0 && ex.workspace && out_mode == 0 && m_tiles * (c_out_rows / block_n) <= sms && (block_n <= 64 || m_tiles * (c_out_rows / block_n) < sms / 2)) {
         const int try_n[2] = {128, 256}, try_s[2] = {2, 4};
         for (int i = 0; i < 2 && splits == 1; ++i) {
             const int bn = try_n[i], sp = try_s[i];
@@ -809,7 +1052,10 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     // same-address atomics of a 256 x 256 layer serialise in L2 (measured: +15 % on the K = 2304 layers).
     // few M tiles => every weight tile is used by a handful of CTAs right after its first (HBM) read: with only
     // STAGES loads in flight the main loop would run at HBM latency; prefetch the weight stream into L2 ahead of use
-    p.prefetch_kb = g_knob[AZB_CONV_KNOB_PREFETCH] >= 0 ? g_knob[AZB_CONV_KNOB_PREFETCH] : (m_tiles <= 32 ? 24 : 0);
+    p.prefetch_kb = halo ? 0 : g_knob[AZB_CONV_KNOB_PREFETCH] >= 0 ? g_knob[AZB_CONV_KNOB_PREFETCH] : (m_tiles <= 32 ? 24 : 0);
+    p.in_coef = reinterpret_cast<const float2*>(ex.in_coef), p.in_silu = ex.in_silu, p.c_in = (int)c_in;
+    p.sa = g_knob[AZB_CONV_KNOB_HALO_SA] >= 2 && g_knob[AZB_CONV_KNOB_HALO_SA] <= 4 ? g_knob[AZB_CONV_KNOB_HALO_SA] : 3;
+    p.a_ahead = g_knob[AZB_CONV_KNOB_HALO_AHEAD] >= 0 ? g_knob[AZB_CONV_KNOB_HALO_AHEAD] : 0;
     p.chunked = (ex.gn_acc && p.n_tiles <= 2 && p.BN == 1 && stat_gran == 8 && block_n >= 64 && splits == 1) ? 1 : 0;
     const int64_t k_total = taps * k_per_tap + (ex.act2 ? ex.k2 : 0);
 
@@ -821,6 +1067,7 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
         uint64_t dims[4] = {(uint64_t)c_in, (uint64_t)w_in, (uint64_t)h_in, (uint64_t)n};
         uint64_t str[3] = {(uint64_t)act_ld * 2, (uint64_t)act_ld * 2 * w_in, (uint64_t)act_ld * 2 * w_in * h_in};
         uint32_t box[4] = {BLOCK_K, (uint32_t)p.BW * st, (uint32_t)p.BH * st, (uint32_t)p.BN};
+        if (halo) box[1] = HALO_PITCH, box[2] = HALO_H + 2;
         uint32_t es[4] = {1, st, st, 1};
         if (box[1] > 256 || box[2] > 256) return AZB_E_SHAPE;
         int rc = make_map(&ta, act, 4, dims, str, box, es);
@@ -843,8 +1090,24 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
         ta2 = ta;
     }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    const bool lean = g_knob[AZB_CONV_KNOB_LEAN] != 0 && out_mode == 0 && ex.act == AZB_ACT_NONE && !ex.gate && !colsum &&
+    const bool lean = (halo || g_knob[AZB_CONV_KNOB_LEAN] != 0) && out_mode == 0 && ex.act == AZB_ACT_NONE && !ex.gate && !colsum &&
                       splits == 1 && (!ex.gn_acc || stat_gran == 8) && block_n >= 128;
+    if (ex.choice) {
+        ex.choice->halo = halo, ex.choice->pair = pair, ex.choice->lean = lean, ex.choice->block_n = block_n, ex.choice->splits = splits;
+        ex.choice->tiles = p.total_tiles;
+        return AZB_OK;
+    }
+    if (halo) {
+        const int b_stage = out_mode == 1 ? Cfg<16, false, true>::STAGE_BYTES
+                                          : pair ? Cfg<256, true, true>::STAGE_BYTES * block_n / 256 : Cfg<256, false, true>::STAGE_BYTES * block_n / 256;
+        p.sb = (SMEM_BUDGET - p.sa * Cfg<256, true, true>::A_SLOT) / b_stage;
+        if (p.sb > 8) p.sb = 8;
+        if (g_knob[AZB_CONV_KNOB_HALO_SB] >= 2 && g_knob[AZB_CONV_KNOB_HALO_SB] < p.sb) p.sb = g_knob[AZB_CONV_KNOB_HALO_SB];
+        if (p.sb < 2) return AZB_E_SHAPE;
+        if (out_mode == 1) return launch<16, false, false, true>(ta, tb, ta2, p, s);
+        if (pair) return block_n == 256 ? launch<256, true, true, true>(ta, tb, ta2, p, s) : launch<128, true, true, true>(ta, tb, ta2, p, s);
+        return block_n == 256 ? launch<256, false, true, true>(ta, tb, ta2, p, s) : launch<128, false, true, true>(ta, tb, ta2, p, s);
+    }
     if (pair && lean) return block_n == 256 ? launch<256, true, true>(ta, tb, ta2, p, s) : launch<128, true, true>(ta, tb, ta2, p, s);
     if (pair) return block_n == 256 ? launch<256, true>(ta, tb, ta2, p, s) : launch<128, true>(ta, tb, ta2, p, s);
     if (lean) return block_n == 256 ? launch<256, false, true>(ta, tb, ta2, p, s) : launch<128, false, true>(ta, tb, ta2, p, s);
@@ -918,7 +1181,24 @@ extern "C" int azb_conv_bf16(const AzbConv* d, void* stream) {
     ex.act2 = d->act2, ex.c_in2 = d->c_in2, ex.act2_ld = d->act2_ld, ex.k2 = d->k2;
     ex.gn_acc = d->gn_acc;
     ex.workspace = d->workspace, ex.workspace_bytes = d->workspace_bytes;
+    ex.in_coef = d->in_coef, ex.in_silu = d->in_silu;
     return conv_impl(d->act, d->n, d->h, d->w, d->c_in, d->act_ld, d->wpack, d->c_out, d->c_out_rows, d->taps, d->k_per_tap,
                      d->bias, d->residual, d->res_ld, d->out, d->out_ld, d->out_mode, d->colsum,
                      (d->colsum || d->gn_acc) ? d->stat_gran : 1, stream, ex);
+}
+
+extern "C" int azb_conv_choice(const AzbConv* d, AzbConvChoice* choice) {
+    AZB_CHECK_PTR(d);
+    AZB_CHECK_PTR(choice);
+    ConvExtra ex;
+    ex.stride = d->stride ? d->stride : 1, ex.act = d->act_fn;
+    ex.gate = d->gate, ex.gate_ld = d->gate_ld, ex.gate_rows = d->gate_rows;
+    ex.act2 = d->act2, ex.c_in2 = d->c_in2, ex.act2_ld = d->act2_ld, ex.k2 = d->k2;
+    ex.gn_acc = d->gn_acc;
+    ex.workspace = d->workspace, ex.workspace_bytes = d->workspace_bytes;
+    ex.in_coef = d->in_coef, ex.in_silu = d->in_silu;
+    ex.choice = choice;
+    return conv_impl(d->act, d->n, d->h, d->w, d->c_in, d->act_ld, d->wpack, d->c_out, d->c_out_rows, d->taps, d->k_per_tap,
+                     d->bias, d->residual, d->res_ld, d->out, d->out_ld, d->out_mode, d->colsum,
+                     (d->colsum || d->gn_acc) ? d->stat_gran : 1, nullptr, ex);
 }

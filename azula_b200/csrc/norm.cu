@@ -146,12 +146,6 @@ struct ApplyParams {
     double acc_scale;  // 2^-40 / (h * w * channels per group)
 };
 
-__device__ __forceinline__ float tanh_approx(float v) {
-    float r;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
-    return r;
-}
-
 // With SILU the caller passes HALVED coefficients, h = (A x + B) / 2, and SiLU(2h) = h + h tanh(h): one FMA, one
 // SFU operation (tanh.approx, absolute error ~2^-11 on tanh, i.e. <= |h| 2^-11 on the result: a tenth of the bf16
 // rounding that follows) and one FMA per element.  The exp + reciprocal form (2 SFU operations and ~10 issue slots
@@ -176,6 +170,55 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], float mul) {
     o.x = *reinterpret_cast<uint32_t*>(&t0), o.y = *reinterpret_cast<uint32_t*>(&t1);
     o.z = *reinterpret_cast<uint32_t*>(&t2), o.w = *reinterpret_cast<uint32_t*>(&t3);
     return o;
+}
+
+// (mean, rstd) of group g of image n: copied from `stats`, or folded from the producers' exact accumulators (integer
+// fold, then a handful of double-precision operations)
+__device__ __forceinline__ float2 group_stat(const ApplyParams& p, int n, int g, int cg) {
+    if (p.stats)
+        return make_float2(__ldg(p.stats + ((int64_t)n * p.groups + g) * 2), __ldg(p.stats + ((int64_t)n * p.groups + g) * 2 + 1));
+    long long s_hi = 0, s_lo = 0, q_hi = 0, q_lo = 0;
+    for (int ch = g * cg; ch < (g + 1) * cg; ch += p.acc_gran) {
+        const int which = ch >= p.acc_c[0];
+        const int local = which ? ch - p.acc_c[0] : ch;
+        const long long* src = p.acc[which] + ((int64_t)n * (p.acc_c[which] / p.acc_gran) + local / p.acc_gran) * 4;
+        s_hi += __ldg(src), s_lo += __ldg(src + 1), q_hi += __ldg(src + 2), q_lo += __ldg(src + 3);
+    }
+    // double precision only where the cancellation is (E[x^2] - mean^2); the slow DP pipe never sees a
+    // division or a square root (acc_scale = 2^-40 / count comes from the host)
+    const double m = ((double)s_hi * 4294967296.0 + (double)s_lo) * p.acc_scale;
+    const double var = fma(-m, m, ((double)q_hi * 4294967296.0 + (double)q_lo) * p.acc_scale);
+    return make_float2((float)m, rsqrtf(fmaxf((float)var, 0.f) + p.eps));
+}
+
+// {A, B} of channel c: y = act(A x + B) with A = rstd gamma (1 + scale), B = (beta - mean rstd gamma)(1 + scale) + shift;
+// halved when the activation is SiLU (evaluated as h + h tanh(h), h = (A x + B) / 2)
+__device__ __forceinline__ float2 channel_coef(const ApplyParams& p, const float2* s_stat, const float* ss, int c, int cg,
+                                               bool silu) {
+    float aa = 1.f, bb = 0.f;
+    if (p.stats || p.acc[0]) {
+        const float2 st = s_stat[c / cg];
+        aa = __fmul_rn(st.y, __ldg(p.gamma + c));
+        bb = __fsub_rn(__ldg(p.beta + c), __fmul_rn(st.x, aa));
+    }
+    if (ss) {
+        const float sc = __fadd_rn(1.0f, __ldg(ss + c));
+        aa = __fmul_rn(aa, sc);
+        bb = __fadd_rn(__fmul_rn(bb, sc), __ldg(ss + p.c + c));
+    }
+    return silu ? make_float2(0.5f * aa, 0.5f * bb) : make_float2(aa, bb);
+}
+
+// coef[n][c] = {A, B} for the convolution kernels that apply the normalisation to their input on the fly
+// (AzbConv::in_coef): one CTA per image.
+__global__ void __launch_bounds__(THREADS) gn_coef_kernel(const ApplyParams p, float2* coef) {
+    const int n = blockIdx.x;
+    const int cg = p.c / p.groups;
+    const float* ss = p.scale_shift ? p.scale_shift + (int64_t)n * p.ss_stride : nullptr;
+    __shared__ float2 s_stat[THREADS];
+    if (threadIdx.x < p.groups) s_stat[threadIdx.x] = group_stat(p, n, threadIdx.x, cg);
+    __syncthreads();
+    for (int c = threadIdx.x; c < p.c; c += THREADS) coef[(int64_t)n * p.c + c] = channel_coef(p, s_stat, ss, c, cg, p.silu != 0);
 }
 
 // y = act(A[c]*x + B[c]) with A = rstd*gamma*(1+scale), B = (beta - mean*rstd*gamma)*(1+scale) + shift.
@@ -205,26 +248,7 @@ __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) 
     // (mean, rstd) of every group of image n, once per CTA: copied from `stats`, or folded from the producers' exact
     // accumulators (integer fold, then a handful of double-precision operations by <= 256 threads)
     __shared__ float2 s_stat[THREADS];
-    if ((p.stats || p.acc[0]) && threadIdx.x < p.groups) {
-        const int g = threadIdx.x;
-        if (p.stats) {
-            s_stat[g] = make_float2(__ldg(p.stats + ((int64_t)n * p.groups + g) * 2),
-                                    __ldg(p.stats + ((int64_t)n * p.groups + g) * 2 + 1));
-        } else {
-            long long s_hi = 0, s_lo = 0, q_hi = 0, q_lo = 0;
-            for (int ch = g * cg; ch < (g + 1) * cg; ch += p.acc_gran) {
-                const int which = ch >= p.acc_c[0];
-                const int local = which ? ch - p.acc_c[0] : ch;
-                const long long* src = p.acc[which] + ((int64_t)n * (p.acc_c[which] / p.acc_gran) + local / p.acc_gran) * 4;
-                s_hi += __ldg(src), s_lo += __ldg(src + 1), q_hi += __ldg(src + 2), q_lo += __ldg(src + 3);
-            }
-            // double precision only where the cancellation is (E[x^2] - mean^2); the slow DP pipe never sees a
-            // division or a square root (acc_scale = 2^-40 / count comes from the host)
-            const double m = ((double)s_hi * 4294967296.0 + (double)s_lo) * p.acc_scale;
-            const double var = fma(-m, m, ((double)q_hi * 4294967296.0 + (double)q_lo) * p.acc_scale);
-            s_stat[g] = make_float2((float)m, rsqrtf(fmaxf((float)var, 0.f) + p.eps));
-        }
-    }
+    if ((p.stats || p.acc[0]) && threadIdx.x < p.groups) s_stat[threadIdx.x] = group_stat(p, n, threadIdx.x, cg);
     __syncthreads();
     if (r >= R) return;
 
@@ -233,18 +257,8 @@ __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = v * 8 + j;
-            float aa = 1.f, bb = 0.f;
-            if (p.stats || p.acc[0]) {
-                const float2 st = s_stat[c / cg];
-                aa = st.y * __ldg(p.gamma + c);
-                bb = __ldg(p.beta + c) - st.x * aa;
-            }
-            if (ss) {
-                const float sc = 1.0f + __ldg(ss + c);
-                aa *= sc;
-                bb = bb * sc + __ldg(ss + p.c + c);
-            }
-            a[j] = SILU ? 0.5f * aa : aa, b[j] = SILU ? 0.5f * bb : bb;
+            const float2 ab = channel_coef(p, s_stat, ss, c, cg, SILU);
+            a[j] = ab.x, b[j] = ab.y;
         }
         const __nv_bfloat16* xc = xin + v * 8;
         __nv_bfloat16* yc = yout + v * 8;
@@ -488,6 +502,28 @@ extern "C" int azb_gn_apply_acc_bf16(const void* x, int64_t x_ld, void* y, int64
     AZB_CHECK_PTR(acc_a);
     return gn_apply_impl(x, x_ld, y, y_ld, n, h, w, c, groups, nullptr, acc_a, c_a, acc_b, c_b, gran, eps, gamma, beta,
                          scale_shift, ss_stride, nullptr, 0, silu, mode, stream);
+}
+
+extern "C" int azb_gn_coef_f32(int64_t n, int64_t h, int64_t w, int64_t c, int64_t groups, const int64_t* acc_a, int64_t c_a,
+                               const int64_t* acc_b, int64_t c_b, int64_t gran, float eps, const float* gamma,
+                               const float* beta, const float* scale_shift, int64_t ss_stride, int silu, float* coef,
+                               void* stream) {
+    AZB_CHECK_PTR(acc_a);
+    AZB_CHECK_PTR(gamma);
+    AZB_CHECK_PTR(beta);
+    AZB_CHECK_PTR(coef);
+    if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || groups <= 0 || groups > THREADS || c % groups || c > MAX_C) return AZB_E_SHAPE;
+    if (c_a <= 0 || c_b < 0 || c_a + c_b != c || (c_b > 0 && !acc_b) || (gran != 1 && gran != 8)) return AZB_E_SHAPE;
+    if (c_a % gran || c_b % gran || (c / groups) % gran) return AZB_E_SHAPE;
+    if (!azb_aligned(coef, 16)) return AZB_E_ALIGN;
+    ApplyParams p{};
+    p.n = (int)n, p.h = (int)h, p.w = (int)w, p.c = (int)c, p.groups = (int)groups;
+    p.gamma = gamma, p.beta = beta, p.scale_shift = scale_shift, p.ss_stride = ss_stride, p.silu = silu;
+    p.acc[0] = reinterpret_cast<const long long*>(acc_a), p.acc[1] = reinterpret_cast<const long long*>(acc_b);
+    p.acc_c[0] = (int)c_a, p.acc_c[1] = (int)c_b, p.acc_gran = (int)gran, p.eps = eps;
+    p.acc_scale = 1.0 / (1099511627776.0 * (double)h * (double)w * (double)(c / groups));
+    gn_coef_kernel<<<(unsigned)n, THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, reinterpret_cast<float2*>(coef));
+    return azb_launch_status();
 }
 
 extern "C" int azb_gn_finalize_f32(const float* colsum_a, int64_t c_a, int gran_a, const float* colsum_b, int64_t c_b,

@@ -34,6 +34,7 @@ from .. import _lib
 from . import ops
 
 _MAX_PLANS = 2
+FUSE_NORM = True  # GroupNorm + SiLU ride on the halo tiles of the convolution that consumes them (A/B switch)
 
 
 class Packed:
@@ -204,7 +205,12 @@ class Plan:
             cur = self._block(block, self.cat[j][0], dest)
         # ---- head: GroupNorm + SiLU in place; the last convolution is bound per call (output tensor)
         st = self._stats(self.final)
-        self._apply(self.final, self.final, st, packed.out_gn, None, True, 0)
+        self.out_coef = None
+        # (the output tensor is bound per call: any valid pointer serves the query)
+        if self._fusable(st, self.final, packed.out_conv, self.final, nchw_f32=True):
+            self.out_coef = self._coef(self.final, st, packed.out_gn, None, True)
+        else:
+            self._apply(self.final, self.final, st, packed.out_gn, None, True, 0)
 
         self.gn_partial = torch.empty(max(self.gn_partial_need, 1), **f32)
         self._bind_partial()
@@ -236,27 +242,57 @@ class Plan:
         return acc
 
     def _conv(self, x: Tensor, pc, out: Tensor, residual: Tensor | None = None, stats: bool = False,
-              x2: Tensor | None = None) -> None:
+              x2: Tensor | None = None, in_coef: Tensor | None = None, in_silu: bool = True) -> None:
         r"""Queues a convolution (``azb_conv_bf16``); with ``stats`` its epilogue also adds the exact sums from
         which the GroupNorm(s) consuming ``out`` derive their statistics (no read pass over ``out``, no reduction
-        launch).  With ``x2`` the ResBlock's 1x1 skip connection is part of the same GEMM."""
+        launch).  With ``x2`` the ResBlock's 1x1 skip connection is part of the same GEMM.  With ``in_coef``
+        (:meth:`_coef`) the GroupNorm + SiLU of the INPUT is applied on the fly to the halo tiles."""
         n, h, w, _ = x.shape
         acc = self._acc_for(out, pc.c_out) if stats else None
         if not stats:
             self.acc_of.pop(self._key(out), None)
-        d = ops.conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=self.stat_gran, workspace=self.splitk_ws)
-        self.keep += [d, x, out, pc.w] + [t for t in (residual, pc.bias, x2) if t is not None]
+        d = ops.conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=self.stat_gran, workspace=self.splitk_ws,
+                          in_coef=in_coef, in_silu=in_silu)
+        self.keep += [d, x, out, pc.w] + [t for t in (residual, pc.bias, x2, in_coef) if t is not None]
         taps = 9 if x2 is not None else pc.taps
         k_extra = pc.c_in2 if x2 is not None else 0
         flops = 2.0 * n * h * w * pc.c_out * (taps * pc.c_in + k_extra)
         nbytes = 2.0 * (n * h * w * (pc.c_in + k_extra + pc.c_out * (2 if residual is not None else 1))
                         + pc.c_out * (taps * pc.c_in + k_extra))
-        desc = f"{n}x{h}x{w} {pc.c_in}->{pc.c_out}" + (" +res" if residual is not None else "") + (
+        desc = f"{n}x{h}x{w} {pc.c_in}->{pc.c_out}" + (" gn+" if in_coef is not None else "") + (
+            " +res" if residual is not None else "") + (
             f" +skip1x1({pc.c_in2})" if x2 is not None else "") + (" +stats" if acc is not None else "")
         self._emit("conv3x3" if taps == 9 else "conv1x1", flops, nbytes, self.lib.azb_conv_bf16, byref(d), desc=desc)
 
-    def _conv_skip(self, x: Tensor, x2: Tensor, pc: ops.PackedConvSkip, out: Tensor) -> None:
-        self._conv(x, pc, out, stats=True, x2=x2)
+    def _conv_skip(self, x: Tensor, x2: Tensor, pc: ops.PackedConvSkip, out: Tensor, in_coef: Tensor | None = None) -> None:
+        self._conv(x, pc, out, stats=True, x2=x2, in_coef=in_coef)
+
+    def _fusable(self, stats, x: Tensor, pc, out: Tensor, residual: Tensor | None = None, x2: Tensor | None = None,
+                 nchw_f32: bool = False) -> bool:
+        r"""Whether the GroupNorm (+ SiLU) in front of this convolution can ride on its halo tiles: statistics from
+        exact accumulators and a halo kernel for the shape (``azb_conv_choice``)."""
+        if not FUSE_NORM or stats is None or stats[0] != "acc":
+            return False
+        d = ops.conv_desc(x, pc, out, residual=residual, x2=x2, gran=self.stat_gran, nchw_f32=nchw_f32)
+        return bool(ops.conv_choice(d).halo)
+
+    def _coef(self, x: Tensor, stats, affine, emb_offset: int | None, silu: bool) -> Tensor:
+        r"""Queues ``azb_gn_coef_f32`` for the GroupNorm over ``x``: fp32 (N, C, 2) transform coefficients."""
+        n, h, w, c = x.shape
+        gamma, beta = affine
+        ss_ptr, ss_stride = None, 0
+        if emb_offset is not None:
+            ss_ptr = self.emb_all.data_ptr() + 4 * emb_offset
+            ss_stride = self.packed.emb_total if (self.rows == n and n > 1) else 0
+        (a, ca), (b, cb) = stats[1][0], (stats[1][1] if len(stats[1]) > 1 else (None, 0))
+        coef = torch.empty(n, c, 2, dtype=torch.float32, device=self.device)
+        self.keep += [coef, a, gamma, beta] + ([b] if b is not None else [])
+        self._emit(
+            "gn_coef", 0.0, 8.0 * n * c, self.lib.azb_gn_coef_f32, n, h, w, c, ops.GN_GROUPS, a.data_ptr(), ca,
+            _lib.ptr(b), cb, self.stat_gran, ops.GN_EPS, gamma.data_ptr(), beta.data_ptr(), ss_ptr, ss_stride, int(silu),
+            coef.data_ptr(), desc=f"{n}x{c}",
+        )
+        return coef
 
     def _stats(self, x: Tensor):
         r"""Where the GroupNorm over ``x`` finds its statistics: ``("acc", parts)`` -- the exact accumulators of
@@ -341,28 +377,36 @@ class Plan:
         w_, arena = self.packed.unit[u.path], self.arena
         n, ho, wo, _ = out.shape
         st1 = self._stats(x)
-        h1 = arena.take(n, ho, wo, u.cin)
-        self._apply(x, h1, st1, w_["gn1"], None, True, u.resample)  # SiLU(GN(x)) then up / down
-        if u.resample:
-            xr = arena.take(n, ho, wo, u.cin)
-            self._apply(x, xr, None, None, None, False, u.resample)  # x_upd on the raw input
-        else:
-            xr = x
         h2 = arena.take(n, ho, wo, u.cout)
-        self._conv(h1, w_["conv1"], h2, stats=True)
-        arena.give(h1)
+        if not u.resample and self._fusable(st1, x, w_["conv1"], h2):
+            # SiLU(GN(x)) is applied to the halo tiles of conv1: no normalised copy of x in HBM
+            self._conv(x, w_["conv1"], h2, stats=True, in_coef=self._coef(x, st1, w_["gn1"], None, True))
+            xr = x
+        else:
+            h1 = arena.take(n, ho, wo, u.cin)
+            self._apply(x, h1, st1, w_["gn1"], None, True, u.resample)  # SiLU(GN(x)) then up / down
+            if u.resample:
+                xr = arena.take(n, ho, wo, u.cin)
+                self._apply(x, xr, None, None, None, False, u.resample)  # x_upd on the raw input
+            else:
+                xr = x
+            self._conv(h1, w_["conv1"], h2, stats=True)
+            arena.give(h1)
         st2 = self._stats(h2)
-        self._apply(h2, h2, st2, w_["gn2"], w_["emb_offset"], True, 0)  # SiLU(GN(h) (1 + scale) + shift), in place
-        if isinstance(w_["conv2"], ops.PackedConvSkip):
-            self._conv_skip(h2, xr, w_["conv2"], out)  # skip_connection(x) + h, the 1x1 folded into the GEMM's K
-            sk = xr
-        elif w_["skip"] is not None:
+        skip_fused = isinstance(w_["conv2"], ops.PackedConvSkip)
+        sk = xr
+        if not skip_fused and w_["skip"] is not None:
             sk = arena.take(n, ho, wo, u.cout)
             self._conv(xr, w_["skip"], sk)
-            self._conv(h2, w_["conv2"], out, residual=sk, stats=True)
+        if self._fusable(st2, h2, w_["conv2"], out, residual=None if skip_fused else sk, x2=xr if skip_fused else None):
+            coef2 = self._coef(h2, st2, w_["gn2"], w_["emb_offset"], True)  # SiLU(GN(h) (1 + scale) + shift) on the fly
         else:
-            sk = xr
-            self._conv(h2, w_["conv2"], out, residual=sk, stats=True)  # x + h
+            coef2 = None
+            self._apply(h2, h2, st2, w_["gn2"], w_["emb_offset"], True, 0)  # the same, in place
+        if skip_fused:
+            self._conv_skip(h2, xr, w_["conv2"], out, in_coef=coef2)  # skip_connection(x) + h, the 1x1 folded into the GEMM's K
+        else:
+            self._conv(h2, w_["conv2"], out, residual=sk, stats=True, in_coef=coef2)  # x + h
         arena.give(h2)
         if sk is not xr:
             arena.give(sk)
@@ -439,10 +483,8 @@ class Plan:
             rc = fn(*args, s)
             if rc:
                 chk(rc, fn.__name__)
-        oc = pk.out_conv
-        chk(lib.azb_conv_gemm_bf16(self.final.data_ptr(), n, h, w, oc.c_in, ops._ld(self.final), oc.w.data_ptr(),
-                                   oc.c_out, oc.c_out_rows, oc.taps, oc.k_per_tap, _lib.ptr(oc.bias), None, 0,
-                                   out.data_ptr(), 0, 1, s), "azb_conv_gemm_bf16")
+        d = ops.conv_desc(self.final, pk.out_conv, out, nchw_f32=True, in_coef=self.out_coef, in_silu=True)
+        chk(lib.azb_conv_bf16(byref(d), s), "azb_conv_bf16")
         return out
 
 

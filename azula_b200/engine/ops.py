@@ -31,11 +31,25 @@ class AzbConv(ctypes.Structure):
         ("residual", c_void_p), ("res_ld", c_int64), ("out", c_void_p), ("out_ld", c_int64), ("colsum", c_void_p),
         ("act2", c_void_p), ("c_in2", c_int64), ("act2_ld", c_int64), ("k2", c_int64), ("gn_acc", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("in_coef", c_void_p), ("in_silu", c_int64),
     ]
+
+
+class AzbConvChoice(ctypes.Structure):
+    r"""``AzbConvChoice`` of ``include/azb.h``: what the convolution launcher would do for a descriptor."""
+
+    _fields_ = [("halo", c_int32), ("pair", c_int32), ("lean", c_int32), ("block_n", c_int32), ("splits", c_int32),
+                ("tiles", c_int32)]
 
 
 _lib.register({
     "azb_conv_bf16": (c_int, [POINTER(AzbConv), c_void_p]),
+    "azb_conv_choice": (c_int, [POINTER(AzbConv), POINTER(AzbConvChoice)]),
+    "azb_gn_coef_f32": (
+        c_int,
+        [c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_float, c_void_p,
+         c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p],
+    ),
     "azb_conv_tuning": (c_int, [c_int, c_int]),
     "azb_zero_bytes": (c_int, [c_void_p, c_int64, c_void_p]),
     "azb_gn_apply_acc_bf16": (
@@ -544,10 +558,11 @@ def linear_gather(x: Tensor, xoff: Tensor | None, weight: Tensor, bias: Tensor |
 def conv_desc(x: Tensor, pc, out: Tensor, *, grid: tuple[int, int, int] | None = None, stride: int = 1, act: int = 0,
               gate: int | None = None, gate_ld: int = 0, gate_rows: int = 0, residual: Tensor | None = None,
               nchw_f32: bool = False, x2: Tensor | None = None, gn_acc: Tensor | None = None, gran: int = 8,
-              workspace: Tensor | None = None) -> AzbConv:
+              workspace: Tensor | None = None, in_coef: Tensor | None = None, in_silu: bool = False) -> AzbConv:
     r"""Fills an :class:`AzbConv` for ``azb_conv_bf16``; ``pc`` is a :class:`PackedConv` or, with ``x2``, a
     :class:`PackedConvSkip``.  ``gn_acc``: int64 (N, C_out / gran, 4) exact GroupNorm accumulators (zeroed by the
-    caller)."""
+    caller).  ``in_coef``: fp32 (N, C_in, 2) from :func:`gn_coef` -- the convolution then reads
+    ``act(a x + b)`` instead of ``x`` (only where :func:`conv_choice` reports ``halo``)."""
     n, h, w = grid if grid is not None else x.shape[:3]
     d = AzbConv()
     d.act, d.n, d.h, d.w, d.c_in, d.act_ld = x.data_ptr(), n, h, w, pc.c_in, x.stride(-2)
@@ -564,22 +579,56 @@ def conv_desc(x: Tensor, pc, out: Tensor, *, grid: tuple[int, int, int] | None =
         d.gn_acc = gn_acc.data_ptr()
     if workspace is not None:  # zero-initialised uint8 scratch for split-K (flags stay zero between launches)
         d.workspace, d.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    if in_coef is not None:
+        assert in_coef.dtype == torch.float32 and in_coef.is_contiguous() and in_coef.numel() == n * pc.c_in * 2
+        d.in_coef, d.in_silu = in_coef.data_ptr(), int(in_silu)
     return d
 
 
+def conv_choice(d: AzbConv) -> AzbConvChoice:
+    r"""``azb_conv_choice``: the launcher's decision for a descriptor (halo tiles, CTA pairs, N tile, split-K)."""
+    c = AzbConvChoice()
+    _lib.check(_lib.lib().azb_conv_choice(byref(d), byref(c)), "azb_conv_choice")
+    return c
+
+
+def gn_coef(n: int, h: int, w: int, parts: list[tuple[Tensor, int]], gamma: Tensor, beta: Tensor,
+            scale_shift: Tensor | None = None, silu: bool = True, gran: int = 8, groups: int = GN_GROUPS,
+            eps: float = GN_EPS, out: Tensor | None = None) -> Tensor:
+    r"""``azb_gn_coef_f32``: fp32 (N, C, 2) coefficients {A, B} of the GroupNorm (+ scale / shift, + SiLU) transform
+    of an (N, H, W, C) tensor whose producers accumulated ``parts`` = [(acc, channels), ...]."""
+    (a, ca), (b, cb) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
+    c = ca + cb
+    if out is None:
+        out = torch.empty(n, c, 2, dtype=torch.float32, device=a.device)
+    ss_stride = 0
+    if scale_shift is not None and scale_shift.ndim == 2 and scale_shift.shape[0] == n and n > 1:
+        ss_stride = scale_shift.stride(0)
+    _lib.check(
+        _lib.lib().azb_gn_coef_f32(n, h, w, c, groups, a.data_ptr(), ca, _lib.ptr(b), cb, gran, eps, gamma.data_ptr(),
+                                   beta.data_ptr(), _lib.ptr(scale_shift), ss_stride, int(silu), out.data_ptr(),
+                                   _lib.stream_ptr(a.device)),
+        "azb_gn_coef_f32",
+    )
+    return out
+
+
 def conv_acc(x: Tensor, pc, out: Tensor | None = None, residual: Tensor | None = None, x2: Tensor | None = None,
-             gran: int = 8, workspace: Tensor | None = None) -> tuple[Tensor, Tensor]:
+             gran: int = 8, workspace: Tensor | None = None, in_coef: Tensor | None = None,
+             in_silu: bool = False) -> tuple[Tensor, Tensor]:
     r"""Convolution that also returns the exact GroupNorm accumulators of its output: (out, int64 (N, C_out / gran, 4))."""
     n, h, w, _ = x.shape
     if out is None:
         out = torch.empty(n, h, w, pc.c_out, dtype=torch.bfloat16, device=x.device)
     acc = torch.zeros(n, pc.c_out // gran, 4, dtype=torch.int64, device=x.device)
-    d = conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=gran, workspace=workspace)
+    d = conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=gran, workspace=workspace, in_coef=in_coef,
+                  in_silu=in_silu)
     _lib.check(_lib.lib().azb_conv_bf16(byref(d), _lib.stream_ptr(x.device)), "azb_conv_bf16")
     return out, acc
 
 
-KNOB_PAIR, KNOB_PREFETCH, KNOB_SPLITK, KNOB_GN_WAVE, KNOB_BLOCKN, KNOB_LEAN = 0, 1, 2, 3, 4, 5
+KNOB_PAIR, KNOB_PREFETCH, KNOB_SPLITK, KNOB_GN_WAVE, KNOB_BLOCKN, KNOB_LEAN, KNOB_HALO = 0, 1, 2, 3, 4, 5, 6
+KNOB_HALO_SA, KNOB_HALO_SB, KNOB_HALO_AHEAD = 7, 8, 9
 
 
 def conv_tuning(knob: int, value: int) -> None:

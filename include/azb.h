@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define AZB_VERSION 1
+#define AZB_VERSION 2
 
 enum {
     AZB_OK = 0,
@@ -204,9 +204,22 @@ typedef struct AzbConv {
     int64_t* gn_acc;
     void* workspace;          /* optional split-K scratch, 256-byte aligned, ZERO-initialised once by the caller (the */
     int64_t workspace_bytes;  /* kernel leaves its flags zeroed); 16 MiB covers every shape.  NULL = never split K    */
+    /* Fused input transform (3 x 3, stride 1, feature maps >= 16 x 8, c_in % 64 == 0; AZB_E_UNSUPPORTED otherwise --
+     * ask azb_conv_choice first): the convolution reads  bf16(act(a[n][c] * x + b[n][c]))  instead of x, i.e. the
+     * GroupNorm (+ scale / shift) + SiLU that precedes it in the reference (_src/unet.py:177-181,203-207,238-243)
+     * without a normalisation pass over HBM.  in_coef: fp32 [n][c_in][2] from azb_gn_coef_f32; in_silu as given there. */
+    const float* in_coef;
+    int64_t in_silu;
 } AzbConv;
 
 int azb_conv_bf16(const AzbConv* desc, void* stream);
+
+/* What the launcher would do for `desc` (nothing is launched, no pointer is dereferenced): halo = 1 when the 3 x 3
+ * operand is staged as halo tiles (the condition for in_coef), pair / lean / block_n / splits as described above. */
+typedef struct AzbConvChoice {
+    int32_t halo, pair, lean, block_n, splits, tiles;
+} AzbConvChoice;
+int azb_conv_choice(const AzbConv* desc, AzbConvChoice* choice);
 
 /* Tuning hooks of the launchers (process-wide, not thread-safe; meant for A/B measurements).
  * value -1 restores the automatic choice.
@@ -217,14 +230,19 @@ int azb_conv_bf16(const AzbConv* desc, void* stream);
  *   AZB_GN_KNOB_WAVE        GroupNorm apply: resident CTAs per SM of the single-wave grid (0 = short CTAs of 16
  *                           vectors per thread, the pre-wave policy)
  *   AZB_CONV_KNOB_BLOCKN    force the N tile (16 .. 256; ignored unless it divides the padded C_out)
- *   AZB_CONV_KNOB_LEAN      0: always the generic epilogue (all switches at run time) */
+ *   AZB_CONV_KNOB_LEAN      0: always the generic epilogue (all switches at run time)
+ *   AZB_CONV_KNOB_HALO      0: never stage 3 x 3 operands as halo tiles (tap-wise TMA loads instead) */
 #define AZB_CONV_KNOB_PAIR 0
 #define AZB_CONV_KNOB_PREFETCH 1
 #define AZB_CONV_KNOB_SPLITK 2
 #define AZB_GN_KNOB_WAVE 3
 #define AZB_CONV_KNOB_BLOCKN 4
 #define AZB_CONV_KNOB_LEAN 5
-#define AZB_CONV_KNOBS 6
+#define AZB_CONV_KNOB_HALO 6
+#define AZB_CONV_KNOB_HALO_SA 7    /* halo kernels: A slots (2 .. 4; the rest of the ring holds weight stages) */
+#define AZB_CONV_KNOB_HALO_SB 8    /* halo kernels: cap on the weight stages */
+#define AZB_CONV_KNOB_HALO_AHEAD 9 /* halo kernels: 1 = load A items into every free slot as early as possible */
+#define AZB_CONV_KNOBS 10
 int azb_conv_tuning(int knob, int value);
 
 /* Rows of the colsum buffer for an (n, h, w) activation; *slab_in_image = 1 when every 32-row slab
@@ -271,6 +289,14 @@ int azb_gn_apply_acc_bf16(const void* x, int64_t x_ld, void* y, int64_t y_ld, in
                           int64_t c, int64_t groups, const int64_t* acc_a, int64_t c_a, const int64_t* acc_b,
                           int64_t c_b, int64_t gran, float eps, const float* gamma, const float* beta,
                           const float* scale_shift, int64_t ss_stride, int silu, int mode, void* stream);
+
+/* The per-(image, channel) coefficients {A, B} of azb_gn_apply_acc_bf16's transform y = act(A x + B), written to
+ * coef fp32 [n][c][2] for a convolution that applies it to its input on the fly (AzbConv::in_coef): GroupNorm +
+ * scale / shift + SiLU cost one launch over n * c values instead of a pass over the activation.  With silu the
+ * pair is halved (SiLU(2h) = h + h tanh(h)); pass the same flag as AzbConv::in_silu. */
+int azb_gn_coef_f32(int64_t n, int64_t h, int64_t w, int64_t c, int64_t groups, const int64_t* acc_a, int64_t c_a,
+                    const int64_t* acc_b, int64_t c_b, int64_t gran, float eps, const float* gamma, const float* beta,
+                    const float* scale_shift, int64_t ss_stride, int silu, float* coef, void* stream);
 
 /*
  * softmax(q k^T / sqrt(d)) v per (image, head) without materialising the T x T logits

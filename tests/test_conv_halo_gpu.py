@@ -1,0 +1,200 @@
+"""GPU parity of the halo-tile convolution kernels and of the GroupNorm + SiLU transform fused into their A path.
+
+Checkers: (1) torch fp32 convolution (TF32 off) of the same bf16 operands, 2^-8 of the output scale;
+(2) the tap-wise kernel (AZB_CONV_KNOB_HALO = 0): same products, different fp32 summation order;
+(3) for the fused transform: azb_gn_apply_acc_bf16 followed by the same halo kernel -- the transform warps use the
+same coefficients and the same arithmetic as the stand-alone pass, so the two must agree BIT FOR BIT.
+"""
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ctypes import byref
+
+from azula_b200 import _lib
+from azula_b200.engine import ops
+
+from test_conv_gpu import _acc_to_sums, _check, _mk, _ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _exact_reference():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    for knob in (ops.KNOB_HALO, ops.KNOB_PAIR, ops.KNOB_BLOCKN):
+        ops.conv_tuning(knob, -1)
+
+
+def _wide_tiles(co):
+    """Small test problems would get narrow N tiles (to fill the SMs); the halo kernels exist for N >= 128."""
+    ops.conv_tuning(ops.KNOB_BLOCKN, 256 if co % 256 == 0 else 128)
+
+
+def _choice(x, pc, out, **kw):
+    return ops.conv_choice(ops.conv_desc(x, pc, out, **kw))
+
+
+HALO_SHAPES = [
+    # n, h, w, c_in, c_out: 3 x 3, stride 1
+    (2, 16, 16, 64, 128),     # 2 x 2 tiles per image, one channel block
+    (1, 32, 32, 128, 256),    # N = 256
+    (2, 32, 32, 256, 256),    # 4 channel blocks: the A ring wraps
+    (1, 64, 64, 320, 512),    # two N tiles, 5 channel blocks
+    (3, 16, 8, 64, 128),      # ONE tile per image (odd tile count: single-CTA kernel)
+    (1, 20, 24, 192, 128),    # extents that are no multiples of the patch: partial tiles
+    (3, 48, 40, 192, 256),
+    (1, 128, 128, 256, 256),
+    (1, 16, 16, 768, 512),
+]
+
+
+@pytest.mark.parametrize("shape", HALO_SHAPES)
+@pytest.mark.parametrize("pair", [0, 1])
+def test_halo_conv_matches_torch_and_tapwise(shape, pair):
+    n, h, w, ci, co = shape
+    x, wt, b = _mk(n, h, w, ci, co, 3, seed=11)
+    res = torch.randn(n, h, w, co, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3)).to(torch.bfloat16)
+    pc = ops.pack_conv(wt.float(), b)
+    ops.conv_tuning(ops.KNOB_PAIR, pair)
+    _wide_tiles(co)
+    out = torch.empty(n, h, w, co, dtype=torch.bfloat16, device=DEV)
+    ch = _choice(x, pc, out, residual=res)
+    assert ch.halo == 1, (shape, ch.halo, ch.block_n)
+    got, acc = ops.conv_acc(x, pc, residual=res)
+    ops.conv_tuning(ops.KNOB_HALO, 0)
+    assert _choice(x, pc, out, residual=res).halo == 0
+    tap, acc_t = ops.conv_acc(x, pc, residual=res)
+    torch.cuda.synchronize()
+    ref = _ref(x, wt, b, res)
+    _check(got, ref, ("halo", shape, pair))
+    _check(tap, ref, ("tap-wise", shape))
+    # same products, another summation order: differences are single bf16 roundings of nearly tied values
+    d = (got.float() - tap.float()).abs()
+    assert (d > 0).float().mean().item() < 0.02 and d.max().item() <= 2.0**-7 * ref.abs().max().item()
+    assert torch.allclose(_acc_to_sums(acc), _acc_to_sums(acc_t), rtol=1e-3, atol=0.5)
+    # statistics are those of the stored values, and reproducible
+    o = got.double().reshape(n, h * w, co // 8, 8)
+    want = torch.stack((o.sum(dim=(1, 3)), o.square().sum(dim=(1, 3))), dim=-1)
+    assert torch.allclose(_acc_to_sums(acc), want, rtol=1e-5, atol=1e-3)
+    ops.conv_tuning(ops.KNOB_HALO, -1)
+    got2, acc2 = ops.conv_acc(x, pc, residual=res)
+    assert torch.equal(got, got2) and torch.equal(acc, acc2)
+
+
+def _normalised_input(n, h, w, c, split=None, seed=0):
+    """A tensor with exact GroupNorm accumulators (as a producing convolution leaves them) + affine + scale/shift."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    parts, outs = [], []
+    for cc in ([c] if split is None else [split, c - split]):
+        x, wt, b = _mk(n, h, w, 64, cc, 3, seed=seed + cc)
+        out, acc = ops.conv_acc(x, ops.pack_conv(wt.float() * 3, b))
+        parts.append((acc, cc)), outs.append(out)
+    t = torch.cat(outs, dim=-1).contiguous()
+    gamma, beta = 1 + 0.1 * torch.randn(c, device=DEV, generator=g), 0.1 * torch.randn(c, device=DEV, generator=g)
+    ss = 0.2 * torch.randn(n, 2 * c, device=DEV, generator=g)
+    return t, parts, gamma, beta, ss
+
+
+FUSED_SHAPES = [
+    # n, h, w, c_in, c_out, split of the input into two producers, scale/shift, silu
+    # (32 groups with one accumulator entry per 8 channels: C_in is a multiple of 256)
+    (2, 16, 16, 256, 128, None, False, True),
+    (2, 32, 32, 256, 256, None, True, True),
+    (3, 16, 8, 256, 128, None, True, True),      # one tile per image, single-CTA kernel
+    (1, 64, 64, 768, 256, 512, False, True),     # decoder concatenation: group 21 straddles the two producers
+    (2, 20, 24, 512, 128, None, True, False),    # partial tiles, no activation (attention-style norm)
+    (1, 128, 128, 256, 256, None, True, True),
+]
+
+
+@pytest.mark.parametrize("shape", FUSED_SHAPES)
+@pytest.mark.parametrize("pair", [0, 1])
+def test_fused_groupnorm_silu_conv_is_bit_exact_with_two_passes(shape, pair):
+    n, h, w, ci, co, split, use_ss, silu = shape
+    t, parts, gamma, beta, ss = _normalised_input(n, h, w, ci, split, seed=17)
+    ss = ss if use_ss else None
+    _, wt, b = _mk(n, h, w, ci, co, 3, seed=23)
+    pc = ops.pack_conv(wt.float(), b)
+    ops.conv_tuning(ops.KNOB_PAIR, pair)
+    _wide_tiles(co)
+    # two passes: normalise to HBM, then convolve
+    y = ops.gn_apply_acc(t, parts, gamma, beta, scale_shift=ss, silu=silu)
+    two, acc_two = ops.conv_acc(y, pc)
+    # fused: coefficients (N x C values), then ONE convolution that reads the raw tensor
+    coef = ops.gn_coef(n, h, w, parts, gamma, beta, scale_shift=ss, silu=silu)
+    one, acc_one = ops.conv_acc(t, pc, in_coef=coef, in_silu=silu)
+    torch.cuda.synchronize()
+    assert torch.equal(one, two), (one.float() - two.float()).abs().max().item()
+    assert torch.equal(acc_one, acc_two)
+    # and against torch: group_norm -> modulation -> SiLU -> (bf16) -> conv
+    ref = F.group_norm(t.float().permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5)
+    if ss is not None:
+        ref = ref * (1 + ss[:, :ci, None, None]) + ss[:, ci:, None, None]
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    _check(y, ref, "normalised input")
+    _check(one, _ref(y, wt, b), ("fused conv", shape))
+
+
+def test_fused_transform_with_skip_operand_and_residual():
+    """The ResBlock tail at an ADM decoder shape: conv3x3(SiLU(GN(h) (1 + scale) + shift)) + conv1x1(x) as one GEMM
+    (K = [9 taps | skip]); the 1 x 1 operand passes the transform warps untouched."""
+    n, h, w, ci, co, skip = 2, 32, 32, 256, 256, 512
+    t, parts, gamma, beta, ss = _normalised_input(n, h, w, ci, None, seed=29)
+    _, wt, b = _mk(n, h, w, ci, co, 3, seed=31)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x2 = torch.randn(n, h, w, skip, device=DEV, generator=g).to(torch.bfloat16)
+    w2 = (torch.randn(co, skip, 1, 1, device=DEV, generator=g) / skip**0.5).to(torch.bfloat16)
+    b2 = torch.randn(co, device=DEV, generator=g)
+    pc = ops.pack_conv_skip(ops.pack_conv(wt.float(), b), ops.pack_conv(w2.float(), b2))
+    y = ops.gn_apply_acc(t, parts, gamma, beta, scale_shift=ss)
+    coef = ops.gn_coef(n, h, w, parts, gamma, beta, scale_shift=ss)
+    _wide_tiles(co)
+    for pair in (1, 0):
+        ops.conv_tuning(ops.KNOB_PAIR, pair)
+        two, acc_two = ops.conv_acc(y, pc, x2=x2)
+        one, acc_one = ops.conv_acc(t, pc, x2=x2, in_coef=coef, in_silu=True)
+        assert torch.equal(one, two) and torch.equal(acc_one, acc_two)
+        _check(one, _ref(y, wt, b) + _ref(x2, w2, b2), ("fused conv + skip", pair))
+
+
+def test_fused_transform_into_network_output():
+    """The head of the network (out.0 GroupNorm + SiLU, out.2 conv to 6 channels, fp32 NCHW, _src/unet.py:599-602)."""
+    n, h, w, ci, co = 2, 32, 32, 256, 6
+    t, parts, gamma, beta, _ = _normalised_input(n, h, w, ci, None, seed=37)
+    _, wt, b = _mk(n, h, w, ci, co, 3, seed=41)
+    pc = ops.pack_conv(wt.float(), b)
+    y = ops.gn_apply_acc(t, parts, gamma, beta)
+    coef = ops.gn_coef(n, h, w, parts, gamma, beta)
+    out2 = torch.empty(n, co, h, w, device=DEV)
+    out1 = torch.empty(n, co, h, w, device=DEV)
+    s = _lib.stream_ptr(t.device)
+    d2 = ops.conv_desc(y, pc, out2, nchw_f32=True)
+    d1 = ops.conv_desc(t, pc, out1, nchw_f32=True, in_coef=coef, in_silu=True)
+    assert ops.conv_choice(d1).halo == 1 and ops.conv_choice(d1).block_n == 16
+    _lib.check(_lib.lib().azb_conv_bf16(byref(d2), s), "azb_conv_bf16")
+    _lib.check(_lib.lib().azb_conv_bf16(byref(d1), s), "azb_conv_bf16")
+    torch.cuda.synchronize()
+    assert torch.equal(out1, out2)
+    ref = _ref(y, wt, b).permute(0, 3, 1, 2)
+    assert torch.allclose(out1, ref, rtol=1e-3, atol=1e-3 * ref.abs().mean().item())
+
+
+def test_fused_transform_refused_where_no_halo_kernel_exists():
+    """8 x 8 maps (and 1 x 1 / strided layers) keep the tap-wise kernel: in_coef must be rejected, not ignored."""
+    n, h, w, ci, co = 2, 8, 8, 256, 128
+    t, parts, gamma, beta, _ = _normalised_input(n, h, w, ci, None, seed=43)
+    _, wt, b = _mk(n, h, w, ci, co, 3, seed=47)
+    pc = ops.pack_conv(wt.float(), b)
+    coef = ops.gn_coef(n, h, w, parts, gamma, beta)
+    out = torch.empty(n, h, w, co, dtype=torch.bfloat16, device=DEV)
+    d = ops.conv_desc(t, pc, out, in_coef=coef, in_silu=True)
+    assert _lib.lib().azb_conv_bf16(byref(d), _lib.stream_ptr(t.device)) == -6  # AZB_E_UNSUPPORTED
+    d0 = ops.conv_desc(t, pc, out)
+    assert ops.conv_choice(d0).halo == 0
