@@ -92,7 +92,7 @@ struct ConvParams {
     int in_silu;              // the transform ends in SiLU (coefficients are halved, see azb_gn_coef_f32)
     int c_in;                 // row length of in_coef
     int sa, sb;               // halo kernels: A slots and weight stages in the shared-memory budget
-    int a_ahead;              // halo kernels: 1 = load A items into every free slot as early as possible
+    int a_ahead;              // halo kernels: A items are loaded this many items ahead of the weight stream (<= sa - 2)
 };
 
 // Adds v * 2^40 to a 96-bit fixed-point accumulator held as two int64 words (value = hi * 2^32 + lo, 0 <= lo < 2^32):
@@ -272,10 +272,9 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
             uint32_t pb = 1, pa = 1;  // parities of the `empty` barriers: the first pass finds every slot free
             int ai = 0, a_local = 0, a_it = 0;  // next A item to issue
             const uint32_t full_b0 = PAIR ? tc::mapa(tc::smem_u32(&bar_full[0]), 0) : tc::smem_u32(&bar_full[0]);
-            // Issues the load of A item `ai` into its slot; `must` = the weight stream is about to need it (block until
-            // the slot is free), otherwise only if the slot is free right now.  Returns false when nothing was issued.
-            auto issue_a = [&](bool must) -> bool {
-                if (!must && !tc::mbar_test(tc::smem_u32(&bar_a_empty[sa]), pa)) return false;
+            // Issues the load of A item `ai` into its slot (never blocks in steady state: with a_ahead <= sa - 2 the
+            // slot was released before the weight stream of the previous item began)
+            auto issue_a = [&]() {
                 const int a_tile = unit_to_tile(tile_first + a_local * tile_step);
                 int n_tile, w0, h0, n0;
                 tile_coords(p, a_tile, n_tile, w0, h0, n0);
@@ -292,24 +291,21 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                 if (++a_it == items) a_it = 0, ++a_local;
                 ++ai;
                 if (++sa == SA) sa = 0, pa ^= 1u;
-                return true;
             };
             int bi = 0;
             for (int local = 0; local < tile_count; ++local) {
                 const int tile = unit_to_tile(tile_first + local * tile_step);
                 const int b_row0 = (tile % p.n_tiles) * BLOCK_N + (int)cta_rank * C::B_ROWS;
                 for (int it = 0; it < items; ++it, ++bi) {
-                    while (ai < total_items && ai <= bi + (p.a_ahead ? 0 : 1)) issue_a(true);
+                    // A items run a_ahead items ahead of the weight stream: the transform warps need a landed tile
+                    // (TMA latency) plus their own pass before the MMA reaches it
+                    while (ai < total_items && ai <= bi + p.a_ahead) issue_a();
                     const bool halo = it < p.kb_per_tap;
                     const int nb = halo ? 9 : 1;
                     // weights are packed [tap][channel block]: tap t of channel block `it` is k-block t * kb_per_tap + it
                     int kbx = halo ? it : num_kb_taps + (it - p.kb_per_tap);
                     for (int t = 0; t < nb; ++t, kbx += p.kb_per_tap) {
                         // keep every free A slot loading: the transform warps need a landed tile well before the MMA does
-                        if (p.a_ahead) {
-                            while (ai < total_items && issue_a(false)) {
-                            }
-                        }
                         tc::mbar_wait(tc::smem_u32(&bar_empty[sb]), pb);
                         const uint32_t b_dst = b_ring + sb * C::STAGE_BYTES;
                         const uint32_t full = full_b0 + 8u * (uint32_t)sb;
@@ -399,24 +395,46 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                 }
                 tc::mbar_wait(tc::smem_u32(&bar_a_full[sa]), pa);
                 if (xf) {
-                    const uint32_t slot = smem_base + sa * C::A_SLOT;
-#pragma unroll 4
-                    for (int i = rg; i < HALO_ROWS; i += 4 * XF_WARPS) {
-                        const int y = i / HALO_PITCH, x = i - y * HALO_PITCH;
-                        // out-of-image pixels stay at the zero the TMA unit wrote: the convolution pads the NORMALISED tensor
-                        if ((unsigned)(h0 - 1 + y) >= (unsigned)p.H || (unsigned)(w0 - 1 + x) >= (unsigned)p.W) continue;
-                        const uint32_t addr = slot + (uint32_t)i * 128u + ((uint32_t)(chunk ^ (i & 7)) << 4);
-                        uint32_t v[4];
-                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory");
+                    // rows i = rg + 16 k, k = 0 .. 11 (i & 7 == rg & 7: the chunk sits at the same swizzled position in
+                    // each of them).  One warp per scheduler does this work, so instruction-level parallelism has to hide
+                    // the shared-memory and SFU latencies: branch-free groups of four rows, all loads first.
+                    const uint32_t base = smem_base + sa * C::A_SLOT + (uint32_t)rg * 128u + ((uint32_t)(chunk ^ (rg & 7)) << 4);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float f0 = fmaf(a[2 * j], bf16_bits_to_f32(v[j] & 0xffffu), b[2 * j]);
-                            float f1 = fmaf(a[2 * j + 1], __uint_as_float(v[j] & 0xffff0000u), b[2 * j + 1]);
-                            if (p.in_silu) f0 = fmaf(f0, tanh_approx(f0), f0), f1 = fmaf(f1, tanh_approx(f1), f1);
-                            __nv_bfloat162 r = __floats2bfloat162_rn(f0, f1);
-                            v[j] = *reinterpret_cast<uint32_t*>(&r);
+                    for (int k0 = 0; k0 < 12; k0 += 4) {
+                        uint32_t v[4][4];
+                        bool inside[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = rg + 16 * (k0 + u);
+                            const int y = i / HALO_PITCH, x = i - y * HALO_PITCH;
+                            // out-of-image pixels stay at the zero the TMA unit wrote: the convolution pads the NORMALISED tensor
+                            inside[u] = (unsigned)(h0 - 1 + y) < (unsigned)p.H && (unsigned)(w0 - 1 + x) < (unsigned)p.W;
+                            if (k0 + u < 11 || i < HALO_ROWS)
+                                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                                             : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3])
+                                             : "r"(base + (uint32_t)(k0 + u) * 2048u)
+                                             : "memory");
+                            else v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0u;
                         }
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float f0 = fmaf(a[2 * j], bf16_bits_to_f32(v[u][j] & 0xffffu), b[2 * j]);
+                                float f1 = fmaf(a[2 * j + 1], __uint_as_float(v[u][j] & 0xffff0000u), b[2 * j + 1]);
+                                if (p.in_silu) f0 = fmaf(f0, tanh_approx(f0), f0), f1 = fmaf(f1, tanh_approx(f1), f1);
+                                __nv_bfloat162 r = __floats2bfloat162_rn(f0, f1);
+                                v[u][j] = inside[u] ? *reinterpret_cast<uint32_t*>(&r) : 0u;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = rg + 16 * (k0 + u);
+                            if (k0 + u < 11 || i < HALO_ROWS)
+                                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + (uint32_t)(k0 + u) * 2048u),
+                                             "r"(v[u][0]), "r"(v[u][1]), "r"(v[u][2]), "r"(v[u][3])
+                                             : "memory");
+                        }
                     }
                     tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's (async proxy) reads
                 }
@@ -961,7 +979,11 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     const int64_t h = (h_in + ex.stride - 1) / ex.stride, w = (w_in + ex.stride - 1) / ex.stride;
 
     // Halo tiles: 3 x 3, stride 1, maps of at least one 8 x 16 patch, whole 64-channel blocks (see the kernel's header)
-    bool halo = g_knob[AZB_CONV_KNOB_HALO] != 0 && taps == 9 && ex.stride == 1 && h >= HALO_H && w >= HALO_W &&
+    // (With a fused 1 x 1 operand the halo kernels are available -- in_coef or AZB_CONV_KNOB_HALO = 1 selects them -- but
+    // not the default: its one-k-block A items get only a_ahead items = 1 - 2 k-blocks of load lead, and the tap-wise
+    // kernel is 20 - 25 % faster on those layers, scripts/halo_ab.py.)
+    bool halo = g_knob[AZB_CONV_KNOB_HALO] != 0 && (!ex.act2 || ex.in_coef || g_knob[AZB_CONV_KNOB_HALO] == 1) && taps == 9 &&
+                ex.stride == 1 && h >= HALO_H && w >= HALO_W &&
                 c_in % BLOCK_K == 0 && k_per_tap == c_in && (!ex.act2 || (ex.c_in2 % BLOCK_K == 0 && ex.k2 == ex.c_in2)) &&
                 !colsum && ex.act == AZB_ACT_NONE && !ex.gate && (!ex.gn_acc || stat_gran == 8);
     if (ex.in_coef && !azb_aligned(ex.in_coef, 16)) return AZB_E_ALIGN;
@@ -1055,7 +1077,8 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     p.prefetch_kb = halo ? 0 : g_knob[AZB_CONV_KNOB_PREFETCH] >= 0 ? g_knob[AZB_CONV_KNOB_PREFETCH] : (m_tiles <= 32 ? 24 : 0);
     p.in_coef = reinterpret_cast<const float2*>(ex.in_coef), p.in_silu = ex.in_silu, p.c_in = (int)c_in;
     p.sa = g_knob[AZB_CONV_KNOB_HALO_SA] >= 2 && g_knob[AZB_CONV_KNOB_HALO_SA] <= 4 ? g_knob[AZB_CONV_KNOB_HALO_SA] : 3;
-    p.a_ahead = g_knob[AZB_CONV_KNOB_HALO_AHEAD] >= 0 ? g_knob[AZB_CONV_KNOB_HALO_AHEAD] : 0;
+    p.a_ahead = g_knob[AZB_CONV_KNOB_HALO_AHEAD] >= 0 ? g_knob[AZB_CONV_KNOB_HALO_AHEAD] : p.sa - 2;
+    if (p.a_ahead > p.sa - 1) p.a_ahead = p.sa - 1;
     p.chunked = (ex.gn_acc && p.n_tiles <= 2 && p.BN == 1 && stat_gran == 8 && block_n >= 64 && splits == 1) ? 1 : 0;
     const int64_t k_total = taps * k_per_tap + (ex.act2 ? ex.k2 : 0);
 

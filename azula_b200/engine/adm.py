@@ -35,6 +35,7 @@ from . import ops
 
 _MAX_PLANS = 2
 FUSE_NORM = True  # GroupNorm + SiLU ride on the halo tiles of the convolution that consumes them (A/B switch)
+FUSE_NORM_SKIP = False  # ... also when the ResBlock's 1x1 skip operand is part of the GEMM (slower today, scripts/halo_ab.py)
 
 
 class Packed:
@@ -271,7 +272,7 @@ class Plan:
                  nchw_f32: bool = False) -> bool:
         r"""Whether the GroupNorm (+ SiLU) in front of this convolution can ride on its halo tiles: statistics from
         exact accumulators and a halo kernel for the shape (``azb_conv_choice``)."""
-        if not FUSE_NORM or stats is None or stats[0] != "acc":
+        if not FUSE_NORM or stats is None or stats[0] != "acc" or (x2 is not None and not FUSE_NORM_SKIP):
             return False
         d = ops.conv_desc(x, pc, out, residual=residual, x2=x2, gran=self.stat_gran, nchw_f32=nchw_f32)
         return bool(ops.conv_choice(d).halo)

@@ -23,6 +23,10 @@ def main():
     ap.add_argument("--k", type=int, default=3)
     ap.add_argument("--pair", type=int, default=-1)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--halo", type=int, default=-1)
+    ap.add_argument("--fused", type=int, default=0, help="apply act(a x + b) to the halo tiles (in_coef)")
+    ap.add_argument("--sa", type=int, default=-1)
+    ap.add_argument("--ahead", type=int, default=-1)
     a = ap.parse_args()
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(0)
@@ -31,8 +35,14 @@ def main():
                        torch.randn(a.co, device=dev, generator=g))
     out = torch.empty(a.batch, a.hw, a.hw, a.co, dtype=torch.bfloat16, device=dev)
     ops.conv_tuning(ops.KNOB_PAIR, a.pair)
+    ops.conv_tuning(ops.KNOB_HALO, a.halo)
+    ops.conv_tuning(ops.KNOB_HALO_SA, a.sa)
+    ops.conv_tuning(ops.KNOB_HALO_AHEAD, a.ahead)
+    coef = None
+    if a.fused:
+        coef = torch.stack((torch.full((a.batch, a.ci), 0.5, device=dev), torch.zeros(a.batch, a.ci, device=dev)), dim=-1).contiguous()
     for _ in range(a.reps):
-        ops.conv_acc(x, pc, out=out)
+        ops.conv_acc(x, pc, out=out, in_coef=coef, in_silu=True)
     torch.cuda.synchronize()
     print("ok", float(out.float().abs().mean()))
 

@@ -33,23 +33,29 @@ SHAPES = [
 ]
 
 
-def timed(fn, reps):
-    for _ in range(3):
-        fn()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
-    ev[0].record()
-    for i in range(reps):
-        fn()
-        ev[i + 1].record()
-    torch.cuda.synchronize()
-    ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
-    return ts[len(ts) // 2]
+def timed_interleaved(variants, reps):
+    """variants: list of callables; one launch of each per round, round after round (robust against clock drift);
+    returns the median milliseconds of each."""
+    for fn in variants:
+        for _ in range(2):
+            fn()
+    times = [[] for _ in variants]
+    for _ in range(reps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(variants) + 1)]
+        ev[0].record()
+        for i, fn in enumerate(variants):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        for i in range(len(variants)):
+            times[i].append(ev[i].elapsed_time(ev[i + 1]))
+    return [sorted(t)[len(t) // 2] for t in times]
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=15)
-    ap.add_argument("--configs", default="3:0,4:0,4:1,2:0")
+    ap.add_argument("--configs", default="3:1,4:2,4:1,3:2")
     a = ap.parse_args()
     g = torch.Generator(device=DEV).manual_seed(0)
     configs = [tuple(int(v) for v in c.split(":")) for c in a.configs.split(",")]
@@ -67,17 +73,20 @@ def main():
         out = torch.empty(n, hw, hw, co, dtype=torch.bfloat16, device=DEV)
         coef = torch.stack((torch.full((n, ci), 0.5, device=DEV), torch.zeros(n, ci, device=DEV)), dim=-1).contiguous()
         flops = 2.0 * n * hw * hw * co * (9 * ci + skip)
-        run = lambda c=None: ops.conv_acc(x, pc, out=out, residual=r, x2=x2, in_coef=c, in_silu=True)  # noqa: E731
-        ops.conv_tuning(ops.KNOB_HALO, 0)
-        row = [flops / timed(run, a.reps) * 1e-9]
-        ops.conv_tuning(ops.KNOB_HALO, -1)
+        def variant(halo, sa, ahead, c):
+            def fn():
+                ops.conv_tuning(ops.KNOB_HALO, halo)
+                ops.conv_tuning(ops.KNOB_HALO_SA, sa)
+                ops.conv_tuning(ops.KNOB_HALO_AHEAD, ahead)
+                ops.conv_acc(x, pc, out=out, residual=r, x2=x2, in_coef=c, in_silu=True)
+            return fn
+
+        variants = [variant(0, -1, -1, None)]
         for sa, ahead in configs:
-            ops.conv_tuning(ops.KNOB_HALO_SA, sa)
-            ops.conv_tuning(ops.KNOB_HALO_AHEAD, ahead)
-            row.append(flops / timed(run, a.reps) * 1e-9)
-            row.append(flops / timed(lambda: run(coef), a.reps) * 1e-9)
-        ops.conv_tuning(ops.KNOB_HALO_SA, -1)
-        ops.conv_tuning(ops.KNOB_HALO_AHEAD, -1)
+            variants += [variant(-1, sa, ahead, None), variant(-1, sa, ahead, coef)]
+        row = [flops / t * 1e-9 for t in timed_interleaved(variants, a.reps)]
+        for k in (ops.KNOB_HALO, ops.KNOB_HALO_SA, ops.KNOB_HALO_AHEAD):
+            ops.conv_tuning(k, -1)
         name = f"{n}x{hw}x{hw} {ci}->{co}" + (f" +skip{skip}" if skip else "") + (" +res" if res else "")
         print(name.ljust(44) + f"{row[0]:9.0f}" + "".join(f"{v:14.0f}" for v in row[1:]))
         del x, x2, r, out
