@@ -51,7 +51,7 @@ constexpr int UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
 constexpr int XF_WARPS = 4;                          // halo kernels: warps that transform the A tiles in place
-constexpr int THREADS_HALO = THREADS + 32 * XF_WARPS;
+constexpr int THREADS_HALO = THREADS + 32 * XF_WARPS + 32;  // + the A producer warp
 constexpr int HALO_W = 8, HALO_H = 16;               // patch of one M tile (pixels)
 constexpr int HALO_PITCH = HALO_W + 2;               // pixels per halo row
 constexpr int HALO_ROWS = (HALO_H + 2) * HALO_PITCH; // 128-byte rows of one halo tile
@@ -92,7 +92,9 @@ struct ConvParams {
     int in_silu;              // the transform ends in SiLU (coefficients are halved, see azb_gn_coef_f32)
     int c_in;                 // row length of in_coef
     int sa, sb;               // halo kernels: A slots and weight stages in the shared-memory budget
-    int a_ahead;              // halo kernels: A items are loaded this many items ahead of the weight stream (<= sa - 2)
+    unsigned long long item_mask;  // halo kernels: bit i = item i of a tile is a halo item (else a 1 x 1 block): the blocks
+                                   // of the fused 1 x 1 operand are spread between the halo items, so that every halo item
+                                   // is preceded by >= 9 k-blocks of MMA time in which it can land and be transformed
 };
 
 // Adds v * 2^40 to a 96-bit fixed-point accumulator held as two int64 words (value = hi * 2^32 + lo, 0 <= lo < 2^32):
@@ -263,49 +265,39 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
     const uint32_t b_ring = smem_base + (uint32_t)(SA * C::A_SLOT);
 
     if (HALO && warp == 0) {
-        // ===== TMA producer (halo) =====
-        // Two rings: A slots (one halo tile per 64-channel block, issued one item AHEAD of the weight stream so that the
-        // transform warps have a full item -- nine k-blocks of MMA time -- for their pass) and weight tiles.
+        // ===== TMA producer (halo): the stage ring =====
+        // One stage per k-block of a halo item (its weight tile).  A k-block of the fused 1 x 1 operand takes TWO
+        // consecutive stages, the plain 128-pixel A tile and the weight tile -- the tap-wise kernel's scheme, so these
+        // blocks need no A slot, no pass through the transform warps and no extra handshake, and are requested a full
+        // ring ahead of the MMA like everything else in the ring.
         if (tc::elect_one()) {
-            const int total_items = tile_count * items;
-            int sb = 0, sa = 0;
-            uint32_t pb = 1, pa = 1;  // parities of the `empty` barriers: the first pass finds every slot free
-            int ai = 0, a_local = 0, a_it = 0;  // next A item to issue
+            int sb = 0;
+            uint32_t pb = 1;  // parity of the `empty` barriers: the first pass finds every slot free
             const uint32_t full_b0 = PAIR ? tc::mapa(tc::smem_u32(&bar_full[0]), 0) : tc::smem_u32(&bar_full[0]);
-            // Issues the load of A item `ai` into its slot (never blocks in steady state: with a_ahead <= sa - 2 the
-            // slot was released before the weight stream of the previous item began)
-            auto issue_a = [&]() {
-                const int a_tile = unit_to_tile(tile_first + a_local * tile_step);
-                int n_tile, w0, h0, n0;
-                tile_coords(p, a_tile, n_tile, w0, h0, n0);
-                tc::mbar_wait(tc::smem_u32(&bar_a_empty[sa]), pa);
-                const uint32_t dst = smem_base + sa * C::A_SLOT;
-                const uint32_t full = tc::smem_u32(&bar_a_full[sa]);
-                if (a_it < p.kb_per_tap) {
-                    tc::mbar_expect_tx(full, HALO_BYTES);
-                    tc::tma_load_4d(dst, &tmap_a, full, a_it * BLOCK_K, w0 - 1, h0 - 1, n0);
-                } else {
-                    tc::mbar_expect_tx(full, C::A_BYTES);
-                    tc::tma_load_4d(dst, &tmap_a2, full, (a_it - p.kb_per_tap) * BLOCK_K, w0, h0, n0);
-                }
-                if (++a_it == items) a_it = 0, ++a_local;
-                ++ai;
-                if (++sa == SA) sa = 0, pa ^= 1u;
-            };
-            int bi = 0;
             for (int local = 0; local < tile_count; ++local) {
                 const int tile = unit_to_tile(tile_first + local * tile_step);
-                const int b_row0 = (tile % p.n_tiles) * BLOCK_N + (int)cta_rank * C::B_ROWS;
-                for (int it = 0; it < items; ++it, ++bi) {
-                    // A items run a_ahead items ahead of the weight stream: the transform warps need a landed tile
-                    // (TMA latency) plus their own pass before the MMA reaches it
-                    while (ai < total_items && ai <= bi + p.a_ahead) issue_a();
-                    const bool halo = it < p.kb_per_tap;
+                int n_tile, w0, h0, n0;
+                tile_coords(p, tile, n_tile, w0, h0, n0);
+                const int b_row0 = n_tile * BLOCK_N + (int)cta_rank * C::B_ROWS;
+                for (int it = 0, hi = 0, pi = 0; it < items; ++it) {
+                    const bool halo = (p.item_mask >> it) & 1ull;
                     const int nb = halo ? 9 : 1;
-                    // weights are packed [tap][channel block]: tap t of channel block `it` is k-block t * kb_per_tap + it
-                    int kbx = halo ? it : num_kb_taps + (it - p.kb_per_tap);
+                    if (!halo) {
+                        tc::mbar_wait(tc::smem_u32(&bar_empty[sb]), pb);
+                        const uint32_t a_dst = b_ring + sb * C::STAGE_BYTES;
+                        const uint32_t full = full_b0 + 8u * (uint32_t)sb;
+                        if constexpr (PAIR) {
+                            if (leader) tc::mbar_expect_tx(tc::smem_u32(&bar_full[sb]), 2 * C::A_BYTES);
+                            tc::tma_load_4d_pair(a_dst, &tmap_a2, full, pi * BLOCK_K, w0, h0, n0);
+                        } else {
+                            tc::mbar_expect_tx(full, C::A_BYTES);
+                            tc::tma_load_4d(a_dst, &tmap_a2, full, pi * BLOCK_K, w0, h0, n0);
+                        }
+                        if (++sb == SB) sb = 0, pb ^= 1u;
+                    }
+                    // weights are packed [tap][channel block]: tap t of channel block hi is k-block t * kb_per_tap + hi
+                    int kbx = halo ? hi++ : num_kb_taps + pi++;
                     for (int t = 0; t < nb; ++t, kbx += p.kb_per_tap) {
-                        // keep every free A slot loading: the transform warps need a landed tile well before the MMA does
                         tc::mbar_wait(tc::smem_u32(&bar_empty[sb]), pb);
                         const uint32_t b_dst = b_ring + sb * C::STAGE_BYTES;
                         const uint32_t full = full_b0 + 8u * (uint32_t)sb;
@@ -321,54 +313,90 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                 }
             }
         }
+    } else if (HALO && warp == 2 + EPI_WARPS + XF_WARPS) {
+        // ===== TMA producer (halo): the halo tiles, a lane of its own =====
+        // Every free A slot is put to work at once, independently of the stage ring: a halo tile needs TMA latency plus
+        // the transform pass before the MMA reaches it.
+        if (tc::elect_one()) {
+            int sa = 0;
+            uint32_t pa = 1;
+            for (int local = 0; local < tile_count; ++local) {
+                const int tile = unit_to_tile(tile_first + local * tile_step);
+                int n_tile, w0, h0, n0;
+                tile_coords(p, tile, n_tile, w0, h0, n0);
+                for (int hi = 0; hi < p.kb_per_tap; ++hi) {
+                    tc::mbar_wait(tc::smem_u32(&bar_a_empty[sa]), pa);
+                    const uint32_t full = tc::smem_u32(&bar_a_full[sa]);
+                    tc::mbar_expect_tx(full, HALO_BYTES);
+                    tc::tma_load_4d(smem_base + sa * C::A_SLOT, &tmap_a, full, hi * BLOCK_K, w0 - 1, h0 - 1, n0);
+                    if (++sa == SA) sa = 0, pa ^= 1u;
+                }
+            }
+        }
     } else if (HALO && warp == 1) {
         // ===== MMA issuer (halo) =====
         if (leader && tc::elect_one()) {
             constexpr uint32_t idesc = tc::idesc_bf16_f32(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
             int sb = 0, sa = 0;
             uint32_t pb = 0, pa = 0;
+            auto mma4 = [&](uint64_t da, uint64_t db, uint32_t tmem_acc, bool first) {
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    // +32 bytes per K = 16 step inside the 128-byte swizzle row (address field is >> 4)
+                    if constexpr (PAIR)
+                        tc::mma_f16_ss_pair(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, !first || k != 0);
+                    else
+                        tc::mma_f16_ss(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, !first || k != 0);
+                }
+            };
+            auto release = [&](uint64_t* bar) {  // the barrier (of both CTAs of a pair) arrives when the MMAs so far retire
+                if constexpr (PAIR) tc::mma_commit_pair(tc::smem_u32(bar), 0b11);
+                else tc::mma_commit(tc::smem_u32(bar));
+            };
             for (int local = 0; local < tile_count; ++local) {
                 const int as = local & 1;
                 tc::mbar_wait(tc::smem_u32(&bar_acc_empty[as]), ((local >> 1) & 1) ^ 1);
                 tc::fence_after_sync();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(as * C::ACC_COLS);
                 for (int it = 0; it < items; ++it) {
-                    // the A slot has landed AND been transformed (by the transform warps of both CTAs of a pair)
-                    if constexpr (PAIR) tc::mbar_wait_cluster(tc::smem_u32(&bar_a_ready[sa]), pa);
-                    else tc::mbar_wait(tc::smem_u32(&bar_a_ready[sa]), pa);
-                    tc::fence_after_sync();
-                    const bool halo = it < p.kb_per_tap;
-                    const int nb = halo ? 9 : 1;
-                    const uint32_t sbo = halo ? HALO_PITCH * 128u : 1024u;
-                    uint32_t a_src = smem_base + sa * C::A_SLOT;  // tap (0, 0): the view that starts at halo pixel (0, 0)
-                    for (int t = 0, kw = 0; t < nb; ++t) {
+                    if ((p.item_mask >> it) & 1ull) {
+                        // the halo tile has landed AND been transformed (by the transform warps of both CTAs of a pair;
+                        // they arrive with release.cluster after fence.proxy.async, and what they wrote is read by each
+                        // CTA's own tensor core, never by this thread: the CTA-scope acquire of try_wait suffices)
+                        tc::mbar_wait(tc::smem_u32(&bar_a_ready[sa]), pa);
+                        tc::fence_after_sync();
+                        uint32_t a_src = smem_base + sa * C::A_SLOT;  // tap (0, 0): the view that starts at halo pixel (0, 0)
+                        for (int t = 0, kw = 0; t < 9; ++t) {
+                            tc::mbar_wait(tc::smem_u32(&bar_full[sb]), pb);
+                            tc::fence_after_sync();
+                            mma4(tc::smem_desc_sw128_sbo(a_src, HALO_PITCH * 128u), tc::smem_desc_sw128(b_ring + sb * C::STAGE_BYTES),
+                                 tmem_acc, (it | t) == 0);
+                            release(&bar_empty[sb]);
+                            if (++sb == SB) sb = 0, pb ^= 1u;
+                            // next tap: one pixel to the right, or back to column 0 of the next halo row
+                            if (++kw == 3) kw = 0, a_src += (HALO_PITCH - 2) * 128u;
+                            else a_src += 128u;
+                        }
+                        release(&bar_a_empty[sa]);
+                        if (++sa == SA) sa = 0, pa ^= 1u;
+                    } else {
+                        // a k-block of the fused 1 x 1 operand: plain A tile in this stage, its weights in the next
+                        const int s_a = sb;
+                        tc::mbar_wait(tc::smem_u32(&bar_full[sb]), pb);
+                        if (++sb == SB) sb = 0, pb ^= 1u;
                         tc::mbar_wait(tc::smem_u32(&bar_full[sb]), pb);
                         tc::fence_after_sync();
-                        const uint64_t da = tc::smem_desc_sw128_sbo(a_src, sbo);
-                        const uint64_t db = tc::smem_desc_sw128(b_ring + sb * C::STAGE_BYTES);
-#pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            if constexpr (PAIR)
-                                tc::mma_f16_ss_pair(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | t | k) != 0);
-                            else
-                                tc::mma_f16_ss(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it | t | k) != 0);
-                        }
-                        if constexpr (PAIR) tc::mma_commit_pair(tc::smem_u32(&bar_empty[sb]), 0b11);
-                        else tc::mma_commit(tc::smem_u32(&bar_empty[sb]));
+                        mma4(tc::smem_desc_sw128(b_ring + s_a * C::STAGE_BYTES), tc::smem_desc_sw128(b_ring + sb * C::STAGE_BYTES),
+                             tmem_acc, it == 0);
+                        release(&bar_empty[s_a]);
+                        release(&bar_empty[sb]);
                         if (++sb == SB) sb = 0, pb ^= 1u;
-                        // next tap: one pixel to the right, or back to column 0 of the next halo row
-                        if (++kw == 3) kw = 0, a_src += (HALO_PITCH - 2) * 128u;
-                        else a_src += 128u;
                     }
-                    if constexpr (PAIR) tc::mma_commit_pair(tc::smem_u32(&bar_a_empty[sa]), 0b11);
-                    else tc::mma_commit(tc::smem_u32(&bar_a_empty[sa]));
-                    if (++sa == SA) sa = 0, pa ^= 1u;
                 }
-                if constexpr (PAIR) tc::mma_commit_pair(tc::smem_u32(&bar_acc_full[as]), 0b11);
-                else tc::mma_commit(tc::smem_u32(&bar_acc_full[as]));
+                release(&bar_acc_full[as]);
             }
         }
-    } else if (HALO && warp >= 2 + EPI_WARPS) {
+    } else if (HALO && warp >= 2 + EPI_WARPS && warp < 2 + EPI_WARPS + XF_WARPS) {
         // ===== input transform (halo) =====
         // Thread (rg, chunk) owns the 16-byte chunk `chunk` (8 channels) of halo rows rg, rg + 16, ...: a warp
         // instruction touches 4 full 128-byte rows (conflict free for any swizzle phase).  Same arithmetic as
@@ -378,15 +406,15 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
         int sa = 0;
         uint32_t pa = 0;
         const uint32_t ready0 = PAIR ? tc::mapa(tc::smem_u32(&bar_a_ready[0]), 0) : tc::smem_u32(&bar_a_ready[0]);
+        const bool xf = p.in_coef != nullptr;
         for (int local = 0; local < tile_count; ++local) {
             const int tile = unit_to_tile(tile_first + local * tile_step);
             int n_tile, w0, h0, n0;
             tile_coords(p, tile, n_tile, w0, h0, n0);
-            for (int it = 0; it < items; ++it) {
-                const bool xf = p.in_coef != nullptr && it < p.kb_per_tap;
+            for (int hi = 0; hi < p.kb_per_tap; ++hi) {
                 float a[8], b[8];
                 if (xf) {
-                    const float4* cp = reinterpret_cast<const float4*>(p.in_coef + (int64_t)n0 * p.c_in + it * BLOCK_K + chunk * 8);
+                    const float4* cp = reinterpret_cast<const float4*>(p.in_coef + (int64_t)n0 * p.c_in + hi * BLOCK_K + chunk * 8);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float4 v = __ldg(cp + j);
@@ -979,13 +1007,11 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     const int64_t h = (h_in + ex.stride - 1) / ex.stride, w = (w_in + ex.stride - 1) / ex.stride;
 
     // Halo tiles: 3 x 3, stride 1, maps of at least one 8 x 16 patch, whole 64-channel blocks (see the kernel's header)
-    // (With a fused 1 x 1 operand the halo kernels are available -- in_coef or AZB_CONV_KNOB_HALO = 1 selects them -- but
-    // not the default: its one-k-block A items get only a_ahead items = 1 - 2 k-blocks of load lead, and the tap-wise
-    // kernel is 20 - 25 % faster on those layers, scripts/halo_ab.py.)
-    bool halo = g_knob[AZB_CONV_KNOB_HALO] != 0 && (!ex.act2 || ex.in_coef || g_knob[AZB_CONV_KNOB_HALO] == 1) && taps == 9 &&
+    bool halo = g_knob[AZB_CONV_KNOB_HALO] != 0 && taps == 9 &&
                 ex.stride == 1 && h >= HALO_H && w >= HALO_W &&
                 c_in % BLOCK_K == 0 && k_per_tap == c_in && (!ex.act2 || (ex.c_in2 % BLOCK_K == 0 && ex.k2 == ex.c_in2)) &&
-                !colsum && ex.act == AZB_ACT_NONE && !ex.gate && (!ex.gn_acc || stat_gran == 8);
+                !colsum && ex.act == AZB_ACT_NONE && !ex.gate && (!ex.gn_acc || stat_gran == 8) &&
+                c_in / BLOCK_K + (ex.act2 ? ex.c_in2 / BLOCK_K : 0) <= 64 && !(ex.act2 && out_mode == 1);
     if (ex.in_coef && !azb_aligned(ex.in_coef, 16)) return AZB_E_ALIGN;
 
     ConvParams p{};
@@ -1047,6 +1073,8 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     // measured on the ADM shapes (scripts/conv_ab.py): pairs win 5 - 20 % whenever the reduction is at least 16 k-blocks;
     // with short reductions (1x1 layers, K <= 512) the epilogue dominates and the pair's extra handshakes cost 5 - 8 %
     if (pair && g_knob[AZB_CONV_KNOB_PAIR] < 0) pair = num_kb_total >= 16;
+    // halo kernels stage the plain tiles of a fused 1 x 1 operand in the weight ring: a stage must hold 128 x 64 bf16
+    if (halo && ex.act2 && block_n == 128) pair = false;
     p.total_tiles = pair ? p.tiles_out / 2 : p.tiles_out * splits;
     p.splits = splits;
     if (splits > 1) {
@@ -1077,8 +1105,17 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     p.prefetch_kb = halo ? 0 : g_knob[AZB_CONV_KNOB_PREFETCH] >= 0 ? g_knob[AZB_CONV_KNOB_PREFETCH] : (m_tiles <= 32 ? 24 : 0);
     p.in_coef = reinterpret_cast<const float2*>(ex.in_coef), p.in_silu = ex.in_silu, p.c_in = (int)c_in;
     p.sa = g_knob[AZB_CONV_KNOB_HALO_SA] >= 2 && g_knob[AZB_CONV_KNOB_HALO_SA] <= 4 ? g_knob[AZB_CONV_KNOB_HALO_SA] : 3;
-    p.a_ahead = g_knob[AZB_CONV_KNOB_HALO_AHEAD] >= 0 ? g_knob[AZB_CONV_KNOB_HALO_AHEAD] : p.sa - 2;
-    if (p.a_ahead > p.sa - 1) p.a_ahead = p.sa - 1;
+    if (halo) {
+        // item order of a tile: halo item h is followed by the 1 x 1 blocks [h P / H, (h + 1) P / H)
+        const int H = p.kb_per_tap, P = p.kb_extra, spread = g_knob[AZB_CONV_KNOB_HALO_AHEAD] != 0;
+        p.item_mask = 0;
+        int pos = 0;
+        for (int hh = 0, done = 0; hh < H; ++hh) {
+            p.item_mask |= 1ull << pos++;
+            const int until = spread ? ((hh + 1) * P) / H : (hh + 1 == H ? P : 0);
+            for (; done < until; ++done) ++pos;
+        }
+    }
     p.chunked = (ex.gn_acc && p.n_tiles <= 2 && p.BN == 1 && stat_gran == 8 && block_n >= 64 && splits == 1) ? 1 : 0;
     const int64_t k_total = taps * k_per_tap + (ex.act2 ? ex.k2 : 0);
 

@@ -35,7 +35,7 @@ from . import ops
 
 _MAX_PLANS = 2
 FUSE_NORM = True  # GroupNorm + SiLU ride on the halo tiles of the convolution that consumes them (A/B switch)
-FUSE_NORM_SKIP = False  # ... also when the ResBlock's 1x1 skip operand is part of the GEMM (slower today, scripts/halo_ab.py)
+FUSE_NORM_SKIP = True  # ... also when the ResBlock's 1x1 skip operand is part of the GEMM
 
 
 class Packed:

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--halo", type=int, default=-1)
     ap.add_argument("--fused", type=int, default=0, help="apply act(a x + b) to the halo tiles (in_coef)")
+    ap.add_argument("--skip", type=int, default=0, help="channels of a fused 1x1 operand")
     ap.add_argument("--sa", type=int, default=-1)
     ap.add_argument("--ahead", type=int, default=-1)
     a = ap.parse_args()
@@ -34,6 +35,11 @@ def main():
     pc = ops.pack_conv(torch.randn(a.co, a.ci, a.k, a.k, device=dev, generator=g) / (a.ci * a.k * a.k) ** 0.5,
                        torch.randn(a.co, device=dev, generator=g))
     out = torch.empty(a.batch, a.hw, a.hw, a.co, dtype=torch.bfloat16, device=dev)
+    x2 = None
+    if a.skip:
+        x2 = torch.randn(a.batch, a.hw, a.hw, a.skip, device=dev, generator=g).to(torch.bfloat16)
+        pc = ops.pack_conv_skip(pc, ops.pack_conv(torch.randn(a.co, a.skip, 1, 1, device=dev, generator=g) / a.skip**0.5,
+                                                  torch.randn(a.co, device=dev, generator=g)))
     ops.conv_tuning(ops.KNOB_PAIR, a.pair)
     ops.conv_tuning(ops.KNOB_HALO, a.halo)
     ops.conv_tuning(ops.KNOB_HALO_SA, a.sa)
@@ -42,7 +48,7 @@ def main():
     if a.fused:
         coef = torch.stack((torch.full((a.batch, a.ci), 0.5, device=dev), torch.zeros(a.batch, a.ci, device=dev)), dim=-1).contiguous()
     for _ in range(a.reps):
-        ops.conv_acc(x, pc, out=out, in_coef=coef, in_silu=True)
+        ops.conv_acc(x, pc, out=out, x2=x2, in_coef=coef, in_silu=True)
     torch.cuda.synchronize()
     print("ok", float(out.float().abs().mean()))
 

@@ -156,7 +156,6 @@ def test_fused_transform_with_skip_operand_and_residual():
     y = ops.gn_apply_acc(t, parts, gamma, beta, scale_shift=ss)
     coef = ops.gn_coef(n, h, w, parts, gamma, beta, scale_shift=ss)
     _wide_tiles(co)
-    ops.conv_tuning(ops.KNOB_HALO, 1)  # without in_coef, layers with a fused 1 x 1 operand default to the tap-wise kernel
     for pair in (1, 0):
         ops.conv_tuning(ops.KNOB_PAIR, pair)
         two, acc_two = ops.conv_acc(y, pc, x2=x2)
