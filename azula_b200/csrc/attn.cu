@@ -74,6 +74,7 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat1
 
 template <int D>
 __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
+    pdl_enter();
     constexpr int PITCH = D + 8;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
@@ -216,7 +217,7 @@ int launch_attn(const AttnParams& p, int n, cudaStream_t s) {
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    attention_kernel<D><<<dim3((p.T + BM - 1) / BM, p.heads, n), 128, smem, s>>>(p);
+    azb_launch(attention_kernel<D>, dim3((p.T + BM - 1) / BM, p.heads, n), dim3(128), smem, s, p);
     return azb_launch_status();
 }
 

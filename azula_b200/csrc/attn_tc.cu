@@ -68,6 +68,7 @@ template <int BK>
 __global__ void __launch_bounds__(THREADS, Cfg<BK>::CTAS_PER_SM)
     attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                         const AttnTcParams p) {
+    pdl_enter();
     using C = Cfg<BK>;
     constexpr int TILE_BYTES = C::TILE_BYTES, P_BYTES = C::P_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -316,7 +317,7 @@ int launch_tc(const void* qkv, int64_t ld, int64_t n, int64_t t, const AttnTcPar
         configured = true;
     }
     dim3 grid((unsigned)((t + BQ - 1) / BQ), (unsigned)p.heads, (unsigned)n);
-    attention_tc_kernel<BK><<<grid, THREADS, C::SMEM, stream>>>(tq, tkv, p);
+    azb_launch(attention_tc_kernel<BK>, grid, dim3(THREADS), C::SMEM, stream, tq, tkv, p);
     return azb_launch_status();
 }
 

@@ -20,6 +20,31 @@ static inline int azb_launch_status() {
     return e == cudaSuccess ? AZB_OK : (int)e;
 }
 
+// Programmatic dependent launch: every kernel of the sampling step is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs are scheduled (and run their prologue) while the
+// previous kernel of the stream drains, instead of after a full launch gap -- ~250 dependent launches per step.  The
+// kernel side of the contract: pdl_trigger() first thing (lets the NEXT kernel begin launching once all CTAs of this
+// one have started), pdl_wait() before the first access to global memory (waits until the previous kernel has completed
+// and its writes are visible).  Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+    pdl_trigger();
+    pdl_wait();
+}
+
+template <typename... KArgs, typename... Args>
+static inline int azb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = azb_knob[AZB_KNOB_PDL] != 0 ? 1 : 0;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    return e == cudaSuccess ? AZB_OK : (int)e;
+}
+
 static inline bool azb_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // Streaming 128-bit accesses: data touched once per step, keep it out of L1.

@@ -180,6 +180,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
     constexpr int STAGES = C::STAGES;
     static_assert(!PAIR || BLOCK_N >= 128, "a CTA pair splits the weight tile in two halves of >= 64 rows");
 
+    pdl_trigger();  // the next kernel of the stream may begin launching; it waits for this grid before touching memory
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ __align__(8) uint64_t bar_full[STAGES];
@@ -233,6 +234,9 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
     if constexpr (PAIR) tc::cluster_sync();  // the peer's barriers are initialised before anything is sent to them
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
+    // barrier setup, tensor-memory allocation and descriptor prefetch overlapped the tail of the previous kernel; its
+    // results (activations, GroupNorm sums, coefficients) are read and this kernel's outputs written only from here on
+    pdl_wait();
 
     const int num_kb_taps = p.taps * p.kb_per_tap;
     const int num_kb = num_kb_taps + p.kb_extra;
@@ -922,10 +926,12 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2,
         // one cluster of two CTAs (the two SMs of a TPC) per scheduling unit, at most one cluster per TPC
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)sm_count() & ~1u), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = s;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr, cfg.numAttrs = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see pdl_trigger / pdl_wait
+        attr[1].val.programmaticStreamSerializationAllowed = g_knob[AZB_KNOB_PDL] != 0 ? 1 : 0;
+        cfg.attrs = attr, cfg.numAttrs = 2;
         static int resident = 0;  // clusters that fit on the device at once: the persistent grid is one wave of them
         if (!resident) {
             if (cudaOccupancyMaxActiveClusters(&resident, kernel, &cfg) != cudaSuccess || resident < 1) {
@@ -939,7 +945,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2,
         if (e != cudaSuccess) return (int)e;
     } else {
         const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-        kernel<<<(unsigned)grid, threads, smem, s>>>(ta, tb, ta2, p);
+        return azb_launch(kernel, dim3((unsigned)grid), dim3(threads), smem, s, ta, tb, ta2, p);
     }
     return azb_launch_status();
 }

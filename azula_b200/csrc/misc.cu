@@ -16,6 +16,7 @@ namespace {
 template <int CT>
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                         int n, int c_rt, int h, int w, int K) {
+    pdl_enter();
     const int c = CT > 0 ? CT : c_rt;
     const int vecs = K / 8;
     const int live = (9 * c + 7) / 8;  // vectors that hold at least one tap; the rest of a row is zero padding
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const float* __restrict_
 // emb[r][0:half] = cos(t_r * f_i), emb[r][half:2half] = sin(t_r * f_i), f_i = exp(-ln(max_period) i / half)
 __global__ void timestep_features_kernel(const int64_t* __restrict__ t_i64, const float* __restrict__ t_f32, int rows,
                                          int dim, float max_period, float* __restrict__ out) {
+    pdl_enter();
     const int half = dim / 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * half; i += gridDim.x * blockDim.x) {
         const int r = i / half, j = i - r * half;
@@ -70,6 +72,7 @@ __global__ void timestep_features_kernel(const int64_t* __restrict__ t_i64, cons
 __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ W,
                                                          const float* __restrict__ b, float* __restrict__ y, int M, int N,
                                                          int K, int silu_in) {
+    pdl_enter();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= N) return;
@@ -94,6 +97,7 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const float* __restrict
 
 __global__ void add_rows_kernel(float* __restrict__ y, const float* __restrict__ table, const int64_t* __restrict__ idx,
                                 int rows, int dim) {
+    pdl_enter();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows * dim; i += gridDim.x * blockDim.x) {
         const int r = i / dim, j = i - r * dim;
         y[i] += table[idx[r] * (int64_t)dim + j];
@@ -113,10 +117,10 @@ extern "C" int azb_im2col3x3_f32(const float* x, void* out, int64_t n, int64_t c
     if (blocks > 148 * 32) blocks = 148 * 32;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-    if (c == 3) im2col3x3_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(x, o, (int)n, 3, (int)h, (int)w, (int)k_pad);
-    else if (c == 4) im2col3x3_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, o, (int)n, 4, (int)h, (int)w, (int)k_pad);
-    else im2col3x3_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(x, o, (int)n, (int)c, (int)h, (int)w, (int)k_pad);
-    return azb_launch_status();
+    const dim3 grid((unsigned)blocks), block(256);
+    if (c == 3) return azb_launch(im2col3x3_kernel<3>, grid, block, 0, st, x, o, (int)n, 3, (int)h, (int)w, (int)k_pad);
+    if (c == 4) return azb_launch(im2col3x3_kernel<4>, grid, block, 0, st, x, o, (int)n, 4, (int)h, (int)w, (int)k_pad);
+    return azb_launch(im2col3x3_kernel<0>, grid, block, 0, st, x, o, (int)n, (int)c, (int)h, (int)w, (int)k_pad);
 }
 
 extern "C" int azb_timestep_features_f32(const void* t, int t_dtype, int64_t rows, int64_t dim, float max_period,
@@ -126,10 +130,9 @@ extern "C" int azb_timestep_features_f32(const void* t, int t_dtype, int64_t row
     if (rows <= 0 || dim < 2) return AZB_E_SHAPE;
     if (t_dtype != AZB_I64 && t_dtype != AZB_F32) return AZB_E_DTYPE;
     const int64_t work = rows * (dim / 2);
-    timestep_features_kernel<<<(unsigned)((work + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    return azb_launch(timestep_features_kernel, dim3((unsigned)((work + 255) / 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
         t_dtype == AZB_I64 ? reinterpret_cast<const int64_t*>(t) : nullptr,
         t_dtype == AZB_F32 ? reinterpret_cast<const float*>(t) : nullptr, (int)rows, (int)dim, max_period, out);
-    return azb_launch_status();
 }
 
 extern "C" int azb_linear_f32(const float* x, const float* w, const float* b, float* y, int64_t m, int64_t n, int64_t k,
@@ -140,9 +143,8 @@ extern "C" int azb_linear_f32(const float* x, const float* w, const float* b, fl
     if (m <= 0 || n <= 0 || k <= 0 || k % 4) return AZB_E_SHAPE;
     if (!azb_aligned(x, 16) || !azb_aligned(w, 16)) return AZB_E_ALIGN;
     dim3 grid((unsigned)((n + 7) / 8), (unsigned)(m < 64 ? m : 64));
-    linear_f32_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, w, b, y, (int)m, (int)n, (int)k,
+    return azb_launch(linear_f32_kernel, grid, dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), x, w, b, y, (int)m, (int)n, (int)k,
                                                                                 silu_in);
-    return azb_launch_status();
 }
 
 extern "C" int azb_zero_bytes(void* ptr, int64_t bytes, void* stream) {
@@ -158,7 +160,6 @@ extern "C" int azb_add_rows_f32(float* y, const float* table, const int64_t* idx
     AZB_CHECK_PTR(table);
     AZB_CHECK_PTR(idx);
     if (rows <= 0 || dim <= 0) return AZB_E_SHAPE;
-    add_rows_kernel<<<(unsigned)((rows * dim + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    return azb_launch(add_rows_kernel, dim3((unsigned)((rows * dim + 255) / 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
         y, table, idx, (int)rows, (int)dim);
-    return azb_launch_status();
 }

@@ -212,6 +212,7 @@ __device__ __forceinline__ float2 channel_coef(const ApplyParams& p, const float
 // coef[n][c] = {A, B} for the convolution kernels that apply the normalisation to their input on the fly
 // (AzbConv::in_coef): one CTA per image.
 __global__ void __launch_bounds__(THREADS) gn_coef_kernel(const ApplyParams p, float2* coef) {
+    pdl_enter();
     const int n = blockIdx.x;
     const int cg = p.c / p.groups;
     const float* ss = p.scale_shift ? p.scale_shift + (int64_t)n * p.ss_stride : nullptr;
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(THREADS) gn_coef_kernel(const ApplyParams p, f
 // MODE: 0 same size, 1 nearest x2 upsample, 2 2x2 average pool (of the activated values).
 template <int MODE, bool SILU>
 __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) {
+    pdl_enter();
     const int n = blockIdx.y;
     const int V = p.c >> 3;
     const int VT = V < THREADS ? V : THREADS;  // vector columns handled per pass
@@ -320,9 +322,9 @@ __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) 
 template <int MODE>
 void launch_apply(const ApplyParams& p, dim3 grid, cudaStream_t s) {
     if (p.silu)
-        gn_apply_kernel<MODE, true><<<grid, THREADS, 0, s>>>(p);
+        azb_launch(gn_apply_kernel<MODE, true>, grid, dim3(THREADS), 0, s, p);
     else
-        gn_apply_kernel<MODE, false><<<grid, THREADS, 0, s>>>(p);
+        azb_launch(gn_apply_kernel<MODE, false>, grid, dim3(THREADS), 0, s, p);
 }
 
 struct FinalizeParams {
@@ -522,8 +524,8 @@ extern "C" int azb_gn_coef_f32(int64_t n, int64_t h, int64_t w, int64_t c, int64
     p.acc[0] = reinterpret_cast<const long long*>(acc_a), p.acc[1] = reinterpret_cast<const long long*>(acc_b);
     p.acc_c[0] = (int)c_a, p.acc_c[1] = (int)c_b, p.acc_gran = (int)gran, p.eps = eps;
     p.acc_scale = 1.0 / (1099511627776.0 * (double)h * (double)w * (double)(c / groups));
-    gn_coef_kernel<<<(unsigned)n, THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, reinterpret_cast<float2*>(coef));
-    return azb_launch_status();
+    return azb_launch(gn_coef_kernel, dim3((unsigned)n), dim3(THREADS), 0, reinterpret_cast<cudaStream_t>(stream), p,
+                      reinterpret_cast<float2*>(coef));
 }
 
 extern "C" int azb_gn_finalize_f32(const float* colsum_a, int64_t c_a, int gran_a, const float* colsum_b, int64_t c_b,

@@ -184,6 +184,7 @@ __device__ __forceinline__ void finish4(const StepArgs& a, const Row& r, int64_t
 // Vector path: numel, n_per_sample, f_bstride, elem_off multiples of 4; 16-byte aligned pointers.
 template <typename FT, typename IT>
 __global__ void __launch_bounds__(256) step_vec4_kernel(const StepArgs a) {
+    pdl_enter();
     const Row r = load_row(a.table, a.step_idx);
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(256) step_vec4_kernel(const StepArgs a) {
 // Scalar path for small / unaligned tensors (e.g. the (64,5) MLP case, batch-less shapes).
 template <typename FT, typename IT>
 __global__ void __launch_bounds__(256) step_scalar_kernel(const StepArgs a) {
+    pdl_enter();
     const Row r = load_row(a.table, a.step_idx);
     const bool generate = (a.eps == nullptr) && (r.n != 0.0f);
     const uint64_t offset = (uint64_t)((a.off_dev ? a.off_dev[0] : 0) + a.off_host);
@@ -269,6 +271,7 @@ __global__ void __launch_bounds__(256) step_scalar_kernel(const StepArgs a) {
 
 __global__ void advance_kernel(int32_t* step_idx, int64_t* off, int64_t inc, const unsigned char* table,
                                unsigned char* out, int elem_bytes, int count, int32_t steps) {
+    pdl_enter();
     __shared__ int32_t s_next;
     if (threadIdx.x == 0) {
         s_next = *step_idx + 1;
@@ -342,11 +345,9 @@ int launch_step(const StepArgs& a, bool vec, cudaStream_t s) {
         int64_t spans = ((a.elem_off + a.numel - 1) / a.T >> 2) - ((a.elem_off / a.T) >> 2) + 1;
         int64_t work = a.eps ? (a.numel >> 2) : ((a.numel >> 2) > T4 * spans ? (a.numel >> 2) : T4 * spans);
         // no-noise path consumes 4 float4 per thread and iteration
-        step_vec4_kernel<FT, IT><<<grid_for(work, 16), 256, 0, s>>>(a);
-    } else {
-        step_scalar_kernel<FT, IT><<<grid_for(a.numel, 16), 256, 0, s>>>(a);
+        return azb_launch(step_vec4_kernel<FT, IT>, dim3(grid_for(work, 16)), dim3(256), 0, s, a);
     }
-    return azb_launch_status();
+    return azb_launch(step_scalar_kernel<FT, IT>, dim3(grid_for(a.numel, 16)), dim3(256), 0, s, a);
 }
 
 template <typename FT>
@@ -415,10 +416,9 @@ extern "C" int azb_advance(int32_t* step_idx, int64_t* philox_state, int64_t off
     AZB_CHECK_PTR(step_idx);
     if ((time_table == nullptr) != (time_out == nullptr)) return AZB_E_NULL;
     if (time_table && (time_elem_bytes <= 0 || time_count <= 0 || steps <= 0)) return AZB_E_SHAPE;
-    advance_kernel<<<1, 64, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        step_idx, philox_state, offset_inc, reinterpret_cast<const unsigned char*>(time_table),
-        reinterpret_cast<unsigned char*>(time_out), time_elem_bytes, time_count, steps);
-    return azb_launch_status();
+    return azb_launch(advance_kernel, dim3(1), dim3(64), 0, reinterpret_cast<cudaStream_t>(stream), step_idx, philox_state,
+                      offset_inc, reinterpret_cast<const unsigned char*>(time_table), reinterpret_cast<unsigned char*>(time_out),
+                      time_elem_bytes, time_count, steps);
 }
 
 extern "C" int azb_init_noise_f32(float* x, int64_t numel, float mean_T, float std_T, uint64_t seed, int64_t offset_host,

@@ -437,8 +437,8 @@ class Plan:
     # ------------------------------------------------------------------------------ running
     @property
     def launches(self) -> int:
-        r"""Kernels launched by one :meth:`run` (without the label lookup)."""
-        return len(self.ops) + 6
+        r"""Kernels launched by one :meth:`run` (without the label lookup; the accumulator memset is not a kernel)."""
+        return sum(1 for kind, *_ in self.meta if kind != "zero") + 6
 
     def profile(self, detail: list | None = None) -> dict[str, dict]:
         r"""Times every queued launch with CUDA events on the current stream (buffers keep whatever

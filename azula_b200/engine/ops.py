@@ -9,6 +9,7 @@ Nothing here falls back to torch arithmetic: a missing library raises.
 from __future__ import annotations
 
 import math
+import os
 import torch
 
 import ctypes
@@ -628,13 +629,19 @@ def conv_acc(x: Tensor, pc, out: Tensor | None = None, residual: Tensor | None =
 
 
 KNOB_PAIR, KNOB_PREFETCH, KNOB_SPLITK, KNOB_GN_WAVE, KNOB_BLOCKN, KNOB_LEAN, KNOB_HALO = 0, 1, 2, 3, 4, 5, 6
-KNOB_HALO_SA, KNOB_HALO_SB, KNOB_HALO_AHEAD = 7, 8, 9
+KNOB_HALO_SA, KNOB_HALO_SB, KNOB_HALO_AHEAD, KNOB_PDL = 7, 8, 9, 10
 
 
 def conv_tuning(knob: int, value: int) -> None:
     r"""``azb_conv_tuning``: overrides an automatic choice of the convolution launcher (-1 restores it)."""
     _lib.check(_lib.lib().azb_conv_tuning(knob, value), "azb_conv_tuning")
 
+
+if os.environ.get("AZB_PDL", "") == "0":  # A/B switch: plain stream-ordered launches
+    try:
+        conv_tuning(KNOB_PDL, 0)
+    except Exception:  # library not built yet: the first real call reports it
+        pass
 
 SPLITK_WORKSPACE_BYTES = 16 << 20
 

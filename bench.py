@@ -304,12 +304,13 @@ def run_engine(args) -> None:
         pk = peaks()
         conv_tflops = conv["flops"] / conv["ms"] / 1e9
         # the dominant kernel class: 3x3 convolution 256 -> 256 at 256 x 256 (6 launches per forward, each 1.24 TFLOP
-        # at batch 16); its DRAM traffic comes from the committed ncu --set full capture of exactly this launch
+        # at batch 16; 5 of them with the GroupNorm + SiLU of their input fused into the halo tiles); its DRAM traffic
+        # comes from the committed ncu --set full capture of exactly this launch
         dom = [d for d in detail if d[0] == "conv3x3" and f"x{SIZE}x{SIZE} 256->256" in d[1] and "skip" not in d[1]]
         dom_ms = sum(d[2] for d in dom) / max(len(dom), 1)
         dom_flop = dom[0][3] if dom else 0.0
         dom_tflops = dom_flop / dom_ms / 1e9 if dom else 0.0
-        traffic = 1170448896 if args.batch == 16 else None  # profiles/r1_ncu_full_conv3x3_256x256.csv: read + write
+        traffic = 1098542848 if args.batch == 16 else None  # profiles/r1_ncu_full_conv_fused_v4.csv: dram read + write
         e2e_tflops = value / world * SAMPLER_STEPS * FLOP_PER_IMAGE_FORWARD / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -322,7 +323,8 @@ def run_engine(args) -> None:
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4},
             "gpu_launches": args.steps * SAMPLER_STEPS * launches_per_sampler_step,
             "roofline": {"bound": "tensor",
-                         "kernel": f"conv_gemm_kernel<256>: 3x3 conv 256->256 on {args.batch}x{SIZE}x{SIZE} (implicit GEMM, tcgen05)",
+                         "kernel": f"conv_gemm_kernel<256, pair, lean, halo>: GroupNorm+SiLU+3x3 conv 256->256 on "
+                                   f"{args.batch}x{SIZE}x{SIZE} (halo-tile implicit GEMM, tcgen05 cta_group::2)",
                          "achieved": round(dom_tflops, 1), "peak": pk["tflops"], "unit": "TFLOP/s",
                          "frac": round(dom_tflops / pk["tflops"], 4), "traffic": traffic,
                          "flop_per_launch": dom_flop, "us_per_launch": round(1e3 * dom_ms, 1), "launches_per_forward": len(dom),
