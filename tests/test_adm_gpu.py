@@ -159,3 +159,75 @@ def test_sharded_sampling_equals_global_batch_bits(S):
         torch.manual_seed(1)
         parts.append(smp(mine))
     assert torch.equal(torch.cat(parts), x0)
+
+
+# The card's width (256 channels: GroupNorm groups of 8+ channels, one accumulator entry per 8-channel block) at a small
+# spatial size: the configuration class in which GroupNorm + SiLU ride on the halo tiles of the 3 x 3 convolutions.
+WIDE_ADM = dict(
+    image_size=32,
+    num_channels=256,
+    channel_mult=(1, 2),
+    num_res_blocks=1,
+    attention_resolutions=(2,),
+    num_head_channels=64,
+    resblock_updown=True,
+    use_scale_shift_norm=True,
+)
+
+
+def _plan(den):
+    return next(v for k, v in den.backbone._native.items() if k != "packed")
+
+
+def test_fused_groupnorm_path_end_to_end_at_card_width():
+    """Width-256 U-Net: the plan must actually fuse (gn_coef launches, convolutions with an input transform), match the
+    oracle within the stated bf16 tolerance, and equal the un-fused plan (GroupNorm as a separate pass over HBM, same
+    halo kernels) BIT FOR BIT -- the transform warps and azb_gn_apply_acc_bf16 share coefficients and arithmetic."""
+    from azula_b200.engine import adm as engine_adm
+
+    den, sd = _seeded(WIDE_ADM, seed=11)
+    tab = AU.block_table(**WIDE_ADM)
+    # (batch 8: enough 8 x 16 patches that the launcher picks the wide N tiles the halo kernels exist for)
+    x = torch.randn(8, 3, 32, 32, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
+    ts = torch.randint(0, 1000, (8,), device=DEV)
+    fused = den.backbone(x, ts)
+    kinds = [m[0] for m in _plan(den).meta]
+    descs = [m[3] for m in _plan(den).meta]
+    assert kinds.count("gn_coef") >= 4 and sum(" gn+" in d for d in descs) == kinds.count("gn_coef") - (
+        1 if _plan(den).out_coef is not None else 0), (kinds.count("gn_coef"), descs)
+    _report(fused, AU.forward(sd, tab, x, ts), "width 256, fused GroupNorm")
+    try:
+        engine_adm.FUSE_NORM = False
+        den.backbone._native.clear()
+        plain = den.backbone(x, ts)
+        assert "gn_coef" not in [m[0] for m in _plan(den).meta]
+    finally:
+        engine_adm.FUSE_NORM = True
+        den.backbone._native.clear()
+    assert torch.equal(fused, plain), (fused - plain).abs().max().item()
+
+
+def test_programmatic_dependent_launch_does_not_change_results():
+    """Every kernel of the step is launched with programmatic stream serialization (its CTAs may start while the
+    previous kernel drains and wait in griddepcontrol.wait): same bits as plain stream-ordered launches, eagerly and
+    through the captured graph."""
+    from azula_b200.engine import ops
+
+    den, _ = _seeded(WIDE_ADM, seed=13)
+    x = torch.randn(8, 3, 32, 32, device=DEV, generator=torch.Generator(device=DEV).manual_seed(7))
+    ts = torch.tensor([321], device=DEV)
+    outs = {}
+    try:
+        for pdl in (1, 0):
+            ops.conv_tuning(ops.KNOB_PDL, pdl)
+            den.backbone._native.clear()
+            outs[pdl] = den.backbone(x, ts)
+            smp = DDIMSampler(den, steps=3, silent=True, graph=True)
+            torch.manual_seed(3)
+            outs[pdl, "sample"] = smp(x)
+            assert next(iter(smp._loops.values())).graph is not None
+    finally:
+        ops.conv_tuning(ops.KNOB_PDL, -1)
+        den.backbone._native.clear()
+    assert torch.equal(outs[1], outs[0])
+    assert torch.equal(outs[1, "sample"], outs[0, "sample"])
