@@ -70,6 +70,7 @@ struct ConvParams {
     const float* bias;        // [c_out] or null
     const __nv_bfloat16* res; // residual, NHWC bf16, or null
     int64_t res_ld;
+    int res_up;               // 1: residual at (H / 2, W / 2), pixel (h, w) adds residual pixel (h / 2, w / 2)
     void* out;
     int64_t out_ld;           // NHWC pixel stride (mode 0)
     int out_mode;             // 0: bf16 NHWC, 1: fp32 NCHW
@@ -670,7 +671,10 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                         okc[it] = (n < p.N) && (h < p.H) && (w < p.W);
                         pixc[it] = ((int64_t)n * p.H + h) * p.W + w;
                         outp[it] = reinterpret_cast<__nv_bfloat16*>(p.out) + pixc[it] * p.out_ld + col_base + cg4 * 8;
-                        resp[it] = p.res + pixc[it] * p.res_ld + col_base + cg4 * 8;
+                        // res_up: the residual lives at half the resolution and is read through a nearest-neighbour 2x
+                        // upsampling (Upsample of the ResBlock's skip branch, _src/unet.py:101-109,231-233), never stored
+                        const int64_t rpix = p.res_up ? ((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : pixc[it];
+                        resp[it] = p.res + rpix * p.res_ld + col_base + cg4 * 8;
                     }
 #pragma unroll 1
                     for (int c0 = 0; c0 < C::COLS_PER_WARP; c0 += 32) {
@@ -978,6 +982,7 @@ struct ConvExtra {
     int64_t* gn_acc = nullptr;   // exact per-(image, channel block) sums of `out` for the GroupNorms that consume it
     void* workspace = nullptr;   // split-K scratch: flags (zero between launches) + fp32 partial tiles
     int64_t workspace_bytes = 0;
+    int res_up = 0;              // residual given at half resolution (nearest 2x upsampling on the fly)
     const float* in_coef = nullptr;  // [N][c_in] {a, b}: the input is act(a x + b), applied on the fly (halo kernels only)
     int in_silu = 0;
     AzbConvChoice* choice = nullptr;  // dry run: report the launcher's choice instead of launching
@@ -1058,7 +1063,7 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
                          out, out_ld, out_mode, colsum, stat_gran, stream, ex);
     }
     if (!halo && ex.in_coef) return AZB_E_UNSUPPORTED;
-    if (!halo && g_knob[AZB_CONV_KNOB_SPLITK] != 0 && ex.workspace && out_mode == 0 && m_tiles * (c_out_rows / block_n) <= sms && (block_n <= 64 || m_tiles * (c_out_rows / block_n) < sms / 2)) {
+    if (!halo && !ex.res_up && g_knob[AZB_CONV_KNOB_SPLITK] != 0 && ex.workspace && out_mode == 0 && m_tiles * (c_out_rows / block_n) <= sms && (block_n <= 64 || m_tiles * (c_out_rows / block_n) < sms / 2)) {
         const int try_n[2] = {128, 256}, try_s[2] = {2, 4};
         for (int i = 0; i < 2 && splits == 1; ++i) {
             const int bn = try_n[i], sp = try_s[i];
@@ -1095,6 +1100,8 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     p.bias = bias;
     p.res = reinterpret_cast<const __nv_bfloat16*>(residual);
     p.res_ld = res_ld;
+    if (ex.res_up && (!residual || (h & 1) || (w & 1) || out_mode != 0 || splits > 1)) return AZB_E_SHAPE;
+    p.res_up = ex.res_up;
     p.out = out, p.out_ld = out_ld, p.out_mode = out_mode;
     p.colsum = reinterpret_cast<float2*>(colsum);
     p.stat_gran = stat_gran;
@@ -1248,6 +1255,7 @@ extern "C" int azb_conv_bf16(const AzbConv* d, void* stream) {
     ex.gn_acc = d->gn_acc;
     ex.workspace = d->workspace, ex.workspace_bytes = d->workspace_bytes;
     ex.in_coef = d->in_coef, ex.in_silu = d->in_silu;
+    ex.res_up = d->res_up;
     return conv_impl(d->act, d->n, d->h, d->w, d->c_in, d->act_ld, d->wpack, d->c_out, d->c_out_rows, d->taps, d->k_per_tap,
                      d->bias, d->residual, d->res_ld, d->out, d->out_ld, d->out_mode, d->colsum,
                      (d->colsum || d->gn_acc) ? d->stat_gran : 1, stream, ex);
@@ -1263,6 +1271,7 @@ extern "C" int azb_conv_choice(const AzbConv* d, AzbConvChoice* choice) {
     ex.gn_acc = d->gn_acc;
     ex.workspace = d->workspace, ex.workspace_bytes = d->workspace_bytes;
     ex.in_coef = d->in_coef, ex.in_silu = d->in_silu;
+    ex.res_up = d->res_up;
     ex.choice = choice;
     return conv_impl(d->act, d->n, d->h, d->w, d->c_in, d->act_ld, d->wpack, d->c_out, d->c_out_rows, d->taps, d->k_per_tap,
                      d->bias, d->residual, d->res_ld, d->out, d->out_ld, d->out_mode, d->colsum,

@@ -129,6 +129,8 @@ struct ApplyParams {
     int64_t x_ld;
     __nv_bfloat16* y;        // (N, Ho, Wo, C), pixel stride y_ld
     int64_t y_ld;
+    __nv_bfloat16* y2;       // DUAL (mode 2): the 2x2 average of the RAW input, same shape as y (the skip branch's x_upd)
+    int64_t y2_ld;
     int n, h, w, c, groups;
     const float* stats;      // (N, groups, 2) or null (identity transform)
     const float* gamma;      // (C)
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(THREADS) gn_coef_kernel(const ApplyParams p, f
 // Thread (r, v) owns vector column v (8 channels, its A/B live in registers) and walks output pixels
 // r, r+R, ... of the CTA's pixel range with UNROLL independent 16-byte loads in flight.
 // MODE: 0 same size, 1 nearest x2 upsample, 2 2x2 average pool (of the activated values).
-template <int MODE, bool SILU>
+template <int MODE, bool SILU, bool DUAL = false>
 __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) {
     pdl_enter();
     const int n = blockIdx.y;
@@ -241,6 +243,7 @@ __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) 
     const int q1 = min(q0 + p.pix_per_cta, out_pix);
     const __nv_bfloat16* xin = p.x + (int64_t)n * p.h * p.w * p.x_ld;
     __nv_bfloat16* yout = p.y + (int64_t)n * out_pix * p.y_ld;
+    __nv_bfloat16* yout2 = DUAL ? p.y2 + (int64_t)n * out_pix * p.y2_ld : nullptr;
     const int cg = p.c / p.groups;
     const float* ss = nullptr;
     if (p.scale_shift) {
@@ -288,6 +291,17 @@ __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) 
 #pragma unroll
                         for (int t = 0; t < 4; ++t) affine8<SILU>(u[k][t], a, b, acc);
                         *reinterpret_cast<uint4*>(yc + (int64_t)qq * p.y_ld) = pack8(acc, 0.25f);
+                        if (DUAL) {  // the same 2x2 window of the raw values (what the identity transform would produce)
+                            float raw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const uint32_t wv[4] = {u[k][t].x, u[k][t].y, u[k][t].z, u[k][t].w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    raw[2 * j] += bf16_bits_to_f32(wv[j] & 0xffffu), raw[2 * j + 1] += __uint_as_float(wv[j] & 0xffff0000u);
+                            }
+                            *reinterpret_cast<uint4*>(yout2 + v * 8 + (int64_t)qq * p.y2_ld) = pack8(raw, 0.25f);
+                        }
                     }
                 }
             } else {
@@ -321,7 +335,10 @@ __global__ void __launch_bounds__(THREADS) gn_apply_kernel(const ApplyParams p) 
 
 template <int MODE>
 void launch_apply(const ApplyParams& p, dim3 grid, cudaStream_t s) {
-    if (p.silu)
+    if (MODE == 2 && p.y2) {
+        if (p.silu) azb_launch(gn_apply_kernel<2, true, true>, grid, dim3(THREADS), 0, s, p);
+        else azb_launch(gn_apply_kernel<2, false, true>, grid, dim3(THREADS), 0, s, p);
+    } else if (p.silu)
         azb_launch(gn_apply_kernel<MODE, true>, grid, dim3(THREADS), 0, s, p);
     else
         azb_launch(gn_apply_kernel<MODE, false>, grid, dim3(THREADS), 0, s, p);
@@ -427,7 +444,8 @@ extern "C" int azb_gn_stats_bf16(const void* x, int64_t ld, int64_t n, int64_t h
     return azb_launch_status();
 }
 
-static int gn_apply_impl(const void* x, int64_t x_ld, void* y, int64_t y_ld, int64_t n, int64_t h, int64_t w, int64_t c,
+static int gn_apply_impl(const void* x, int64_t x_ld, void* y, int64_t y_ld, void* y2, int64_t y2_ld, int64_t n, int64_t h,
+                         int64_t w, int64_t c,
                          int64_t groups, const float* stats, const int64_t* acc, int64_t c_a, const int64_t* acc_b,
                          int64_t c_b, int64_t gran, float eps, const float* gamma,
                          const float* beta, const float* scale_shift, int64_t ss_stride, const int32_t* ss_step,
@@ -442,6 +460,8 @@ static int gn_apply_impl(const void* x, int64_t x_ld, void* y, int64_t y_ld, int
     ApplyParams p{};
     p.x = reinterpret_cast<const __nv_bfloat16*>(x), p.x_ld = x_ld;
     p.y = reinterpret_cast<__nv_bfloat16*>(y), p.y_ld = y_ld;
+    if (y2 && (mode != 2 || y2_ld % 8 || y2_ld < c || !azb_aligned(y2, 16))) return AZB_E_SHAPE;
+    p.y2 = reinterpret_cast<__nv_bfloat16*>(y2), p.y2_ld = y2_ld;
     p.n = (int)n, p.h = (int)h, p.w = (int)w, p.c = (int)c, p.groups = (stats || acc) ? (int)groups : 1;
     p.stats = stats, p.gamma = gamma, p.beta = beta;
     if (acc) {
@@ -493,7 +513,7 @@ extern "C" int azb_gn_apply_bf16(const void* x, int64_t x_ld, void* y, int64_t y
                                  int64_t c, int64_t groups, const float* stats, const float* gamma, const float* beta,
                                  const float* scale_shift, int64_t ss_stride, const int32_t* ss_step,
                                  int64_t ss_step_stride, int silu, int mode, void* stream) {
-    return gn_apply_impl(x, x_ld, y, y_ld, n, h, w, c, groups, stats, nullptr, 0, nullptr, 0, 1, 0.f, gamma, beta,
+    return gn_apply_impl(x, x_ld, y, y_ld, nullptr, 0, n, h, w, c, groups, stats, nullptr, 0, nullptr, 0, 1, 0.f, gamma, beta,
                          scale_shift, ss_stride, ss_step, ss_step_stride, silu, mode, stream);
 }
 
@@ -502,8 +522,18 @@ extern "C" int azb_gn_apply_acc_bf16(const void* x, int64_t x_ld, void* y, int64
                                      int64_t c_b, int64_t gran, float eps, const float* gamma, const float* beta,
                                      const float* scale_shift, int64_t ss_stride, int silu, int mode, void* stream) {
     AZB_CHECK_PTR(acc_a);
-    return gn_apply_impl(x, x_ld, y, y_ld, n, h, w, c, groups, nullptr, acc_a, c_a, acc_b, c_b, gran, eps, gamma, beta,
+    return gn_apply_impl(x, x_ld, y, y_ld, nullptr, 0, n, h, w, c, groups, nullptr, acc_a, c_a, acc_b, c_b, gran, eps, gamma, beta,
                          scale_shift, ss_stride, nullptr, 0, silu, mode, stream);
+}
+
+extern "C" int azb_gn_pool_acc_bf16(const void* x, int64_t x_ld, void* y, int64_t y_ld, void* y_raw, int64_t y_raw_ld, int64_t n,
+                                    int64_t h, int64_t w, int64_t c, int64_t groups, const int64_t* acc_a, int64_t c_a,
+                                    const int64_t* acc_b, int64_t c_b, int64_t gran, float eps, const float* gamma,
+                                    const float* beta, const float* scale_shift, int64_t ss_stride, int silu, void* stream) {
+    AZB_CHECK_PTR(acc_a);
+    AZB_CHECK_PTR(y_raw);
+    return gn_apply_impl(x, x_ld, y, y_ld, y_raw, y_raw_ld, n, h, w, c, groups, nullptr, acc_a, c_a, acc_b, c_b, gran, eps,
+                         gamma, beta, scale_shift, ss_stride, nullptr, 0, silu, 2, stream);
 }
 
 extern "C" int azb_gn_coef_f32(int64_t n, int64_t h, int64_t w, int64_t c, int64_t groups, const int64_t* acc_a, int64_t c_a,

@@ -35,6 +35,7 @@ from . import ops
 
 _MAX_PLANS = 2
 FUSE_NORM = True  # GroupNorm + SiLU ride on the halo tiles of the convolution that consumes them (A/B switch)
+RESAMPLE_SHORTCUTS = True  # up blocks: residual read through the upsampling; down blocks: both branches in one pass
 FUSE_NORM_SKIP = True  # ... also when the ResBlock's 1x1 skip operand is part of the GEMM
 
 
@@ -243,7 +244,7 @@ class Plan:
         return acc
 
     def _conv(self, x: Tensor, pc, out: Tensor, residual: Tensor | None = None, stats: bool = False,
-              x2: Tensor | None = None, in_coef: Tensor | None = None, in_silu: bool = True) -> None:
+              x2: Tensor | None = None, in_coef: Tensor | None = None, in_silu: bool = True, res_up: bool = False) -> None:
         r"""Queues a convolution (``azb_conv_bf16``); with ``stats`` its epilogue also adds the exact sums from
         which the GroupNorm(s) consuming ``out`` derive their statistics (no read pass over ``out``, no reduction
         launch).  With ``x2`` the ResBlock's 1x1 skip connection is part of the same GEMM.  With ``in_coef``
@@ -253,7 +254,7 @@ class Plan:
         if not stats:
             self.acc_of.pop(self._key(out), None)
         d = ops.conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=self.stat_gran, workspace=self.splitk_ws,
-                          in_coef=in_coef, in_silu=in_silu)
+                          in_coef=in_coef, in_silu=in_silu, res_up=res_up)
         self.keep += [d, x, out, pc.w] + [t for t in (residual, pc.bias, x2, in_coef) if t is not None]
         taps = 9 if x2 is not None else pc.taps
         k_extra = pc.c_in2 if x2 is not None else 0
@@ -261,12 +262,27 @@ class Plan:
         nbytes = 2.0 * (n * h * w * (pc.c_in + k_extra + pc.c_out * (2 if residual is not None else 1))
                         + pc.c_out * (taps * pc.c_in + k_extra))
         desc = f"{n}x{h}x{w} {pc.c_in}->{pc.c_out}" + (" gn+" if in_coef is not None else "") + (
-            " +res" if residual is not None else "") + (
+            (" +res(up)" if res_up else " +res") if residual is not None else "") + (
             f" +skip1x1({pc.c_in2})" if x2 is not None else "") + (" +stats" if acc is not None else "")
         self._emit("conv3x3" if taps == 9 else "conv1x1", flops, nbytes, self.lib.azb_conv_bf16, byref(d), desc=desc)
 
     def _conv_skip(self, x: Tensor, x2: Tensor, pc: ops.PackedConvSkip, out: Tensor, in_coef: Tensor | None = None) -> None:
         self._conv(x, pc, out, stats=True, x2=x2, in_coef=in_coef)
+
+    def _pool_dual(self, x: Tensor, out: Tensor, out_raw: Tensor, stats, affine) -> None:
+        r"""Queues ``azb_gn_pool_acc_bf16``: both branches of a downsampling ResBlock from one read of ``x``."""
+        n, h, w, c = x.shape
+        gamma, beta = affine
+        (a, ca), (b, cb) = stats[1][0], (stats[1][1] if len(stats[1]) > 1 else (None, 0))
+        for t in (out, out_raw):
+            self.acc_of.pop(self._key(t), None)
+        self.keep += [x, out, out_raw, a, gamma, beta] + ([b] if b is not None else [])
+        self._emit(
+            "gn_apply", 0.0, 2.0 * c * (n * h * w + 2 * n * h * w // 4), self.lib.azb_gn_pool_acc_bf16, x.data_ptr(), ops._ld(x),
+            out.data_ptr(), ops._ld(out), out_raw.data_ptr(), ops._ld(out_raw), n, h, w, c, ops.GN_GROUPS, a.data_ptr(), ca,
+            _lib.ptr(b), cb, self.stat_gran, ops.GN_EPS, gamma.data_ptr(), beta.data_ptr(), None, 0, 1,
+            desc=f"{n}x{h}x{w}x{c} mode2 dual",
+        )
 
     def _fusable(self, stats, x: Tensor, pc, out: Tensor, residual: Tensor | None = None, x2: Tensor | None = None,
                  nchw_f32: bool = False) -> bool:
@@ -379,18 +395,29 @@ class Plan:
         n, ho, wo, _ = out.shape
         st1 = self._stats(x)
         h2 = arena.take(n, ho, wo, u.cout)
+        res_up = False
         if not u.resample and self._fusable(st1, x, w_["conv1"], h2):
             # SiLU(GN(x)) is applied to the halo tiles of conv1: no normalised copy of x in HBM
             self._conv(x, w_["conv1"], h2, stats=True, in_coef=self._coef(x, st1, w_["gn1"], None, True))
             xr = x
         else:
             h1 = arena.take(n, ho, wo, u.cin)
-            self._apply(x, h1, st1, w_["gn1"], None, True, u.resample)  # SiLU(GN(x)) then up / down
-            if u.resample:
+            identity_skip = w_["skip"] is None and not isinstance(w_["conv2"], ops.PackedConvSkip)
+            if u.resample == 1 and identity_skip and RESAMPLE_SHORTCUTS:
+                # upsampling block: x_upd = up(x) is never stored, conv2's epilogue reads x through the 2x upsampling
+                self._apply(x, h1, st1, w_["gn1"], None, True, 1)
+                xr, res_up = x, True
+            elif u.resample == 2 and st1[0] == "acc" and RESAMPLE_SHORTCUTS:
+                # downsampling block: ONE pass over x writes pool(SiLU(GN(x))) and x_upd = pool(x)
                 xr = arena.take(n, ho, wo, u.cin)
-                self._apply(x, xr, None, None, None, False, u.resample)  # x_upd on the raw input
+                self._pool_dual(x, h1, xr, st1, w_["gn1"])
             else:
-                xr = x
+                self._apply(x, h1, st1, w_["gn1"], None, True, u.resample)  # SiLU(GN(x)) then up / down
+                if u.resample:
+                    xr = arena.take(n, ho, wo, u.cin)
+                    self._apply(x, xr, None, None, None, False, u.resample)  # x_upd on the raw input
+                else:
+                    xr = x
             self._conv(h1, w_["conv1"], h2, stats=True)
             arena.give(h1)
         st2 = self._stats(h2)
@@ -399,7 +426,8 @@ class Plan:
         if not skip_fused and w_["skip"] is not None:
             sk = arena.take(n, ho, wo, u.cout)
             self._conv(xr, w_["skip"], sk)
-        if self._fusable(st2, h2, w_["conv2"], out, residual=None if skip_fused else sk, x2=xr if skip_fused else None):
+        if self._fusable(st2, h2, w_["conv2"], out, residual=None if (skip_fused or res_up) else sk,
+                         x2=xr if skip_fused else None):
             coef2 = self._coef(h2, st2, w_["gn2"], w_["emb_offset"], True)  # SiLU(GN(h) (1 + scale) + shift) on the fly
         else:
             coef2 = None
@@ -407,7 +435,7 @@ class Plan:
         if skip_fused:
             self._conv_skip(h2, xr, w_["conv2"], out, in_coef=coef2)  # skip_connection(x) + h, the 1x1 folded into the GEMM's K
         else:
-            self._conv(h2, w_["conv2"], out, residual=sk, stats=True, in_coef=coef2)  # x + h
+            self._conv(h2, w_["conv2"], out, residual=sk, stats=True, in_coef=coef2, res_up=res_up)  # x + h
         arena.give(h2)
         if sk is not xr:
             arena.give(sk)

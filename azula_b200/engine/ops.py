@@ -27,7 +27,7 @@ class AzbConv(ctypes.Structure):
         ("act", c_void_p), ("n", c_int64), ("h", c_int64), ("w", c_int64), ("c_in", c_int64), ("act_ld", c_int64),
         ("wpack", c_void_p), ("c_out", c_int64), ("c_out_rows", c_int64), ("k_per_tap", c_int64),
         ("taps", c_int32), ("stride", c_int32), ("act_fn", c_int32), ("out_mode", c_int32), ("stat_gran", c_int32),
-        ("reserved", c_int32),
+        ("res_up", c_int32),
         ("bias", c_void_p), ("gate", c_void_p), ("gate_ld", c_int64), ("gate_rows", c_int64),
         ("residual", c_void_p), ("res_ld", c_int64), ("out", c_void_p), ("out_ld", c_int64), ("colsum", c_void_p),
         ("act2", c_void_p), ("c_in2", c_int64), ("act2_ld", c_int64), ("k2", c_int64), ("gn_acc", c_void_p),
@@ -50,6 +50,11 @@ _lib.register({
         c_int,
         [c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_float, c_void_p,
          c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p],
+    ),
+    "azb_gn_pool_acc_bf16": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64,
+         c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
     ),
     "azb_conv_tuning": (c_int, [c_int, c_int]),
     "azb_zero_bytes": (c_int, [c_void_p, c_int64, c_void_p]),
@@ -559,7 +564,8 @@ def linear_gather(x: Tensor, xoff: Tensor | None, weight: Tensor, bias: Tensor |
 def conv_desc(x: Tensor, pc, out: Tensor, *, grid: tuple[int, int, int] | None = None, stride: int = 1, act: int = 0,
               gate: int | None = None, gate_ld: int = 0, gate_rows: int = 0, residual: Tensor | None = None,
               nchw_f32: bool = False, x2: Tensor | None = None, gn_acc: Tensor | None = None, gran: int = 8,
-              workspace: Tensor | None = None, in_coef: Tensor | None = None, in_silu: bool = False) -> AzbConv:
+              workspace: Tensor | None = None, in_coef: Tensor | None = None, in_silu: bool = False,
+              res_up: bool = False) -> AzbConv:
     r"""Fills an :class:`AzbConv` for ``azb_conv_bf16``; ``pc`` is a :class:`PackedConv` or, with ``x2``, a
     :class:`PackedConvSkip``.  ``gn_acc``: int64 (N, C_out / gran, 4) exact GroupNorm accumulators (zeroed by the
     caller).  ``in_coef``: fp32 (N, C_in, 2) from :func:`gn_coef` -- the convolution then reads
@@ -572,6 +578,7 @@ def conv_desc(x: Tensor, pc, out: Tensor, *, grid: tuple[int, int, int] | None =
     d.bias = _lib.ptr(pc.bias)
     d.gate, d.gate_ld, d.gate_rows = gate, gate_ld, gate_rows
     d.residual, d.res_ld = _lib.ptr(residual), (0 if residual is None else residual.stride(-2))
+    d.res_up = int(res_up)  # residual given at half resolution, upsampled (nearest) while it is added
     d.out, d.out_ld = out.data_ptr(), (0 if nchw_f32 else out.stride(-2))
     if x2 is not None:
         d.act2, d.c_in2, d.act2_ld, d.k2 = x2.data_ptr(), pc.c_in2, x2.stride(-2), pc.k2
@@ -616,14 +623,14 @@ def gn_coef(n: int, h: int, w: int, parts: list[tuple[Tensor, int]], gamma: Tens
 
 def conv_acc(x: Tensor, pc, out: Tensor | None = None, residual: Tensor | None = None, x2: Tensor | None = None,
              gran: int = 8, workspace: Tensor | None = None, in_coef: Tensor | None = None,
-             in_silu: bool = False) -> tuple[Tensor, Tensor]:
+             in_silu: bool = False, res_up: bool = False) -> tuple[Tensor, Tensor]:
     r"""Convolution that also returns the exact GroupNorm accumulators of its output: (out, int64 (N, C_out / gran, 4))."""
     n, h, w, _ = x.shape
     if out is None:
         out = torch.empty(n, h, w, pc.c_out, dtype=torch.bfloat16, device=x.device)
     acc = torch.zeros(n, pc.c_out // gran, 4, dtype=torch.int64, device=x.device)
     d = conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=gran, workspace=workspace, in_coef=in_coef,
-                  in_silu=in_silu)
+                  in_silu=in_silu, res_up=res_up)
     _lib.check(_lib.lib().azb_conv_bf16(byref(d), _lib.stream_ptr(x.device)), "azb_conv_bf16")
     return out, acc
 

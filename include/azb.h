@@ -190,7 +190,8 @@ typedef struct AzbConv {
     int64_t n, h, w, c_in, act_ld;
     const void* wpack;
     int64_t c_out, c_out_rows, k_per_tap;
-    int32_t taps, stride, act_fn, out_mode, stat_gran, reserved;
+    int32_t taps, stride, act_fn, out_mode, stat_gran;
+    int32_t res_up;           /* 1: `residual` is (n, h / 2, w / 2, c_out): added through a nearest-neighbour 2x upsampling */
     const float* bias;
     const float* gate;
     int64_t gate_ld, gate_rows;
@@ -290,6 +291,13 @@ int azb_gn_apply_acc_bf16(const void* x, int64_t x_ld, void* y, int64_t y_ld, in
                           int64_t c, int64_t groups, const int64_t* acc_a, int64_t c_a, const int64_t* acc_b,
                           int64_t c_b, int64_t gran, float eps, const float* gamma, const float* beta,
                           const float* scale_shift, int64_t ss_stride, int silu, int mode, void* stream);
+
+/* azb_gn_apply_acc_bf16 in pooling mode (2) that reads x ONCE and writes both branches of a downsampling ResBlock
+ * (_src/unet.py:229-233): y = avgpool2x2(act(A x + B)) and y_raw = avgpool2x2(x), both (n, h / 2, w / 2, c). */
+int azb_gn_pool_acc_bf16(const void* x, int64_t x_ld, void* y, int64_t y_ld, void* y_raw, int64_t y_raw_ld, int64_t n,
+                         int64_t h, int64_t w, int64_t c, int64_t groups, const int64_t* acc_a, int64_t c_a,
+                         const int64_t* acc_b, int64_t c_b, int64_t gran, float eps, const float* gamma, const float* beta,
+                         const float* scale_shift, int64_t ss_stride, int silu, void* stream);
 
 /* The per-(image, channel) coefficients {A, B} of azb_gn_apply_acc_bf16's transform y = act(A x + B), written to
  * coef fp32 [n][c][2] for a convolution that applies it to its input on the fly (AzbConv::in_coef): GroupNorm +

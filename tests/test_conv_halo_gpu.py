@@ -198,3 +198,40 @@ def test_fused_transform_refused_where_no_halo_kernel_exists():
     assert _lib.lib().azb_conv_bf16(byref(d), _lib.stream_ptr(t.device)) == -6  # AZB_E_UNSUPPORTED
     d0 = ops.conv_desc(t, pc, out)
     assert ops.conv_choice(d0).halo == 0
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32, 256, 256), (3, 16, 16, 128, 128), (2, 8, 8, 64, 64)])
+def test_residual_read_through_nearest_upsampling(shape):
+    """Upsampling ResBlock tail (_src/unet.py:231-233,247): out = up(x) + conv(h) with up(x) never stored -- the epilogue
+    reads the half-resolution tensor at (h / 2, w / 2).  Bit-equal to adding the materialised upsampled tensor."""
+    n, h, w, ci, co = shape
+    x, wt, b = _mk(n, h, w, ci, co, 3, seed=51)
+    low = torch.randn(n, h // 2, w // 2, co, device=DEV, generator=torch.Generator(device=DEV).manual_seed(6)).to(torch.bfloat16)
+    up = low.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous()
+    pc = ops.pack_conv(wt.float(), b)
+    want, acc_w = ops.conv_acc(x, pc, residual=up, gran=8 if co % 256 == 0 else 1)
+    got, acc_g = ops.conv_acc(x, pc, residual=low, res_up=True, gran=8 if co % 256 == 0 else 1)
+    assert torch.equal(got, want) and torch.equal(acc_g, acc_w)
+    _check(got, _ref(x, wt, b, up), ("res_up", shape))
+
+
+def test_pooling_both_branches_in_one_pass():
+    """Downsampling ResBlock head (_src/unet.py:229-233): pool(SiLU(GN(x))) and pool(x) from one read of x, bit-equal
+    to the two single-output passes."""
+    from azula_b200 import _lib as L
+
+    n, h, w, c = 2, 32, 32, 256
+    t, parts, gamma, beta, _ = _normalised_input(n, h, w, c, None, seed=53)
+    a = ops.gn_apply_acc(t, parts, gamma, beta, mode=2)
+    raw = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=DEV)
+    L.check(L.lib().azb_gn_apply_bf16(t.data_ptr(), c, raw.data_ptr(), c, n, h, w, c, 32, None, None, None, None, 0, None, 0,
+                                      0, 2, L.stream_ptr(t.device)), "azb_gn_apply_bf16")
+    a2, raw2 = torch.empty_like(a), torch.empty_like(raw)
+    (acc, ca) = parts[0]
+    L.check(L.lib().azb_gn_pool_acc_bf16(t.data_ptr(), c, a2.data_ptr(), c, raw2.data_ptr(), c, n, h, w, c, 32, acc.data_ptr(),
+                                         ca, None, 0, 8, 1e-5, gamma.data_ptr(), beta.data_ptr(), None, 0, 1,
+                                         L.stream_ptr(t.device)), "azb_gn_pool_acc_bf16")
+    torch.cuda.synchronize()
+    assert torch.equal(a2, a) and torch.equal(raw2, raw)
+    ref = F.avg_pool2d(t.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    _check(raw2, ref, "pooled raw branch")
