@@ -56,6 +56,10 @@ constexpr int HALO_W = 8, HALO_H = 16;               // patch of one M tile (pix
 constexpr int HALO_PITCH = HALO_W + 2;               // pixels per halo row
 constexpr int HALO_ROWS = (HALO_H + 2) * HALO_PITCH; // 128-byte rows of one halo tile
 constexpr int HALO_BYTES = HALO_ROWS * 128;
+// Upsampling input (in_up): the tile is loaded from the HALF-resolution tensor through a tensor map whose x / y
+// replication dimensions have stride 0 -- (2 x 6) x (2 x 10) = 12 x 20 pixels that cover the 10 x 18 halo region, whose
+// origin sits one row and one column inside
+constexpr int UP_PITCH = 12, UP_ROWS = 20 * UP_PITCH, UP_BYTES = UP_ROWS * 128, UP_ORIGIN = UP_PITCH + 1;
 constexpr int SMEM_BUDGET = 193 * 1024;  // operand ring; + 32 KiB epilogue staging + alignment <= 227 KiB
 
 struct ConvParams {
@@ -92,6 +96,8 @@ struct ConvParams {
     const float2* in_coef;    // halo kernels: [N][c_in] {a, b} of the input transform act(a x + b), or null (identity)
     int in_silu;              // the transform ends in SiLU (coefficients are halved, see azb_gn_coef_f32)
     int c_in;                 // row length of in_coef
+    int in_up;                // halo kernels: the 3 x 3 operand is given at half resolution (nearest 2x upsampling on load)
+    int a_slot;               // halo kernels: bytes per A slot
     int sa, sb;               // halo kernels: A slots and weight stages in the shared-memory budget
     unsigned long long item_mask;  // halo kernels: bit i = item i of a tile is a halo item (else a 1 x 1 block): the blocks
                                    // of the fused 1 x 1 operand are spread between the halo items, so that every halo item
@@ -169,6 +175,56 @@ __device__ __forceinline__ void tile_coords(const ConvParams& p, int tile, int& 
     const int th = m_tile % p.tiles_h;
     const int tn = m_tile / p.tiles_h;
     w0 = tw * p.BW, h0 = th * p.BH, n0 = tn * p.BN;
+}
+
+// In-place input transform of one landed A tile (see the kernel's halo notes): thread (rg, chunk) owns the 16-byte chunk
+// `chunk` (8 channels) of tile rows rg, rg + 16, ... (i & 7 == rg & 7: the chunk sits at the same swizzled position in
+// each of them; a warp instruction touches 4 full 128-byte rows, conflict free).  Tile row i is pixel
+// (h0 - OFF + i / PITCH, w0 - OFF + i % PITCH).  One warp per scheduler does this work, so instruction-level parallelism
+// has to hide the shared-memory and SFU latencies: branch-free groups of four rows, all loads first.  Same arithmetic as
+// gn_apply_kernel: f = fma(a, x, b), SiLU as f + f tanh(f) on halved coefficients, round to bf16.
+template <int PITCH, int ROWS, int OFF>
+__device__ __forceinline__ void transform_tile(uint32_t slot, int rg, int chunk, const float (&a)[8], const float (&b)[8],
+                                               int silu, int h0, int w0, int H, int W) {
+    const uint32_t base = slot + (uint32_t)rg * 128u + ((uint32_t)(chunk ^ (rg & 7)) << 4);
+    constexpr int KS = (ROWS + 15) / 16;
+#pragma unroll
+    for (int k0 = 0; k0 < KS; k0 += 4) {
+        uint32_t v[4][4];
+        bool inside[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = rg + 16 * (k0 + u);
+            const int y = i / PITCH, x = i - y * PITCH;
+            // out-of-image pixels stay at (are reset to) zero: the convolution pads the NORMALISED tensor
+            inside[u] = (unsigned)(h0 - OFF + y) < (unsigned)H && (unsigned)(w0 - OFF + x) < (unsigned)W;
+            if (16 * (k0 + u) + 15 < ROWS || i < ROWS)
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3])
+                             : "r"(base + (uint32_t)(k0 + u) * 2048u)
+                             : "memory");
+            else v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float f0 = fmaf(a[2 * j], bf16_bits_to_f32(v[u][j] & 0xffffu), b[2 * j]);
+                float f1 = fmaf(a[2 * j + 1], __uint_as_float(v[u][j] & 0xffff0000u), b[2 * j + 1]);
+                if (silu) f0 = fmaf(f0, tanh_approx(f0), f0), f1 = fmaf(f1, tanh_approx(f1), f1);
+                __nv_bfloat162 r = __floats2bfloat162_rn(f0, f1);
+                v[u][j] = inside[u] ? *reinterpret_cast<uint32_t*>(&r) : 0u;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = rg + 16 * (k0 + u);
+            if (16 * (k0 + u) + 15 < ROWS || i < ROWS)
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + (uint32_t)(k0 + u) * 2048u), "r"(v[u][0]),
+                             "r"(v[u][1]), "r"(v[u][2]), "r"(v[u][3])
+                             : "memory");
+        }
+    }
 }
 
 // LEAN: the epilogue of the common case -- bf16 NHWC output, no activation, no gate, no split-K, GroupNorm sums (if
@@ -267,7 +323,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
     // followed by the 64-channel blocks of the fused 1 x 1 operand (one plain 128-pixel tile, one weight tile each)
     const int items = p.kb_per_tap + p.kb_extra;
     const int SA = p.sa, SB = p.sb;
-    const uint32_t b_ring = smem_base + (uint32_t)(SA * C::A_SLOT);
+    const uint32_t b_ring = smem_base + (uint32_t)(SA * p.a_slot);
 
     if (HALO && warp == 0) {
         // ===== TMA producer (halo): the stage ring =====
@@ -332,8 +388,14 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                 for (int hi = 0; hi < p.kb_per_tap; ++hi) {
                     tc::mbar_wait(tc::smem_u32(&bar_a_empty[sa]), pa);
                     const uint32_t full = tc::smem_u32(&bar_a_full[sa]);
-                    tc::mbar_expect_tx(full, HALO_BYTES);
-                    tc::tma_load_4d(smem_base + sa * C::A_SLOT, &tmap_a, full, hi * BLOCK_K, w0 - 1, h0 - 1, n0);
+                    const uint32_t dst = smem_base + (uint32_t)(sa * p.a_slot);
+                    if (p.in_up) {  // (channels, x replica, x / 2, y replica, image rows / 2): see UP_PITCH
+                        tc::mbar_expect_tx(full, UP_BYTES);
+                        tc::tma_load_5d(dst, &tmap_a, full, hi * BLOCK_K, 0, (w0 >> 1) - 1, 0, n0 * (p.H >> 1) + (h0 >> 1) - 1);
+                    } else {
+                        tc::mbar_expect_tx(full, HALO_BYTES);
+                        tc::tma_load_4d(dst, &tmap_a, full, hi * BLOCK_K, w0 - 1, h0 - 1, n0);
+                    }
                     if (++sa == SA) sa = 0, pa ^= 1u;
                 }
             }
@@ -370,16 +432,18 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                         // CTA's own tensor core, never by this thread: the CTA-scope acquire of try_wait suffices)
                         tc::mbar_wait(tc::smem_u32(&bar_a_ready[sa]), pa);
                         tc::fence_after_sync();
-                        uint32_t a_src = smem_base + sa * C::A_SLOT;  // tap (0, 0): the view that starts at halo pixel (0, 0)
+                        // tap (0, 0): the view that starts at halo pixel (0, 0)
+                        uint32_t a_src = smem_base + (uint32_t)(sa * p.a_slot) + (p.in_up ? UP_ORIGIN * 128u : 0u);
+                        const uint32_t pitch = p.in_up ? UP_PITCH : HALO_PITCH;
                         for (int t = 0, kw = 0; t < 9; ++t) {
                             tc::mbar_wait(tc::smem_u32(&bar_full[sb]), pb);
                             tc::fence_after_sync();
-                            mma4(tc::smem_desc_sw128_sbo(a_src, HALO_PITCH * 128u), tc::smem_desc_sw128(b_ring + sb * C::STAGE_BYTES),
+                            mma4(tc::smem_desc_sw128_sbo(a_src, pitch * 128u), tc::smem_desc_sw128(b_ring + sb * C::STAGE_BYTES),
                                  tmem_acc, (it | t) == 0);
                             release(&bar_empty[sb]);
                             if (++sb == SB) sb = 0, pb ^= 1u;
                             // next tap: one pixel to the right, or back to column 0 of the next halo row
-                            if (++kw == 3) kw = 0, a_src += (HALO_PITCH - 2) * 128u;
+                            if (++kw == 3) kw = 0, a_src += (pitch - 2) * 128u;
                             else a_src += 128u;
                         }
                         release(&bar_a_empty[sa]);
@@ -428,47 +492,9 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                 }
                 tc::mbar_wait(tc::smem_u32(&bar_a_full[sa]), pa);
                 if (xf) {
-                    // rows i = rg + 16 k, k = 0 .. 11 (i & 7 == rg & 7: the chunk sits at the same swizzled position in
-                    // each of them).  One warp per scheduler does this work, so instruction-level parallelism has to hide
-                    // the shared-memory and SFU latencies: branch-free groups of four rows, all loads first.
-                    const uint32_t base = smem_base + sa * C::A_SLOT + (uint32_t)rg * 128u + ((uint32_t)(chunk ^ (rg & 7)) << 4);
-#pragma unroll
-                    for (int k0 = 0; k0 < 12; k0 += 4) {
-                        uint32_t v[4][4];
-                        bool inside[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int i = rg + 16 * (k0 + u);
-                            const int y = i / HALO_PITCH, x = i - y * HALO_PITCH;
-                            // out-of-image pixels stay at the zero the TMA unit wrote: the convolution pads the NORMALISED tensor
-                            inside[u] = (unsigned)(h0 - 1 + y) < (unsigned)p.H && (unsigned)(w0 - 1 + x) < (unsigned)p.W;
-                            if (k0 + u < 11 || i < HALO_ROWS)
-                                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                                             : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3])
-                                             : "r"(base + (uint32_t)(k0 + u) * 2048u)
-                                             : "memory");
-                            else v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0u;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float f0 = fmaf(a[2 * j], bf16_bits_to_f32(v[u][j] & 0xffffu), b[2 * j]);
-                                float f1 = fmaf(a[2 * j + 1], __uint_as_float(v[u][j] & 0xffff0000u), b[2 * j + 1]);
-                                if (p.in_silu) f0 = fmaf(f0, tanh_approx(f0), f0), f1 = fmaf(f1, tanh_approx(f1), f1);
-                                __nv_bfloat162 r = __floats2bfloat162_rn(f0, f1);
-                                v[u][j] = inside[u] ? *reinterpret_cast<uint32_t*>(&r) : 0u;
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int i = rg + 16 * (k0 + u);
-                            if (k0 + u < 11 || i < HALO_ROWS)
-                                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + (uint32_t)(k0 + u) * 2048u),
-                                             "r"(v[u][0]), "r"(v[u][1]), "r"(v[u][2]), "r"(v[u][3])
-                                             : "memory");
-                        }
-                    }
+                    const uint32_t slot = smem_base + (uint32_t)(sa * p.a_slot);
+                    if (p.in_up) transform_tile<UP_PITCH, UP_ROWS, 2>(slot, rg, chunk, a, b, p.in_silu, h0, w0, p.H, p.W);
+                    else transform_tile<HALO_PITCH, HALO_ROWS, 1>(slot, rg, chunk, a, b, p.in_silu, h0, w0, p.H, p.W);
                     tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's (async proxy) reads
                 }
                 __syncwarp();
@@ -983,6 +1009,7 @@ struct ConvExtra {
     void* workspace = nullptr;   // split-K scratch: flags (zero between launches) + fp32 partial tiles
     int64_t workspace_bytes = 0;
     int res_up = 0;              // residual given at half resolution (nearest 2x upsampling on the fly)
+    int in_up = 0;               // act given at half resolution: the convolution reads its nearest 2x upsampling (halo + in_coef)
     const float* in_coef = nullptr;  // [N][c_in] {a, b}: the input is act(a x + b), applied on the fly (halo kernels only)
     int in_silu = 0;
     AzbConvChoice* choice = nullptr;  // dry run: report the launcher's choice instead of launching
@@ -1024,6 +1051,8 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
                 !colsum && ex.act == AZB_ACT_NONE && !ex.gate && (!ex.gn_acc || stat_gran == 8) &&
                 c_in / BLOCK_K + (ex.act2 ? ex.c_in2 / BLOCK_K : 0) <= 64 && !(ex.act2 && out_mode == 1);
     if (ex.in_coef && !azb_aligned(ex.in_coef, 16)) return AZB_E_ALIGN;
+    // in_up: (h_in, w_in) are the UPSAMPLED extents; the zero padding is restored by the input transform, so it needs one
+    if (ex.in_up && (!ex.in_coef || (h_in & 1) || (w_in & 1) || ex.stride != 1 || taps != 9)) return AZB_E_SHAPE;
 
     ConvParams p{};
     p.N = (int)n, p.H = (int)h, p.W = (int)w;
@@ -1117,6 +1146,8 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     // STAGES loads in flight the main loop would run at HBM latency; prefetch the weight stream into L2 ahead of use
     p.prefetch_kb = halo ? 0 : g_knob[AZB_CONV_KNOB_PREFETCH] >= 0 ? g_knob[AZB_CONV_KNOB_PREFETCH] : (m_tiles <= 32 ? 24 : 0);
     p.in_coef = reinterpret_cast<const float2*>(ex.in_coef), p.in_silu = ex.in_silu, p.c_in = (int)c_in;
+    p.in_up = ex.in_up;
+    p.a_slot = ex.in_up ? UP_BYTES : Cfg<256, true, true>::A_SLOT;
     p.sa = g_knob[AZB_CONV_KNOB_HALO_SA] >= 2 && g_knob[AZB_CONV_KNOB_HALO_SA] <= 4 ? g_knob[AZB_CONV_KNOB_HALO_SA] : 3;
     if (halo) {
         // item order of a tile: halo item h is followed by the 1 x 1 blocks [h P / H, (h + 1) P / H)
@@ -1133,7 +1164,16 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     const int64_t k_total = taps * k_per_tap + (ex.act2 ? ex.k2 : 0);
 
     CUtensorMap ta, tb, ta2;
-    {
+    if (ex.in_up) {
+        // virtual nearest-neighbour upsampling of the (n, h / 2, w / 2, c_in) tensor: (channel, x replica [stride 0], x / 2,
+        // y replica [stride 0], image row / 2 over all images); out-of-range columns are zero-filled, out-of-image rows
+        // read the neighbouring image -- either way the input transform resets out-of-image pixels to zero
+        uint64_t dims[5] = {(uint64_t)c_in, 2, (uint64_t)(w_in / 2), 2, (uint64_t)(n * (h_in / 2))};
+        uint64_t str[4] = {0, (uint64_t)act_ld * 2, 0, (uint64_t)act_ld * 2 * (uint64_t)(w_in / 2)};
+        uint32_t box[5] = {BLOCK_K, 2, UP_PITCH / 2, 2, UP_ROWS / UP_PITCH / 2};
+        int rc = make_map(&ta, act, 5, dims, str, box);
+        if (rc) return rc;
+    } else {
         // strided convolutions traverse the input with element strides (2, 2): the box spans stride * B pixels
         // of the input and delivers B of them; coordinates stay in input pixels
         const uint32_t st = (uint32_t)ex.stride;
@@ -1173,7 +1213,7 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     if (halo) {
         const int b_stage = out_mode == 1 ? Cfg<16, false, true>::STAGE_BYTES
                                           : pair ? Cfg<256, true, true>::STAGE_BYTES * block_n / 256 : Cfg<256, false, true>::STAGE_BYTES * block_n / 256;
-        p.sb = (SMEM_BUDGET - p.sa * Cfg<256, true, true>::A_SLOT) / b_stage;
+        p.sb = (SMEM_BUDGET - p.sa * p.a_slot) / b_stage;
         if (p.sb > 8) p.sb = 8;
         if (g_knob[AZB_CONV_KNOB_HALO_SB] >= 2 && g_knob[AZB_CONV_KNOB_HALO_SB] < p.sb) p.sb = g_knob[AZB_CONV_KNOB_HALO_SB];
         if (p.sb < 2) return AZB_E_SHAPE;
@@ -1255,7 +1295,7 @@ extern "C" int azb_conv_bf16(const AzbConv* d, void* stream) {
     ex.gn_acc = d->gn_acc;
     ex.workspace = d->workspace, ex.workspace_bytes = d->workspace_bytes;
     ex.in_coef = d->in_coef, ex.in_silu = d->in_silu;
-    ex.res_up = d->res_up;
+    ex.res_up = d->res_up, ex.in_up = d->in_up;
     return conv_impl(d->act, d->n, d->h, d->w, d->c_in, d->act_ld, d->wpack, d->c_out, d->c_out_rows, d->taps, d->k_per_tap,
                      d->bias, d->residual, d->res_ld, d->out, d->out_ld, d->out_mode, d->colsum,
                      (d->colsum || d->gn_acc) ? d->stat_gran : 1, stream, ex);
@@ -1271,7 +1311,7 @@ extern "C" int azb_conv_choice(const AzbConv* d, AzbConvChoice* choice) {
     ex.gn_acc = d->gn_acc;
     ex.workspace = d->workspace, ex.workspace_bytes = d->workspace_bytes;
     ex.in_coef = d->in_coef, ex.in_silu = d->in_silu;
-    ex.res_up = d->res_up;
+    ex.res_up = d->res_up, ex.in_up = d->in_up;
     ex.choice = choice;
     return conv_impl(d->act, d->n, d->h, d->w, d->c_in, d->act_ld, d->wpack, d->c_out, d->c_out_rows, d->taps, d->k_per_tap,
                      d->bias, d->residual, d->res_ld, d->out, d->out_ld, d->out_mode, d->colsum,

@@ -244,24 +244,27 @@ class Plan:
         return acc
 
     def _conv(self, x: Tensor, pc, out: Tensor, residual: Tensor | None = None, stats: bool = False,
-              x2: Tensor | None = None, in_coef: Tensor | None = None, in_silu: bool = True, res_up: bool = False) -> None:
+              x2: Tensor | None = None, in_coef: Tensor | None = None, in_silu: bool = True, res_up: bool = False,
+              in_up: bool = False) -> None:
         r"""Queues a convolution (``azb_conv_bf16``); with ``stats`` its epilogue also adds the exact sums from
         which the GroupNorm(s) consuming ``out`` derive their statistics (no read pass over ``out``, no reduction
         launch).  With ``x2`` the ResBlock's 1x1 skip connection is part of the same GEMM.  With ``in_coef``
         (:meth:`_coef`) the GroupNorm + SiLU of the INPUT is applied on the fly to the halo tiles."""
         n, h, w, _ = x.shape
+        if in_up:  # x at half resolution, read through a nearest 2x upsampling
+            h, w = 2 * h, 2 * w
         acc = self._acc_for(out, pc.c_out) if stats else None
         if not stats:
             self.acc_of.pop(self._key(out), None)
-        d = ops.conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=self.stat_gran, workspace=self.splitk_ws,
-                          in_coef=in_coef, in_silu=in_silu, res_up=res_up)
+        d = ops.conv_desc(x, pc, out, grid=(n, h, w), residual=residual, x2=x2, gn_acc=acc, gran=self.stat_gran,
+                          workspace=self.splitk_ws, in_coef=in_coef, in_silu=in_silu, res_up=res_up, in_up=in_up)
         self.keep += [d, x, out, pc.w] + [t for t in (residual, pc.bias, x2, in_coef) if t is not None]
         taps = 9 if x2 is not None else pc.taps
         k_extra = pc.c_in2 if x2 is not None else 0
         flops = 2.0 * n * h * w * pc.c_out * (taps * pc.c_in + k_extra)
         nbytes = 2.0 * (n * h * w * (pc.c_in + k_extra + pc.c_out * (2 if residual is not None else 1))
                         + pc.c_out * (taps * pc.c_in + k_extra))
-        desc = f"{n}x{h}x{w} {pc.c_in}->{pc.c_out}" + (" gn+" if in_coef is not None else "") + (
+        desc = f"{n}x{h}x{w} {pc.c_in}->{pc.c_out}" + (" gn+" if in_coef is not None else "") + (" up+" if in_up else "") + (
             (" +res(up)" if res_up else " +res") if residual is not None else "") + (
             f" +skip1x1({pc.c_in2})" if x2 is not None else "") + (" +stats" if acc is not None else "")
         self._emit("conv3x3" if taps == 9 else "conv1x1", flops, nbytes, self.lib.azb_conv_bf16, byref(d), desc=desc)
@@ -285,12 +288,14 @@ class Plan:
         )
 
     def _fusable(self, stats, x: Tensor, pc, out: Tensor, residual: Tensor | None = None, x2: Tensor | None = None,
-                 nchw_f32: bool = False) -> bool:
+                 nchw_f32: bool = False, in_up: bool = False) -> bool:
         r"""Whether the GroupNorm (+ SiLU) in front of this convolution can ride on its halo tiles: statistics from
         exact accumulators and a halo kernel for the shape (``azb_conv_choice``)."""
         if not FUSE_NORM or stats is None or stats[0] != "acc" or (x2 is not None and not FUSE_NORM_SKIP):
             return False
-        d = ops.conv_desc(x, pc, out, residual=residual, x2=x2, gran=self.stat_gran, nchw_f32=nchw_f32)
+        n, h, w, _ = x.shape
+        grid = (n, 2 * h, 2 * w) if in_up else (n, h, w)
+        d = ops.conv_desc(x, pc, out, grid=grid, residual=residual, x2=x2, gran=self.stat_gran, nchw_f32=nchw_f32)
         return bool(ops.conv_choice(d).halo)
 
     def _coef(self, x: Tensor, stats, affine, emb_offset: int | None, silu: bool) -> Tensor:
@@ -401,12 +406,17 @@ class Plan:
             self._conv(x, w_["conv1"], h2, stats=True, in_coef=self._coef(x, st1, w_["gn1"], None, True))
             xr = x
         else:
-            h1 = arena.take(n, ho, wo, u.cin)
+            h1, h1_done = arena.take(n, ho, wo, u.cin), False
             identity_skip = w_["skip"] is None and not isinstance(w_["conv2"], ops.PackedConvSkip)
             if u.resample == 1 and identity_skip and RESAMPLE_SHORTCUTS:
-                # upsampling block: x_upd = up(x) is never stored, conv2's epilogue reads x through the 2x upsampling
-                self._apply(x, h1, st1, w_["gn1"], None, True, 1)
+                # upsampling block: x_upd = up(x) is never stored, conv2's epilogue reads x through the 2x upsampling;
+                # nor is up(SiLU(GN(x))) when conv1 can load its halo tiles through an upsampling tensor map
                 xr, res_up = x, True
+                if self._fusable(st1, x, w_["conv1"], h2, in_up=True):
+                    self._conv(x, w_["conv1"], h2, stats=True, in_coef=self._coef(x, st1, w_["gn1"], None, True), in_up=True)
+                    h1_done = True
+                else:
+                    self._apply(x, h1, st1, w_["gn1"], None, True, 1)
             elif u.resample == 2 and st1[0] == "acc" and RESAMPLE_SHORTCUTS:
                 # downsampling block: ONE pass over x writes pool(SiLU(GN(x))) and x_upd = pool(x)
                 xr = arena.take(n, ho, wo, u.cin)
@@ -418,7 +428,8 @@ class Plan:
                     self._apply(x, xr, None, None, None, False, u.resample)  # x_upd on the raw input
                 else:
                     xr = x
-            self._conv(h1, w_["conv1"], h2, stats=True)
+            if not h1_done:
+                self._conv(h1, w_["conv1"], h2, stats=True)
             arena.give(h1)
         st2 = self._stats(h2)
         skip_fused = isinstance(w_["conv2"], ops.PackedConvSkip)

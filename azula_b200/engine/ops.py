@@ -32,7 +32,7 @@ class AzbConv(ctypes.Structure):
         ("residual", c_void_p), ("res_ld", c_int64), ("out", c_void_p), ("out_ld", c_int64), ("colsum", c_void_p),
         ("act2", c_void_p), ("c_in2", c_int64), ("act2_ld", c_int64), ("k2", c_int64), ("gn_acc", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
-        ("in_coef", c_void_p), ("in_silu", c_int64),
+        ("in_coef", c_void_p), ("in_silu", c_int32), ("in_up", c_int32),
     ]
 
 
@@ -565,7 +565,7 @@ def conv_desc(x: Tensor, pc, out: Tensor, *, grid: tuple[int, int, int] | None =
               gate: int | None = None, gate_ld: int = 0, gate_rows: int = 0, residual: Tensor | None = None,
               nchw_f32: bool = False, x2: Tensor | None = None, gn_acc: Tensor | None = None, gran: int = 8,
               workspace: Tensor | None = None, in_coef: Tensor | None = None, in_silu: bool = False,
-              res_up: bool = False) -> AzbConv:
+              res_up: bool = False, in_up: bool = False) -> AzbConv:
     r"""Fills an :class:`AzbConv` for ``azb_conv_bf16``; ``pc`` is a :class:`PackedConv` or, with ``x2``, a
     :class:`PackedConvSkip``.  ``gn_acc``: int64 (N, C_out / gran, 4) exact GroupNorm accumulators (zeroed by the
     caller).  ``in_coef``: fp32 (N, C_in, 2) from :func:`gn_coef` -- the convolution then reads
@@ -590,6 +590,7 @@ def conv_desc(x: Tensor, pc, out: Tensor, *, grid: tuple[int, int, int] | None =
     if in_coef is not None:
         assert in_coef.dtype == torch.float32 and in_coef.is_contiguous() and in_coef.numel() == n * pc.c_in * 2
         d.in_coef, d.in_silu = in_coef.data_ptr(), int(in_silu)
+    d.in_up = int(in_up)  # x is (n, h / 2, w / 2, c): read through a nearest 2x upsampling, `grid` = the upsampled extents
     return d
 
 
@@ -623,14 +624,16 @@ def gn_coef(n: int, h: int, w: int, parts: list[tuple[Tensor, int]], gamma: Tens
 
 def conv_acc(x: Tensor, pc, out: Tensor | None = None, residual: Tensor | None = None, x2: Tensor | None = None,
              gran: int = 8, workspace: Tensor | None = None, in_coef: Tensor | None = None,
-             in_silu: bool = False, res_up: bool = False) -> tuple[Tensor, Tensor]:
+             in_silu: bool = False, res_up: bool = False, in_up: bool = False) -> tuple[Tensor, Tensor]:
     r"""Convolution that also returns the exact GroupNorm accumulators of its output: (out, int64 (N, C_out / gran, 4))."""
     n, h, w, _ = x.shape
+    if in_up:
+        h, w = 2 * h, 2 * w
     if out is None:
         out = torch.empty(n, h, w, pc.c_out, dtype=torch.bfloat16, device=x.device)
     acc = torch.zeros(n, pc.c_out // gran, 4, dtype=torch.int64, device=x.device)
-    d = conv_desc(x, pc, out, residual=residual, x2=x2, gn_acc=acc, gran=gran, workspace=workspace, in_coef=in_coef,
-                  in_silu=in_silu, res_up=res_up)
+    d = conv_desc(x, pc, out, grid=(n, h, w), residual=residual, x2=x2, gn_acc=acc, gran=gran, workspace=workspace,
+                  in_coef=in_coef, in_silu=in_silu, res_up=res_up, in_up=in_up)
     _lib.check(_lib.lib().azb_conv_bf16(byref(d), _lib.stream_ptr(x.device)), "azb_conv_bf16")
     return out, acc
 

@@ -210,7 +210,11 @@ typedef struct AzbConv {
      * GroupNorm (+ scale / shift) + SiLU that precedes it in the reference (_src/unet.py:177-181,203-207,238-243)
      * without a normalisation pass over HBM.  in_coef: fp32 [n][c_in][2] from azb_gn_coef_f32; in_silu as given there. */
     const float* in_coef;
-    int64_t in_silu;
+    int32_t in_silu;
+    /* in_up = 1 (needs in_coef): `act` is (n, h / 2, w / 2, c_in) and the convolution reads its nearest-neighbour 2x
+     * upsampling, (h, w) being the upsampled extents: conv(up(act(A x + B))) of an upsampling ResBlock
+     * (_src/unet.py:101-109,229-233) without the 4x larger intermediate. */
+    int32_t in_up;
 } AzbConv;
 
 int azb_conv_bf16(const AzbConv* desc, void* stream);

@@ -235,3 +235,29 @@ def test_pooling_both_branches_in_one_pass():
     assert torch.equal(a2, a) and torch.equal(raw2, raw)
     ref = F.avg_pool2d(t.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
     _check(raw2, ref, "pooled raw branch")
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 256, 256, True), (3, 8, 8, 256, 128, False), (1, 32, 16, 512, 256, True),
+                                   (2, 24, 20, 256, 128, True)])
+@pytest.mark.parametrize("pair", [0, 1])
+def test_upsampling_on_load_is_bit_exact_with_materialised_upsampling(shape, pair):
+    """conv(up(SiLU(GN(x) ...))) of an upsampling ResBlock (_src/unet.py:101-109,229-233): the halo tiles come from the
+    HALF-resolution tensor through a tensor map with zero-stride replication dimensions and are normalised in place;
+    bit-equal to normalise + upsample to HBM (azb_gn_apply_acc_bf16 mode 1) followed by the same halo kernel."""
+    n, h, w, ci, co, use_ss = shape  # (h, w): the half resolution
+    t, parts, gamma, beta, ss = _normalised_input(n, h, w, ci, None, seed=61)
+    ss = ss if use_ss else None
+    _, wt, b = _mk(n, 2 * h, 2 * w, ci, co, 3, seed=67)
+    pc = ops.pack_conv(wt.float(), b)
+    ops.conv_tuning(ops.KNOB_PAIR, pair)
+    _wide_tiles(co)
+    y = ops.gn_apply_acc(t, parts, gamma, beta, scale_shift=ss, mode=1)
+    assert y.shape == (n, 2 * h, 2 * w, ci)
+    two, acc_two = ops.conv_acc(y, pc)
+    coef = ops.gn_coef(n, h, w, parts, gamma, beta, scale_shift=ss)
+    one, acc_one = ops.conv_acc(t, pc, in_coef=coef, in_silu=True, in_up=True)
+    torch.cuda.synchronize()
+    assert one.shape == two.shape
+    assert torch.equal(one, two), (one.float() - two.float()).abs().max().item()
+    assert torch.equal(acc_one, acc_two)
+    _check(one, _ref(y, wt, b), ("upsampling on load", shape))
