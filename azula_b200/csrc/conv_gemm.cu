@@ -1151,7 +1151,7 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     p.sa = g_knob[AZB_CONV_KNOB_HALO_SA] >= 2 && g_knob[AZB_CONV_KNOB_HALO_SA] <= 4 ? g_knob[AZB_CONV_KNOB_HALO_SA] : 3;
     if (halo) {
         // item order of a tile: halo item h is followed by the 1 x 1 blocks [h P / H, (h + 1) P / H)
-        const int H = p.kb_per_tap, P = p.kb_extra, spread = g_knob[AZB_CONV_KNOB_HALO_AHEAD] != 0;
+        const int H = p.kb_per_tap, P = p.kb_extra, spread = g_knob[AZB_CONV_KNOB_HALO_SPREAD] != 0;
         p.item_mask = 0;
         int pos = 0;
         for (int hh = 0, done = 0; hh < H; ++hh) {

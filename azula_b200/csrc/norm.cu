@@ -196,10 +196,10 @@ __device__ __forceinline__ float2 group_stat(const ApplyParams& p, int n, int g,
 // {A, B} of channel c: y = act(A x + B) with A = rstd gamma (1 + scale), B = (beta - mean rstd gamma)(1 + scale) + shift;
 // halved when the activation is SiLU (evaluated as h + h tanh(h), h = (A x + B) / 2)
 __device__ __forceinline__ float2 channel_coef(const ApplyParams& p, const float2* s_stat, const float* ss, int c, int cg,
-                                               bool silu) {
+                                               bool silu, int g_first = 0) {
     float aa = 1.f, bb = 0.f;
     if (p.stats || p.acc[0]) {
-        const float2 st = s_stat[c / cg];
+        const float2 st = s_stat[c / cg - g_first];
         aa = __fmul_rn(st.y, __ldg(p.gamma + c));
         bb = __fsub_rn(__ldg(p.beta + c), __fmul_rn(st.x, aa));
     }
@@ -212,16 +212,18 @@ __device__ __forceinline__ float2 channel_coef(const ApplyParams& p, const float
 }
 
 // coef[n][c] = {A, B} for the convolution kernels that apply the normalisation to their input on the fly
-// (AzbConv::in_coef): one CTA per image.
+// (AzbConv::in_coef): one CTA per (256 channels, image); the first thread of each group folds its statistics.
 __global__ void __launch_bounds__(THREADS) gn_coef_kernel(const ApplyParams p, float2* coef) {
     pdl_enter();
-    const int n = blockIdx.x;
+    const int n = blockIdx.y;
     const int cg = p.c / p.groups;
+    const int c = blockIdx.x * THREADS + threadIdx.x;
     const float* ss = p.scale_shift ? p.scale_shift + (int64_t)n * p.ss_stride : nullptr;
-    __shared__ float2 s_stat[THREADS];
-    if (threadIdx.x < p.groups) s_stat[threadIdx.x] = group_stat(p, n, threadIdx.x, cg);
+    __shared__ float2 s_stat[THREADS];  // indexed by group - first group of this CTA
+    const int g0 = (blockIdx.x * THREADS) / cg;
+    if (c < p.c && (c % cg == 0 || threadIdx.x == 0)) s_stat[c / cg - g0] = group_stat(p, n, c / cg, cg);
     __syncthreads();
-    for (int c = threadIdx.x; c < p.c; c += THREADS) coef[(int64_t)n * p.c + c] = channel_coef(p, s_stat, ss, c, cg, p.silu != 0);
+    if (c < p.c) coef[(int64_t)n * p.c + c] = channel_coef(p, s_stat, ss, c, cg, p.silu != 0, g0);
 }
 
 // y = act(A[c]*x + B[c]) with A = rstd*gamma*(1+scale), B = (beta - mean*rstd*gamma)*(1+scale) + shift.
@@ -554,8 +556,8 @@ extern "C" int azb_gn_coef_f32(int64_t n, int64_t h, int64_t w, int64_t c, int64
     p.acc[0] = reinterpret_cast<const long long*>(acc_a), p.acc[1] = reinterpret_cast<const long long*>(acc_b);
     p.acc_c[0] = (int)c_a, p.acc_c[1] = (int)c_b, p.acc_gran = (int)gran, p.eps = eps;
     p.acc_scale = 1.0 / (1099511627776.0 * (double)h * (double)w * (double)(c / groups));
-    return azb_launch(gn_coef_kernel, dim3((unsigned)n), dim3(THREADS), 0, reinterpret_cast<cudaStream_t>(stream), p,
-                      reinterpret_cast<float2*>(coef));
+    return azb_launch(gn_coef_kernel, dim3((unsigned)((c + THREADS - 1) / THREADS), (unsigned)n), dim3(THREADS), 0,
+                      reinterpret_cast<cudaStream_t>(stream), p, reinterpret_cast<float2*>(coef));
 }
 
 extern "C" int azb_gn_finalize_f32(const float* colsum_a, int64_t c_a, int gran_a, const float* colsum_b, int64_t c_b,

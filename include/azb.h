@@ -246,7 +246,7 @@ int azb_conv_choice(const AzbConv* desc, AzbConvChoice* choice);
 #define AZB_CONV_KNOB_HALO 6
 #define AZB_CONV_KNOB_HALO_SA 7    /* halo kernels: A slots (2 .. 4; the rest of the ring holds weight stages) */
 #define AZB_CONV_KNOB_HALO_SB 8    /* halo kernels: cap on the weight stages */
-#define AZB_CONV_KNOB_HALO_AHEAD 9 /* halo kernels: 0 = the fused 1 x 1 blocks follow the last halo item (default: spread) */
+#define AZB_CONV_KNOB_HALO_SPREAD 9 /* halo kernels: 0 = the fused 1 x 1 blocks follow the last halo item (default: spread) */
 #define AZB_KNOB_PDL 10 /* 0: plain stream-ordered launches instead of programmatic dependent launches */
 #define AZB_CONV_KNOBS 11
 int azb_conv_tuning(int knob, int value);

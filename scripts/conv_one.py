@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--fused", type=int, default=0, help="apply act(a x + b) to the halo tiles (in_coef)")
     ap.add_argument("--skip", type=int, default=0, help="channels of a fused 1x1 operand")
     ap.add_argument("--sa", type=int, default=-1)
-    ap.add_argument("--ahead", type=int, default=-1)
+    ap.add_argument("--ahead", type=int, default=-1, help="0: fused 1x1 blocks after the last halo item (default: spread)")
     a = ap.parse_args()
     dev = "cuda"
     g = torch.Generator(device=dev).manual_seed(0)
@@ -43,7 +43,7 @@ def main():
     ops.conv_tuning(ops.KNOB_PAIR, a.pair)
     ops.conv_tuning(ops.KNOB_HALO, a.halo)
     ops.conv_tuning(ops.KNOB_HALO_SA, a.sa)
-    ops.conv_tuning(ops.KNOB_HALO_AHEAD, a.ahead)
+    ops.conv_tuning(ops.KNOB_HALO_SPREAD, a.ahead)
     coef = None
     if a.fused:
         coef = torch.stack((torch.full((a.batch, a.ci), 0.5, device=dev), torch.zeros(a.batch, a.ci, device=dev)), dim=-1).contiguous()

@@ -4,7 +4,8 @@
     halo     halo tiles, normalised input read from HBM
     fused    halo tiles + GroupNorm/SiLU transform in the A path (raw input + coefficients)
 
-and of the halo kernels' ring split (A slots / early A loads).  python scripts/halo_ab.py [--reps 20]
+and of the halo kernels' ring split: --configs "sa:spread,..." = A slots : 1x1 blocks spread between the halo items.
+python scripts/halo_ab.py [--reps 20]
 """
 
 import argparse
@@ -77,7 +78,7 @@ def main():
             def fn():
                 ops.conv_tuning(ops.KNOB_HALO, halo)
                 ops.conv_tuning(ops.KNOB_HALO_SA, sa)
-                ops.conv_tuning(ops.KNOB_HALO_AHEAD, ahead)
+                ops.conv_tuning(ops.KNOB_HALO_SPREAD, ahead)
                 ops.conv_acc(x, pc, out=out, residual=r, x2=x2, in_coef=c, in_silu=True)
             return fn
 
@@ -86,7 +87,7 @@ def main():
         for sa, ahead in configs:
             variants += [variant(1, sa, ahead, None), variant(1, sa, ahead, coef)]
         row = [flops / t * 1e-9 for t in timed_interleaved(variants, a.reps)][1:]
-        for k in (ops.KNOB_HALO, ops.KNOB_HALO_SA, ops.KNOB_HALO_AHEAD):
+        for k in (ops.KNOB_HALO, ops.KNOB_HALO_SA, ops.KNOB_HALO_SPREAD):
             ops.conv_tuning(k, -1)
         name = f"{n}x{hw}x{hw} {ci}->{co}" + (f" +skip{skip}" if skip else "") + (" +res" if res else "")
         print(name.ljust(44) + f"{row[0]:9.0f}" + "".join(f"{v:14.0f}" for v in row[1:]))
