@@ -35,6 +35,7 @@ from . import ops
 
 _MAX_PLANS = 2
 FUSE_NORM = True  # GroupNorm + SiLU ride on the halo tiles of the convolution that consumes them (A/B switch)
+UP_PHASES = True  # upsampling blocks: conv1(up(.)) as four 2 x 2 convolutions of the half-resolution tensor
 RESAMPLE_SHORTCUTS = True  # up blocks: residual read through the upsampling; down blocks: both branches in one pass
 FUSE_NORM_SKIP = True  # ... also when the ResBlock's 1x1 skip operand is part of the GEMM
 
@@ -68,6 +69,9 @@ class Packed:
                 self.unit[u.path] = {
                     "gn1": (f32(u.path + ".in_layers.0.weight"), f32(u.path + ".in_layers.0.bias")),
                     "conv1": ops.pack_conv(p[u.path + ".in_layers.2.weight"], p[u.path + ".in_layers.2.bias"]),
+                    # upsampling block: conv1(up(.)) as four 2 x 2 convolutions of the half-resolution tensor
+                    "conv1_up": (ops.pack_conv_up(p[u.path + ".in_layers.2.weight"], p[u.path + ".in_layers.2.bias"])
+                                 if u.resample == 1 and UP_PHASES else None),
                     "gn2": (f32(u.path + ".out_layers.0.weight"), f32(u.path + ".out_layers.0.bias")),
                     "conv2": conv2,
                     "skip": skip,
@@ -261,12 +265,17 @@ class Plan:
         self.keep += [d, x, out, pc.w] + [t for t in (residual, pc.bias, x2, in_coef) if t is not None]
         taps = 9 if x2 is not None else pc.taps
         k_extra = pc.c_in2 if x2 is not None else 0
+        phased = getattr(pc, "taps", 9) == 16
+        if phased:    # phase-decomposed upsampling convolution: 4 taps per output pixel EXECUTED; the algorithmic
+            taps = 9  # work of the reference layer (what the rates are quoted on) stays 9 taps
         flops = 2.0 * n * h * w * pc.c_out * (taps * pc.c_in + k_extra)
         nbytes = 2.0 * (n * h * w * (pc.c_in + k_extra + pc.c_out * (2 if residual is not None else 1))
                         + pc.c_out * (taps * pc.c_in + k_extra))
         desc = f"{n}x{h}x{w} {pc.c_in}->{pc.c_out}" + (" gn+" if in_coef is not None else "") + (" up+" if in_up else "") + (
             (" +res(up)" if res_up else " +res") if residual is not None else "") + (
             f" +skip1x1({pc.c_in2})" if x2 is not None else "") + (" +stats" if acc is not None else "")
+        if phased:
+            desc += " (4 x 2x2 phases)"
         self._emit("conv3x3" if taps == 9 else "conv1x1", flops, nbytes, self.lib.azb_conv_bf16, byref(d), desc=desc)
 
     def _conv_skip(self, x: Tensor, x2: Tensor, pc: ops.PackedConvSkip, out: Tensor, in_coef: Tensor | None = None) -> None:
@@ -295,8 +304,19 @@ class Plan:
             return False
         n, h, w, _ = x.shape
         grid = (n, 2 * h, 2 * w) if in_up else (n, h, w)
-        d = ops.conv_desc(x, pc, out, grid=grid, residual=residual, x2=x2, gran=self.stat_gran, nchw_f32=nchw_f32)
-        return bool(ops.conv_choice(d).halo)
+        d = ops.conv_desc(x, pc, out, grid=grid, residual=residual, x2=x2, gran=self.stat_gran, nchw_f32=nchw_f32,
+                          in_up=in_up, in_coef=self._probe_coef(n, pc.c_in) if in_up else None)
+        try:
+            return bool(ops.conv_choice(d).halo)
+        except _lib.AzbError:  # e.g. the phase-decomposed form on a map below 16 x 8 half-resolution pixels
+            return False
+
+    def _probe_coef(self, n: int, c: int) -> Tensor:
+        r"""A correctly shaped coefficient buffer for ``azb_conv_choice`` queries (nothing is launched)."""
+        t = getattr(self, "_probe", None)
+        if t is None or t.numel() < n * c * 2:
+            t = self._probe = torch.empty(n * c * 2, dtype=torch.float32, device=self.device)
+        return t[: n * c * 2]
 
     def _coef(self, x: Tensor, stats, affine, emb_offset: int | None, silu: bool) -> Tensor:
         r"""Queues ``azb_gn_coef_f32`` for the GroupNorm over ``x``: fp32 (N, C, 2) transform coefficients."""
@@ -412,7 +432,11 @@ class Plan:
                 # upsampling block: x_upd = up(x) is never stored, conv2's epilogue reads x through the 2x upsampling;
                 # nor is up(SiLU(GN(x))) when conv1 can load its halo tiles through an upsampling tensor map
                 xr, res_up = x, True
-                if self._fusable(st1, x, w_["conv1"], h2, in_up=True):
+                if w_.get("conv1_up") is not None and self._fusable(st1, x, w_["conv1_up"], h2, in_up=True):
+                    # ... as four 2 x 2 convolutions of x (one per output phase): 2.25 x fewer FLOPs
+                    self._conv(x, w_["conv1_up"], h2, stats=True, in_coef=self._coef(x, st1, w_["gn1"], None, True), in_up=True)
+                    h1_done = True
+                elif self._fusable(st1, x, w_["conv1"], h2, in_up=True):
                     self._conv(x, w_["conv1"], h2, stats=True, in_coef=self._coef(x, st1, w_["gn1"], None, True), in_up=True)
                     h1_done = True
                 else:

@@ -261,3 +261,37 @@ def test_upsampling_on_load_is_bit_exact_with_materialised_upsampling(shape, pai
     assert torch.equal(one, two), (one.float() - two.float()).abs().max().item()
     assert torch.equal(acc_one, acc_two)
     _check(one, _ref(y, wt, b), ("upsampling on load", shape))
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 256, 256, True), (1, 32, 16, 512, 256, True), (2, 24, 20, 256, 128, False),
+                                   (3, 16, 8, 256, 128, True)])
+@pytest.mark.parametrize("pair", [0, 1])
+def test_phase_decomposed_upsampling_convolution(shape, pair):
+    """conv3x3(up2(z)) as four 2 x 2 convolutions of z (azb.h: AzbConv::in_up = 2, weights from pack_conv_up): the same
+    function with 2.25 x fewer multiply-adds.  The taps that fall on one half-resolution pixel are summed in fp32 before
+    the bf16 rounding of the weights, so the result is held to the fp32 convolution of the upsampled tensor (with the
+    ORIGINAL fp32 weights) within the bf16 tolerance of weights and outputs, and to the 9-tap kernel within twice that."""
+    n, h, w, ci, co, use_ss = shape  # (h, w): the half resolution
+    t, parts, gamma, beta, ss = _normalised_input(n, h, w, ci, None, seed=71)
+    ss = ss if use_ss else None
+    g = torch.Generator(device=DEV).manual_seed(73)
+    wt = torch.randn(co, ci, 3, 3, device=DEV, generator=g) / (9 * ci) ** 0.5  # fp32 weights
+    b = torch.randn(co, device=DEV, generator=g)
+    ops.conv_tuning(ops.KNOB_PAIR, pair)
+    _wide_tiles(co)
+    coef = ops.gn_coef(n, h, w, parts, gamma, beta, scale_shift=ss)
+    y = ops.gn_apply_acc(t, parts, gamma, beta, scale_shift=ss, mode=1)  # bf16 up(SiLU(GN(t))): what both kernels convolve
+    nine, _ = ops.conv_acc(t, ops.pack_conv(wt, b), in_coef=coef, in_silu=True, in_up=True)
+    pc_up = ops.pack_conv_up(wt, b)
+    assert pc_up.taps == 16
+    four, acc = ops.conv_acc(t, pc_up, in_coef=coef, in_silu=True, in_up=True)
+    torch.cuda.synchronize()
+    assert four.shape == (n, 2 * h, 2 * w, co)
+    ref = F.conv2d(y.float().permute(0, 3, 1, 2), wt, b, padding=1).permute(0, 2, 3, 1)
+    tol = 2.0**-7 * ref.abs() + 2.0**-7 * ref.abs().mean()  # bf16 weights (2^-9 each, ~sqrt(K) of them) + bf16 output
+    assert ((four.float() - ref).abs() <= tol).all(), (four.float() - ref).abs().max().item()
+    assert ((nine.float() - ref).abs() <= tol).all()
+    # statistics of the stored values, per image and 8-channel block
+    o = four.double().reshape(n, 4 * h * w, co // 8, 8)
+    want = torch.stack((o.sum(dim=(1, 3)), o.square().sum(dim=(1, 3))), dim=-1)
+    assert torch.allclose(_acc_to_sums(acc), want, rtol=1e-5, atol=1e-3)
