@@ -48,6 +48,8 @@ def main():
         "s128": {ops.KNOB_PAIR: 0, ops.KNOB_BLOCKN: 128, ops.KNOB_SPLITK: 0},
         "s64": {ops.KNOB_PAIR: 0, ops.KNOB_BLOCKN: 64, ops.KNOB_SPLITK: 0},
         "generic": {ops.KNOB_LEAN: 0},
+        "tap": {ops.KNOB_HALO: 0},  # tap-wise TMA loads instead of halo tiles
+        "tap_p128": {ops.KNOB_HALO: 0, ops.KNOB_PAIR: 1, ops.KNOB_BLOCKN: 128, ops.KNOB_SPLITK: 0},
     }
     names = args.configs.split(",")
     ws = ops.splitk_workspace(dev)
@@ -73,7 +75,7 @@ def main():
         ref = None
         for rep in range(args.reps + 1):
             for c in names:
-                for kn in (ops.KNOB_PAIR, ops.KNOB_PREFETCH, ops.KNOB_SPLITK, ops.KNOB_BLOCKN, ops.KNOB_LEAN):
+                for kn in (ops.KNOB_PAIR, ops.KNOB_PREFETCH, ops.KNOB_SPLITK, ops.KNOB_BLOCKN, ops.KNOB_LEAN, ops.KNOB_HALO):
                     ops.conv_tuning(kn, configs[c].get(kn, -1))
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -94,7 +96,7 @@ def main():
         out_rows.append(row)
         print("  ".join(f"{k}={v}" for k, v in row.items()), flush=True)
         del x, x2, out, pc
-    for kn in (ops.KNOB_PAIR, ops.KNOB_PREFETCH, ops.KNOB_SPLITK, ops.KNOB_BLOCKN, ops.KNOB_LEAN):
+    for kn in (ops.KNOB_PAIR, ops.KNOB_PREFETCH, ops.KNOB_SPLITK, ops.KNOB_BLOCKN, ops.KNOB_LEAN, ops.KNOB_HALO):
         ops.conv_tuning(kn, -1)
     print(json.dumps(out_rows))
 
