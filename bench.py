@@ -310,7 +310,7 @@ def run_engine(args) -> None:
         dom_ms = sum(d[2] for d in dom) / max(len(dom), 1)
         dom_flop = dom[0][3] if dom else 0.0
         dom_tflops = dom_flop / dom_ms / 1e9 if dom else 0.0
-        traffic = 1098542848 if args.batch == 16 else None  # profiles/r1_ncu_full_conv_fused_v4.csv: dram read + write
+        traffic = 1099858432 if args.batch == 16 else None  # profiles/r1_ncu_full_conv_fused_v5.csv: dram read + write
         e2e_tflops = value / world * SAMPLER_STEPS * FLOP_PER_IMAGE_FORWARD / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
