@@ -14,6 +14,8 @@ from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libazb.so")
+if os.environ.get("AZB_LIBRARY"):  # A/B measurements of two builds on one box (scripts/build_ab.sh)
+    LIB_PATH = os.environ["AZB_LIBRARY"]
 ABI_VERSION = 2
 
 F32, BF16, F16, I64 = 0, 1, 2, 3
