@@ -28,17 +28,29 @@
 // other half of B from the peer's shared memory.  Per CTA and k-block that is 32 KiB from L2 instead of 48
 // (N = 256) -- the L2 -> SM path (~ 15 TB/s chip-wide at the single-CTA rate) is what caps the tensor pipe of
 // the single-CTA kernel at ~ 75 % -- and 6 pipeline stages instead of 4 in the same shared memory.
-
 //
 // Halo tiles (HALO = true, 3 x 3 stride-1 layers on feature maps of at least 16 x 8 pixels with C_in % 64 == 0): an M tile
 // is an 8-wide x 16-tall patch of ONE image and the A operand of a 64-channel block is ONE TMA box of (16 + 2) x (8 + 2)
 // pixels.  The nine taps are shifted views of that tile (descriptor start + (kh * 10 + kw) * 128 bytes, 1280 bytes
 // between 8-pixel row groups; the swizzle is a function of the absolute address, see tc::smem_desc_sw128_sbo), so the
-// activation crosses the L2 -> SM path 1.4 times instead of 9 times.  Four extra warps sit between the TMA unit and
-// the tensor core: they rewrite each landed halo tile in place as  bf16(act(a[n, c] * x + b[n, c]))  -- the GroupNorm
-// (+ scale / shift + SiLU) that precedes the convolution in the reference (_src/unet.py:177-181,203-207,238-243), with
-// the per-(image, channel) coefficients of azb_gn_coef_f32 -- and leave out-of-image pixels at the zero the TMA unit
-// filled in (padding applies to the NORMALISED tensor).  The separate normalisation pass over HBM disappears.
+// activation crosses the L2 -> SM path 1.4 times instead of 9 times.  Warp roles of a halo kernel (480 threads):
+//   warp 0       stage ring: one weight tile per k-block; a k-block of the fused 1 x 1 operand (ResBlock skip
+//                connection) takes two consecutive stages, plain A tile + weight tile, and these blocks are spread
+//                between the halo items of a tile (ConvParams::item_mask)
+//   warp 1       MMA issuer (as above; nine, or four, shifted views per halo item)
+//   warps 2..9   epilogue (as above)
+//   warps 10..13 input transform: rewrite each landed halo tile in place as  bf16(act(a[n, c] * x + b[n, c]))  -- the
+//                GroupNorm (+ scale / shift + SiLU) that precedes the convolution in the reference
+//                (_src/unet.py:177-181,203-207,238-243), coefficients from azb_gn_coef_f32 -- and reset out-of-image
+//                pixels to zero (the reference pads the NORMALISED tensor).  No normalisation pass over HBM.
+//   warp 14      halo-tile producer: keeps every free A slot loading, independently of the stage ring
+// Upsampling inputs (the conv1 of an upsampling ResBlock, _src/unet.py:101-109,229-233) never exist in HBM either:
+//   in_up = 1    the halo tile is loaded from the half-resolution tensor through a 5-d tensor map whose replication
+//                dimensions have stride 0 (12 x 20 pixels of the virtual upsampled tensor, halo origin one row and one
+//                column inside)
+//   in_up = 2    phase decomposition: four 2 x 2 convolutions of the half-resolution tensor with pre-summed taps, each
+//                (M tile, N tile, phase) a tile of this kernel (conv_impl)
+// and the skip branch up(x) is read by the epilogue at pixel (h / 2, w / 2) (res_up).
 
 #include "common.cuh"
 #include "tc.cuh"
