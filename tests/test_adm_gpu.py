@@ -260,3 +260,28 @@ def test_class_conditional_sampling_through_the_fused_loop():
     ref2 = RM.sample_loop(mean2, sched, x1, steps=3, eta=0.0)
     x02 = smp(x1, label=y2)
     assert (x02 - ref2).abs().mean().item() <= 2e-2 and (x02 - x0).abs().mean().item() > 1e-3
+
+
+def test_full_card_forward_vs_oracle():
+    """The bench configuration itself -- the imagenet_256x256 card (552.8 M parameters, cards.yaml:36-50) at 256 x 256 --
+    against the oracle's fp32 forward (TF32 off) with every parameter overwritten from a seed: all layer shapes of the
+    flagship path (halo tiles with fused GroupNorm at 256^2 .. 16^2, skip-operand convolutions, phase-decomposed
+    upsampling convolutions, split-K at 8^2, attention at 32^2 / 16^2 / 8^2) inside the stated bf16 tolerance."""
+    from oracle.gen_golden_cfg import IMAGENET_256
+
+    den, sd = _seeded(IMAGENET_256, seed=31)
+    tab = AU.block_table(**IMAGENET_256)
+    # the bench's own plan: batch 16, one shared timestep (as in the sampling loop)
+    x = torch.randn(16, 3, 256, 256, device=DEV, generator=torch.Generator(device=DEV).manual_seed(11))
+    ts = torch.tensor([537], device=DEV)
+    got = den.backbone(x, ts)
+    kinds = [m[0] for m in _plan(den).meta]
+    descs = [m[3] for m in _plan(den).meta]
+    fused, phased, up = kinds.count("gn_coef"), sum("phases" in d for d in descs), sum("up+" in d for d in descs)
+    print(f"fused GroupNorm sites {fused}, phase-decomposed {phased}, upsampling on load {up}")
+    assert fused == 65 and phased == 4 and up == 5
+    ref = torch.cat([AU.forward(sd, tab, x[i : i + 4], ts.expand(4)) for i in range(0, 16, 4)])  # fp32, 4 images at a time
+    assert got.shape == ref.shape == (16, 6, 256, 256)
+    _report(got, ref, "imagenet_256x256 card, 256 x 256")
+    del den, sd
+    torch.cuda.empty_cache()
