@@ -283,5 +283,18 @@ def test_full_card_forward_vs_oracle():
     ref = torch.cat([AU.forward(sd, tab, x[i : i + 4], ts.expand(4)) for i in range(0, 16, 4)])  # fp32, 4 images at a time
     assert got.shape == ref.shape == (16, 6, 256, 256)
     _report(got, ref, "imagenet_256x256 card, 256 x 256")
-    del den, sd
+    # ... and four DDIM steps of it through the captured graph against the oracle loop (mean |d| on [-1, 1] outputs)
+    sched = lambda t: RM.vp_alpha_sigma(t, 1e-2, 1e-2)  # noqa: E731
+    sig = RM.adm_sigmas().to(DEV)
+    net = lambda xx, tt, y=None: torch.cat([AU.forward(sd, tab, xx[i : i + 4], tt.expand(4)) for i in range(0, 16, 4)])  # noqa: E731
+    mean = lambda xx, tt: RM.adm_mean_var(net, sched, sig, xx, tt)[0]  # noqa: E731
+    smp = DDIMSampler(den, steps=4, silent=True, graph=True)
+    torch.manual_seed(0)
+    x1 = smp.init((16, 3, 256, 256), device=DEV)
+    x0 = smp(x1)
+    want = RM.sample_loop(mean, sched, x1, steps=4, eta=0.0)
+    err = (x0 - want).abs().mean().item()
+    print(f"imagenet_256x256 card, DDIM-4, graph: mean|d| {err:.2e} max|d| {(x0 - want).abs().max().item():.2e}")
+    assert next(iter(smp._loops.values())).graph is not None and torch.isfinite(x0).all() and err <= 2e-2
+    del den, sd, smp
     torch.cuda.empty_cache()
