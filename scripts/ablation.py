@@ -31,8 +31,25 @@ VARIANTS = [
 ]
 
 
+KNOB_VARIANTS = [
+    ("all on (default)", {}, {}),
+    ("halo kernels: 2 A slots", {}, {ops.KNOB_HALO_SA: 2}),
+    ("halo kernels: 3 A slots", {}, {ops.KNOB_HALO_SA: 3}),
+    ("halo kernels: 4 A slots", {}, {ops.KNOB_HALO_SA: 4}),
+    ("halo kernels: 4 A slots, again", {}, {ops.KNOB_HALO_SA: 4}),
+    ("halo kernels: fused 1x1 blocks after the last halo item", {}, {ops.KNOB_HALO_SPREAD: 0}),
+    ("CTA pairs wherever the shape allows", {}, {ops.KNOB_PAIR: 1}),
+    ("no weight prefetch into L2 on small maps", {}, {ops.KNOB_PREFETCH: 0}),
+    ("GroupNorm pass: short CTAs (no single wave)", {}, {ops.KNOB_GN_WAVE: 0}),
+    ("all on (default), again", {}, {}),
+]
+ALL_KNOBS = (ops.KNOB_HALO, ops.KNOB_PDL, ops.KNOB_HALO_SA, ops.KNOB_HALO_SPREAD, ops.KNOB_PAIR, ops.KNOB_PREFETCH,
+             ops.KNOB_GN_WAVE)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--knobs", action="store_true", help="launcher knobs instead of plan-level decisions")
     ap.add_argument("--rounds", type=int, default=8)
     ap.add_argument("--batch", type=int, default=16)
     args = ap.parse_args()
@@ -45,10 +62,10 @@ def main():
     plans = []
     defaults = {k: getattr(engine, k) for k in ("UP_PHASES", "RESAMPLE_SHORTCUTS", "FUSE_NORM")}
     with torch.no_grad():
-        for name, flags, knobs in VARIANTS:
+        for name, flags, knobs in (KNOB_VARIANTS if args.knobs else VARIANTS):
             for k, v in {**defaults, **flags}.items():
                 setattr(engine, k, v)
-            for k in (ops.KNOB_HALO, ops.KNOB_PDL):
+            for k in ALL_KNOBS:
                 ops.conv_tuning(k, knobs.get(k, -1))
             den.backbone._native.clear()  # weights are repacked too (the phase weights depend on UP_PHASES)
             den.backbone(x, ts)
@@ -57,9 +74,15 @@ def main():
             plans.append((name, knobs, plan, packed))
         torch.cuda.synchronize()
         times = [[] for _ in plans]
+        import random
+
+        rng = random.Random(0)
         for rnd in range(args.rounds + 1):
-            for i, (name, knobs, plan, _) in enumerate(plans):
-                for k in (ops.KNOB_HALO, ops.KNOB_PDL):
+            order = list(range(len(plans)))
+            rng.shuffle(order)  # a fixed position in the round is worth +-2 % (what ran just before sets the clocks)
+            for i in order:
+                name, knobs, plan, _ = plans[i]
+                for k in ALL_KNOBS:
                     ops.conv_tuning(k, knobs.get(k, -1))
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -69,7 +92,7 @@ def main():
                 torch.cuda.synchronize()
                 if rnd:
                     times[i].append(e0.elapsed_time(e1) / 2)
-    for k in (ops.KNOB_HALO, ops.KNOB_PDL):
+    for k in ALL_KNOBS:
         ops.conv_tuning(k, -1)
     base = statistics.median(times[0])
     print(f"{'variant':62s} {'ms / forward':>12s} {'vs default':>10s} {'kernels':>8s} {'scratch GiB':>11s}")
