@@ -25,6 +25,19 @@ MID_ADM = dict(
     use_scale_shift_norm=True,
 )
 
+# The card's width (256 channels: GroupNorm groups of 8+ channels) at a small spatial size: the configuration class in
+# which GroupNorm + SiLU ride on the halo tiles of the 3 x 3 convolutions (no reference fixture: oracle-checked on GPU).
+WIDE_ADM = dict(
+    image_size=32,
+    num_channels=256,
+    channel_mult=(1, 2),
+    num_res_blocks=1,
+    attention_resolutions=(2,),
+    num_head_channels=64,
+    resblock_updown=True,
+    use_scale_shift_norm=True,
+)
+
 # The card itself (cards.yaml:36-50): 552.8 M parameters.
 IMAGENET_256 = dict(
     discrete_schedule="linear",

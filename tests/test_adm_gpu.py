@@ -19,7 +19,7 @@ import torch
 from conftest import load_golden
 from oracle import adm_unet as AU
 from oracle import ref_math as RM
-from oracle.gen_golden_cfg import MID_ADM, TINY_ADM
+from oracle.gen_golden_cfg import MID_ADM, TINY_ADM, WIDE_ADM
 
 from azula_b200.plugins import adm
 from azula_b200.sample import DDIMSampler, DDPMSampler
@@ -159,20 +159,6 @@ def test_sharded_sampling_equals_global_batch_bits(S):
         torch.manual_seed(1)
         parts.append(smp(mine))
     assert torch.equal(torch.cat(parts), x0)
-
-
-# The card's width (256 channels: GroupNorm groups of 8+ channels, one accumulator entry per 8-channel block) at a small
-# spatial size: the configuration class in which GroupNorm + SiLU ride on the halo tiles of the 3 x 3 convolutions.
-WIDE_ADM = dict(
-    image_size=32,
-    num_channels=256,
-    channel_mult=(1, 2),
-    num_res_blocks=1,
-    attention_resolutions=(2,),
-    num_head_channels=64,
-    resblock_updown=True,
-    use_scale_shift_norm=True,
-)
 
 
 def _plan(den):
