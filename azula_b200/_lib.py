@@ -16,12 +16,31 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libazb.so")
 if os.environ.get("AZB_LIBRARY"):  # A/B measurements of two builds on one box (scripts/build_ab.sh)
     LIB_PATH = os.environ["AZB_LIBRARY"]
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 F32, BF16, F16, I64 = 0, 1, 2, 3
 DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16, torch.int64: I64}
 
 _lib = None
+
+ROW_COLS = 32  # floats per extended coefficient row (include/azb.h AZB_ROW_COLS)
+R_P, R_Q, R_R, R_FLAGS, R_DRAW, R_W = 8, 9, 10, 12, 13, 16
+MAX_SLOTS = 8
+
+
+class AzbStep(ctypes.Structure):
+    """Mirror of ``struct AzbStep`` (include/azb.h)."""
+
+    _fields_ = [
+        ("src", c_void_p * 2), ("dst", c_void_p * 2), ("f", c_void_p), ("f_neg", c_void_p), ("guidance", c_void_p),
+        ("eps", c_void_p), ("x_in_next", c_void_p), ("hist", c_void_p), ("table", c_void_p), ("step_idx", c_void_p),
+        ("philox_state", c_void_p),
+        ("f_batch_stride", c_int64), ("n_per_sample", c_int64), ("batch", c_int64), ("hist_stride", c_int64),
+        ("offset_host", c_int64), ("offset_inc", c_int64), ("rng_threads", c_int64), ("rng_elem_offset", c_int64),
+        ("seed", c_uint64),
+        ("f_dtype", c_int32), ("in_dtype", c_int32), ("row_floats", c_int32), ("x_in_copies", c_int32),
+    ]
+
 
 _SIGNATURES = {
     "azb_version": (c_int, []),
@@ -32,6 +51,7 @@ _SIGNATURES = {
         [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64,
          c_void_p, c_void_p, c_uint64, c_void_p, c_int64, c_int64, c_int64, c_void_p],
     ),
+    "azb_step_ex_f32": (c_int, [ctypes.POINTER(AzbStep), c_void_p]),
     "azb_advance": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int32, c_void_p]),
     "azb_init_noise_f32": (c_int, [c_void_p, c_int64, c_float, c_float, c_uint64, c_int64, c_int64, c_int64, c_void_p]),
 }

@@ -211,7 +211,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
 template <int D>
 int launch_attn(const AttnParams& p, int n, cudaStream_t s) {
     constexpr int smem = (BM + 4 * BN) * (D + 8) * 2;
-    static bool configured = false;
+    static AzbPerDevice<bool> configured_dev;
+    bool& configured = configured_dev.get();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;

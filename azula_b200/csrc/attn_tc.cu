@@ -310,7 +310,8 @@ int launch_tc(const void* qkv, int64_t ld, int64_t n, int64_t t, const AttnTcPar
     int rc = tc::make_map_bf16(&tq, qkv, 3, dims, str, box_q);
     if (!rc) rc = tc::make_map_bf16(&tkv, qkv, 3, dims, str, box_kv);
     if (rc) return rc == -1 ? AZB_E_DRIVER : AZB_E_SHAPE;
-    static bool configured = false;
+    static AzbPerDevice<bool> configured_dev;
+    bool& configured = configured_dev.get();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) return (int)e;

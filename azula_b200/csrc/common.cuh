@@ -45,6 +45,30 @@ static inline int azb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
     return e == cudaSuccess ? AZB_OK : (int)e;
 }
 
+// Per-device host-side caches.  cudaFuncSetAttribute, SM counts and cluster occupancy belong to ONE device: a process
+// that drives several GPUs (or moves from one to another) must not reuse the first device's values.  Entries are
+// idempotent (every thread computes the same value), so unsynchronised concurrent first use is benign.
+constexpr int AZB_MAX_DEVICES = 64;
+static inline int azb_current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= AZB_MAX_DEVICES) return 0;
+    return d;
+}
+template <typename T>
+struct AzbPerDevice {
+    T v[AZB_MAX_DEVICES] = {};
+    T& get() { return v[azb_current_device()]; }
+};
+static inline int azb_sm_count() {
+    static AzbPerDevice<int> sms;
+    int& n = sms.get();
+    if (!n) {
+        int dev = azb_current_device();
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    }
+    return n;
+}
+
 static inline bool azb_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // Streaming 128-bit accesses: data touched once per step, keep it out of L1.

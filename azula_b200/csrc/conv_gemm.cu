@@ -955,15 +955,7 @@ int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, c
     return rc == 0 ? AZB_OK : rc == -1 ? AZB_E_DRIVER : AZB_E_SHAPE;
 }
 
-int sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-    }
-    return sms;
-}
+int sm_count() { return azb_sm_count(); }
 
 #define g_knob azb_knob
 
@@ -972,7 +964,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2,
     constexpr int smem = Cfg<BLOCK_N, PAIR, HALO>::SMEM;
     constexpr int threads = HALO ? THREADS_HALO : THREADS;
     auto kernel = conv_gemm_kernel<BLOCK_N, PAIR, LEAN, HALO>;
-    static bool configured = false;
+    static AzbPerDevice<bool> configured_dev;
+    bool& configured = configured_dev.get();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
@@ -988,7 +981,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2,
         attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see pdl_trigger / pdl_wait
         attr[1].val.programmaticStreamSerializationAllowed = g_knob[AZB_KNOB_PDL] != 0 ? 1 : 0;
         cfg.attrs = attr, cfg.numAttrs = 2;
-        static int resident = 0;  // clusters that fit on the device at once: the persistent grid is one wave of them
+        static AzbPerDevice<int> resident_dev;  // clusters that fit on the device at once: the persistent grid is one wave
+        int& resident = resident_dev.get();
         if (!resident) {
             if (cudaOccupancyMaxActiveClusters(&resident, kernel, &cfg) != cudaSuccess || resident < 1) {
                 cudaGetLastError();

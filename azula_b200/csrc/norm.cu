@@ -435,7 +435,8 @@ extern "C" int azb_gn_stats_bf16(const void* x, int64_t ld, int64_t n, int64_t h
     size_t smem = (size_t)(2 * R * c + 2 * c) * sizeof(float);
     const size_t fold = (size_t)(THREADS / groups) * groups * 2 * sizeof(double);
     if (smem < fold) smem = fold;
-    static bool configured = false;
+    static AzbPerDevice<bool> configured_dev;
+    bool& configured = configured_dev.get();
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         if (e != cudaSuccess) return (int)e;

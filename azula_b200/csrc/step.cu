@@ -17,28 +17,6 @@ struct Row {
     float c_skip, c_out, alpha_s, k, alpha_t, n, c_in_next, clip;
 };
 
-__device__ __forceinline__ Row load_row(const float* table, const int32_t* step_idx) {
-    const float4* r = reinterpret_cast<const float4*>(table + (int64_t)(*step_idx) * AZB_COEF_COLS);
-    float4 a = __ldg(r), b = __ldg(r + 1);
-    return Row{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-}
-
-// The update of ONE element, every operation rounded separately (no FMA contraction) so that
-// it reproduces the eager op sequence bit for bit given the same F and eps:
-//   mean = c_skip*x + c_out*F               denoise.py:322 / adm/__init__.py:125-130
-//   mean = clip(mean)                       adm/__init__.py:133-134
-//   x_s  = alpha_s*mean                     sample.py:212,257
-//   x_s += k*(x - alpha_t*mean)             sample.py:213,258
-//   x_s += n*eps                            sample.py:214,259
-__device__ __forceinline__ float transition(const Row& r, float x, float f, float eps) {
-    float m = __fadd_rn(__fmul_rn(r.c_skip, x), __fmul_rn(r.c_out, f));
-    if (m == m) m = fminf(fmaxf(m, -r.clip), r.clip);
-    float xs = __fmul_rn(r.alpha_s, m);
-    xs = __fadd_rn(xs, __fmul_rn(r.k, __fsub_rn(x, __fmul_rn(r.alpha_t, m))));
-    xs = __fadd_rn(xs, __fmul_rn(r.n, eps));
-    return xs;
-}
-
 // ------------------------------------------------------------------------------- Philox
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -148,19 +126,66 @@ struct Vec4<NoOut> {
     static __device__ __forceinline__ void store1(void*, int64_t, float) {}
 };
 
+// Coherent streaming load of the sampler state: the fused loop updates x in place (src == dst), so the
+// read-only (.nc) path is not allowed for it.
+__device__ __forceinline__ float4 ld_state4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ float ld_state1(const float* p) {
+    float r;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+    return r;
+}
+
+// Extended row (include/azb.h AZB_R_*): selectors, stored-quantity / update coefficients, history weights.
+struct RowX {
+    float p, q, r;
+    uint32_t flags;
+    int32_t draw;
+    float w[AZB_STEP_MAX_SLOTS];
+};
+
 struct StepArgs {
-    const float* x;
+    const float* src[2];
+    float* dst[2];
     const void* f;
+    const void* fneg;
+    const float* guidance;
     const float* eps;
-    float* out;
     void* xin;
-    int64_t n_per_sample, numel, f_bstride;
+    float* hist;
+    int64_t n_per_sample, numel, f_bstride, hist_stride;
     const float* table;
     const int32_t* step_idx;
     uint64_t seed;
     const int64_t* off_dev;
-    int64_t off_host, T, elem_off;
+    int64_t off_host, off_inc, T, elem_off;
+    int row_floats, xin_copies;
 };
+
+__device__ __forceinline__ Row load_row_n(const StepArgs& a, RowX& rx) {
+    const int32_t idx = *a.step_idx;
+    const float* base = a.table + (int64_t)idx * a.row_floats;
+    const float4* r = reinterpret_cast<const float4*>(base);
+    float4 u = __ldg(r), v = __ldg(r + 1);
+    rx.p = rx.q = rx.r = 0.f;
+    rx.flags = 0u, rx.draw = 0;
+#pragma unroll
+    for (int j = 0; j < AZB_STEP_MAX_SLOTS; ++j) rx.w[j] = 0.f;
+    if (a.row_floats >= AZB_ROW_COLS) {
+        float4 c = __ldg(r + 2), d = __ldg(r + 3), w0 = __ldg(r + 4), w1 = __ldg(r + 5);
+        rx.p = c.x, rx.q = c.y, rx.r = c.z;
+        rx.flags = __float_as_uint(d.x), rx.draw = __float_as_int(d.y);
+        rx.w[0] = w0.x, rx.w[1] = w0.y, rx.w[2] = w0.z, rx.w[3] = w0.w;
+        rx.w[4] = w1.x, rx.w[5] = w1.y, rx.w[6] = w1.z, rx.w[7] = w1.w;
+    }
+    return Row{u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+}
 
 __device__ __forceinline__ int64_t f_index(const StepArgs& a, int64_t i) {
     if (a.f_bstride == a.n_per_sample) return i;
@@ -168,46 +193,128 @@ __device__ __forceinline__ int64_t f_index(const StepArgs& a, int64_t i) {
     return b * a.f_bstride + (i - b * a.n_per_sample);
 }
 
-template <typename FT, typename IT>
-__device__ __forceinline__ void finish4(const StepArgs& a, const Row& r, int64_t i, float4 x, float4 f, float4 e) {
-    float4 o;
-    o.x = transition(r, x.x, f.x, e.x);
-    o.y = transition(r, x.y, f.y, e.y);
-    o.z = transition(r, x.z, f.z, e.z);
-    o.w = transition(r, x.w, f.w, e.w);
-    stg_stream4(a.out + i, o);
-    Vec4<IT>::store(a.xin, i,
-                    make_float4(__fmul_rn(r.c_in_next, o.x), __fmul_rn(r.c_in_next, o.y), __fmul_rn(r.c_in_next, o.z),
-                                __fmul_rn(r.c_in_next, o.w)));
+// Posterior mean of ONE element: mean = clip(c_skip*x + c_out*F) (denoise.py:322, adm/__init__.py:125-134); under
+// classifier-free guidance each branch is clipped on its own and mu = m+ + w*(m+ - m-) (guidance/cfg.py:62-64),
+// every operation rounded separately as eager does.
+__device__ __forceinline__ float mean_of(const Row& r, float x, float f) {
+    float m = __fadd_rn(__fmul_rn(r.c_skip, x), __fmul_rn(r.c_out, f));
+    if (m == m) m = fminf(fmaxf(m, -r.clip), r.clip);
+    return m;
+}
+template <bool CFG>
+__device__ __forceinline__ float mean_cfg(const Row& r, float x, float f, float fn, float w) {
+    float m = mean_of(r, x, f);
+    if constexpr (CFG) {
+        float mn = mean_of(r, x, fn);
+        m = __fadd_rn(m, __fmul_rn(w, __fsub_rn(m, mn)));
+    }
+    return m;
+}
+//   x_s  = alpha_s*mean; x_s += k*(x - alpha_t*mean); x_s += n*eps        sample.py:212-214,257-259
+__device__ __forceinline__ float affine_of(const Row& r, float x, float m, float eps) {
+    float xs = __fmul_rn(r.alpha_s, m);
+    xs = __fadd_rn(xs, __fmul_rn(r.k, __fsub_rn(x, __fmul_rn(r.alpha_t, m))));
+    xs = __fadd_rn(xs, __fmul_rn(r.n, eps));
+    return xs;
 }
 
+template <typename IT>
+__device__ __forceinline__ void store_out4(const StepArgs& a, const Row& r, float* out, int64_t i, float4 o) {
+    stg_stream4(out + i, o);
+    float4 s = make_float4(__fmul_rn(r.c_in_next, o.x), __fmul_rn(r.c_in_next, o.y), __fmul_rn(r.c_in_next, o.z),
+                           __fmul_rn(r.c_in_next, o.w));
+    Vec4<IT>::store(a.xin, i, s);
+    if (a.xin_copies > 1) Vec4<IT>::store(a.xin, i + a.numel, s);
+}
+
+template <typename FT, typename IT, bool CFG>
+__device__ __forceinline__ void finish4(const StepArgs& a, const Row& r, float* out, float w, int64_t i, float4 x, float4 f,
+                                        float4 fn, float4 e) {
+    float4 o;
+    o.x = affine_of(r, x.x, mean_cfg<CFG>(r, x.x, f.x, fn.x, w), e.x);
+    o.y = affine_of(r, x.y, mean_cfg<CFG>(r, x.y, f.y, fn.y, w), e.y);
+    o.z = affine_of(r, x.z, mean_cfg<CFG>(r, x.z, f.z, fn.z, w), e.z);
+    o.w = affine_of(r, x.w, mean_cfg<CFG>(r, x.w, f.w, fn.w, w), e.w);
+    store_out4<IT>(a, r, out, i, o);
+}
+
+#define AZB_AXPY4(acc, s, v) \
+    (acc).x = fmaf((s), (v).x, (acc).x), (acc).y = fmaf((s), (v).y, (acc).y), (acc).z = fmaf((s), (v).z, (acc).z), \
+    (acc).w = fmaf((s), (v).w, (acc).w)
+
 // Vector path: numel, n_per_sample, f_bstride, elem_off multiples of 4; 16-byte aligned pointers.
-template <typename FT, typename IT>
+template <typename FT, typename IT, bool CFG>
 __global__ void __launch_bounds__(256) step_vec4_kernel(const StepArgs a) {
     pdl_enter();
-    const Row r = load_row(a.table, a.step_idx);
+    RowX rx;
+    const Row r = load_row_n(a, rx);
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    const bool generate = (a.eps == nullptr) && (r.n != 0.0f);
+    const float* xe_p = a.src[rx.flags & 1u];
+    const float* xb_p = a.src[(rx.flags >> 1) & 1u];
+    float* out_p = a.dst[(rx.flags >> 2) & 1u];
+    const float gw = CFG ? __ldg(a.guidance) : 0.f;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    if (rx.flags & 8u) {
+        // History mode (Heun, Adams-Bashforth family): h = p*x_e + q*m,  x_out = r*x_b + sum_j W[j]*H[j].
+        const int wslot = (int)((rx.flags >> 4) & 15u), nslots = (int)((rx.flags >> 12) & 15u);
+        const bool store_h = (rx.flags >> 8) & 1u, same = xe_p == xb_p;
+        const int64_t n4 = a.numel >> 2;
+        for (int64_t i4 = tid; i4 < n4; i4 += nthreads) {
+            const int64_t i = i4 << 2;
+            const float4 xe = ld_state4(xe_p + i);
+            const float4 xb = same ? xe : ld_state4(xb_p + i);
+            const int64_t fi = f_index(a, i);
+            const float4 f = Vec4<FT>::load(a.f, fi);
+            const float4 fn = CFG ? Vec4<FT>::load(a.fneg, fi) : zero4;
+            float4 hs[AZB_STEP_MAX_SLOTS];
+#pragma unroll
+            for (int j = 0; j < AZB_STEP_MAX_SLOTS; ++j)
+                if (j < nslots && j != wslot && rx.w[j] != 0.f) hs[j] = ld_state4(a.hist + j * a.hist_stride + i);
+            float4 m, h, acc;
+            m.x = mean_cfg<CFG>(r, xe.x, f.x, fn.x, gw), m.y = mean_cfg<CFG>(r, xe.y, f.y, fn.y, gw);
+            m.z = mean_cfg<CFG>(r, xe.z, f.z, fn.z, gw), m.w = mean_cfg<CFG>(r, xe.w, f.w, fn.w, gw);
+            h.x = fmaf(rx.p, xe.x, rx.q * m.x), h.y = fmaf(rx.p, xe.y, rx.q * m.y);
+            h.z = fmaf(rx.p, xe.z, rx.q * m.z), h.w = fmaf(rx.p, xe.w, rx.q * m.w);
+            acc = make_float4(rx.r * xb.x, rx.r * xb.y, rx.r * xb.z, rx.r * xb.w);
+#pragma unroll
+            for (int j = 0; j < AZB_STEP_MAX_SLOTS; ++j) {
+                if (j < nslots) {
+                    if (j == wslot) {
+                        AZB_AXPY4(acc, rx.w[j], h);
+                    } else if (rx.w[j] != 0.f) {
+                        AZB_AXPY4(acc, rx.w[j], hs[j]);
+                    }
+                }
+            }
+            if (store_h) stg_stream4(a.hist + wslot * a.hist_stride + i, h);
+            store_out4<IT>(a, r, out_p, i, acc);
+        }
+        return;
+    }
+
+    const bool generate = (a.eps == nullptr) && (r.n != 0.0f);
     if (!generate) {
         const int64_t n4 = a.numel >> 2;
         constexpr int U = 4;
         for (int64_t base = tid; base < n4; base += nthreads * U) {
-            float4 x[U], f[U], e[U];
+            float4 x[U], f[U], fn[U], e[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 int64_t i = (base + u * nthreads) << 2;
                 if (i < a.numel) {
-                    x[u] = ldg_stream4(a.x + i);
-                    f[u] = Vec4<FT>::load(a.f, f_index(a, i));
-                    e[u] = a.eps ? ldg_stream4(a.eps + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    x[u] = ld_state4(xe_p + i);
+                    const int64_t fi = f_index(a, i);
+                    f[u] = Vec4<FT>::load(a.f, fi);
+                    fn[u] = CFG ? Vec4<FT>::load(a.fneg, fi) : zero4;
+                    e[u] = a.eps ? ldg_stream4(a.eps + i) : zero4;
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 int64_t i = (base + u * nthreads) << 2;
-                if (i < a.numel) finish4<FT, IT>(a, r, i, x[u], f[u], e[u]);
+                if (i < a.numel) finish4<FT, IT, CFG>(a, r, out_p, gw, i, x[u], f[u], fn[u], e[u]);
             }
         }
         return;
@@ -215,7 +322,7 @@ __global__ void __launch_bounds__(256) step_vec4_kernel(const StepArgs a) {
 
     // In-register noise.  Work item (g, j): Philox streams 4g..4g+3 at call j produce 16 normals
     // that belong to the four float4 groups at global elements (4j+ii)*T + 4g, ii = 0..3.
-    const uint64_t offset = (uint64_t)((a.off_dev ? a.off_dev[0] : 0) + a.off_host);
+    const uint64_t offset = (uint64_t)((a.off_dev ? a.off_dev[0] : 0) + a.off_host + (int64_t)rx.draw * a.off_inc);
     const uint64_t seed = a.off_dev ? (uint64_t)a.off_dev[1] : a.seed;
     const uint64_t ctr0 = offset >> 2;
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
@@ -227,45 +334,76 @@ __global__ void __launch_bounds__(256) step_vec4_kernel(const StepArgs a) {
         const int64_t jj = w / T4;
         const int64_t g = w - jj * T4;
         const int64_t j = j_lo + jj;
-        float4 x[4], f[4];
+        float4 x[4], f[4], fn[4];
         int64_t loc[4];
         bool ok[4];
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
             loc[ii] = ((j << 2) + ii) * T + (g << 2) - a.elem_off;
             ok[ii] = loc[ii] >= 0 && loc[ii] < a.numel;
+            fn[ii] = zero4;
             if (ok[ii]) {
-                x[ii] = ldg_stream4(a.x + loc[ii]);
-                f[ii] = Vec4<FT>::load(a.f, f_index(a, loc[ii]));
+                x[ii] = ld_state4(xe_p + loc[ii]);
+                const int64_t fi = f_index(a, loc[ii]);
+                f[ii] = Vec4<FT>::load(a.f, fi);
+                if (CFG) fn[ii] = Vec4<FT>::load(a.fneg, fi);
             }
         }
         if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;
         float4 z[4];  // z[e] = normals of stream 4g+e, lanes ii
 #pragma unroll
         for (int e = 0; e < 4; ++e) z[e] = normal4(ctr0 + (uint64_t)j, (uint64_t)((g << 2) + e), key);
-        if (ok[0]) finish4<FT, IT>(a, r, loc[0], x[0], f[0], make_float4(z[0].x, z[1].x, z[2].x, z[3].x));
-        if (ok[1]) finish4<FT, IT>(a, r, loc[1], x[1], f[1], make_float4(z[0].y, z[1].y, z[2].y, z[3].y));
-        if (ok[2]) finish4<FT, IT>(a, r, loc[2], x[2], f[2], make_float4(z[0].z, z[1].z, z[2].z, z[3].z));
-        if (ok[3]) finish4<FT, IT>(a, r, loc[3], x[3], f[3], make_float4(z[0].w, z[1].w, z[2].w, z[3].w));
+        if (ok[0]) finish4<FT, IT, CFG>(a, r, out_p, gw, loc[0], x[0], f[0], fn[0], make_float4(z[0].x, z[1].x, z[2].x, z[3].x));
+        if (ok[1]) finish4<FT, IT, CFG>(a, r, out_p, gw, loc[1], x[1], f[1], fn[1], make_float4(z[0].y, z[1].y, z[2].y, z[3].y));
+        if (ok[2]) finish4<FT, IT, CFG>(a, r, out_p, gw, loc[2], x[2], f[2], fn[2], make_float4(z[0].z, z[1].z, z[2].z, z[3].z));
+        if (ok[3]) finish4<FT, IT, CFG>(a, r, out_p, gw, loc[3], x[3], f[3], fn[3], make_float4(z[0].w, z[1].w, z[2].w, z[3].w));
     }
 }
 
 // Scalar path for small / unaligned tensors (e.g. the (64,5) MLP case, batch-less shapes).
-template <typename FT, typename IT>
+template <typename FT, typename IT, bool CFG>
 __global__ void __launch_bounds__(256) step_scalar_kernel(const StepArgs a) {
     pdl_enter();
-    const Row r = load_row(a.table, a.step_idx);
-    const bool generate = (a.eps == nullptr) && (r.n != 0.0f);
-    const uint64_t offset = (uint64_t)((a.off_dev ? a.off_dev[0] : 0) + a.off_host);
+    RowX rx;
+    const Row r = load_row_n(a, rx);
+    const float* xe_p = a.src[rx.flags & 1u];
+    const float* xb_p = a.src[(rx.flags >> 1) & 1u];
+    float* out_p = a.dst[(rx.flags >> 2) & 1u];
+    const float gw = CFG ? __ldg(a.guidance) : 0.f;
+    const bool hist = rx.flags & 8u;
+    const int wslot = (int)((rx.flags >> 4) & 15u), nslots = (int)((rx.flags >> 12) & 15u);
+    const bool store_h = (rx.flags >> 8) & 1u;
+    const bool generate = !hist && (a.eps == nullptr) && (r.n != 0.0f);
+    const uint64_t offset = (uint64_t)((a.off_dev ? a.off_dev[0] : 0) + a.off_host + (int64_t)rx.draw * a.off_inc);
     const uint64_t seed = a.off_dev ? (uint64_t)a.off_dev[1] : a.seed;
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.numel; i += (int64_t)gridDim.x * blockDim.x) {
-        float x = __ldg(a.x + i);
-        float f = Vec4<FT>::load1(a.f, f_index(a, i));
-        float e = a.eps ? __ldg(a.eps + i) : (generate ? normal_at(a.elem_off + i, a.T, offset >> 2, key) : 0.0f);
-        float o = transition(r, x, f, e);
-        a.out[i] = o;
-        Vec4<IT>::store1(a.xin, i, __fmul_rn(r.c_in_next, o));
+        const float x = ld_state1(xe_p + i);
+        const int64_t fi = f_index(a, i);
+        const float f = Vec4<FT>::load1(a.f, fi);
+        const float fn = CFG ? Vec4<FT>::load1(a.fneg, fi) : 0.f;
+        const float m = mean_cfg<CFG>(r, x, f, fn, gw);
+        float o;
+        if (hist) {
+            const float xb = ld_state1(xb_p + i);
+            const float h = fmaf(rx.p, x, rx.q * m);
+            o = rx.r * xb;
+#pragma unroll
+            for (int j = 0; j < AZB_STEP_MAX_SLOTS; ++j) {
+                if (j < nslots) {
+                    if (j == wslot) o = fmaf(rx.w[j], h, o);
+                    else if (rx.w[j] != 0.f) o = fmaf(rx.w[j], ld_state1(a.hist + j * a.hist_stride + i), o);
+                }
+            }
+            if (store_h) a.hist[wslot * a.hist_stride + i] = h;
+        } else {
+            float e = a.eps ? __ldg(a.eps + i) : (generate ? normal_at(a.elem_off + i, a.T, offset >> 2, key) : 0.0f);
+            o = affine_of(r, x, m, e);
+        }
+        out_p[i] = o;
+        const float s = __fmul_rn(r.c_in_next, o);
+        Vec4<IT>::store1(a.xin, i, s);
+        if (a.xin_copies > 1) Vec4<IT>::store1(a.xin, i + a.numel, s);
     }
 }
 
@@ -320,15 +458,7 @@ __global__ void __launch_bounds__(256) init_noise_kernel(float* x, int64_t numel
     }
 }
 
-int sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-    }
-    return sms;
-}
+int sm_count() { return azb_sm_count(); }
 
 int grid_for(int64_t work_items, int per_sm) {
     int64_t blocks = (work_items + 255) / 256;
@@ -338,27 +468,32 @@ int grid_for(int64_t work_items, int per_sm) {
     return (int)blocks;
 }
 
-template <typename FT, typename IT>
+template <typename FT, typename IT, bool CFG>
 int launch_step(const StepArgs& a, bool vec, cudaStream_t s) {
     if (vec) {
         int64_t T4 = a.T >> 2;
         int64_t spans = ((a.elem_off + a.numel - 1) / a.T >> 2) - ((a.elem_off / a.T) >> 2) + 1;
         int64_t work = a.eps ? (a.numel >> 2) : ((a.numel >> 2) > T4 * spans ? (a.numel >> 2) : T4 * spans);
         // no-noise path consumes 4 float4 per thread and iteration
-        return azb_launch(step_vec4_kernel<FT, IT>, dim3(grid_for(work, 16)), dim3(256), 0, s, a);
+        return azb_launch(step_vec4_kernel<FT, IT, CFG>, dim3(grid_for(work, 16)), dim3(256), 0, s, a);
     }
-    return azb_launch(step_scalar_kernel<FT, IT>, dim3(grid_for(a.numel, 16)), dim3(256), 0, s, a);
+    return azb_launch(step_scalar_kernel<FT, IT, CFG>, dim3(grid_for(a.numel, 16)), dim3(256), 0, s, a);
+}
+
+template <typename FT, bool CFG>
+int dispatch_in(const StepArgs& a, int in_dtype, bool vec, cudaStream_t s) {
+    if (a.xin == nullptr) return launch_step<FT, NoOut, CFG>(a, vec, s);
+    switch (in_dtype) {
+        case AZB_F32: return launch_step<FT, float, CFG>(a, vec, s);
+        case AZB_BF16: return launch_step<FT, __nv_bfloat16, CFG>(a, vec, s);
+        case AZB_F16: return launch_step<FT, __half, CFG>(a, vec, s);
+    }
+    return AZB_E_DTYPE;
 }
 
 template <typename FT>
-int dispatch_in(const StepArgs& a, int in_dtype, bool vec, cudaStream_t s) {
-    if (a.xin == nullptr) return launch_step<FT, NoOut>(a, vec, s);
-    switch (in_dtype) {
-        case AZB_F32: return launch_step<FT, float>(a, vec, s);
-        case AZB_BF16: return launch_step<FT, __nv_bfloat16>(a, vec, s);
-        case AZB_F16: return launch_step<FT, __half>(a, vec, s);
-    }
-    return AZB_E_DTYPE;
+int dispatch_cfg(const StepArgs& a, int in_dtype, bool vec, cudaStream_t s) {
+    return a.fneg ? dispatch_in<FT, true>(a, in_dtype, vec, s) : dispatch_in<FT, false>(a, in_dtype, vec, s);
 }
 
 size_t dtype_size(int d) { return d == AZB_F32 ? 4 : (d == AZB_BF16 || d == AZB_F16) ? 2 : d == AZB_I64 ? 8 : 0; }
@@ -381,34 +516,59 @@ extern "C" int azb_rng_policy(int64_t numel, int64_t* rng_threads, int64_t* offs
     return AZB_OK;
 }
 
+extern "C" int azb_step_ex_f32(const AzbStep* d, void* stream) {
+    AZB_CHECK_PTR(d);
+    AZB_CHECK_PTR(d->src[0]);
+    AZB_CHECK_PTR(d->dst[0]);
+    AZB_CHECK_PTR(d->f);
+    AZB_CHECK_PTR(d->table);
+    AZB_CHECK_PTR(d->step_idx);
+    if (d->f_neg && !d->guidance) return AZB_E_NULL;
+    const int64_t n_per_sample = d->n_per_sample, batch = d->batch;
+    if (n_per_sample <= 0 || batch <= 0 || d->f_batch_stride < n_per_sample) return AZB_E_SHAPE;
+    if (d->rng_threads <= 0 || (d->rng_threads & 3) || d->rng_elem_offset < 0) return AZB_E_SHAPE;
+    if (d->row_floats != AZB_COEF_COLS && d->row_floats < AZB_ROW_COLS) return AZB_E_SHAPE;
+    if (d->row_floats % 4 || !azb_aligned(d->table, 16)) return AZB_E_ALIGN;
+    if (d->x_in_copies != 1 && d->x_in_copies != 2) return AZB_E_SHAPE;
+    if (d->hist && d->hist_stride < n_per_sample * batch) return AZB_E_SHAPE;
+    const size_t fsz = dtype_size(d->f_dtype), isz = dtype_size(d->in_dtype);
+    if (fsz == 0 || d->f_dtype == AZB_I64) return AZB_E_DTYPE;
+    if (d->x_in_next && (isz == 0 || d->in_dtype == AZB_I64)) return AZB_E_DTYPE;
+    StepArgs a{};
+    a.src[0] = d->src[0], a.src[1] = d->src[1] ? d->src[1] : d->src[0];
+    a.dst[0] = d->dst[0], a.dst[1] = d->dst[1] ? d->dst[1] : d->dst[0];
+    a.f = d->f, a.fneg = d->f_neg, a.guidance = d->guidance, a.eps = d->eps, a.xin = d->x_in_next, a.hist = d->hist;
+    a.n_per_sample = n_per_sample, a.numel = n_per_sample * batch, a.f_bstride = d->f_batch_stride;
+    a.hist_stride = d->hist_stride, a.table = d->table, a.step_idx = d->step_idx, a.seed = d->seed;
+    a.off_dev = d->philox_state, a.off_host = d->offset_host, a.off_inc = d->offset_inc, a.T = d->rng_threads;
+    a.elem_off = d->rng_elem_offset, a.row_floats = d->row_floats, a.xin_copies = d->x_in_copies;
+    const bool vec = (n_per_sample % 4 == 0) && (d->f_batch_stride % 4 == 0) && (d->rng_elem_offset % 4 == 0) &&
+                     azb_aligned(a.src[0], 16) && azb_aligned(a.src[1], 16) && azb_aligned(a.dst[0], 16) &&
+                     azb_aligned(a.dst[1], 16) && azb_aligned(a.f, 4 * fsz) && (!a.fneg || azb_aligned(a.fneg, 4 * fsz)) &&
+                     (!a.eps || azb_aligned(a.eps, 16)) && (!a.xin || azb_aligned(a.xin, 4 * isz)) &&
+                     (!a.hist || (azb_aligned(a.hist, 16) && d->hist_stride % 4 == 0));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    switch (d->f_dtype) {
+        case AZB_F32: return dispatch_cfg<float>(a, d->in_dtype, vec, s);
+        case AZB_BF16: return dispatch_cfg<__nv_bfloat16>(a, d->in_dtype, vec, s);
+        case AZB_F16: return dispatch_cfg<__half>(a, d->in_dtype, vec, s);
+    }
+    return AZB_E_DTYPE;
+}
+
 extern "C" int azb_step_f32(const float* x_t, const void* f, int f_dtype, int64_t f_batch_stride, const float* eps,
                             float* x_s, void* x_in_next, int in_dtype, int64_t n_per_sample, int64_t batch,
                             const float* coef_table, const int32_t* step_idx, uint64_t seed,
                             const int64_t* philox_state, int64_t offset_host, int64_t rng_threads,
                             int64_t rng_elem_offset, void* stream) {
     AZB_CHECK_PTR(x_t);
-    AZB_CHECK_PTR(f);
     AZB_CHECK_PTR(x_s);
-    AZB_CHECK_PTR(coef_table);
-    AZB_CHECK_PTR(step_idx);
-    if (n_per_sample <= 0 || batch <= 0 || f_batch_stride < n_per_sample) return AZB_E_SHAPE;
-    if (rng_threads <= 0 || (rng_threads & 3) || rng_elem_offset < 0) return AZB_E_SHAPE;
-    if (!azb_aligned(coef_table, 16)) return AZB_E_ALIGN;
-    size_t fsz = dtype_size(f_dtype), isz = dtype_size(in_dtype);
-    if (fsz == 0 || f_dtype == AZB_I64) return AZB_E_DTYPE;
-    if (x_in_next && (isz == 0 || in_dtype == AZB_I64)) return AZB_E_DTYPE;
-    StepArgs a{x_t,        f,        eps,  x_s,           x_in_next,   n_per_sample, n_per_sample * batch, f_batch_stride,
-               coef_table, step_idx, seed, philox_state, offset_host, rng_threads,  rng_elem_offset};
-    bool vec = (n_per_sample % 4 == 0) && (f_batch_stride % 4 == 0) && (rng_elem_offset % 4 == 0) &&
-               azb_aligned(x_t, 16) && azb_aligned(x_s, 16) && azb_aligned(f, 4 * fsz) &&
-               (!eps || azb_aligned(eps, 16)) && (!x_in_next || azb_aligned(x_in_next, 4 * isz));
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    switch (f_dtype) {
-        case AZB_F32: return dispatch_in<float>(a, in_dtype, vec, s);
-        case AZB_BF16: return dispatch_in<__nv_bfloat16>(a, in_dtype, vec, s);
-        case AZB_F16: return dispatch_in<__half>(a, in_dtype, vec, s);
-    }
-    return AZB_E_DTYPE;
+    AzbStep d{};
+    d.src[0] = x_t, d.dst[0] = x_s, d.f = f, d.eps = eps, d.x_in_next = x_in_next, d.table = coef_table, d.step_idx = step_idx;
+    d.philox_state = philox_state, d.f_batch_stride = f_batch_stride, d.n_per_sample = n_per_sample, d.batch = batch;
+    d.offset_host = offset_host, d.rng_threads = rng_threads, d.rng_elem_offset = rng_elem_offset, d.seed = seed;
+    d.f_dtype = f_dtype, d.in_dtype = in_dtype, d.row_floats = AZB_COEF_COLS, d.x_in_copies = 1;
+    return azb_step_ex_f32(&d, stream);
 }
 
 extern "C" int azb_advance(int32_t* step_idx, int64_t* philox_state, int64_t offset_inc, const void* time_table,

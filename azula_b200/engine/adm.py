@@ -32,6 +32,7 @@ from torch import Tensor
 
 from .. import _lib
 from . import ops
+from .plan import note_use
 
 _MAX_PLANS = 2
 FUSE_NORM = True  # GroupNorm + SiLU ride on the halo tiles of the convolution that consumes them (A/B switch)
@@ -586,6 +587,7 @@ def forward(model, x: Tensor, timesteps: Tensor, y: Tensor | None = None) -> Ten
             while len(plans) >= _MAX_PLANS:
                 del cache[plans.pop(0)]
             plan = cache[key] = Plan(model, packed, n, h, w, rows, device)
+        note_use(model, packed, plan)
 
         xin = x.to(torch.float32).contiguous()
         out = torch.empty((n, lay.out_channels, h, w), dtype=torch.float32, device=device)

@@ -29,7 +29,7 @@ from torch import Tensor
 
 from .. import _lib
 from . import ops
-from .plan import LaunchPlan, ModulationBank, fingerprint
+from .plan import LaunchPlan, ModulationBank, fingerprint, note_use
 
 _MAX_PLANS = 2
 _ACTS = {"silu": 1, "relu": 2, "relu2": 3}
@@ -210,6 +210,7 @@ def _plan(model, cache, packed, key, batch, tokens, rows, pos_fn, device) -> Pla
         while len(plans) >= _MAX_PLANS:
             del cache[plans.pop(0)]
         plan = cache[key] = Plan(model, packed, batch, tokens, rows, pos_fn(), device)
+    note_use(model, packed, plan)
     return plan
 
 

@@ -9,6 +9,7 @@ transition kernel (:mod:`azula_b200.engine.loop`).
 
 from __future__ import annotations
 
+import contextlib
 import math
 import torch
 
@@ -193,3 +194,24 @@ class ModulationBank:
 
 def fingerprint(model) -> tuple:
     return tuple((q.data_ptr(), q._version) for q in model.parameters())
+
+
+# ---- which packed weights / plans a piece of code used (the fused loop pins them for the lifetime of its graph)
+_tracker: list | None = None
+
+
+def note_use(model, packed, plan) -> None:
+    r"""Called by the native forwards with the objects whose device memory their launches address."""
+    if _tracker is not None and not any(p is plan for _, _, p in _tracker):
+        _tracker.append((model, packed, plan))
+
+
+@contextlib.contextmanager
+def track_use():
+    r"""Collects (model, packed weights, plan) triples of every native forward executed inside the context."""
+    global _tracker
+    previous, _tracker = _tracker, []
+    try:
+        yield _tracker
+    finally:
+        _tracker = previous

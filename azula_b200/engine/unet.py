@@ -25,7 +25,7 @@ from torch import Tensor
 
 from .. import _lib
 from . import ops
-from .plan import LaunchPlan, ModulationBank, fingerprint
+from .plan import LaunchPlan, ModulationBank, fingerprint, note_use
 
 _MAX_PLANS = 2
 _NORM_KIND = {"layer": 0, "rms": 1}
@@ -294,6 +294,7 @@ def forward(model, x: Tensor, mod: Tensor | None = None) -> Tensor:
             while len(plans) >= _MAX_PLANS:
                 del cache[plans.pop(0)]
             plan = cache[key] = Plan(model, packed, n, h, w, rows, device)
+        note_use(model, packed, plan)
 
         xin = x.to(torch.float32).contiguous()
         out = torch.empty((n, plan.out_conv.c_out, h, w), dtype=torch.float32, device=device)

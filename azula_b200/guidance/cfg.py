@@ -22,17 +22,30 @@ class CFGDenoiser(Denoiser):
 
     .. math:: \mu = (1 + \omega) \, \mu_\phi(x_t \mid c_+) - \omega \, \mu_\phi(x_t \mid c_-)
 
-    Both evaluations go through the wrapped denoiser, i.e. through its native backbone on a CUDA device; the
-    samplers see a plain :class:`Denoiser` and run their generic loop with the fused transition kernel.
+    Called directly, both evaluations go through the wrapped denoiser as in the reference.  Inside a sampler on a
+    CUDA device the wrapper dissolves into the fused loop (:mod:`azula_b200.engine.loop`): when the two branches
+    take the same keywords (e.g. two label tensors) they are evaluated by ONE backbone forward over the 2B-sample
+    batch :math:`[c_+; c_-]` held in static buffers, otherwise by two forwards of B; in both cases the combination
+    above -- each branch's mean clipped on its own, as the wrapped denoiser would -- is computed inside the
+    transition kernel from the two output pointers (``azb_step_ex_f32``), so no guided mean is ever materialised.
 
     Arguments:
         denoiser: A denoiser :math:`q_\phi(X \mid X_t)`.
+        batched: Engine knob. :py:`None` batches the two branches into one forward when possible,
+            :py:`False` always evaluates them one after the other.
     """
 
-    def __init__(self, denoiser: Denoiser) -> None:
+    guided_inner = True  # the fused loop looks through this wrapper (engine/table.py: inner_denoiser)
+
+    def __init__(self, denoiser: Denoiser, batched: bool | None = None) -> None:
         super().__init__()
 
         self.denoiser = denoiser
+        self.batched = batched
+
+    def fusable(self) -> bool:
+        r"""Whether :meth:`forward` is the stock one (a subclass overriding it must see its own code run)."""
+        return type(self).forward is CFGDenoiser.forward
 
     @property
     def schedule(self) -> Schedule:

@@ -33,6 +33,7 @@ __all__ = [
 ]
 
 import abc
+import inspect
 import math
 import torch
 
@@ -43,7 +44,14 @@ from tqdm import tqdm
 from . import _lib
 from .denoise import Denoiser
 from .engine import loop as _loop
+from .engine import table as _table
 from .engine.table import transition_scalars
+
+
+def _unchanged(obj, base: type, *names: str) -> bool:
+    r"""Whether ``type(obj)`` still uses ``base``'s definitions of ``names`` (a subclass that overrides one of
+    them must see its own code run, i.e. take the generic path)."""
+    return all(inspect.getattr_static(type(obj), n) is inspect.getattr_static(base, n) for n in names)
 
 
 class Sampler(abc.ABC):
@@ -161,18 +169,40 @@ class Sampler(abc.ABC):
     def _fusable(self, x: Tensor) -> bool:
         return False
 
+    def _eta(self) -> float | None:
+        return None
+
+    def _signature(self) -> tuple:
+        r"""The sampler's own hyper-parameters that are frozen into a coefficient table."""
+        return ()
+
+    def _table(self, grid):
+        r"""The per-stage coefficient table of this sampler (:mod:`azula_b200.engine.table`), or :py:`None`."""
+        return None
+
+    def _fused(self, x: Tensor, kwargs: dict) -> Tensor | None:
+        r"""Runs the whole loop as graph replays of [backbone + one transition kernel] when the (sampler, denoiser,
+        input) triple allows it; :py:`None` tells the caller to run its generic loop."""
+        if not (self._fusable(x) and _loop.supports(self, x, kwargs)):
+            return None
+        with torch.cuda.device(x.device):
+            key = _loop.signature(self, x, kwargs)
+            loop = self._loops.get(key)
+            if loop is None:
+                self._loops.clear()  # one live graph per sampler keeps device memory bounded
+                loop = _loop.FusedLoop(self, x, kwargs, self.graph, self.unroll)
+                if loop.table is None:  # the sampler has no table for these hyper-parameters
+                    return None
+                self._loops[key] = loop
+            return loop.run(x, kwargs, self.progress_bar)
+
     @torch.no_grad()
     def __call__(self, x: Tensor, **kwargs) -> Tensor:
         r"""Simulates the reverse process from :math:`t_T` to :math:`t_0`
         (``azula/sample.py:139-161``); never mutates :py:`x`."""
-        if self._fusable(x) and _loop.supports(self, x):
-            with torch.cuda.device(x.device):
-                key = _loop.signature(self, x, kwargs)
-                loop = self._loops.get(key)
-                if loop is None:
-                    self._loops.clear()  # one live graph per sampler keeps device memory bounded
-                    loop = self._loops[key] = _loop.FusedLoop(self, x, kwargs, self.graph, self.unroll)
-                return loop.run(x, kwargs, self.progress_bar)
+        out = self._fused(x, kwargs)
+        if out is not None:
+            return out
 
         time_pairs = self.timesteps.unfold(0, 2, 1).to(device=x.device)
 
@@ -202,12 +232,15 @@ class _Ancestral(Sampler):
 
         self.denoiser = denoiser
 
-    def _eta(self) -> float | None:
-        return None
-
     def _fusable(self, x: Tensor) -> bool:
         # a subclass that overrides step() (e.g. guidance samplers) must see its own step run
         return type(self).step is _Ancestral.step
+
+    def _signature(self) -> tuple:
+        return (self._eta(),)
+
+    def _table(self, grid):
+        return _table.ancestral(grid, self._eta())
 
     def step(self, x_t: Tensor, t: Tensor, s: Tensor, **kwargs) -> Tensor:
         alpha_s, sigma_s = self.denoiser.schedule(s)
@@ -282,6 +315,12 @@ class EulerSampler(Sampler):
 
         self.denoiser = denoiser
 
+    def _fusable(self, x: Tensor) -> bool:
+        return _unchanged(self, EulerSampler, "step")
+
+    def _table(self, grid):
+        return _table.euler(grid)
+
     def step(self, x_t: Tensor, t: Tensor, s: Tensor, **kwargs) -> Tensor:
         alpha_s, sigma_s = self.denoiser.schedule(s)
         alpha_t, sigma_t = self.denoiser.schedule(t)
@@ -311,6 +350,12 @@ class HeunSampler(Sampler):
         super().__init__(**kwargs)
 
         self.denoiser = denoiser
+
+    def _fusable(self, x: Tensor) -> bool:
+        return _unchanged(self, HeunSampler, "step")
+
+    def _table(self, grid):
+        return _table.heun(grid)
 
     def step(self, x_t: Tensor, t: Tensor, s: Tensor, **kwargs) -> Tensor:
         alpha_s, sigma_s = self.denoiser.schedule(s)
@@ -345,6 +390,15 @@ class ItoSampler(Sampler):
         self.denoiser = denoiser
         self.eta = eta
         self.temperature = temperature
+
+    def _fusable(self, x: Tensor) -> bool:
+        return _unchanged(self, ItoSampler, "step") and self.temperature != 0
+
+    def _signature(self) -> tuple:
+        return (self.eta, self.temperature)
+
+    def _table(self, grid):
+        return _table.ito(grid, self.eta, self.temperature)
 
     def step(self, x_t: Tensor, t: Tensor, s: Tensor, **kwargs) -> Tensor:
         alpha_s, sigma_s = self.denoiser.schedule(s)
@@ -384,6 +438,15 @@ class PCSampler(Sampler):
         self.denoiser = denoiser
         self.corrections = corrections
         self.delta = delta
+
+    def _fusable(self, x: Tensor) -> bool:
+        return _unchanged(self, PCSampler, "step") and self.corrections >= 0 and 0 <= self.delta <= 1
+
+    def _signature(self) -> tuple:
+        return (self.corrections, self.delta)
+
+    def _table(self, grid):
+        return _table.predictor_corrector(grid, int(self.corrections), float(self.delta))
 
     def step(self, x_t: Tensor, t: Tensor, s: Tensor, **kwargs) -> Tensor:
         alpha_s, sigma_s = self.denoiser.schedule(s)
@@ -439,6 +502,25 @@ class _Multistep(Sampler):
     def _update(self, x_t: Tensor, integral: Tensor, alpha: Tensor, sigma: Tensor, i: int) -> Tensor:
         raise NotImplementedError()
 
+    # -- the same two hooks as scalar coefficients, for the fused loop's table: h = p x + q mean, x_s = r x + g integral
+    def _stored_coef(self, alpha: Tensor, sigma: Tensor) -> tuple[Tensor, Tensor]:
+        raise NotImplementedError()
+
+    def _update_coef(self, alpha_t: Tensor, sigma_t: Tensor, alpha_s: Tensor, sigma_s: Tensor) -> tuple[Tensor, Tensor]:
+        raise NotImplementedError()
+
+    _HOOKS = ("__call__", "_variable", "_moments", "_stored", "_update", "_weights", "_stored_coef", "_update_coef")
+
+    def _fusable(self, x: Tensor) -> bool:
+        base = next((b for b in type(self).__mro__ if b in _MULTISTEP_TYPES), None)
+        return base is not None and _unchanged(self, base, *self._HOOKS)
+
+    def _signature(self) -> tuple:
+        return (self.order,)
+
+    def _table(self, grid):
+        return _table.multistep(grid, self)
+
     # -- shared
     @classmethod
     def _weights(cls, u: Tensor, i: int, n: int) -> Tensor:
@@ -451,6 +533,10 @@ class _Multistep(Sampler):
 
     @torch.no_grad()
     def __call__(self, x: Tensor, **kwargs) -> Tensor:
+        out = self._fused(x, kwargs)
+        if out is not None:
+            return out
+
         time = self.timesteps.to(device=x.device)
         alpha, sigma = self.denoiser.schedule(time)
         u = self._variable(alpha, sigma)
@@ -493,6 +579,12 @@ class zABSampler(_Multistep):
     def _update(self, x_t, integral, alpha, sigma, i):
         return alpha[i + 1] / alpha[i] * x_t + alpha[i + 1] * integral
 
+    def _stored_coef(self, alpha, sigma):
+        return 1 / sigma, -alpha / sigma
+
+    def _update_coef(self, alpha_t, sigma_t, alpha_s, sigma_s):
+        return alpha_s / alpha_t, alpha_s
+
 
 class vABSampler(zABSampler):
     r"""Adams-Bashforth sampler with velocity (:math:`v`) prediction in :math:`u = \sigma / (\alpha +
@@ -513,6 +605,12 @@ class vABSampler(zABSampler):
     def _update(self, x_t, integral, alpha, sigma, i):
         total_s, total_t = alpha[i + 1] + sigma[i + 1], alpha[i] + sigma[i]
         return total_s / total_t * x_t + total_s * integral
+
+    def _stored_coef(self, alpha, sigma):
+        return 1 / sigma, -(1 + alpha / sigma)
+
+    def _update_coef(self, alpha_t, sigma_t, alpha_s, sigma_s):
+        return (alpha_s + sigma_s) / (alpha_t + sigma_t), alpha_s + sigma_s
 
 
 def _factorials(k: Tensor) -> Tensor:
@@ -547,6 +645,12 @@ class zEABSampler(_Multistep):
     def _update(self, x_t, integral, alpha, sigma, i):
         return alpha[i + 1] / alpha[i] * x_t + alpha[i + 1] * integral
 
+    def _stored_coef(self, alpha, sigma):
+        return 1 / sigma, -alpha / sigma
+
+    def _update_coef(self, alpha_t, sigma_t, alpha_s, sigma_s):
+        return alpha_s / alpha_t, alpha_s
+
 
 class xEABSampler(_Multistep):
     r"""Exponential Adams-Bashforth sampler with data (:math:`x`) prediction: a multi-step DPM-Solver++
@@ -575,6 +679,12 @@ class xEABSampler(_Multistep):
 
     def _update(self, x_t, integral, alpha, sigma, i):
         return sigma[i + 1] / sigma[i] * x_t - sigma[i + 1] * integral
+
+    def _stored_coef(self, alpha, sigma):
+        return torch.zeros_like(alpha), torch.ones_like(alpha)
+
+    def _update_coef(self, alpha_t, sigma_t, alpha_s, sigma_s):
+        return sigma_s / sigma_t, -sigma_s
 
 
 class REABSampler(_Multistep):
@@ -611,6 +721,17 @@ class REABSampler(_Multistep):
             torch.sqrt((alpha_s**2 + sigma_s**2) / (alpha_t**2 + sigma_t**2)) * x_t
             + torch.sqrt(alpha_s**2 + sigma_t**2) * integral
         )
+
+    def _stored_coef(self, alpha, sigma):
+        a_t = sigma**2 / (alpha**2 + sigma**2)
+        b_t = sigma * torch.rsqrt(alpha**2 + sigma**2)
+        return (1 - a_t) / b_t / alpha, -1 / b_t
+
+    def _update_coef(self, alpha_t, sigma_t, alpha_s, sigma_s):
+        return torch.sqrt((alpha_s**2 + sigma_s**2) / (alpha_t**2 + sigma_t**2)), torch.sqrt(alpha_s**2 + sigma_t**2)
+
+
+_MULTISTEP_TYPES = (REABSampler, xEABSampler, zEABSampler, vABSampler, zABSampler)
 
 
 # ---------------------------------------------------------------- eager step on a CUDA device

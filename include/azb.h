@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define AZB_VERSION 2
+#define AZB_VERSION 3
 
 enum {
     AZB_OK = 0,
@@ -93,6 +93,49 @@ int azb_step_f32(const float* x_t, const void* f, int f_dtype, int64_t f_batch_s
                  int64_t n_per_sample, int64_t batch, const float* coef_table,
                  const int32_t* step_idx, uint64_t seed, const int64_t* philox_state,
                  int64_t offset_host, int64_t rng_threads, int64_t rng_elem_offset, void* stream);
+
+/*
+ * The same kernel behind a descriptor, extended to every sampler of azula/sample.py and to classifier-free guidance
+ * (azula/guidance/cfg.py:35-65).  One call = one STAGE of a sampler step (one backbone evaluation followed by one
+ * update); row = table[*step_idx] holds row_floats floats: the 8 columns above, then (row_floats >= AZB_ROW_COLS)
+ *
+ *     AZB_R_P, AZB_R_Q     stored quantity   h = p*x_e + q*m                         sample.py:345,349,525,664,...
+ *     AZB_R_R              x_out = r*x_b + sum_j W[j]*H[j]   (H[write_slot] = the fresh h)  sample.py:351,528-535
+ *     AZB_R_FLAGS (int32)  bit 0 x_e = src[bit], bit 1 x_b = src[bit], bit 2 out = dst[bit], bit 3 history mode,
+ *                          bits 4-7 write slot, bit 8 store h into hist[write_slot], bits 12-15 slots in use
+ *     AZB_R_DRAW (int32)   number of noise draws of the loop BEFORE this stage (Philox offset = base + draw*offset_inc)
+ *     AZB_R_W .. +8        W[0..7]
+ *
+ * Affine mode (bit 3 clear) is azb_step_f32's arithmetic on x = src[x_e], bit for bit.  History mode serves Heun
+ * (stage A: predictor into the alternate state buffer, slope kept in slot 0; stage B: corrector from both slopes,
+ * sample.py:337-352) and the Adams-Bashforth family (ring of `order` slopes, weights solved in float64 at table-build
+ * time, sample.py:487-508).  With f_neg the posterior mean is the guided one, each branch clipped on its own as the
+ * wrapped denoiser would:  m = m+ + guidance[0] * (m+ - m-),  m+- = clamp(c_skip*x + c_out*F+-).
+ * x_in_next receives x_in_copies (1 or 2) consecutive copies of c_in_next * x_out (2: the input of a 2B-batch forward
+ * evaluating both guidance branches at once).  Loads of the state buffers are coherent: src and dst may alias.
+ */
+enum { AZB_R_P = 8, AZB_R_Q = 9, AZB_R_R = 10, AZB_R_FLAGS = 12, AZB_R_DRAW = 13, AZB_R_W = 16, AZB_ROW_COLS = 32 };
+enum { AZB_STEP_MAX_SLOTS = 8 };
+
+typedef struct AzbStep {
+    const float* src[2];    /* state buffers a row may read (legacy rows: src[0])                       */
+    float* dst[2];          /* state buffers a row may write (legacy rows: dst[0])                      */
+    const void* f;          /* backbone output F (F+ under guidance)                                    */
+    const void* f_neg;      /* F- or NULL                                                               */
+    const float* guidance;  /* device scalar omega (required with f_neg)                                */
+    const float* eps;       /* explicit noise or NULL (affine mode)                                     */
+    void* x_in_next;        /* next backbone input or NULL                                              */
+    float* hist;            /* history slots, slot j at hist + j*hist_stride (history mode)             */
+    const float* table;     /* float32[stages][row_floats]                                              */
+    const int32_t* step_idx;
+    const int64_t* philox_state; /* device {offset, seed} or NULL (then `seed`, offset_host)            */
+    int64_t f_batch_stride, n_per_sample, batch, hist_stride;
+    int64_t offset_host, offset_inc, rng_threads, rng_elem_offset;
+    uint64_t seed;
+    int32_t f_dtype, in_dtype, row_floats, x_in_copies;
+} AzbStep;
+
+int azb_step_ex_f32(const AzbStep* desc, void* stream);
 
 /* Bookkeeping between two steps of a captured loop: ++*step_idx, philox_state[0] += offset_inc,
  * and (optionally) time_out[0..time_count) = time_table[min(*step_idx, steps-1)][0..time_count)

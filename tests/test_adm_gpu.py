@@ -284,3 +284,109 @@ def test_full_card_forward_vs_oracle():
     assert next(iter(smp._loops.values())).graph is not None and torch.isfinite(x0).all() and err <= 2e-2
     del den, sd, smp
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("kind", ["ddim", "ddpm"])
+def test_full_card_64_steps_vs_oracle(kind):
+    """The HEADLINE configuration end to end -- exactly the call bench.py times: imagenet_256x256 card, batch 16,
+    ``DDIMSampler(steps=64)`` through the captured graph (and ``DDPMSampler(steps=64)`` with equal Philox bits) --
+    against the oracle's fp32 loop (TF32 off) on the same x1.  ADM's c_skip = 1/alpha and c_out = -sigma/alpha are
+    ~ +-100 near t = 1 (hard part 2), so this is where bf16 error could compound; the test prints
+    the drift |x_engine - x_oracle| along the trajectory (free-running) and the LOCAL error of single steps started
+    from the oracle's own states (teacher-forced), and holds the final sample to the stated bf16 bar."""
+    from oracle.gen_golden_cfg import IMAGENET_256
+
+    steps = 64
+    den, sd = _seeded(IMAGENET_256, seed=1234)
+    tab = AU.block_table(**IMAGENET_256)
+    sched = lambda t: RM.vp_alpha_sigma(t, 1e-2, 1e-2)  # noqa: E731
+    sig = RM.adm_sigmas().to(DEV)
+    net = lambda xx, tt, y=None: torch.cat([AU.forward(sd, tab, xx[i : i + 4], tt.expand(4)) for i in range(0, 16, 4)])  # noqa: E731
+    mean = lambda xx, tt: RM.adm_mean_var(net, sched, sig, xx, tt)[0]  # noqa: E731
+    S, eta = (DDIMSampler, 0.0) if kind == "ddim" else (DDPMSampler, None)
+    smp = S(den, steps=steps, silent=True, graph=True)
+    torch.manual_seed(1000)
+    x1 = smp.init((16, 3, 256, 256), device=DEV)
+
+    torch.manual_seed(1)
+    x0 = smp(x1)  # the bench's call (also captures the graph)
+    loop = next(iter(smp._loops.values()))
+    assert loop.graph is not None and loop.unroll == 1
+
+    # the same loop once more, replay by replay, keeping every intermediate state
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    torch.manual_seed(1)
+    loop._reset(x1, {}, gen.initial_seed(), gen.get_offset())
+    mine = []
+    for _ in range(steps):
+        loop.graph.replay()
+        mine.append(loop.x.clone())
+    assert torch.equal(mine[-1], x0)
+
+    torch.manual_seed(1)
+    trace: list = []
+    want = RM.sample_loop(mean, sched, x1, steps=steps, eta=eta, trace=trace)
+    drift = [(a - b).abs().mean().item() for a, b in zip(mine, trace)]
+    print(f"{kind}-64 free-running drift mean|d| at steps 1,8,16,...,64: " + " ".join(f"{drift[i]:.2e}" for i in (0, 7, 15, 23, 31, 39, 47, 55, 63)))
+
+    # teacher-forced: one engine step from the oracle's state x_t -> compare with the oracle's x_s
+    pairs = RM.time_grid(1.0, 0.0, steps).to(DEV)
+    local = []
+    for i in (1, 8, 24, 40, 56, 63):
+        t, s = pairs[i]
+        if kind == "ddpm":  # noise of step i: replay the generator to where the loop's i-th draw starts
+            torch.manual_seed(1)
+            gen.set_offset(gen.get_offset() + i * loop.offset_inc)
+        got = smp.step(trace[i - 1], t, s)
+        local.append((got - trace[i]).abs().mean().item())
+    print(f"{kind}-64 local (teacher-forced) step error mean|d| at steps 2,9,25,41,57,64: " + " ".join(f"{e:.2e}" for e in local))
+
+    err = (x0 - want).abs()
+    print(f"imagenet_256x256 card, {kind.upper()}-64, batch 16, graph: mean|d| {err.mean().item():.3e} "
+          f"p99 {err.flatten().kthvalue(int(0.99 * err.numel())).values.item():.3e} max|d| {err.max().item():.3e} "
+          f"(outputs in [{want.min().item():.2f}, {want.max().item():.2f}], std {want.std().item():.3f})")
+    assert torch.isfinite(x0).all()
+    assert max(local) <= 2e-2, local  # every single step inside the per-step bf16 bar
+    assert err.mean().item() <= 3e-2, err.mean().item()  # the 64-step sample: stated bf16 bar for the whole trajectory
+    del den, sd, smp, loop, mine, trace
+    torch.cuda.empty_cache()
+
+
+def test_sampler_follows_weight_updates_and_outlives_plan_eviction():
+    """a captured graph bakes in the addresses of the PACKED weights and of the plan's arena.
+    (1) Evicting the plan from the model's cache / clearing the cache with a no-op ``.to()`` must not free them
+    (the loop pins what its capture used); (2) after ``load_state_dict`` or an in-place update the SAME sampler
+    object must sample from the new weights -- bit-equal to a fresh sampler -- instead of replaying the old graph."""
+    den, _ = _seeded(TINY_ADM)
+    smp = DDIMSampler(den, steps=4, silent=True, graph=True)
+    torch.manual_seed(0)
+    x1 = smp.init((2, 3, 16, 16), device=DEV)
+    a = smp(x1)
+    loop = next(iter(smp._loops.values()))
+    assert loop.graph is not None and len(loop.pinned) == 1
+
+    # (1) other shapes evict the sampler's plan (cache of 2); .to() clears the whole cache; fresh allocations would
+    # land in whatever that freed
+    ts = torch.tensor([5], device=DEV)
+    for shape in ((1, 3, 16, 16), (3, 3, 16, 16), (5, 3, 32, 32)):
+        den.backbone(torch.randn(shape, device=DEV), ts)
+    assert all(plan is not loop.pinned[0][2] for k, plan in den.backbone._native.items() if k != "packed")
+    den.to(DEV)
+    junk = [torch.full((1 << 18,), float("nan"), device=DEV) for _ in range(64)]
+    assert torch.equal(smp(x1), a)
+    del junk
+
+    # (2) new weights: new loop, same bits as a fresh sampler
+    sd2 = {k: v.to(DEV) for k, v in AU.seeded_state(den.backbone.state_dict(), seed=99).items()}
+    den.backbone.load_state_dict(sd2)
+    b = smp(x1)
+    assert next(iter(smp._loops.values())) is not loop
+    assert torch.equal(b, DDIMSampler(den, steps=4, silent=True, graph=True)(x1)) and not torch.equal(a, b)
+    for p in den.backbone.parameters():  # an optimiser-like in-place step
+        p.mul_(1.05)
+    c = smp(x1)
+    assert torch.equal(c, DDIMSampler(den, steps=4, silent=True, graph=True)(x1)) and not torch.equal(b, c)
+    # a mutated schedule invalidates the frozen coefficient table as well
+    den.schedule.alpha_min = 2e-2
+    d = smp(x1)
+    assert torch.equal(d, DDIMSampler(den, steps=4, silent=True, graph=True)(x1)) and not torch.equal(c, d)
