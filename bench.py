@@ -1,26 +1,30 @@
 #!/usr/bin/env python
 r"""Headline benchmark: images/sec of ADM 256x256 DDIM-64 sampling (BASELINE.json `metric`).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config adm|unet64|dit_b2|mlp]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-One bench "step" = one pass of the hot path over one batch: ``DDIMSampler(steps=64)`` called on a
-(16, 3, 256, 256) batch per GPU with the ``imagenet_256x256`` ADM card (BASELINE.json configs[2],
-the configuration the metric is quoted on; random-init seeded weights, synthetic x1).  Inside a
-step the device runs 64 x [native U-Net forward (~370 launches) + fused transition + advance]
-as CUDA-graph replays.  Ranks are independent replicas of the sampler over disjoint slices of the
-global batch (weak scaling); the only collective is the weight broadcast at init.
+One bench "step" = one pass of the hot path over one batch: ``sampler(x1)`` -- for the default workload
+``DDIMSampler(steps=64)`` on a (16, 3, 256, 256) batch per GPU with the ``imagenet_256x256`` ADM card
+(BASELINE.json configs[2], the configuration the metric is quoted on; random-init seeded weights, synthetic x1).
+Inside a step the device runs 64 x [native U-Net forward (~250 launches) + fused transition + advance] as
+CUDA-graph replays.  Ranks are independent replicas of the sampler over disjoint slices of the global batch
+(weak scaling); the only collective is the weight broadcast at init.  ``--config`` selects the other BASELINE
+configurations (unet64 = configs[1], dit_b2 = configs[3], mlp = configs[0]); the default line is unchanged.
 
-Printed JSON (rank 0, one line): see the bench contract in the task statement.  Extra keys:
-``roofline`` (dominant kernel = tcgen05 convolution, tensor bound), ``roofline_e2e`` (whole
-sampler vs the tensor roofline), ``step_kernel`` (HBM GB/s of the transition kernel, the second
-half of BASELINE.json's metric), ``cpu_baseline``, ``clocks``, ``e2e``, ``gpu_launches``.
+Printed JSON (rank 0, one line): see the bench contract.  Extra keys: ``roofline`` (dominant kernel), ``roofline_e2e``
+(whole sampler vs the tensor roofline), ``step_kernel`` / ``step_kernel_noise`` (HBM GB/s of the transition kernel
+without / with the in-register Philox draw: the second half of BASELINE.json's metric), ``cpu_baseline`` (the
+UNMODIFIED reference from baseline/_ref on the host cores), ``eager_gpu`` (the unmodified reference's eager sampler
+on the SAME GPU, default flags and TF32 off: the denominator of the north star's ">= 10x"), ``shard_check`` (N > 1),
+``setup`` (plan build + weight packing + graph capture latency), ``clocks``, ``e2e``, ``gpu_launches``.
 """
 
 from __future__ import annotations
 
 import argparse
+import csv
 import json
 import os
 import subprocess
@@ -33,13 +37,25 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-METRIC = "images/sec ADM 256x256 DDIM-64"
 UNIT = "images/s"
 CARD = "imagenet_256x256"
-BATCH = 16  # per GPU
-SAMPLER_STEPS = 64
-SIZE = 256
-FLOP_PER_IMAGE_FORWARD = 2239.7e9  # FlopCounterMode on the reference module
+
+WORKLOADS = {
+    # name: metric, sampler class, sampler steps, per-GPU shape, FLOP per image and forward
+    "adm": dict(metric="images/sec ADM 256x256 DDIM-64", sampler="DDIMSampler", steps=64, shape=(16, 3, 256, 256),
+                flop=2239.7e9, what=f"ADM {CARD} (552.8M params, seeded random init), DDIMSampler(steps=64, eta=0)",
+                cpu_batch=1, cpu_steps=2),
+    "unet64": dict(metric="images/sec azula.nn.unet UNet 64x64 DDIM-50", sampler="DDIMSampler", steps=50, shape=(32, 3, 64, 64),
+                   flop=13.02e9, what="azula.nn.unet UNet 64x64x3 hid (64,128,256) blocks (3,3,3) mod 256 (13.5M params, "
+                   "seeded random init), KarrasDenoiser + VPSchedule, DDIMSampler(steps=50)", cpu_batch=4, cpu_steps=3),
+    "dit_b2": dict(metric="images/sec DiT-B/2 32x32x4 DDPM-250", sampler="DDPMSampler", steps=250, shape=(64, 4, 32, 32),
+                   flop=46.58e9, what="DiT-B/2 = azula.nn.vit ViT hid 768 x 12 blocks x 12 heads, patch 2 on 32x32x4 latents "
+                   "(114.6M params, seeded random init), KarrasDenoiser + VPSchedule, DDPMSampler(steps=250)",
+                   cpu_batch=4, cpu_steps=3),
+    "mlp": dict(metric="samples/sec README MLP DDPM-1000", sampler="DDPMSampler", steps=1000, shape=(64, 5), flop=2 * 2 * 5 * 64,
+                what="KarrasDenoiser + 5-feature MLP (README example), VPSchedule, DDPMSampler(steps=1000)", cpu_batch=64,
+                cpu_steps=1000),
+}
 
 
 def peaks() -> dict:
@@ -50,6 +66,24 @@ def peaks() -> dict:
         return {"hbm_gbs": p["hbm_gbs"], "tflops": p["bf16_tflops_sustained"], "tflops_burst": p["bf16_tflops"],
                 "source": "measured (MEASURED_PEAKS.json)"}
     return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def ncu_traffic(name: str) -> tuple[int | None, str | None]:
+    r"""DRAM bytes (read + write) per launch of the dominant kernel, parsed from the committed ``ncu --set full``
+    capture under profiles/ (a run cannot measure it on itself: that needs the profiler)."""
+    for rnd in ("r2", "r1"):
+        path = os.path.join(ROOT, "profiles", name.format(rnd=rnd))
+        if not os.path.exists(path):
+            continue
+        vals = {}
+        with open(path) as f:
+            for row in csv.reader(f):
+                if len(row) >= 3 and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(row[1], 1)
+                    vals[row[0]] = float(row[2]) * scale
+        if len(vals) == 2:
+            return int(sum(vals.values())), os.path.relpath(path, ROOT)
+    return None, None
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -108,41 +142,101 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------- engine arm
+# ------------------------------------------------------------------------------- model builders
 
 
-def build_denoiser(device, rank: int, world: int):
-    from azula_b200.nn.utils import skip_init
-    from azula_b200.plugins import adm
+class TimeWrapper(torch.nn.Module):
+    r"""The tutorial pattern (reference docs/tutorials/mnist.ipynb cell 8): mod = MLP(log_snr)."""
 
-    config = adm.cards()[CARD].config
-    with torch.device(device), skip_init():
-        den = adm.make_model(**config).eval()
-    if rank == 0:
-        adm.seed_parameters(den.backbone, seed=1234)
-    if world > 1:  # the ONE collective of the path: weights from rank 0 at init (no per-step collective)
-        from azula_b200 import parallel
+    def __init__(self, net: torch.nn.Module, features: int) -> None:
+        super().__init__()
+        self.net = net
+        self.time_embedding = torch.nn.Sequential(
+            torch.nn.Linear(1, features), torch.nn.SiLU(), torch.nn.Linear(features, features)
+        )
 
-        parallel.broadcast_parameters(den.backbone, src=0)
-    return den
+    def forward(self, x_t, log_snr_t):
+        return self.net(x_t, self.time_embedding(log_snr_t[..., None]))
 
 
-def step_kernel_bandwidth(device) -> dict:
-    r"""HBM GB/s of the fused transition at a footprint far above L2 (3 x 512 MiB): 12 B/element."""
+class ReadmeMlp(torch.nn.Module):
+    r"""The README / tests backbone of BASELINE configs[0] (reference tests/test_sample.py:28-51)."""
+
+    def __init__(self, sine_encoding, features: int = 5) -> None:
+        super().__init__()
+        self.l1 = torch.nn.Linear(features, 64)
+        self.l2 = torch.nn.Linear(64, features)
+        self.enc = sine_encoding(64)
+
+    def forward(self, x, t):
+        return self.l2(torch.relu(self.l1(x) + self.enc(t)))
+
+
+def build_denoiser(pkg: str, config: str, device):
+    r"""The workload's denoiser built from package ``pkg`` (``azula_b200`` = the engine, ``azula`` = the unmodified
+    reference from baseline/_ref): same constructor calls, parameters left uninitialised (seeded afterwards)."""
+    import importlib
+
+    mod = lambda name: importlib.import_module(f"{pkg}.{name}")  # noqa: E731
+    skip_init = mod("nn.utils").skip_init
+    if config == "adm":
+        adm = mod("plugins.adm")
+        cards = mod("plugins.utils").load_cards(adm.__name__)
+        with torch.device(device), skip_init():
+            return adm.make_model(**cards[CARD].config).eval()
+    KarrasDenoiser, VPSchedule = mod("denoise").KarrasDenoiser, mod("noise").VPSchedule
+    with torch.device(device):
+        if config == "unet64":
+            net = TimeWrapper(mod("nn.unet").UNet(3, 3, hid_channels=(64, 128, 256), hid_blocks=(3, 3, 3), mod_features=256), 256)
+        elif config == "dit_b2":
+            net = TimeWrapper(mod("nn.vit").ViT(4, 4, mod_features=768, hid_channels=768, hid_blocks=12, attention_heads=12,
+                                                patch_size=2), 768)
+        else:
+            net = ReadmeMlp(mod("nn.layers").SineEncoding)
+    return KarrasDenoiser(net, VPSchedule()).eval()
+
+
+def seed_backbone(den, seed: int = 1234) -> None:
+    r"""Overwrites every parameter from a seeded generator (same values for the engine's and the reference's module:
+    both expose the same parameter names and shapes)."""
+    from azula_b200.plugins.adm import seed_parameters
+
+    seed_parameters(den.backbone, seed=seed)
+
+
+def sampler_of(pkg: str, config: str, den, **kw):
+    import importlib
+
+    wl = WORKLOADS[config]
+    return getattr(importlib.import_module(f"{pkg}.sample"), wl["sampler"])(den, steps=wl["steps"], silent=True, **kw)
+
+
+def load_reference():
+    from baseline import ref_loader
+
+    return ref_loader.load() if ref_loader.available() else None
+
+
+# ------------------------------------------------------------------------------- side measurements
+
+
+def step_kernel_bandwidth(device, noise: bool) -> dict:
+    r"""HBM GB/s of the fused transition at a footprint far above L2 (3 x 512 MiB): 12 B/element.  ``noise``: a row
+    with n != 0, i.e. the in-register Philox4x32-10 + Box-Muller draw of DDPM (eps never touches memory)."""
     from azula_b200 import _lib
 
     n = 128 * 1024 * 1024
     x = torch.randn(n, device=device)
     f = torch.randn(n, device=device)
     out = torch.empty_like(x)
-    row = torch.tensor([[0.9, -0.4, 0.8, 0.5, 0.7, 0.0, 1.0, float("inf")]], device=device)
+    row = torch.tensor([[0.9, -0.4, 0.8, 0.5, 0.7, 0.3 if noise else 0.0, 1.0, float("inf")]], device=device)
     idx = torch.zeros((), dtype=torch.int32, device=device)
     lib, s = _lib.lib(), _lib.stream_ptr(device)
     T, _ = _lib.rng_policy(n)
 
     def launch():
         _lib.check(lib.azb_step_f32(x.data_ptr(), f.data_ptr(), _lib.F32, n, None, out.data_ptr(), None, _lib.F32, n, 1,
-                                    row.data_ptr(), idx.data_ptr(), 0, None, 0, T, 0, s), "azb_step_f32")
+                                    row.data_ptr(), idx.data_ptr(), 1234, None, 0, T, 0, s), "azb_step_f32")
 
     for _ in range(3):
         launch()
@@ -159,17 +253,44 @@ def step_kernel_bandwidth(device) -> dict:
     pk = peaks()
     return {"bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": round(gbs / pk["hbm_gbs"], 4), "bytes_per_launch": 12 * n, "us_per_launch": round(1e3 * ms, 1),
-            "note": "azb_step_f32 alone, fp32 x_t + F -> x_s, deterministic (n=0) row, 1.5 GiB footprint >> L2"}
+            "note": "azb_step_f32 alone, fp32 x_t + F -> x_s, " + (
+                "stochastic row (n != 0: DDPM, noise generated in registers)" if noise else "deterministic row (n = 0: DDIM eta 0)")
+                    + ", 1.5 GiB footprint >> L2"}
 
 
-def cpu_baseline_sample(threads: int, forwards: int = 2) -> dict:
-    r"""The oracle's fp32 restatement of the reference path on the host cores: ADM-256, batch 1,
-    ``forwards`` DDIM steps out of 64, extrapolated linearly to images/sec."""
+def cpu_reference_sample(config: str, threads: int, batch: int, n_steps: int, warm: int = 1) -> dict:
+    r"""The reference's OWN implementation on the host cores: ``Sampler.step`` of the unmodified reference package
+    (baseline/_ref/azula) -- or, when that copy is absent, of the oracle port -- on a bounded sample of the workload:
+    ``batch`` items, ``warm + n_steps`` sampler steps out of the workload's, extrapolated linearly."""
+    wl = WORKLOADS[config]
+    torch.set_num_threads(threads)
+    az = load_reference()
+    if az is None:
+        if config != "adm":
+            raise RuntimeError("baseline/_ref is missing (scripts/fetch_ref.sh) and the oracle port only covers the ADM workload")
+        return dict(_cpu_port_sample(warm + n_steps), kind="port", warm=warm)
+    with torch.no_grad():
+        den = build_denoiser("azula", config, "cpu")
+        seed_backbone(den)
+        smp = sampler_of("azula", config, den)
+        torch.manual_seed(0)
+        x = smp.init((batch, *wl["shape"][1:]))
+        pairs = smp.timesteps.unfold(0, 2, 1)
+        times = []
+        for i in range(min(warm + n_steps, wl["steps"])):
+            t, s = pairs[i]
+            t0 = time.perf_counter()
+            x = smp.step(x, t, s)
+            times.append(time.perf_counter() - t0)
+    return {"step_s": times, "kind": "reference", "warm": min(warm, len(times) - 1)}
+
+
+def _cpu_port_sample(forwards: int) -> dict:
+    r"""Fallback (no baseline/_ref): the oracle's fp32 restatement of the ADM path, batch 1."""
     from oracle import adm_unet as AU
     from oracle import ref_math as RM
     from oracle.gen_golden_cfg import IMAGENET_256
 
-    torch.set_num_threads(threads)
     cfg = {k: v for k, v in IMAGENET_256.items() if not k.startswith("discrete")}
     tab = AU.block_table(**cfg)
     sd = AU.seeded_state({k: torch.empty(s) for k, s in AU.state_shapes(tab).items()}, seed=1234)
@@ -177,8 +298,8 @@ def cpu_baseline_sample(threads: int, forwards: int = 2) -> dict:
     sig = RM.adm_sigmas()
     net = lambda x, t, y=None: AU.forward(sd, tab, x, t)  # noqa: E731
     mean = lambda x, t: RM.adm_mean_var(net, sched, sig, x, t)[0]  # noqa: E731
-    x = torch.randn(1, 3, SIZE, SIZE, generator=torch.Generator().manual_seed(0))
-    pairs = RM.time_grid(1.0, 0.0, SAMPLER_STEPS)
+    x = torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(0))
+    pairs = RM.time_grid(1.0, 0.0, 64)
     times = []
     with torch.no_grad():
         for i in range(forwards):
@@ -192,35 +313,108 @@ def cpu_baseline_sample(threads: int, forwards: int = 2) -> dict:
     return {"step_s": times}
 
 
+def cpu_baseline_object(config: str, threads: int, n_steps: int | None = None) -> dict:
+    wl = WORKLOADS[config]
+    n_steps = n_steps or wl["cpu_steps"]
+    s = cpu_reference_sample(config, threads, wl["cpu_batch"], n_steps)
+    timed = s["step_s"][s["warm"]:] if config != "mlp" else s["step_s"]
+    per = sum(timed) / len(timed)
+    value = wl["cpu_batch"] / (wl["steps"] * per)
+    full = config == "mlp"
+    what = "unmodified reference (baseline/_ref/azula)" if s["kind"] == "reference" else "oracle port (fp32 torch restatement)"
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": s["kind"], "extrapolated": not full,
+            "sample": (f"{what} on the host cores: {len(timed)} sampler steps of {wl['cpu_batch']} item(s) "
+                       + ("(the whole workload)" if full else f"after {s['warm']} warm-up, {per:.3f} s/step, extrapolated x{wl['steps']} steps")),
+            "s_per_step": per}
+
+
+def eager_gpu(config: str, den_engine, x1, device, reps: int = 3) -> dict:
+    r"""The north star's comparator: the UNMODIFIED reference's eager sampler (``azula/sample.py:139-161`` +
+    its own denoiser / backbone modules) on the same B200, same weights and x1, host buffers in and out like ``e2e``;
+    once with PyTorch's default flags (cuDNN convolutions in TF32) and once with TF32 off (strict fp32)."""
+    az = load_reference()
+    if az is None:
+        return {"unavailable": "baseline/_ref/azula is missing (run scripts/fetch_ref.sh in the build container)"}
+    wl = WORKLOADS[config]
+    out: dict = {"what": "unmodified reference (baseline/_ref/azula): Sampler.__call__ + denoiser + backbone in eager PyTorch "
+                         "fp32 on the same GPU, same weights / x1, pinned host buffers in and out",
+                 "timed_samplings": reps}
+    with torch.no_grad():
+        den = build_denoiser("azula", config, device)
+        den.backbone.load_state_dict(den_engine.backbone.state_dict())
+        host_in = x1.cpu().pin_memory()
+        host_out = torch.empty_like(host_in).pin_memory()
+        flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        try:
+            for tag, tf32 in (("tf32", None), ("fp32", False)):
+                if tf32 is not None:
+                    torch.backends.cudnn.allow_tf32 = tf32
+                    torch.backends.cuda.matmul.allow_tf32 = tf32
+                smp = sampler_of("azula", config, den)
+                short = sampler_of("azula", config, den)
+                short.steps = min(4, wl["steps"])
+                short(x1)  # warm-up: cuDNN heuristics, lazy init, allocator
+                torch.cuda.synchronize(device)
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    xd = host_in.to(device, non_blocking=True)
+                    host_out.copy_(smp(xd), non_blocking=True)
+                    torch.cuda.current_stream(device).synchronize()
+                dt = (time.perf_counter() - t0) / reps
+                out[tag] = {"value": x1.shape[0] / dt, "unit": UNIT, "s_per_sampling": dt,
+                            "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32),
+                            "matmul_allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32),
+                            "tflops": x1.shape[0] / dt * wl["steps"] * wl["flop"] / 1e12}
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = flags
+        del den
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------- reference arm
+
+
 def run_reference(args) -> None:
-    r"""``--impl reference``: the reference's own CPU path (the oracle port: plain fp32 torch on the
-    host cores, all threads), one DDIM step of one ADM-256 image per bench step, extrapolated."""
+    r"""``--impl reference``: the reference's own CPU implementation of the path on the box's host cores (the
+    unmodified package from baseline/_ref), all threads, one bounded sample per bench step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = WORKLOADS[args.config]
     threads = os.cpu_count() or 1
-    out = cpu_baseline_sample(threads, forwards=args.warmup + args.steps)["step_s"][args.warmup:]
-    per_step = sum(out) / len(out)
-    value = 1.0 / (SAMPLER_STEPS * per_step)
+    s = cpu_reference_sample(args.config, threads, wl["cpu_batch"], args.steps, warm=args.warmup)
+    timed = s["step_s"][s["warm"]:]
+    per = sum(timed) / len(timed)
+    value = wl["cpu_batch"] / (wl["steps"] * per)
+    what = "unmodified reference (baseline/_ref/azula)" if s["kind"] == "reference" else "oracle port"
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * per_step, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * per, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ADM {CARD} DDIM-{SAMPLER_STEPS}, CPU sample: batch 1, one DDIM step per bench step, "
-                               f"images/s = 1 / ({SAMPLER_STEPS} x step time)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} DDIM steps of 1 image (of {SAMPLER_STEPS}), extrapolated linearly"},
+        "config": {"workload": f"{wl['what']}; CPU sample: batch {wl['cpu_batch']}, one sampler step per bench step, "
+                               f"{UNIT} = batch / ({wl['steps']} x step time)", "extrapolated": True},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": s["kind"], "extrapolated": True,
+                         "sample": f"{what}: {len(timed)} sampler steps of {wl['cpu_batch']} item(s) (of {wl['steps']}), "
+                                   f"extrapolated linearly"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------- engine arm
+
+
+def _checksum(x: torch.Tensor) -> int:
+    return int(x.contiguous().view(torch.int32).to(torch.int64).sum().item())
+
+
 def run_engine(args) -> None:
     import torch.distributed as dist
 
-    from azula_b200.sample import DDIMSampler
-
+    config = args.config
+    wl = WORKLOADS[config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -245,19 +439,32 @@ def run_engine(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    den = build_denoiser(device, rank, world)
+    den = build_denoiser("azula_b200", config, device)
+    if rank == 0:
+        seed_backbone(den)
+    if world > 1:  # the ONE collective of the path: weights from rank 0 at init (no per-step collective)
+        from azula_b200 import parallel
+
+        parallel.broadcast_parameters(den.backbone, src=0)
+    batch = args.batch or wl["shape"][0]
+    shape = (batch, *wl["shape"][1:])
     # rank r owns samples [r*B, (r+1)*B) of the global batch; noise is addressed by global element index,
-    # so the N-GPU run reproduces the one-GPU run on the global batch bit for bit
-    sampler = DDIMSampler(den, steps=SAMPLER_STEPS, silent=True, graph=True, shard=(rank, world))
-    shape = (args.batch, 3, SIZE, SIZE)
+    # so the N-GPU run reproduces the one-GPU run on the global batch
+    sampler = sampler_of("azula_b200", config, den, graph=True, shard=(rank, world))
     torch.manual_seed(1000)
     x1 = sampler.init(shape, device=device)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)  # 2 x L2
 
-    # ---- warm-up (first call builds the plan, the coefficient table and captures the graph)
-    for _ in range(max(args.warmup, 1)):
+    # ---- first call: weight packing, launch plan, coefficient table, graph capture (reported separately)
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    x0 = sampler(x1)
+    torch.cuda.synchronize(device)
+    first_call_s = time.perf_counter() - t0
+    for _ in range(max(args.warmup, 1) - 1):
         x0 = sampler(x1)
     assert torch.isfinite(x0).all(), "non-finite sample"
+    loop = next(iter(sampler._loops.values()))
 
     # ---- timed region: K full samplings, inputs resident in HBM
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -274,7 +481,7 @@ def run_engine(args) -> None:
     if args.profile_range:
         torch.cuda.profiler.stop()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    images = world * args.batch * args.steps
+    images = world * batch * args.steps
     value = images / (ms / 1e3)
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
@@ -290,69 +497,131 @@ def run_engine(args) -> None:
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e = images / e2e_s
 
+    # ---- N > 1: what did the ranks compute?  64-bit checksums of every shard; for N <= 2 rank 0 also samples the
+    # GLOBAL batch in one process and compares it with the gathered shards
+    shard_check = None
+    if world > 1:
+        sums = torch.zeros(world, dtype=torch.int64, device=device)
+        sums[rank] = _checksum(x0)
+        dist.all_reduce(sums)
+        shard_check = {"checksums_int64": [int(v) for v in sums.tolist()], "distinct": len(set(sums.tolist())) == world}
+        if world <= 2:
+            parts = [torch.empty_like(x0) for _ in range(world)]
+            dist.all_gather(parts, x0)
+            if rank == 0:
+                whole = sampler_of("azula_b200", config, den, graph=True)
+                torch.manual_seed(1000)
+                xg = whole.init((world * batch, *shape[1:]), device=device)
+                assert torch.equal(xg[:batch], x1), "shard 0 of the global x1 differs from this rank's x1"
+                x0g = whole(xg)
+                d = (torch.cat(parts) - x0g).abs()
+                shard_check.update(vs_single_process_global_batch={"bit_equal": bool(d.max().item() == 0),
+                                                                   "max_abs_diff": d.max().item(), "mean_abs_diff": d.mean().item()})
+                del whole, x0g, xg
+                torch.cuda.empty_cache()
+
     line = None
     if rank == 0:
-        loop = next(iter(sampler._loops.values()))
-        plan = next(v for k, v in den.backbone._native.items() if k != "packed")
-        launches_per_sampler_step = plan.launches + 2
-        detail: list = []
-        for _ in range(2):  # second pass: warm instruction caches / clocks as inside the loop
-            detail.clear()
-            table = plan.profile(detail)
-        total_ms = sum(r["ms"] for r in table.values())
-        conv = table["conv3x3"]
         pk = peaks()
-        conv_tflops = conv["flops"] / conv["ms"] / 1e9
-        # the dominant kernel class: 3x3 convolution 256 -> 256 at 256 x 256 (6 launches per forward, each 1.24 TFLOP
-        # at batch 16; 5 of them with the GroupNorm + SiLU of their input fused into the halo tiles); its DRAM traffic
-        # comes from the committed ncu --set full capture of exactly this launch
-        dom = [d for d in detail if d[0] == "conv3x3" and f"x{SIZE}x{SIZE} 256->256" in d[1] and "skip" not in d[1]]
-        dom_ms = sum(d[2] for d in dom) / max(len(dom), 1)
-        dom_flop = dom[0][3] if dom else 0.0
-        dom_tflops = dom_flop / dom_ms / 1e9 if dom else 0.0
-        traffic = 1099858432 if args.batch == 16 else None  # profiles/r1_ncu_full_conv_fused_v5.csv: dram read + write
-        e2e_tflops = value / world * SAMPLER_STEPS * FLOP_PER_IMAGE_FORWARD / 1e12
+        per_stage = 2  # azb_step_ex_f32 + azb_advance
+        native = [m for m in den.backbone.modules() if isinstance(getattr(m, "_native", None), dict)]
+        plan = next((v for m in native for k, v in m._native.items() if isinstance(k, tuple)), None) if not loop.pinned else loop.pinned[0][2]
+        stage_launches = (plan.launches if plan is not None else 0) + per_stage
+        e2e_tflops = value / world * wl["steps"] * wl["flop"] / 1e12
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"ADM {CARD} (552.8M params, seeded random init), DDIMSampler(steps={SAMPLER_STEPS}, eta=0), "
-                                   f"batch {args.batch}/GPU x {world} GPU, 3x{SIZE}x{SIZE} fp32 state, bf16 backbone",
-                       "global_batch": world * args.batch, "parallelism": f"replicas x{world} (batch-sharded, no per-step collective)",
-                       "graph": loop.graph is not None, "l2": "256 MiB flush write between timed iterations; working set ~8 GiB >> L2"},
+            "dtype": "bf16" if plan is not None else "f32", "data": "synthetic",
+            "config": {"workload": f"{wl['what']}, batch {batch}/GPU x {world} GPU, {'x'.join(map(str, shape[1:]))} fp32 state"
+                                   + (", bf16 backbone" if plan is not None else ""),
+                       "global_batch": world * batch, "parallelism": f"replicas x{world} (batch-sharded, no per-step collective)",
+                       "graph": loop.graph is not None, "stages_per_graph_replay": loop.unroll,
+                       "l2": "256 MiB flush write between timed iterations"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4},
-            "gpu_launches": args.steps * SAMPLER_STEPS * launches_per_sampler_step,
-            "roofline": {"bound": "tensor",
-                         "kernel": f"conv_gemm_kernel<256, pair, lean, halo>: GroupNorm+SiLU+3x3 conv 256->256 on "
-                                   f"{args.batch}x{SIZE}x{SIZE} (halo-tile implicit GEMM, tcgen05 cta_group::2)",
-                         "achieved": round(dom_tflops, 1), "peak": pk["tflops"], "unit": "TFLOP/s",
-                         "frac": round(dom_tflops / pk["tflops"], 4), "traffic": traffic,
-                         "flop_per_launch": dom_flop, "us_per_launch": round(1e3 * dom_ms, 1), "launches_per_forward": len(dom),
-                         "algorithmic_bytes_per_launch": 2 * 2 * args.batch * SIZE * SIZE * 256 + 2 * 9 * 256 * 256,
-                         "peak_source": pk["source"] + ", sustained bf16 (the kernel is timed inside a full forward pass)",
-                         "peak_burst": pk["tflops_burst"], "frac_of_burst": round(dom_tflops / pk["tflops_burst"], 4),
-                         "all_conv3x3": {"achieved": round(conv_tflops, 1), "frac": round(conv_tflops / pk["tflops"], 4),
-                                         "launches_per_forward": conv["launches"], "flop_per_forward": conv["flops"],
-                                         "share_of_forward": round(conv["ms"] / total_ms, 4)}},
+            "gpu_launches": args.steps * loop.stages * stage_launches,
+            "setup": {"first_call_s": round(first_call_s, 3), "steady_call_s": round(ms / args.steps / 1e3, 4),
+                      "note": "first sampler(x1): weight packing + launch plan + coefficient table + graph capture + one sampling"},
             "roofline_e2e": {"bound": "tensor", "achieved": round(e2e_tflops, 1), "peak": pk["tflops"], "unit": "TFLOP/s",
                              "frac": round(e2e_tflops / pk["tflops"], 4),
-                             "note": "images/s/GPU x 64 x 2239.7 GFLOP (algorithmic FLOPs of the reference forward)"},
-            "forward_kernels": {k: {"launches": r["launches"], "ms": round(r["ms"], 3)} for k, r in table.items()},
+                             "note": f"{UNIT}/GPU x {wl['steps']} x {wl['flop'] / 1e9:.2f} GFLOP (algorithmic FLOPs of the reference forward)"},
             "clocks": clocks.summary(),
         }
-        line["step_kernel"] = step_kernel_bandwidth(device)
+        if plan is not None:
+            detail: list = []
+            for _ in range(2):  # second pass: warm instruction caches / clocks as inside the loop
+                detail.clear()
+                table = plan.profile(detail)
+            line["roofline"] = roofline_of(config, table, detail, batch, pk)
+            line["forward_kernels"] = {k: {"launches": r["launches"], "ms": round(r["ms"], 3)} for k, r in table.items()}
+        if shard_check is not None:
+            line["shard_check"] = shard_check
+        if not args.no_extras:
+            line["step_kernel"] = step_kernel_bandwidth(device, noise=False)
+            line["step_kernel_noise"] = step_kernel_bandwidth(device, noise=True)
+            if "roofline" not in line:
+                line["roofline"] = dict(line["step_kernel"], kernel="step_vec4_kernel (the backbone is an ordinary nn.Module)",
+                                        traffic=None)
+        if world == 1 and not args.no_eager_gpu:
+            eg = eager_gpu(config, den, x1, device)
+            for tag in ("tf32", "fp32"):
+                if tag in eg:
+                    eg[tag]["engine_e2e_over_this"] = round(e2e / eg[tag]["value"], 2)
+            line["eager_gpu"] = eg
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            sample = cpu_baseline_sample(threads, forwards=3)["step_s"][1:]
-            per = sum(sample) / len(sample)
-            line["cpu_baseline"] = {"value": 1.0 / (SAMPLER_STEPS * per), "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"oracle (fp32 torch restatement) on host cores: 2 DDIM steps of 1 ADM-256 image "
-                                              f"after 1 warm-up, {per:.2f} s/step, extrapolated x{SAMPLER_STEPS}"}
+            line["cpu_baseline"] = cpu_baseline_object(config, os.cpu_count() or 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def roofline_of(config: str, table: dict, detail: list, batch: int, pk: dict) -> dict:
+    r"""The dominant kernel of the forward against the tensor roofline; rates on ALGORITHMIC FLOPs of the reference
+    layer (a phase-decomposed upsampling convolution executes 16/36 of its 9-tap FLOPs: algorithmic, not a pipe
+    utilisation -- the per-class table says which launches those are)."""
+    total_ms = sum(r["ms"] for r in table.values())
+    if config == "adm":
+        conv = table["conv3x3"]
+        conv_tflops = conv["flops"] / conv["ms"] / 1e9
+        dom = [d for d in detail if d[0] == "conv3x3" and "x256x256 256->256" in d[1] and "skip" not in d[1]]
+        dom_ms = sum(d[2] for d in dom) / max(len(dom), 1)
+        dom_flop = dom[0][3] if dom else 0.0
+        dom_tflops = dom_flop / dom_ms / 1e9 if dom else 0.0
+        traffic, src = ncu_traffic("{rnd}_ncu_full_conv_fused_v5.csv") if batch == 16 else (None, None)
+        if traffic is None and batch == 16:
+            traffic, src = ncu_traffic("{rnd}_ncu_full_conv_fused.csv")
+        classes = {}
+        for kind, desc, ms_, fl, _ in detail:
+            if kind != "conv3x3":
+                continue
+            cls = "phase-decomposed (executes 16/36 of the algorithmic taps)" if "phases" in desc else "9-tap"
+            c = classes.setdefault(cls, {"launches": 0, "ms": 0.0, "flop": 0.0})
+            c["launches"] += 1
+            c["ms"] += ms_
+            c["flop"] += fl
+        for c in classes.values():
+            c["algorithmic_tflops"] = round(c["flop"] / c["ms"] / 1e9, 1)
+            c["ms"] = round(c["ms"], 3)
+        return {"bound": "tensor",
+                "kernel": f"conv_gemm_kernel<256, pair, lean, halo>: GroupNorm+SiLU+3x3 conv 256->256 on {batch}x256x256 "
+                          "(halo-tile implicit GEMM, tcgen05 cta_group::2)",
+                "achieved": round(dom_tflops, 1), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(dom_tflops / pk["tflops"], 4),
+                "traffic": traffic, "traffic_source": src, "flop_per_launch": dom_flop, "us_per_launch": round(1e3 * dom_ms, 1),
+                "launches_per_forward": len(dom),
+                "algorithmic_bytes_per_launch": 2 * 2 * batch * 256 * 256 * 256 + 2 * 9 * 256 * 256,
+                "peak_source": pk["source"] + ", sustained bf16 (the kernel is timed inside a full forward pass)",
+                "peak_burst": pk["tflops_burst"], "frac_of_burst": round(dom_tflops / pk["tflops_burst"], 4),
+                "all_conv3x3": {"achieved": round(conv_tflops, 1), "frac": round(conv_tflops / pk["tflops"], 4),
+                                "launches_per_forward": conv["launches"], "flop_per_forward": conv["flops"],
+                                "share_of_forward": round(conv["ms"] / total_ms, 4), "by_class": classes}}
+    kind = max((k for k in table if table[k]["flops"] > 0), key=lambda k: table[k]["ms"])
+    row = table[kind]
+    tf = row["flops"] / row["ms"] / 1e9
+    return {"bound": "tensor", "kernel": f"{kind} launches of the native plan (tcgen05 implicit GEMM), all {row['launches']} per forward",
+            "achieved": round(tf, 1), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(tf / pk["tflops"], 4), "traffic": None,
+            "flop_per_forward": row["flops"], "ms_per_forward": round(row["ms"], 4), "share_of_forward": round(row["ms"] / total_ms, 4),
+            "peak_source": pk["source"] + ", sustained bf16"}
 
 
 def main() -> None:
@@ -361,8 +630,11 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU")
+    ap.add_argument("--config", default="adm", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="items per GPU (0 = the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-gpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the stand-alone step-kernel bandwidth measurements")
     ap.add_argument("--profile-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (for ncu --profile-from-start off)")
     args = ap.parse_args()
