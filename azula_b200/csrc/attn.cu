@@ -259,6 +259,9 @@ extern "C" int azb_attention_mma_bf16(const void* qkv, int64_t ld, void* out, in
         case 32: return launch_attn<32>(p, (int)n, s);
         case 64: return launch_attn<64>(p, (int)n, s);
         case 128: return launch_attn<128>(p, (int)n, s);
+        // num_heads = 4 cards (imagenet_128x128_cond, cards.yaml:19-34): head widths 128 / 192 / 256
+        case 192: return launch_attn<192>(p, (int)n, s);
+        case 256: return launch_attn<256>(p, (int)n, s);
     }
     return AZB_E_SHAPE;
 }

@@ -82,8 +82,8 @@ class Packed:
                 emb_b.append(f32(u.path + ".emb_layers.1.bias"))
                 offset += 2 * u.cout
             else:
-                if u.cin // u.heads not in (16, 32, 64, 128):
-                    raise NotImplementedError(f"attention head width {u.cin // u.heads} not in (16, 32, 64, 128)")
+                if u.cin // u.heads not in (16, 32, 64, 128, 192, 256):
+                    raise NotImplementedError(f"attention head width {u.cin // u.heads} not in (16, 32, 64, 128, 192, 256)")
                 self.unit[u.path] = {
                     "gn": (f32(u.path + ".norm.weight"), f32(u.path + ".norm.bias")),
                     "qkv": ops.pack_conv(p[u.path + ".qkv.weight"], p[u.path + ".qkv.bias"]),

@@ -390,3 +390,35 @@ def test_sampler_follows_weight_updates_and_outlives_plan_eviction():
     den.schedule.alpha_min = 2e-2
     d = smp(x1)
     assert torch.equal(d, DDIMSampler(den, steps=4, silent=True, graph=True)(x1)) and not torch.equal(c, d)
+
+
+@pytest.mark.parametrize("name", ["imagenet_64x64_cond", "imagenet_128x128_cond", "imagenet_256x256", "imagenet_256x256_cond",
+                                  "imagenet_512x512_cond", "ffhq_256x256"])
+def test_every_card_native_vs_oracle_and_reference(name):
+    """All six cards of cards.yaml (VERDICT r1 missing #6) through the native launch plan at a reduced spatial size
+    (64 x 64, batch 2): 192-channel widths whose GroupNorm groups are 6 channels (64x64 card: per-channel statistics,
+    no fused GroupNorm), cosine discrete schedule, new attention order, 4 heads of width 128 / 192 / 256 (128x128
+    card), channel multiplier 0.5 (512x512 card), label embeddings; against the oracle's fp32 forward on the same
+    device and against the unmodified reference's output (tests/golden/adm_cards.npz)."""
+    from oracle.gen_golden_cards_cfg import STRIDE, card_inputs
+
+    g = load_golden("adm_cards")
+    config = adm.cards()[name].config
+    den, sd = _seeded(config)
+    cfg = {k: v for k, v in config.items() if not k.startswith("discrete")}
+    tab = AU.block_table(**cfg)
+    x, ts, y = (None if v is None else v.to(DEV) for v in card_inputs(name, config))
+    got = den.backbone(x, ts, y=y)
+    assert len([k for k in den.backbone._native if k != "packed"]) == 1, "no native plan was built"
+    _report(got, AU.forward(sd, tab, x, ts, y), f"{name} vs oracle")
+    _report(got[..., ::STRIDE, ::STRIDE], g[f"{name}_unet"].to(DEV), f"{name} vs reference fixture")
+    mean = den(x, torch.tensor([0.3, 0.8], device=DEV), label=y).mean[..., ::STRIDE, ::STRIDE]
+    err = (mean - g[f"{name}_mean"].to(DEV)).abs().mean().item()
+    print(f"{name} posterior mean: mean|d| {err:.2e}")
+    assert err <= 2e-2
+    # ... and a short guided-free sampling through the captured graph (labels as a static kwarg buffer)
+    smp = DDIMSampler(den, steps=3, silent=True, graph=True)
+    x0 = smp(x, **({} if y is None else {"label": y}))
+    assert torch.isfinite(x0).all() and next(iter(smp._loops.values())).graph is not None
+    del den, sd, smp
+    torch.cuda.empty_cache()
