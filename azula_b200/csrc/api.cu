@@ -4,7 +4,7 @@
 extern "C" int azb_version(void) { return AZB_VERSION; }
 
 // Tuning knobs (azb_conv_tuning): -1 = automatic.
-int azb_knob[AZB_CONV_KNOBS] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+int azb_knob[AZB_CONV_KNOBS] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 
 extern "C" int azb_conv_tuning(int knob, int value) {
     if (knob < 0 || knob >= AZB_CONV_KNOBS) return AZB_E_SHAPE;

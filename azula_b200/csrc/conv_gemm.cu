@@ -242,10 +242,22 @@ __device__ __forceinline__ void transform_tile(uint32_t slot, int rg, int chunk,
 
 // LEAN: the epilogue of the common case -- bf16 NHWC output, no activation, no gate, no split-K, GroupNorm sums (if
 // any) as exact accumulators per 8-channel block -- with those switches resolved at compile time.
-template <int BLOCK_N, bool PAIR, bool LEAN, bool HALO>
+//
+// EPI == 2: the ROW-DOMAIN epilogue with TMA stores.  tcgen05.ld delivers one accumulator row (= one output pixel) per
+// lane; bias, activation, gate and residual are applied right there (the residual / gate rows of a lane are contiguous
+// in memory: whole 32-byte sectors per lane), the 32 values are rounded to bf16 and written as four 16-byte slots into a
+// 128-byte-swizzled staging block of 32 pixels x 64 channels (conflict free: a quarter warp covers eight distinct slots),
+// and ONE elected lane hands the block to the TMA unit (cp.async.bulk.tensor store through a 4-d / 5-d tensor map of the
+// output: partial tiles, channel tails and the (2 h + dy, 2 w + dx) scatter of a phase-decomposed upsampling convolution
+// are the map's business).  ~60-200 instructions per 32-column chunk instead of ~455, no shared-memory transpose, no
+// per-lane global stores.  The GroupNorm sums of the stored values fold 8 channels in the lane, then 32 rows with a
+// transposed butterfly (12 shuffles per chunk).  Serves every bf16 NHWC layer without split-K / per-channel statistics.
+template <int BLOCK_N, bool PAIR, int EPI, bool HALO>
 __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
     conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_a2, const ConvParams p) {
+                     const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_out,
+                     const ConvParams p) {
+    constexpr bool LEAN = EPI == 1;
     using C = Cfg<BLOCK_N, PAIR, HALO>;
     constexpr int STAGES = C::STAGES;
     static_assert(!PAIR || BLOCK_N >= 128, "a CTA pair splits the weight tile in two halves of >= 64 rows");
@@ -289,6 +301,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
         tc::prefetch_tmap(&tmap_a);
         tc::prefetch_tmap(&tmap_b);
         if (p.kb_extra) tc::prefetch_tmap(&tmap_a2);
+        if constexpr (EPI == 2) tc::prefetch_tmap(&tmap_out);
     }
     if (warp == 1) {
         if constexpr (PAIR) {
@@ -614,6 +627,202 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                 else tc::mma_commit(tc::smem_u32(&bar_acc_full[as]));
             }
         }
+    } else if constexpr (EPI == 2) {
+        // ===== epilogue, row domain + TMA store (see the kernel's header) =====
+        const int e = warp - 2;
+        const int quarter = warp & 3;
+        constexpr int CPW = BLOCK_N >= 128 ? BLOCK_N / 2 : BLOCK_N;  // columns per warp: whole 64-column store blocks
+        static_assert(CPW % 64 == 0, "row-domain epilogue: BLOCK_N >= 64");
+        const int half = BLOCK_N >= 128 ? (e >> 2) : 0;
+        const bool active = BLOCK_N >= 128 || e < 4;
+        const uint32_t stage = smem_base + C::RING_BYTES + e * (32 * 128);  // 32 pixels x 128 bytes, 1024-byte aligned
+        const uint32_t my_row = stage + (uint32_t)lane * 128u;
+        const int sw = lane & 7;
+        // the lanes with (lane & 7) == 0 own 8-channel block (lane >> 3) of every chunk: GroupNorm sums carried across
+        // the tiles of an image (chunked mode), slot = n_tile * 4 + chunk
+        float carry_s[8], carry_q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) carry_s[i] = carry_q[i] = 0.f;
+        int carry_img = -1;
+        const bool owner = (lane & 7) == 0;
+        const int own_blk = lane >> 3;
+        auto flush_carry = [&](int img) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int col = (i >> 2) * BLOCK_N + half * CPW + (i & 3) * 32 + own_blk * 8;
+                if (owner && img >= 0 && img < p.N && (i & 3) < CPW / 32 && (i >> 2) < p.n_tiles && col < p.c_out) {
+                    unsigned long long* dst = p.gn_acc + ((int64_t)img * (p.c_out >> 3) + (col >> 3)) * 4;
+                    fixed_add(dst, carry_s[i]);
+                    fixed_add(dst + 2, carry_q[i]);
+                }
+                carry_s[i] = carry_q[i] = 0.f;
+            }
+        };
+        bool store_pending = false;
+        for (int local = 0; local < tile_count; ++local) {
+            const int tile = unit_to_tile(tile_first + local * tile_step);
+            const int as = local & 1;
+            int n_tile, w0, h0, n0;
+            const int out_tile = tile % p.tiles_out, phase = tile / p.tiles_out;
+            tile_coords(p, out_tile, n_tile, w0, h0, n0);
+            const int col_base = n_tile * BLOCK_N + half * CPW;
+            if (p.chunked && n0 != carry_img) {
+                flush_carry(carry_img);
+                carry_img = n0;
+            }
+            tc::mbar_wait_backoff(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
+            tc::fence_after_sync();
+            if (active) {
+                // this lane's pixel
+                const int row = quarter * 32 + lane;
+                const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
+                const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
+                const bool ok = (n < p.N) && (h < p.H) && (w < p.W);
+                const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
+                const int64_t rpix = p.res_up ? ((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : pix;
+                const __nv_bfloat16* resp = p.res ? p.res + rpix * p.res_ld + col_base : nullptr;
+                const float* gatep = p.gate ? p.gate + (pix / p.gate_rows) * p.gate_ld + col_base : nullptr;
+                // first pixel of the 32 this warp stores: tile rows [32 quarter, 32 quarter + 32)
+                const int r0 = quarter * 32;
+                const int sh = h0 + (r0 / p.BW) % p.BH, sn = n0 + r0 / (p.BW * p.BH);
+#pragma unroll 1
+                for (int c0 = 0; c0 < CPW; c0 += 32) {
+                    uint32_t acc[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * C::ACC_COLS + half * CPW + c0);
+                    tc::tmem_ld_32x32b_x32(taddr, acc);
+                    const int col = col_base + c0;
+                    // loads that do not depend on the accumulator go first
+                    uint4 rsd[4];
+                    const bool use_res = resp != nullptr && ok;
+                    if (use_res) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            rsd[q] = col + 8 * q < p.c_out ? __ldg(reinterpret_cast<const uint4*>(resp + c0) + q) : make_uint4(0, 0, 0, 0);
+                    }
+                    tc::tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias && col + 4 * q < p.c_out) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + q);
+                        v[4 * q] = __uint_as_float(acc[4 * q]) + b4.x, v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + b4.y;
+                        v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + b4.z, v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + b4.w;
+                    }
+                    if (p.act) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = activate(v[j], p.act);
+                    }
+                    if (gatep && ok) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (col + 4 * q < p.c_out) {
+                                const float4 g4 = __ldg(reinterpret_cast<const float4*>(gatep + c0) + q);
+                                v[4 * q] *= g4.x, v[4 * q + 1] *= g4.y, v[4 * q + 2] *= g4.z, v[4 * q + 3] *= g4.w;
+                            }
+                        }
+                    }
+                    if (use_res) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t rr[4] = {rsd[q].x, rsd[q].y, rsd[q].z, rsd[q].w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                v[8 * q + 2 * j] += bf16_bits_to_f32(rr[j] & 0xffffu);
+                                v[8 * q + 2 * j + 1] += bf16_bits_to_f32(rr[j] >> 16);
+                            }
+                        }
+                    }
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                        packed[j] = *reinterpret_cast<uint32_t*>(&t);
+                    }
+                    // the staging block is free once the TMA unit has read the previous store out of it
+                    if ((c0 & 32) == 0 && store_pending) {
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        __syncwarp();
+                    }
+                    // 32 channels = slots (c0 & 63) / 8 + 0..3 of this pixel's 128-byte row; slot s lives at s ^ (row & 7)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t slot = (uint32_t)((((c0 & 63) >> 3) + q) ^ sw);
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + (slot << 4)), "r"(packed[4 * q]),
+                                     "r"(packed[4 * q + 1]), "r"(packed[4 * q + 2]), "r"(packed[4 * q + 3])
+                                     : "memory");
+                    }
+                    if ((c0 & 32) != 0) {  // a 64-channel block is complete: hand it to the TMA unit
+                        tc::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int cblk = col_base + (c0 & ~63);
+                            if (cblk < p.c_out) {
+                                if (HALO && p.phases > 1)  // (channel + dx * ld, w, dy, h, n) of the full-resolution tensor
+                                    tc::tma_store_5d(&tmap_out, stage, cblk + (phase & 1) * (int)p.out_ld, w0, phase >> 1, sh, sn);
+                                else
+                                    tc::tma_store_4d(&tmap_out, stage, cblk, w0, sh, sn);
+                            }
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        store_pending = true;
+                    }
+                    if (p.gn_acc) {
+                        // sums of the STORED (rounded) values: 8 channels in the lane, then the 32 rows of the slab
+                        float s4[4], q4[4];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            float s_ = 0.f, q_ = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float lo = bf16_bits_to_f32(packed[4 * b + j] & 0xffffu), hi = bf16_bits_to_f32(packed[4 * b + j] >> 16);
+                                s_ += lo, q_ = fmaf(lo, lo, q_);
+                                s_ += hi, q_ = fmaf(hi, hi, q_);
+                            }
+                            const bool valid = ok && col + 8 * b < p.c_out;
+                            s4[b] = valid ? s_ : 0.f, q4[b] = valid ? q_ : 0.f;
+                        }
+                        // transposed butterfly: after offsets 16 and 8 the lane holds block 2 * bit4 + bit3, then a plain fold
+                        const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
+                        float s0 = (b4 ? s4[2] : s4[0]) + __shfl_xor_sync(0xffffffffu, b4 ? s4[0] : s4[2], 16);
+                        float s1 = (b4 ? s4[3] : s4[1]) + __shfl_xor_sync(0xffffffffu, b4 ? s4[1] : s4[3], 16);
+                        float q0 = (b4 ? q4[2] : q4[0]) + __shfl_xor_sync(0xffffffffu, b4 ? q4[0] : q4[2], 16);
+                        float q1 = (b4 ? q4[3] : q4[1]) + __shfl_xor_sync(0xffffffffu, b4 ? q4[1] : q4[3], 16);
+                        float sa = (b3 ? s1 : s0) + __shfl_xor_sync(0xffffffffu, b3 ? s0 : s1, 8);
+                        float qa = (b3 ? q1 : q0) + __shfl_xor_sync(0xffffffffu, b3 ? q0 : q1, 8);
+#pragma unroll
+                        for (int off = 4; off >= 1; off >>= 1) {
+                            sa += __shfl_xor_sync(0xffffffffu, sa, off);
+                            qa += __shfl_xor_sync(0xffffffffu, qa, off);
+                        }
+                        const int bcol = col + own_blk * 8;
+                        if (owner && bcol < p.c_out) {
+                            if (p.chunked) {
+                                const int slot = n_tile * 4 + (c0 >> 5);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    if (i == slot) carry_s[i] += sa, carry_q[i] += qa;
+                            } else {
+                                const int img = n0 + (quarter * 32) / (p.BW * p.BH);  // the image this 32-row slab lies in
+                                if (img < p.N) {
+                                    unsigned long long* dst = p.gn_acc + ((int64_t)img * (p.c_out >> 3) + (bcol >> 3)) * 4;
+                                    fixed_add(dst, sa);
+                                    fixed_add(dst + 2, qa);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // release the accumulator stage to the MMA warp
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                if (PAIR && !leader) tc::mbar_arrive_cluster(tc::mapa(tc::smem_u32(&bar_acc_empty[as]), 0));
+                else tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[as]));
+            }
+        }
+        if (p.chunked) flush_carry(carry_img);
+        if (lane == 0 && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
     } else {
         // ===== epilogue: warp e reads TMEM lanes [32*(warp%4), +32) and one half of the columns =====
         // Row domain (lane = tile row, as tcgen05.ld delivers it) -> swizzled fp32 staging in shared memory
@@ -959,11 +1168,13 @@ int sm_count() { return azb_sm_count(); }
 
 #define g_knob azb_knob
 
-template <int BLOCK_N, bool PAIR = false, bool LEAN = false, bool HALO = false>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const ConvParams& p, cudaStream_t s) {
+template <int BLOCK_N, bool PAIR = false, int EPI = 0, bool HALO = false>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const ConvParams& p, cudaStream_t s,
+           const CUtensorMap* tout = nullptr) {
     constexpr int smem = Cfg<BLOCK_N, PAIR, HALO>::SMEM;
     constexpr int threads = HALO ? THREADS_HALO : THREADS;
-    auto kernel = conv_gemm_kernel<BLOCK_N, PAIR, LEAN, HALO>;
+    auto kernel = conv_gemm_kernel<BLOCK_N, PAIR, EPI, HALO>;
+    const CUtensorMap& to = tout ? *tout : ta;
     static AzbPerDevice<bool> configured_dev;
     bool& configured = configured_dev.get();
     if (!configured) {
@@ -991,11 +1202,11 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2,
         }
         const int pairs = p.total_tiles < resident ? p.total_tiles : resident;
         cfg.gridDim = dim3((unsigned)(2 * pairs));
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb, ta2, p);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, ta, tb, ta2, to, p);
         if (e != cudaSuccess) return (int)e;
     } else {
         const int grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
-        return azb_launch(kernel, dim3((unsigned)grid), dim3(threads), smem, s, ta, tb, ta2, p);
+        return azb_launch(kernel, dim3((unsigned)grid), dim3(threads), smem, s, ta, tb, ta2, to, p);
     }
     return azb_launch_status();
 }
@@ -1078,11 +1289,14 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
         return AZB_E_ALIGN;
     const int64_t h = (h_in + ex.stride - 1) / ex.stride, w = (w_in + ex.stride - 1) / ex.stride;
 
+    // the row-domain epilogue (EPI == 2) brings activation and gate to the halo kernels
+    const bool rowepi_ok = g_knob[AZB_CONV_KNOB_ROWEPI] != 0 && out_mode == 0 && !colsum && (!ex.gn_acc || stat_gran == 8) &&
+                           (phases == 1 || (c_out % 64 == 0 && out_ld % 8 == 0));
     // Halo tiles: 3 x 3, stride 1, maps of at least one 8 x 16 patch, whole 64-channel blocks (see the kernel's header)
     bool halo = g_knob[AZB_CONV_KNOB_HALO] != 0 && taps == 9 &&
                 ex.stride == 1 && h >= HALO_H && w >= HALO_W &&
                 c_in % BLOCK_K == 0 && k_per_tap == c_in && (!ex.act2 || (ex.c_in2 % BLOCK_K == 0 && ex.k2 == ex.c_in2)) &&
-                !colsum && ex.act == AZB_ACT_NONE && !ex.gate && (!ex.gn_acc || stat_gran == 8) &&
+                !colsum && ((ex.act == AZB_ACT_NONE && !ex.gate) || rowepi_ok) && (!ex.gn_acc || stat_gran == 8) &&
                 c_in / BLOCK_K + (ex.act2 ? ex.c_in2 / BLOCK_K : 0) <= 64 && !(ex.act2 && out_mode == 1);
     if (ex.in_coef && !azb_aligned(ex.in_coef, 16)) return AZB_E_ALIGN;
     // in_up: (h_in, w_in) are the UPSAMPLED extents; the zero padding is restored by the input transform, so it needs one
@@ -1242,10 +1456,51 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const bool lean = (halo || g_knob[AZB_CONV_KNOB_LEAN] != 0) && out_mode == 0 && ex.act == AZB_ACT_NONE && !ex.gate && !colsum &&
                       splits == 1 && (!ex.gn_acc || stat_gran == 8) && block_n >= 128;
+    // Row-domain epilogue with TMA stores (EPI == 2): every bf16 NHWC layer with an N tile of whole 64-channel store
+    // blocks, without split-K / per-channel statistics; activation, gate, residual and exact GroupNorm sums included.
+    // A halo kernel needs a wide tile unless it is this epilogue's 64-column instantiation.
+    const bool rowepi = rowepi_ok && splits == 1 && block_n >= 64 && (!halo || block_n >= 128);
+    if (halo && (ex.act != AZB_ACT_NONE || ex.gate) && !rowepi) return AZB_E_UNSUPPORTED;  // (unreachable: wide halo tiles)
     if (ex.choice) {
-        ex.choice->halo = halo, ex.choice->pair = pair, ex.choice->lean = lean, ex.choice->block_n = block_n, ex.choice->splits = splits;
+        ex.choice->halo = halo, ex.choice->pair = pair, ex.choice->lean = lean || rowepi, ex.choice->block_n = block_n, ex.choice->splits = splits;
         ex.choice->tiles = p.total_tiles;
         return AZB_OK;
+    }
+    if (rowepi) {
+        // the 32 pixels a warp stores: tile rows [32 q, 32 q + 32) = (BW, 32 / BW rows) of one image, or whole small images
+        const int rows_h = p.BW * p.BH >= 32 ? 32 / p.BW : p.BH;
+        const int imgs = p.BW * p.BH >= 32 ? 1 : 32 / (p.BW * p.BH);
+        CUtensorMap tout;
+        int rc;
+        if (phases > 1) {
+            // full-resolution output (n, 2 H, 2 W, ld) seen as (channel + dx * ld, w, dy, h, n): one map serves all phases
+            const uint64_t W2 = 2 * (uint64_t)w, H2 = 2 * (uint64_t)h;
+            uint64_t dims[5] = {(uint64_t)out_ld + (uint64_t)c_out, (uint64_t)w, 2, (uint64_t)h, (uint64_t)n};
+            uint64_t str[4] = {(uint64_t)out_ld * 4, W2 * out_ld * 2, 2 * W2 * out_ld * 2, H2 * W2 * out_ld * 2};
+            uint32_t box[5] = {64, (uint32_t)p.BW, 1, (uint32_t)rows_h, 1};
+            rc = make_map(&tout, out, 5, dims, str, box);
+        } else {
+            uint64_t dims[4] = {(uint64_t)c_out, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+            uint64_t str[3] = {(uint64_t)out_ld * 2, (uint64_t)out_ld * 2 * w, (uint64_t)out_ld * 2 * w * h};
+            uint32_t box[4] = {64, (uint32_t)p.BW, (uint32_t)rows_h, (uint32_t)imgs};
+            rc = make_map(&tout, out, 4, dims, str, box);
+        }
+        if (rc) return rc;
+        if (halo) {
+            const int b_stage = pair ? Cfg<256, true, true>::STAGE_BYTES * block_n / 256 : Cfg<256, false, true>::STAGE_BYTES * block_n / 256;
+            p.sb = (SMEM_BUDGET - p.sa * p.a_slot) / b_stage;
+            if (p.sb > 8) p.sb = 8;
+            if (g_knob[AZB_CONV_KNOB_HALO_SB] >= 2 && g_knob[AZB_CONV_KNOB_HALO_SB] < p.sb) p.sb = g_knob[AZB_CONV_KNOB_HALO_SB];
+            if (p.sb < 2) return AZB_E_SHAPE;
+            if (pair) return block_n == 256 ? launch<256, true, 2, true>(ta, tb, ta2, p, s, &tout) : launch<128, true, 2, true>(ta, tb, ta2, p, s, &tout);
+            return block_n == 256 ? launch<256, false, 2, true>(ta, tb, ta2, p, s, &tout) : launch<128, false, 2, true>(ta, tb, ta2, p, s, &tout);
+        }
+        if (pair) return block_n == 256 ? launch<256, true, 2>(ta, tb, ta2, p, s, &tout) : launch<128, true, 2>(ta, tb, ta2, p, s, &tout);
+        switch (block_n) {
+            case 256: return launch<256, false, 2>(ta, tb, ta2, p, s, &tout);
+            case 128: return launch<128, false, 2>(ta, tb, ta2, p, s, &tout);
+            default: return launch<64, false, 2>(ta, tb, ta2, p, s, &tout);
+        }
     }
     if (halo) {
         const int b_stage = out_mode == 1 ? Cfg<16, false, true>::STAGE_BYTES

@@ -94,6 +94,19 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
         : "memory");
 }
 
+// TMA stores: shared memory (a box laid out as the tensor map's swizzle mode says) -> global, bulk async-group
+// completion (cp.async.bulk.commit_group / wait_group[.read]).  Out-of-bounds parts of the box are not written.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(m), "r"(src),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(m), "r"(src),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+
 // --------------------------------------------------------------- CTA pairs (cluster of 2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

@@ -303,6 +303,10 @@ class Plan:
         exact accumulators and a halo kernel for the shape (``azb_conv_choice``)."""
         if not FUSE_NORM or stats is None or stats[0] != "acc" or (x2 is not None and not FUSE_NORM_SKIP):
             return False
+        if self.stat_gran != 8 and not nchw_f32:
+            # the convolution will also emit per-channel sums for the next GroupNorm (widths whose groups are not
+            # multiples of 8 channels, e.g. the 192-channel imagenet_64x64 card): no halo kernel does that
+            return False
         n, h, w, _ = x.shape
         grid = (n, 2 * h, 2 * w) if in_up else (n, h, w)
         d = ops.conv_desc(x, pc, out, grid=grid, residual=residual, x2=x2, gran=self.stat_gran, nchw_f32=nchw_f32,

@@ -665,7 +665,7 @@ def conv_acc(x: Tensor, pc, out: Tensor | None = None, residual: Tensor | None =
 
 
 KNOB_PAIR, KNOB_PREFETCH, KNOB_SPLITK, KNOB_GN_WAVE, KNOB_BLOCKN, KNOB_LEAN, KNOB_HALO = 0, 1, 2, 3, 4, 5, 6
-KNOB_HALO_SA, KNOB_HALO_SB, KNOB_HALO_SPREAD, KNOB_PDL = 7, 8, 9, 10
+KNOB_HALO_SA, KNOB_HALO_SB, KNOB_HALO_SPREAD, KNOB_PDL, KNOB_ROWEPI = 7, 8, 9, 10, 11
 
 
 def conv_tuning(knob: int, value: int) -> None:

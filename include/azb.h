@@ -291,7 +291,8 @@ int azb_conv_choice(const AzbConv* desc, AzbConvChoice* choice);
 #define AZB_CONV_KNOB_HALO_SB 8    /* halo kernels: cap on the weight stages */
 #define AZB_CONV_KNOB_HALO_SPREAD 9 /* halo kernels: 0 = the fused 1 x 1 blocks follow the last halo item (default: spread) */
 #define AZB_KNOB_PDL 10 /* 0: plain stream-ordered launches instead of programmatic dependent launches */
-#define AZB_CONV_KNOBS 11
+#define AZB_CONV_KNOB_ROWEPI 11 /* 0: never the row-domain epilogue with TMA stores (shared-memory transpose + per-lane stores instead) */
+#define AZB_CONV_KNOBS 12
 int azb_conv_tuning(int knob, int value);
 
 /* Rows of the colsum buffer for an (n, h, w) activation; *slab_in_image = 1 when every 32-row slab
