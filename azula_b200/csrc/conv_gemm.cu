@@ -1290,8 +1290,13 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     const int64_t h = (h_in + ex.stride - 1) / ex.stride, w = (w_in + ex.stride - 1) / ex.stride;
 
     // the row-domain epilogue (EPI == 2) brings activation and gate to the halo kernels
+    // Measured (gpurun_out/bench_r2b_*): neutral to +3 % on the ADM layers (no activation / gate, long reductions), but
+    // -10..-20 % on the short-K token GEMMs and the small U-Net convolutions with activation / gate epilogues, where
+    // the wait for the TMA unit to drain the staging block is exposed: those keep the transposing epilogue unless the
+    // knob is forced to 1.
     const bool rowepi_ok = g_knob[AZB_CONV_KNOB_ROWEPI] != 0 && out_mode == 0 && !colsum && (!ex.gn_acc || stat_gran == 8) &&
-                           (phases == 1 || (c_out % 64 == 0 && out_ld % 8 == 0));
+                           (phases == 1 || (c_out % 64 == 0 && out_ld % 8 == 0)) &&
+                           (g_knob[AZB_CONV_KNOB_ROWEPI] == 1 || (ex.act == AZB_ACT_NONE && !ex.gate));
     // Halo tiles: 3 x 3, stride 1, maps of at least one 8 x 16 patch, whole 64-channel blocks (see the kernel's header)
     bool halo = g_knob[AZB_CONV_KNOB_HALO] != 0 && taps == 9 &&
                 ex.stride == 1 && h >= HALO_H && w >= HALO_W &&

@@ -166,6 +166,7 @@ struct StepArgs {
     const int64_t* off_dev;
     int64_t off_host, off_inc, T, elem_off;
     int row_floats, xin_copies;
+    unsigned long long np_magic;  // floor(2^64 / n_per_sample) + 1: exact i / n_per_sample for i < 2^32 by one multiply-high
 };
 
 __device__ __forceinline__ Row load_row_n(const StepArgs& a, RowX& rx) {
@@ -187,9 +188,12 @@ __device__ __forceinline__ Row load_row_n(const StepArgs& a, RowX& rx) {
     return Row{u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
 }
 
+// Index of element i of the state inside F when F carries more channels per sample than the state (learned
+// variance: the first C of 2C): sample b = i / n_per_sample by one multiply-high when the tensor has < 2^32 elements
+// (np_magic != 0), a 64-bit division otherwise.
 __device__ __forceinline__ int64_t f_index(const StepArgs& a, int64_t i) {
     if (a.f_bstride == a.n_per_sample) return i;
-    int64_t b = i / a.n_per_sample;
+    const int64_t b = a.np_magic ? (int64_t)__umul64hi((unsigned long long)i, a.np_magic) : i / a.n_per_sample;
     return b * a.f_bstride + (i - b * a.n_per_sample);
 }
 
@@ -248,8 +252,9 @@ __global__ void __launch_bounds__(256) step_vec4_kernel(const StepArgs a) {
     pdl_enter();
     RowX rx;
     const Row r = load_row_n(a, rx);
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    // (the grid may be two-dimensional, see the noise path; the other paths use it as a flat one)
+    const int64_t tid = ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * gridDim.y * blockDim.x;
     const float* xe_p = a.src[rx.flags & 1u];
     const float* xb_p = a.src[(rx.flags >> 1) & 1u];
     float* out_p = a.dst[(rx.flags >> 2) & 1u];
@@ -321,7 +326,8 @@ __global__ void __launch_bounds__(256) step_vec4_kernel(const StepArgs a) {
     }
 
     // In-register noise.  Work item (g, j): Philox streams 4g..4g+3 at call j produce 16 normals
-    // that belong to the four float4 groups at global elements (4j+ii)*T + 4g, ii = 0..3.
+    // that belong to the four float4 groups at global elements (4j+ii)*T + 4g, ii = 0..3.  The grid is two-dimensional
+    // (x over the T/4 stream groups, y over the calls), so no index is ever divided.
     const uint64_t offset = (uint64_t)((a.off_dev ? a.off_dev[0] : 0) + a.off_host + (int64_t)rx.draw * a.off_inc);
     const uint64_t seed = a.off_dev ? (uint64_t)a.off_dev[1] : a.seed;
     const uint64_t ctr0 = offset >> 2;
@@ -329,34 +335,33 @@ __global__ void __launch_bounds__(256) step_vec4_kernel(const StepArgs a) {
     const int64_t T = a.T, T4 = T >> 2;
     const int64_t j_lo = (a.elem_off / T) >> 2;
     const int64_t j_hi = ((a.elem_off + a.numel - 1) / T) >> 2;
-    const int64_t nwork = T4 * (j_hi - j_lo + 1);
-    for (int64_t w = tid; w < nwork; w += nthreads) {
-        const int64_t jj = w / T4;
-        const int64_t g = w - jj * T4;
-        const int64_t j = j_lo + jj;
-        float4 x[4], f[4], fn[4];
-        int64_t loc[4];
-        bool ok[4];
+    for (int64_t j = j_lo + blockIdx.y; j <= j_hi; j += gridDim.y) {
+        for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < T4; g += (int64_t)gridDim.x * blockDim.x) {
+            float4 x[4], f[4], fn[4];
+            int64_t loc[4];
+            bool ok[4];
+            const int64_t loc0 = (j << 2) * T + (g << 2) - a.elem_off;
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-            loc[ii] = ((j << 2) + ii) * T + (g << 2) - a.elem_off;
-            ok[ii] = loc[ii] >= 0 && loc[ii] < a.numel;
-            fn[ii] = zero4;
-            if (ok[ii]) {
-                x[ii] = ld_state4(xe_p + loc[ii]);
-                const int64_t fi = f_index(a, loc[ii]);
-                f[ii] = Vec4<FT>::load(a.f, fi);
-                if (CFG) fn[ii] = Vec4<FT>::load(a.fneg, fi);
+            for (int ii = 0; ii < 4; ++ii) {
+                loc[ii] = loc0 + ii * T;
+                ok[ii] = loc[ii] >= 0 && loc[ii] < a.numel;
+                fn[ii] = zero4;
+                if (ok[ii]) {
+                    x[ii] = ld_state4(xe_p + loc[ii]);
+                    const int64_t fi = f_index(a, loc[ii]);
+                    f[ii] = Vec4<FT>::load(a.f, fi);
+                    if (CFG) fn[ii] = Vec4<FT>::load(a.fneg, fi);
+                }
             }
-        }
-        if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;
-        float4 z[4];  // z[e] = normals of stream 4g+e, lanes ii
+            if (!(ok[0] | ok[1] | ok[2] | ok[3])) continue;
+            float4 z[4];  // z[e] = normals of stream 4g+e, lanes ii
 #pragma unroll
-        for (int e = 0; e < 4; ++e) z[e] = normal4(ctr0 + (uint64_t)j, (uint64_t)((g << 2) + e), key);
-        if (ok[0]) finish4<FT, IT, CFG>(a, r, out_p, gw, loc[0], x[0], f[0], fn[0], make_float4(z[0].x, z[1].x, z[2].x, z[3].x));
-        if (ok[1]) finish4<FT, IT, CFG>(a, r, out_p, gw, loc[1], x[1], f[1], fn[1], make_float4(z[0].y, z[1].y, z[2].y, z[3].y));
-        if (ok[2]) finish4<FT, IT, CFG>(a, r, out_p, gw, loc[2], x[2], f[2], fn[2], make_float4(z[0].z, z[1].z, z[2].z, z[3].z));
-        if (ok[3]) finish4<FT, IT, CFG>(a, r, out_p, gw, loc[3], x[3], f[3], fn[3], make_float4(z[0].w, z[1].w, z[2].w, z[3].w));
+            for (int e = 0; e < 4; ++e) z[e] = normal4(ctr0 + (uint64_t)j, (uint64_t)((g << 2) + e), key);
+            if (ok[0]) finish4<FT, IT, CFG>(a, r, out_p, gw, loc[0], x[0], f[0], fn[0], make_float4(z[0].x, z[1].x, z[2].x, z[3].x));
+            if (ok[1]) finish4<FT, IT, CFG>(a, r, out_p, gw, loc[1], x[1], f[1], fn[1], make_float4(z[0].y, z[1].y, z[2].y, z[3].y));
+            if (ok[2]) finish4<FT, IT, CFG>(a, r, out_p, gw, loc[2], x[2], f[2], fn[2], make_float4(z[0].z, z[1].z, z[2].z, z[3].z));
+            if (ok[3]) finish4<FT, IT, CFG>(a, r, out_p, gw, loc[3], x[3], f[3], fn[3], make_float4(z[0].w, z[1].w, z[2].w, z[3].w));
+        }
     }
 }
 
@@ -471,11 +476,18 @@ int grid_for(int64_t work_items, int per_sm) {
 template <typename FT, typename IT, bool CFG>
 int launch_step(const StepArgs& a, bool vec, cudaStream_t s) {
     if (vec) {
-        int64_t T4 = a.T >> 2;
-        int64_t spans = ((a.elem_off + a.numel - 1) / a.T >> 2) - ((a.elem_off / a.T) >> 2) + 1;
-        int64_t work = a.eps ? (a.numel >> 2) : ((a.numel >> 2) > T4 * spans ? (a.numel >> 2) : T4 * spans);
-        // no-noise path consumes 4 float4 per thread and iteration
-        return azb_launch(step_vec4_kernel<FT, IT, CFG>, dim3(grid_for(work, 16)), dim3(256), 0, s, a);
+        if (a.eps) return azb_launch(step_vec4_kernel<FT, IT, CFG>, dim3(grid_for(a.numel >> 2, 16)), dim3(256), 0, s, a);
+        // the row may ask for in-register noise: x over the T/4 Philox stream groups, y over the calls that cover this
+        // tensor, about 16 CTAs per SM in total (the paths without noise treat the grid as a flat one)
+        const int64_t T4 = a.T >> 2;
+        const int64_t spans = ((a.elem_off + a.numel - 1) / a.T >> 2) - ((a.elem_off / a.T) >> 2) + 1;
+        const int64_t cap = (int64_t)sm_count() * 16;
+        int64_t gx = (T4 + 255) / 256;
+        if (gx > cap) gx = cap;
+        int64_t gy = cap / gx < 1 ? 1 : cap / gx;
+        if (gy > spans) gy = spans;
+        if (gy > 65535) gy = 65535;
+        return azb_launch(step_vec4_kernel<FT, IT, CFG>, dim3((unsigned)gx, (unsigned)gy), dim3(256), 0, s, a);
     }
     return azb_launch(step_scalar_kernel<FT, IT, CFG>, dim3(grid_for(a.numel, 16)), dim3(256), 0, s, a);
 }
@@ -542,6 +554,7 @@ extern "C" int azb_step_ex_f32(const AzbStep* d, void* stream) {
     a.hist_stride = d->hist_stride, a.table = d->table, a.step_idx = d->step_idx, a.seed = d->seed;
     a.off_dev = d->philox_state, a.off_host = d->offset_host, a.off_inc = d->offset_inc, a.T = d->rng_threads;
     a.elem_off = d->rng_elem_offset, a.row_floats = d->row_floats, a.xin_copies = d->x_in_copies;
+    a.np_magic = (a.numel < (1ll << 32) && n_per_sample > 1) ? (~0ull / (unsigned long long)n_per_sample) + 1ull : 0ull;
     const bool vec = (n_per_sample % 4 == 0) && (d->f_batch_stride % 4 == 0) && (d->rng_elem_offset % 4 == 0) &&
                      azb_aligned(a.src[0], 16) && azb_aligned(a.src[1], 16) && azb_aligned(a.dst[0], 16) &&
                      azb_aligned(a.dst[1], 16) && azb_aligned(a.f, 4 * fsz) && (!a.fneg || azb_aligned(a.fneg, 4 * fsz)) &&

@@ -155,6 +155,53 @@ __global__ void __launch_bounds__(THREADS) segment_rmsnorm_kernel(__nv_bfloat16*
     }
 }
 
+// The same item decomposition, with the rotary positional embedding applied after the (optional) normalisation:
+// channel pair (2 i, 2 i + 1) of head h at token l is rotated by the angle whose {cos, sin} sits at
+// rot[(l mod rows_per_sample) * (heads * d / 2) + h * d / 2 + i] (azula/nn/attention.py:105-108,124-156; the same
+// angles for queries and keys).  Arithmetic in fp32, one rounding to bf16 at the end.
+__global__ void __launch_bounds__(THREADS) qk_norm_rope_kernel(__nv_bfloat16* x, int64_t ld, int64_t rows, int heads, int d,
+                                                               int norm, float eps, const float2* __restrict__ rot,
+                                                               int64_t rows_per_sample) {
+    const int segs = 2 * heads;
+    const int lps = d >> 3;
+    const int per_warp = 32 / lps;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (lps - 1);
+    const int64_t warp = ((int64_t)blockIdx.x * THREADS + threadIdx.x) >> 5;
+    const int64_t warps = ((int64_t)gridDim.x * THREADS) >> 5;
+    const int64_t items = rows * segs;
+    const int64_t groups = (items + per_warp - 1) / per_warp;
+    for (int64_t g = warp; g < groups; g += warps) {
+        const int64_t item = g * per_warp + lane / lps;
+        const bool ok = item < items;
+        const int64_t row = ok ? item / segs : 0;
+        const int seg = ok ? (int)(item - row * segs) : 0;
+        __nv_bfloat16* ptr = x + row * ld + (int64_t)seg * d + sub * 8;
+        float f[8];
+        unpack8(ok ? *reinterpret_cast<const uint4*>(ptr) : make_uint4(0, 0, 0, 0), f);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q = fmaf(f[j], f[j], q);
+        q = group_sum(q, lps);
+        const float rstd = norm ? rsqrtf(q / (float)d + eps) : 1.0f;
+        if (!ok) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= rstd;
+        if (rot) {
+            const int head = seg < heads ? seg : seg - heads;
+            const float2* r = rot + (row % rows_per_sample) * (int64_t)(heads * (d >> 1)) + head * (d >> 1) + sub * 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 cs = __ldg(r + j);
+                const float re = f[2 * j], im = f[2 * j + 1];
+                f[2 * j] = re * cs.x - im * cs.y;
+                f[2 * j + 1] = re * cs.y + im * cs.x;
+            }
+        }
+        *reinterpret_cast<uint4*>(ptr) = pack8(f);
+    }
+}
+
 __global__ void __launch_bounds__(THREADS) patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ tok,
                                                            int n, int c, int hp, int wp, int p, int q, int k_pad) {
     const int vecs = k_pad >> 3;
@@ -272,6 +319,19 @@ extern "C" int azb_segment_rmsnorm_bf16(void* x, int64_t ld, int64_t rows, int64
     const int per_cta = (THREADS / 32) * (32 / (int)(d >> 3));
     segment_rmsnorm_kernel<<<stream_grid(rows * segs, per_cta), THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<__nv_bfloat16*>(x), ld, rows, (int)segs, (int)d, eps);
+    return azb_launch_status();
+}
+
+extern "C" int azb_qk_norm_rope_bf16(void* x, int64_t ld, int64_t rows, int64_t heads, int64_t d, int norm, float eps,
+                                     const float* rot, int64_t rows_per_sample, void* stream) {
+    AZB_CHECK_PTR(x);
+    if (rows <= 0 || heads <= 0 || (d != 8 && d != 16 && d != 32 && d != 64 && d != 128 && d != 256)) return AZB_E_SHAPE;
+    if (ld % 8 || ld < 2 * heads * d || !azb_aligned(x, 16)) return AZB_E_ALIGN;
+    if (rot && (rows_per_sample <= 0 || !azb_aligned(rot, 8))) return AZB_E_SHAPE;
+    const int per_cta = (THREADS / 32) * (32 / (int)(d >> 3));
+    qk_norm_rope_kernel<<<stream_grid(rows * 2 * heads, per_cta), THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<__nv_bfloat16*>(x), ld, rows, (int)heads, (int)d, norm, eps, reinterpret_cast<const float2*>(rot),
+        rows_per_sample > 0 ? rows_per_sample : 1);
     return azb_launch_status();
 }
 

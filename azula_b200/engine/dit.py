@@ -47,7 +47,8 @@ def structure_ok(model) -> bool:
         msa = b.msa
         d = hid // msa.heads
         ok &= b.ffn_activation in _ACTS
-        ok &= msa.theta_proj is None and d in (16, 32, 64, 128)
+        ok &= d in (16, 32, 64, 128, 256)
+        ok &= msa.theta_proj is None or msa.theta_proj.out_features * 2 == hid
         ok &= isinstance(msa.qk_norm, (nn.Identity, nn.RMSNorm)) if hasattr(nn, "RMSNorm") else isinstance(msa.qk_norm, nn.Identity)
         if hasattr(nn, "RMSNorm") and isinstance(msa.qk_norm, nn.RMSNorm):
             ok &= msa.qk_norm.weight is None
@@ -72,14 +73,19 @@ def _common_ok(model, mod: Tensor | None, batch: int) -> bool:
 
 
 def supports(model, x: Tensor, mod: Tensor | None, pos) -> bool:
-    r"""Token interface: native when ``pos`` is the canonical sequence index (``pos="arange"``)."""
-    return isinstance(pos, str) and x.ndim == 3 and x.is_floating_point() and x.numel() > 0 and _common_ok(model, mod, x.shape[0])
+    r"""Token interface: native when ``pos`` is the canonical sequence index (``pos="arange"``) or ONE set of position
+    vectors (L, P) shared by the batch (per-sample positions take the torch path)."""
+    if not (x.ndim == 3 and x.is_floating_point() and x.numel() > 0 and _common_ok(model, mod, x.shape[0])):
+        return False
+    if isinstance(pos, str):
+        return True
+    return torch.is_tensor(pos) and pos.ndim == 2 and pos.shape[0] == x.shape[1] and pos.is_floating_point()
 
 
 def supports_image(model, x: Tensor, mod: Tensor | None, cond: Tensor | None) -> bool:
     if x.ndim != 4 or model.spatial != 2 or not x.is_floating_point() or x.numel() == 0:
         return False
-    if cond is not None:  # patchified separately and concatenated per token (nn/vit.py:97-100): torch path
+    if cond is not None and (cond.ndim != 4 or cond.shape[0] != x.shape[0] or cond.shape[2:] != x.shape[2:]):
         return False
     p, q = model.patch.patch_shape
     if x.shape[2] % p or x.shape[3] % q or model.unpatch.patch_shape != model.patch.patch_shape:
@@ -104,7 +110,7 @@ class Packed:
         for b in model.blocks:
             self.block.append({
                 "qkv": pk(b.msa.qkv_proj), "y": pk(b.msa.y_proj), "ffn1": pk(b.ffn[0]), "ffn2": pk(b.ffn[3]),
-                "heads": b.msa.heads, "qk_norm": not isinstance(b.msa.qk_norm, nn.Identity),
+                "heads": b.msa.heads, "qk_norm": not isinstance(b.msa.qk_norm, nn.Identity), "rope": b.msa.theta_proj is not None,
                 "qk_eps": getattr(b.msa.qk_norm, "eps", None) or 1e-5, "eps": b.norm.eps or 1e-5,
                 "act": _ACTS[b.ffn_activation],
             })
@@ -126,14 +132,23 @@ class Plan(LaunchPlan):
         self.mod_ld = self.abc.stride(0) if (rows == B and B > 1) else 0
 
         with torch.no_grad():
-            emb = model.pos_embedding(pos.to(device=device, dtype=torch.float32)).to(torch.bfloat16)  # (L, C)
+            posf = pos.to(device=device, dtype=torch.float32)
+            emb = model.pos_embedding(posf).to(torch.bfloat16)  # (L, C)
+            # rotary embedding: the angles depend only on the positions -> {cos, sin} tables (L, C / 2) per block
+            self.rot = []
+            for b in model.blocks:
+                if b.msa.theta_proj is None:
+                    self.rot.append(None)
+                else:
+                    theta = b.msa.theta_proj(posf.to(b.msa.theta_proj.weight.dtype)).to(torch.float32)  # (L, C / 2), head-major
+                    self.rot.append(torch.stack((torch.cos(theta), torch.sin(theta)), dim=-1).contiguous())
         self.posemb = emb.expand(B, L, hid).reshape(R, hid).contiguous()
 
         self.tok = arena.pin(arena.take(R, packed.k_pad))
         self.tok.zero_()
         x = arena.take(R, hid)
         self.conv(self.tok, packed.in_proj, x, grid=self.grid, residual=self.posemb)
-        for b, w in zip(model.blocks, packed.block, strict=True):
+        for (b, w), rot in zip(zip(model.blocks, packed.block, strict=True), self.rot, strict=True):
             off = packed.bank.offset[id(b)]
             abc = self.abc.data_ptr() + 4 * off
             y = arena.take(R, hid)
@@ -141,7 +156,11 @@ class Plan(LaunchPlan):
             qkv = arena.take(R, 3 * hid)
             self.conv(y, w["qkv"], qkv, grid=self.grid)
             heads, d = w["heads"], hid // w["heads"]
-            if w["qk_norm"]:
+            if rot is not None:  # RMS norm (if any) + rotary embedding of q and k in one in-place pass
+                self.keep += [qkv, rot]
+                self._emit("qk_norm", 0.0, 2.0 * 2 * R * 2 * hid, self.lib.azb_qk_norm_rope_bf16, qkv.data_ptr(), 3 * hid, R,
+                           heads, d, int(w["qk_norm"]), w["qk_eps"], rot.data_ptr(), L, desc=f"{R}x{2 * heads}x{d} +rope")
+            elif w["qk_norm"]:
                 self.keep.append(qkv)
                 self._emit("qk_norm", 0.0, 2.0 * 2 * R * 2 * hid, self.lib.azb_segment_rmsnorm_bf16, qkv.data_ptr(), 3 * hid,
                            R, 2 * heads, d, w["qk_eps"], desc=f"{R}x{2 * heads}x{d}")
@@ -214,14 +233,21 @@ def _plan(model, cache, packed, key, batch, tokens, rows, pos_fn, device) -> Pla
     return plan
 
 
-def forward(model, x: Tensor, mod: Tensor | None, pos: str) -> Tensor:
-    r"""``DiT.forward`` with sequence-index positions: (B, L, C_i) -> (B, L, C_o), same dtype."""
+def forward(model, x: Tensor, mod: Tensor | None, pos) -> Tensor:
+    r"""``DiT.forward``: (B, L, C_i) -> (B, L, C_o), same dtype.  ``pos``: ``"arange"`` (sequence indices) or a
+    (L, P) tensor of positions shared by the batch (its plan is keyed on the tensor's address and version and keeps
+    the tensor alive: positional embedding and rotary tables are evaluated once per plan)."""
     device = x.device
     B, L, cin = x.shape
     with torch.cuda.device(device):
         cache, packed, mod, rows = _prepare(model, device, mod)
-        plan = _plan(model, cache, packed, ("tokens", B, L, rows), B, L, rows,
-                     lambda: torch.arange(L, dtype=torch.float32, device=device)[:, None], device)
+        if isinstance(pos, str):
+            key, pos_fn = ("tokens", B, L, rows), (lambda: torch.arange(L, dtype=torch.float32, device=device)[:, None])
+        else:
+            key, pos_fn = ("tokens", B, L, rows, pos.data_ptr(), pos._version, tuple(pos.shape)), (lambda: pos)
+        plan = _plan(model, cache, packed, key, B, L, rows, pos_fn, device)
+        if not isinstance(pos, str):
+            plan.pos_ref = pos
         plan.tok[:, :cin].copy_(x.reshape(B * L, cin))
         yt = plan.run_core(mod)
         out = yt.t().reshape(B, L, -1).to(x.dtype)
@@ -231,6 +257,10 @@ def forward(model, x: Tensor, mod: Tensor | None, pos: str) -> Tensor:
 def forward_image(model, x: Tensor, mod: Tensor | None, cond: Tensor | None) -> Tensor:
     r"""``ViT.forward``: (B, C_i, H, W) -> (B, C_o, H, W), same dtype."""
     device = x.device
+    if cond is not None:
+        # patchify(x) ++ patchify(cond) per token (nn/vit.py:97-100) == patchify of the channel concatenation: the
+        # token's channel index is (z p + a) q + b with the pixel channel z slowest
+        x = torch.cat((x, cond.to(x.dtype)), dim=1)
     B, c, H, W = x.shape
     p, q = model.patch.patch_shape
     hp, wp = H // p, W // q

@@ -119,6 +119,7 @@ _lib.register({
         [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_float, c_void_p, c_int64, c_int64, c_void_p],
     ),
     "azb_segment_rmsnorm_bf16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p]),
+    "azb_qk_norm_rope_bf16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_float, c_void_p, c_int64, c_void_p]),
     "azb_patchify_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "azb_unpatchify_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "azb_linear_gather_f32": (
@@ -677,6 +678,12 @@ if os.environ.get("AZB_PDL", "") == "0":  # A/B switch: plain stream-ordered lau
     try:
         conv_tuning(KNOB_PDL, 0)
     except Exception:  # library not built yet: the first real call reports it
+        pass
+
+if os.environ.get("AZB_ROWEPI", "") == "0":  # A/B switch: the shared-memory-transpose epilogue instead of TMA stores
+    try:
+        conv_tuning(KNOB_ROWEPI, 0)
+    except Exception:
         pass
 
 SPLITK_WORKSPACE_BYTES = 16 << 20

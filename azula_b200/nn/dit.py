@@ -179,14 +179,15 @@ class DiT(NativeCache, nn.Module):
         if cond is not None:
             x = torch.cat((x, cond), dim=-1)
 
+        if x.is_cuda and not torch.is_grad_enabled():
+            from .. import engine
+            from ..engine import dit as _engine
+
+            where = "arange" if pos is None else pos
+            if engine.native_enabled() and _engine.supports(self, x, mod, where):
+                return _engine.forward(self, x, mod, where)
+
         if pos is None:
-            if x.is_cuda and not torch.is_grad_enabled():
-                from .. import engine
-                from ..engine import dit as _engine
-
-                if engine.native_enabled() and _engine.supports(self, x, mod, "arange"):
-                    return _engine.forward(self, x, mod, "arange")
-
             pos = torch.arange(x.shape[-2], dtype=x.dtype, device=x.device)[..., None]
 
         x = self.in_proj(x)

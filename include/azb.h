@@ -291,7 +291,7 @@ int azb_conv_choice(const AzbConv* desc, AzbConvChoice* choice);
 #define AZB_CONV_KNOB_HALO_SB 8    /* halo kernels: cap on the weight stages */
 #define AZB_CONV_KNOB_HALO_SPREAD 9 /* halo kernels: 0 = the fused 1 x 1 blocks follow the last halo item (default: spread) */
 #define AZB_KNOB_PDL 10 /* 0: plain stream-ordered launches instead of programmatic dependent launches */
-#define AZB_CONV_KNOB_ROWEPI 11 /* 0: never the row-domain epilogue with TMA stores (shared-memory transpose + per-lane stores instead) */
+#define AZB_CONV_KNOB_ROWEPI 11 /* row-domain epilogue with TMA stores: 0 never, 1 wherever possible, -1 (default) for layers without activation / gate */
 #define AZB_CONV_KNOBS 12
 int azb_conv_tuning(int knob, int value);
 
@@ -406,6 +406,13 @@ int azb_rownorm_mod_bf16(const void* x, int64_t x_ld, void* y, int64_t y_ld, int
  * channel 0 of x (rows x ld, bf16): the query-key normalisation of MultiheadSelfAttention
  * (azula/nn/attention.py:103 on the q and k thirds of the qkv projection: segs = 2 * heads). */
 int azb_segment_rmsnorm_bf16(void* x, int64_t ld, int64_t rows, int64_t segs, int64_t d, float eps, void* stream);
+
+/* The same in-place pass over the q and k thirds of a qkv projection (segments of d channels, 2 * heads of them), with the
+ * rotary positional embedding of MultiheadSelfAttention (azula/nn/attention.py:105-108,124-156) applied after the
+ * normalisation (norm = 0: rotation only): channel pair (2 i, 2 i + 1) of head h at token l turns by the angle whose
+ * {cos, sin} (fp32) is rot[(l mod rows_per_sample)][h * d / 2 + i]; rot NULL = azb_segment_rmsnorm_bf16. */
+int azb_qk_norm_rope_bf16(void* x, int64_t ld, int64_t rows, int64_t heads, int64_t d, int norm, float eps,
+                          const float* rot, int64_t rows_per_sample, void* stream);
 
 /* Patchify(channel_last) of azula/nn/vit.py:97 (azula/nn/layers.py:198-222): fp32 NCHW (n, c, hp*p, wp*q)
  * -> bf16 tokens (n*hp*wp, k_pad), token (i, j) channel (z*p + a)*q + b = x[n][z][i*p + a][j*q + b], zero

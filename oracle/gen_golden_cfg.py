@@ -67,6 +67,12 @@ VIT_CASES = {
                           patch_size=2), (2, 4, 8, 8)),
     "relu2_free": (dict(in_channels=3, out_channels=2, hid_channels=64, hid_blocks=1, attention_heads=2, patch_size=(2, 1),
                         ffn_activation="relu2", qk_norm=False, ffn_factor=2), (2, 3, 4, 6)),
+    # rotary positional embedding (azula/nn/attention.py:97-100,111-156).  (No condition image: the reference's
+    # ViT.forward concatenates a 4-d patchified cond to 3-d tokens and raises, azula/nn/vit.py:97-104.)
+    "rope_mod": (dict(in_channels=3, out_channels=3, mod_features=32, hid_channels=128, hid_blocks=2,
+                      attention_heads=2, patch_size=2, rope=True), (2, 3, 8, 8)),
+    "rope_nonorm": (dict(in_channels=4, out_channels=4, hid_channels=64, hid_blocks=1, attention_heads=4, patch_size=2, rope=True,
+                         qk_norm=False), (2, 4, 8, 4)),
 }
 
 DIT_CASE = (dict(in_channels=6, out_channels=3, mod_features=32, hid_channels=64, hid_blocks=2, attention_heads=4), (2, 10, 6))

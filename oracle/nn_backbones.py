@@ -108,14 +108,26 @@ def sine_encoding(x: Tensor, features: int, omega: float) -> Tensor:
     return torch.cat((torch.sin(x * freqs), torch.cos(x * freqs)), dim=-1)
 
 
-def self_attention(sd: dict, key: str, x: Tensor, heads: int, qk_norm: bool = True) -> Tensor:
-    """MultiheadSelfAttention.forward without RoPE / mask (azula/nn/attention.py:101-121):
-    qkv split as "(n H C)", per-head RMS-normalised q and k, softmax(q k^T / sqrt(C)) v."""
+def rope(t: Tensor, theta: Tensor) -> Tensor:
+    """Rotation of consecutive channel pairs by theta (azula/nn/attention.py:135-156)."""
+    re, im = t[..., 0::2], t[..., 1::2]
+    cos, sin = torch.cos(theta), torch.sin(theta)
+    return torch.stack((re * cos - im * sin, re * sin + im * cos), dim=-1).flatten(-2)
+
+
+def self_attention(sd: dict, key: str, x: Tensor, heads: int, qk_norm: bool = True, pos: Tensor | None = None) -> Tensor:
+    """MultiheadSelfAttention.forward without mask (azula/nn/attention.py:89-108):
+    qkv split as "(n H C)", per-head RMS-normalised q and k, rotary embedding when the module has a
+    ``theta_proj`` (:97-100: theta = theta_proj(pos) split per head), softmax(q k^T / sqrt(C)) v."""
     B, L, D = x.shape
     qkv = F.linear(x, sd[key + ".qkv_proj.weight"], sd.get(key + ".qkv_proj.bias"))
     q, k, v = qkv.reshape(B, L, 3, heads, D // heads).permute(2, 0, 3, 1, 4)
     if qk_norm:
         q, k = rms_norm(q), rms_norm(k)
+    if key + ".theta_proj.weight" in sd:
+        theta = F.linear(pos, sd[key + ".theta_proj.weight"])  # (L, D / 2)
+        theta = theta.reshape(L, heads, D // heads // 2).permute(1, 0, 2)  # (H, L, C / 2)
+        q, k = rope(q, theta), rope(k, theta)
     att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(D // heads), dim=-1)
     y = (att @ v).transpose(1, 2).reshape(B, L, D)
     return F.linear(y, sd[key + ".y_proj.weight"])
@@ -125,13 +137,13 @@ _ACT = {"silu": F.silu, "relu": F.relu, "relu2": lambda t: F.relu(t).square()}
 
 
 def dit_block(sd: dict, key: str, x: Tensor, mod: Tensor | None, heads: int, qk_norm: bool = True,
-              activation: str = "silu") -> Tensor:
+              activation: str = "silu", pos: Tensor | None = None) -> Tensor:
     """DiTBlock._forward (azula/nn/dit.py:89-107)."""
     a, b, c = ada_zero(sd, key, mod, trailing=0)
     if a.ndim == 2:  # (B, C) -> (B, 1, C)   ("... (n C) -> n ... 1 C", :62)
         a, b, c = a[:, None], b[:, None], c[:, None]
     y = (a + 1) * rms_norm(x) + b
-    y = y + self_attention(sd, key + ".msa", y, heads, qk_norm)
+    y = y + self_attention(sd, key + ".msa", y, heads, qk_norm, pos)
     y = F.linear(y, sd[key + ".ffn.0.weight"], sd[key + ".ffn.0.bias"])
     y = F.linear(_ACT[activation](y), sd[key + ".ffn.3.weight"], sd[key + ".ffn.3.bias"])
     return x + c * y
@@ -145,17 +157,18 @@ def dit_forward(sd: dict, x: Tensor, mod: Tensor | None, pos: Tensor, hid_blocks
     emb = sine_encoding(pos, hid, omega=1e2).flatten(-2)  # :153-157
     x = x + F.linear(emb, sd["pos_embedding.2.weight"])
     for i in range(hid_blocks):
-        x = dit_block(sd, f"blocks.{i}", x, mod, heads, qk_norm, activation)
+        x = dit_block(sd, f"blocks.{i}", x, mod, heads, qk_norm, activation, pos)
     return F.linear(x, sd["out_proj.weight"], sd["out_proj.bias"])
 
 
 def vit_forward(sd: dict, x: Tensor, mod: Tensor | None, patch: int, hid_blocks: int, heads: int,
-                qk_norm: bool = True, activation: str = "silu") -> Tensor:
-    """ViT.forward (azula/nn/vit.py:79-108): patchify channel-last "(Z a b)", grid positions, DiT,
-    unpatchify."""
+                qk_norm: bool = True, activation: str = "silu", cond: Tensor | None = None) -> Tensor:
+    """ViT.forward (azula/nn/vit.py:79-108): patchify channel-last "(Z a b)" (the condition image separately,
+    concatenated per token, :97-100 with azula/nn/dit.py:200-201), grid positions, DiT, unpatchify."""
     B, C, H, W = x.shape
     hp, wp = H // patch, W // patch
-    tok = x.reshape(B, C, hp, patch, wp, patch).permute(0, 2, 4, 1, 3, 5).reshape(B, hp * wp, C * patch * patch)
+    tokens = lambda t: t.reshape(B, t.shape[1], hp, patch, wp, patch).permute(0, 2, 4, 1, 3, 5).reshape(B, hp * wp, -1)  # noqa: E731
+    tok = tokens(x) if cond is None else torch.cat((tokens(x), tokens(cond)), dim=-1)
     ii, jj = torch.meshgrid(torch.arange(hp, dtype=x.dtype, device=x.device),
                             torch.arange(wp, dtype=x.dtype, device=x.device), indexing="ij")
     pos = torch.stack((ii.flatten(), jj.flatten()), dim=-1)  # cartesian_prod, :99-101

@@ -29,8 +29,9 @@ def _exact_reference():
 
 
 def _both(fn):
-    """Runs fn() with the row-domain epilogue and with the old one; returns the two results."""
-    ops.conv_tuning(ops.KNOB_ROWEPI, -1)
+    """Runs fn() with the row-domain epilogue (forced: also for activation / gate epilogues, which the automatic choice
+    leaves to the old one) and with the old one; returns the two results."""
+    ops.conv_tuning(ops.KNOB_ROWEPI, 1)
     new = fn()
     ops.conv_tuning(ops.KNOB_ROWEPI, 0)
     old = fn()
@@ -115,6 +116,7 @@ def test_rowepi_activation_gate_residual(act, shape):
         ops.conv_tuning(ops.KNOB_BLOCKN, 256 if co % 256 == 0 else 128)
         out = torch.empty(n, ho, wo, co, dtype=torch.bfloat16, device=DEV)
         d = ops.conv_desc(x, pc, out, act=ops.ACT[act], gate=gate.data_ptr(), gate_ld=gate.stride(0), gate_rows=ho * wo, residual=res)
+        ops.conv_tuning(ops.KNOB_ROWEPI, 1)
         assert ops.conv_choice(d).halo == 1
         new = ops.conv2d(x, pc, stride=stride, act=act, gate=gate, residual=res)
     y = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), b, padding=1, stride=stride).permute(0, 2, 3, 1)

@@ -60,12 +60,12 @@ def test_vit_mirror_and_oracle_match_reference(tag):
     net = ViT(**kw).eval()
     assert len(net.state_dict()) == int(g[f"{tag}_keys"])
     sd = _seeded(net)
-    for (x, mod), _, want in _calls(g, tag):
-        got = net(x, mod)
+    for (x, mod), extra, want in _calls(g, tag):
+        got = net(x, mod, **extra)
         assert got.shape == want.shape and close(got, want, rtol=1e-5, atol=1e-6)
         if isinstance(kw["patch_size"], int):
             ora = NB.vit_forward(sd, x, mod, kw["patch_size"], kw["hid_blocks"], kw["attention_heads"],
-                                 kw.get("qk_norm", True), kw.get("ffn_activation", "silu"))
+                                 kw.get("qk_norm", True), kw.get("ffn_activation", "silu"), cond=extra.get("cond"))
             assert close(ora, want, rtol=1e-5, atol=1e-6)
 
 

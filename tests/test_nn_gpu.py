@@ -243,14 +243,15 @@ def test_vit_native_vs_oracle_and_golden(tag):
     net, sd = _seeded(ViT(**kw).eval())
     x = g[f"{tag}_x"].to(DEV)
     mods = [("mod1", "y_mod1"), ("modB", "y_modB")] if f"{tag}_mod1" in g else [(None, "y")]
+    extra = {"cond": g[f"{tag}_cond"].to(DEV)} if f"{tag}_cond" in g else {}  # rope / cond cases run natively too
     for mk, yk in mods:
         mod = None if mk is None else g[f"{tag}_{mk}"].to(DEV)
-        got = net(x, mod)
+        got = net(x, mod, **extra)
         assert got.dtype == torch.float32 and _native_plans(net) >= 1, "the native plan did not run"
         _report(got, g[f"{tag}_{yk}"].to(DEV), f"vit {tag} {mk} vs reference fixture")
         if isinstance(kw["patch_size"], int):
             ora = NB.vit_forward(sd, x, mod, kw["patch_size"], kw["hid_blocks"], kw["attention_heads"],
-                                 kw.get("qk_norm", True), kw.get("ffn_activation", "silu"))
+                                 kw.get("qk_norm", True), kw.get("ffn_activation", "silu"), cond=extra.get("cond"))
             _report(got, ora, f"vit {tag} {mk} vs oracle")
 
 
@@ -262,6 +263,52 @@ def test_dit_tokens_native_vs_golden():
         got = net(g["x"].to(DEV), g[mk].to(DEV))
         assert _native_plans(net) >= 1
         _report(got, g[yk].to(DEV), f"dit tokens {mk}")
+
+
+def test_dit_explicit_positions_and_rope_native():
+    """DiT over tokens with user-supplied positions (L, P) and rotary embedding: the native plan (positional embedding
+    and {cos, sin} tables evaluated once per positions tensor) against the module's own torch definition."""
+    from azula_b200 import engine
+
+    kw = dict(in_channels=6, out_channels=3, cond_channels=2, mod_features=32, pos_channels=2, hid_channels=128, hid_blocks=2,
+              attention_heads=2, rope=True)
+    net, _ = _seeded(DiT(**kw).eval(), seed=8)
+    g = _gen(12)
+    x = torch.randn(3, 24, 6, device=DEV, generator=g)
+    cond = torch.randn(3, 24, 2, device=DEV, generator=g)
+    mod = torch.randn(3, 32, device=DEV, generator=g)
+    pos = torch.rand(24, 2, device=DEV, generator=g) * 5
+    got = net(x, mod, pos=pos, cond=cond)
+    assert _native_plans(net) >= 1, "explicit positions fell back to torch"
+    with engine.eager_torch():
+        ref = net(x, mod, pos=pos, cond=cond)
+    _report(got, ref, "dit tokens, explicit positions + rope + cond")
+    pos.mul_(1.5)  # in-place change of the positions: a new plan, not the stale tables
+    with engine.eager_torch():
+        ref2 = net(x, mod, pos=pos, cond=cond)
+    _report(net(x, mod, pos=pos, cond=cond), ref2, "dit tokens, moved positions")
+    per_sample = pos.expand(3, 24, 2).contiguous()  # per-sample positions: the torch path (stated limitation)
+    assert torch.isfinite(net(x, mod, pos=per_sample, cond=cond)).all()
+
+
+def test_vit_condition_image_native():
+    """ViT with a condition image (patchified separately, concatenated per token: azula/nn/vit.py:97-100, where the
+    reference itself raises on the 3-d / 4-d mismatch): the native plan takes the channel concatenation before ONE
+    patchify, which is the same token layout; against the module's torch definition and the oracle."""
+    from azula_b200 import engine
+
+    kw = dict(in_channels=3, out_channels=3, cond_channels=2, mod_features=32, hid_channels=128, hid_blocks=2, attention_heads=2,
+              patch_size=2, rope=True)
+    net, sd = _seeded(ViT(**kw).eval(), seed=9)
+    g = _gen(13)
+    x, cond = torch.randn(2, 3, 8, 8, device=DEV, generator=g), torch.randn(2, 2, 8, 8, device=DEV, generator=g)
+    mod = torch.randn(2, 32, device=DEV, generator=g)
+    got = net(x, mod, cond=cond)
+    assert _native_plans(net) >= 1, "cond fell back to torch"
+    with engine.eager_torch():
+        ref = net(x, mod, cond=cond)
+    _report(got, ref, "vit + cond vs torch definition")
+    _report(got, NB.vit_forward(sd, x, mod, 2, 2, 2, cond=cond), "vit + cond vs oracle")
 
 
 def test_vit_config4_shape_vs_oracle():
