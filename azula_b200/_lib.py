@@ -39,6 +39,7 @@ class AzbStep(ctypes.Structure):
         ("offset_host", c_int64), ("offset_inc", c_int64), ("rng_threads", c_int64), ("rng_elem_offset", c_int64),
         ("seed", c_uint64),
         ("f_dtype", c_int32), ("in_dtype", c_int32), ("row_floats", c_int32), ("x_in_copies", c_int32),
+        ("noise_hint", c_int32), ("reserved_", c_int32),
     ]
 
 

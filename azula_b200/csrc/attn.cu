@@ -46,11 +46,32 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&t);
 }
+// fp16 operands (10-bit mantissa, the TF32 mode's attention: qkv arrive as fp16 from the TF32 projection's epilogue)
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    __half2 t = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+template <bool F16>
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if constexpr (F16) mma_f16(d, a, b0, b1);
+    else mma_bf16(d, a, b0, b1);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    if constexpr (F16) return pack_f16(lo, hi);
+    else return pack_bf16(lo, hi);
+}
 
 struct AttnParams {
-    const __nv_bfloat16* qkv;
+    const __nv_bfloat16* qkv;  // (fp16 when F16: same 2-byte layout)
     int64_t ld;
-    __nv_bfloat16* out;
+    __nv_bfloat16* out;        // (fp32 when F16: the TF32 mode keeps activations in fp32)
     int64_t out_ld;
     int T, heads;
     int head_stride, k_delta, v_delta;
@@ -72,7 +93,7 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat1
     }
 }
 
-template <int D>
+template <int D, bool F16 = false>
 __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     pdl_enter();
     constexpr int PITCH = D + 8;
@@ -127,8 +148,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
             for (int nb = 0; nb < BN / 16; ++nb) {
                 uint32_t b[4];
                 ldsm_x4(b, tK + (nb * 16 + (lane & 7) + (lane >> 4) * 8) * PITCH + kk * 16 + ((lane >> 3) & 1) * 8);
-                mma_bf16(s[2 * nb], a, b[0], b[1]);
-                mma_bf16(s[2 * nb + 1], a, b[2], b[3]);
+                mma_16816<F16>(s[2 * nb], a, b[0], b[1]);
+                mma_16816<F16>(s[2 * nb + 1], a, b[2], b[3]);
             }
         }
         // mask keys beyond T, scale, online softmax (rows g and g+8 of this warp)
@@ -175,16 +196,16 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
 #pragma unroll
         for (int kb = 0; kb < BN / 16; ++kb) {
             uint32_t a[4];
-            a[0] = pack_bf16(s[2 * kb][0], s[2 * kb][1]);
-            a[1] = pack_bf16(s[2 * kb][2], s[2 * kb][3]);
-            a[2] = pack_bf16(s[2 * kb + 1][0], s[2 * kb + 1][1]);
-            a[3] = pack_bf16(s[2 * kb + 1][2], s[2 * kb + 1][3]);
+            a[0] = pack2<F16>(s[2 * kb][0], s[2 * kb][1]);
+            a[1] = pack2<F16>(s[2 * kb][2], s[2 * kb][3]);
+            a[2] = pack2<F16>(s[2 * kb + 1][0], s[2 * kb + 1][1]);
+            a[3] = pack2<F16>(s[2 * kb + 1][2], s[2 * kb + 1][3]);
 #pragma unroll
             for (int nb = 0; nb < D / 16; ++nb) {
                 uint32_t b[4];
                 ldsm_x4_trans(b, tV + (kb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PITCH + nb * 16 + (lane >> 4) * 8);
-                mma_bf16(o[2 * nb], a, b[0], b[1]);
-                mma_bf16(o[2 * nb + 1], a, b[2], b[3]);
+                mma_16816<F16>(o[2 * nb], a, b[0], b[1]);
+                mma_16816<F16>(o[2 * nb + 1], a, b[2], b[3]);
             }
         }
         __syncthreads();  // everyone done with this buffer before it is refilled
@@ -201,24 +222,31 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
     for (int r = 0; r < 2; ++r) {
         const int q = q0 + warp * 16 + g + r * 8;
         if (q >= p.T) continue;
-        __nv_bfloat16* dst = p.out + ((int64_t)n * p.T + q) * p.out_ld + hd * D;
+        if constexpr (F16) {
+            float* dst = reinterpret_cast<float*>(p.out) + ((int64_t)n * p.T + q) * p.out_ld + hd * D;
 #pragma unroll
-        for (int i = 0; i < D / 8; ++i)
-            *reinterpret_cast<uint32_t*>(dst + i * 8 + t4 * 2) = pack_bf16(o[i][2 * r] * inv[r], o[i][2 * r + 1] * inv[r]);
+            for (int i = 0; i < D / 8; ++i)
+                *reinterpret_cast<float2*>(dst + i * 8 + t4 * 2) = make_float2(o[i][2 * r] * inv[r], o[i][2 * r + 1] * inv[r]);
+        } else {
+            __nv_bfloat16* dst = p.out + ((int64_t)n * p.T + q) * p.out_ld + hd * D;
+#pragma unroll
+            for (int i = 0; i < D / 8; ++i)
+                *reinterpret_cast<uint32_t*>(dst + i * 8 + t4 * 2) = pack_bf16(o[i][2 * r] * inv[r], o[i][2 * r + 1] * inv[r]);
+        }
     }
 }
 
-template <int D>
+template <int D, bool F16 = false>
 int launch_attn(const AttnParams& p, int n, cudaStream_t s) {
     constexpr int smem = (BM + 4 * BN) * (D + 8) * 2;
     static AzbPerDevice<bool> configured_dev;
     bool& configured = configured_dev.get();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(attention_kernel<D, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    azb_launch(attention_kernel<D>, dim3((p.T + BM - 1) / BM, p.heads, n), dim3(128), smem, s, p);
+    azb_launch(attention_kernel<D, F16>, dim3((p.T + BM - 1) / BM, p.heads, n), dim3(128), smem, s, p);
     return azb_launch_status();
 }
 
@@ -262,6 +290,30 @@ extern "C" int azb_attention_mma_bf16(const void* qkv, int64_t ld, void* out, in
         // num_heads = 4 cards (imagenet_128x128_cond, cards.yaml:19-34): head widths 128 / 192 / 256
         case 192: return launch_attn<192>(p, (int)n, s);
         case 256: return launch_attn<256>(p, (int)n, s);
+    }
+    return AZB_E_SHAPE;
+}
+
+// The TF32 mode's attention: qkv fp16 (N, T, ld), out fp32 (N, T, out_ld); fp32 softmax and accumulation.
+extern "C" int azb_attention_f16(const void* qkv, int64_t ld, float* out, int64_t out_ld, int64_t n, int64_t t, int64_t heads,
+                                 int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta, void* stream) {
+    AZB_CHECK_PTR(qkv);
+    AZB_CHECK_PTR(out);
+    if (n <= 0 || t <= 0 || heads <= 0 || n > 65535 || heads > 65535) return AZB_E_SHAPE;
+    if (ld % 8 || out_ld % 2 || head_stride % 8 || k_delta % 8 || v_delta % 8) return AZB_E_ALIGN;
+    if (!azb_aligned(qkv, 16) || !azb_aligned(out, 8)) return AZB_E_ALIGN;
+    AttnParams p{};
+    p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv), p.ld = ld;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out), p.out_ld = out_ld;
+    p.T = (int)t, p.heads = (int)heads;
+    p.head_stride = (int)head_stride, p.k_delta = (int)k_delta, p.v_delta = (int)v_delta;
+    p.scale_log2e = 1.4426950408889634f / sqrtf((float)d);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    switch (d) {
+        case 32: return launch_attn<32, true>(p, (int)n, s);
+        case 64: return launch_attn<64, true>(p, (int)n, s);
+        case 128: return launch_attn<128, true>(p, (int)n, s);
+        case 256: return launch_attn<256, true>(p, (int)n, s);
     }
     return AZB_E_SHAPE;
 }

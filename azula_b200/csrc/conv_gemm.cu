@@ -89,7 +89,8 @@ struct ConvParams {
     int res_up;               // 1: residual at (H / 2, W / 2), pixel (h, w) adds residual pixel (h / 2, w / 2)
     void* out;
     int64_t out_ld;           // NHWC pixel stride (mode 0)
-    int out_mode;             // 0: bf16 NHWC, 1: fp32 NCHW
+    int out_mode;             // 0: bf16 NHWC (TF32 mode: fp32 NHWC, or fp16 NHWC with out_f16), 1: fp32 NCHW
+    int out_f16;              // TF32 mode, out_mode 0: store fp16 (the attention kernel's operands) instead of fp32
     float2* colsum;           // [m_tiles * 4][c_out / stat_gran] per-(32-row slab, channel block) {sum, sum of squares}
     int stat_gran;            // channels per colsum entry: 1 or 8
     int stride;               // 1 or 2: input pixel = stride * output pixel + tap - pad
@@ -146,7 +147,13 @@ __device__ __forceinline__ void fixed_add(unsigned long long* acc, float v) {
 
 __device__ __forceinline__ float activate(float v, int act) {
     switch (act) {
-        case AZB_ACT_SILU: return __fdividef(v, 1.0f + __expf(-v));
+        // x sigmoid(x) = t + t tanh(t) with t = x / 2: ONE special-function instruction per element (tanh.approx, 2^-11
+        // relative) instead of an exponential and a reciprocal -- the activation epilogue of the 768 -> 3072 token GEMM
+        // was bound by the SFU pipe (38 % tensor-pipe activity against 64 % of the same GEMM without activation)
+        case AZB_ACT_SILU: {
+            const float t = 0.5f * v;
+            return fmaf(t, tanh_approx(t), t);
+        }
         case AZB_ACT_RELU: return fmaxf(v, 0.f);
         case AZB_ACT_RELU2: v = fmaxf(v, 0.f); return v * v;
     }
@@ -252,12 +259,22 @@ __device__ __forceinline__ void transform_tile(uint32_t slot, int rg, int chunk,
 // are the map's business).  ~60-200 instructions per 32-column chunk instead of ~455, no shared-memory transpose, no
 // per-lane global stores.  The GroupNorm sums of the stored values fold 8 channels in the lane, then 32 rows with a
 // transposed butterfly (12 shuffles per chunk).  Serves every bf16 NHWC layer without split-K / per-channel statistics.
-template <int BLOCK_N, bool PAIR, int EPI, bool HALO>
+//
+// TF32 = true: the REFERENCE-NUMERICS mode.  Activations and weights are fp32 in HBM (what the reference's fp32 modules
+// hold), a k-block is 32 fp32 channels (the same 128-byte swizzle rows, so tiles, ring and descriptors are unchanged),
+// the tensor maps are CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 and the MMA is tcgen05.mma.kind::tf32 (K = 8 per instruction):
+// operands with a 10-bit mantissa, fp32 accumulation -- what cuDNN does for the reference under PyTorch's default
+// flags (torch.backends.cudnn.allow_tf32).  Tap-wise single-CTA kernels with EPI == 3 (row domain: one fp32 / fp16
+// NHWC row segment per lane, direct 16-byte stores of whole 128-byte lines, fp32 residual) or the fp32 NCHW epilogue.
+template <int BLOCK_N, bool PAIR, int EPI, bool HALO, bool TF32 = false>
 __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
     conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_out,
                      const ConvParams p) {
     constexpr bool LEAN = EPI == 1;
+    static_assert(!TF32 || (!HALO && !PAIR), "the TF32 mode uses the tap-wise single-CTA kernels");
+    static_assert((EPI == 3) == (TF32 && EPI != 0), "EPI 3 is the TF32 mode's NHWC epilogue");
+    constexpr int KE = TF32 ? BLOCK_K / 2 : BLOCK_K;  // elements per k-block (128 bytes)
     using C = Cfg<BLOCK_N, PAIR, HALO>;
     constexpr int STAGES = C::STAGES;
     static_assert(!PAIR || BLOCK_N >= 128, "a CTA pair splits the weight tile in two halves of >= 64 rows");
@@ -556,7 +573,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                 const int kb0 = (tile / p.tiles_out) * kb_per_split;
                 const int b_row0 = n_tile * BLOCK_N + (int)cta_rank * C::B_ROWS;
                 for (int j = 0; j < p.prefetch_kb && j < kb_per_split; ++j)
-                    tc::tma_prefetch_l2_2d(&tmap_b, (kb0 + j) * BLOCK_K, n_tile * BLOCK_N);
+                    tc::tma_prefetch_l2_2d(&tmap_b, (kb0 + j) * KE, n_tile * BLOCK_N);
                 // position of k-block kb0 inside the taps: (kh, kw, channel block); one division per tile
                 int tap = kb0 / p.kb_per_tap, cb = kb0 - tap * p.kb_per_tap;
                 int kh = tap / p.ksize, kw = tap - kh * p.ksize;
@@ -569,20 +586,20 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                     const bool in_taps = kb < num_kb_taps;
                     // the fused 1x1 operand (ResBlock skip connection) follows the taps: same pixels, no offset
                     const CUtensorMap* ma = in_taps ? &tmap_a : &tmap_a2;
-                    const int c0 = (in_taps ? cb : kb - num_kb_taps) * BLOCK_K;
+                    const int c0 = (in_taps ? cb : kb - num_kb_taps) * KE;
                     const int cw = in_taps ? wbase + kw : w0, ch = in_taps ? hbase + kh : h0;
                     if constexpr (PAIR) {
                         // both CTAs' bytes are credited to the LEADER's barrier, which its producer arms for the pair
                         if (leader) tc::mbar_expect_tx(tc::smem_u32(&bar_full[s]), 2 * C::STAGE_BYTES);
                         tc::tma_load_4d_pair(a_dst, ma, full, c0, cw, ch, n0);
-                        tc::tma_load_2d_pair(b_dst, &tmap_b, full, kb * BLOCK_K, b_row0);
+                        tc::tma_load_2d_pair(b_dst, &tmap_b, full, kb * KE, b_row0);
                     } else {
                         tc::mbar_expect_tx(full, C::STAGE_BYTES);
                         tc::tma_load_4d(a_dst, ma, full, c0, cw, ch, n0);
-                        tc::tma_load_2d(b_dst, &tmap_b, full, kb * BLOCK_K, b_row0);
+                        tc::tma_load_2d(b_dst, &tmap_b, full, kb * KE, b_row0);
                     }
                     if (p.prefetch_kb && kb + p.prefetch_kb < kb0 + kb_per_split)
-                        tc::tma_prefetch_l2_2d(&tmap_b, (kb + p.prefetch_kb) * BLOCK_K, n_tile * BLOCK_N);
+                        tc::tma_prefetch_l2_2d(&tmap_b, (kb + p.prefetch_kb) * KE, n_tile * BLOCK_N);
                     if (++cb == p.kb_per_tap) {
                         cb = 0;
                         if (++kw == p.ksize) kw = 0, ++kh;
@@ -594,7 +611,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (leader && tc::elect_one()) {
-            constexpr uint32_t idesc = tc::idesc_bf16_f32(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+            constexpr uint32_t idesc = TF32 ? tc::idesc_tf32_f32(BLOCK_M, BLOCK_N) : tc::idesc_bf16_f32(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
             int s = 0;
             uint32_t parity = 0;
             for (int local = 0; local < tile_count; ++local) {
@@ -614,6 +631,8 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                         // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
                         if constexpr (PAIR)
                             tc::mma_f16_ss_pair(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        else if constexpr (TF32)  // K = 8 fp32 words = the same 32 bytes per operand row
+                            tc::mma_tf32_ss(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                         else
                             tc::mma_f16_ss(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                     }
@@ -626,6 +645,93 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                 if constexpr (PAIR) tc::mma_commit_pair(tc::smem_u32(&bar_acc_full[as]), 0b11);
                 else tc::mma_commit(tc::smem_u32(&bar_acc_full[as]));
             }
+        }
+    } else if constexpr (EPI == 3) {
+        // ===== epilogue of the TF32 mode: row domain, fp32 (or fp16) NHWC output, direct stores =====
+        // lane = output pixel; a 32-column chunk of its row is 128 contiguous bytes of fp32 (one full line per lane, eight
+        // 16-byte stores) or 64 bytes of fp16 (the qkv projection feeding the attention kernel).  bias -> activation ->
+        // fp32 residual, no rounding for fp32 outputs.
+        const int e = warp - 2;
+        const int quarter = warp & 3;
+        constexpr int CPW = C::COLS_PER_WARP;
+        constexpr int CHUNK = C::CHUNK;
+        const int half = (BLOCK_N >= 64) ? (e >> 2) : 0;
+        const bool active = (BLOCK_N >= 64) || (e < 4);
+        for (int local = 0; local < tile_count; ++local) {
+            const int tile = unit_to_tile(tile_first + local * tile_step);
+            const int as = local & 1;
+            int n_tile, w0, h0, n0;
+            tile_coords(p, tile % p.tiles_out, n_tile, w0, h0, n0);
+            const int col_base = n_tile * BLOCK_N + half * CPW;
+            tc::mbar_wait_backoff(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
+            tc::fence_after_sync();
+            if (active) {
+                const int row = quarter * 32 + lane;
+                const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
+                const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
+                const bool ok = (n < p.N) && (h < p.H) && (w < p.W);
+                const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
+                const float* resp = p.res ? reinterpret_cast<const float*>(p.res) + pix * p.res_ld + col_base : nullptr;
+#pragma unroll 1
+                for (int c0 = 0; c0 < CPW; c0 += CHUNK) {
+                    uint32_t acc[CHUNK];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * C::ACC_COLS + half * CPW + c0);
+                    if constexpr (CHUNK == 32) tc::tmem_ld_32x32b_x32(taddr, acc);
+                    else tc::tmem_ld_32x32b_x16(taddr, acc);
+                    const int col = col_base + c0;
+                    float4 rsd[CHUNK / 4];
+                    const bool use_res = resp != nullptr && ok;
+                    if (use_res) {
+#pragma unroll
+                        for (int q = 0; q < CHUNK / 4; ++q)
+                            rsd[q] = col + 4 * q < p.c_out ? __ldg(reinterpret_cast<const float4*>(resp + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    tc::tmem_ld_wait();
+                    float v[CHUNK];
+#pragma unroll
+                    for (int q = 0; q < CHUNK / 4; ++q) {
+                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (p.bias && col + 4 * q < p.c_out) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + q);
+                        v[4 * q] = __uint_as_float(acc[4 * q]) + b4.x, v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + b4.y;
+                        v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + b4.z, v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + b4.w;
+                    }
+                    if (p.act) {
+#pragma unroll
+                        for (int j = 0; j < CHUNK; ++j) v[j] = activate(v[j], p.act);
+                    }
+                    if (use_res) {
+#pragma unroll
+                        for (int q = 0; q < CHUNK / 4; ++q)
+                            v[4 * q] += rsd[q].x, v[4 * q + 1] += rsd[q].y, v[4 * q + 2] += rsd[q].z, v[4 * q + 3] += rsd[q].w;
+                    }
+                    if (ok) {
+                        if (p.out_f16) {
+                            __half* dst = reinterpret_cast<__half*>(p.out) + pix * p.out_ld + col;
+#pragma unroll
+                            for (int q = 0; q < CHUNK / 8; ++q) {
+                                if (col + 8 * q < p.c_out) {
+                                    uint32_t w4[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        __half2 t = __floats2half2_rn(v[8 * q + 2 * j], v[8 * q + 2 * j + 1]);
+                                        w4[j] = *reinterpret_cast<uint32_t*>(&t);
+                                    }
+                                    *reinterpret_cast<uint4*>(dst + 8 * q) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                                }
+                            }
+                        } else {
+                            float* dst = reinterpret_cast<float*>(p.out) + pix * p.out_ld + col;
+#pragma unroll
+                            for (int q = 0; q < CHUNK / 4; ++q)
+                                if (col + 4 * q < p.c_out)
+                                    *reinterpret_cast<float4*>(dst + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        }
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[as]));
         }
     } else if constexpr (EPI == 2) {
         // ===== epilogue, row domain + TMA store (see the kernel's header) =====
@@ -1168,12 +1274,12 @@ int sm_count() { return azb_sm_count(); }
 
 #define g_knob azb_knob
 
-template <int BLOCK_N, bool PAIR = false, int EPI = 0, bool HALO = false>
+template <int BLOCK_N, bool PAIR = false, int EPI = 0, bool HALO = false, bool TF32 = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const ConvParams& p, cudaStream_t s,
            const CUtensorMap* tout = nullptr) {
     constexpr int smem = Cfg<BLOCK_N, PAIR, HALO>::SMEM;
     constexpr int threads = HALO ? THREADS_HALO : THREADS;
-    auto kernel = conv_gemm_kernel<BLOCK_N, PAIR, EPI, HALO>;
+    auto kernel = conv_gemm_kernel<BLOCK_N, PAIR, EPI, HALO, TF32>;
     const CUtensorMap& to = tout ? *tout : ta;
     static AzbPerDevice<bool> configured_dev;
     bool& configured = configured_dev.get();
@@ -1530,7 +1636,105 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     }
 }
 
+// The reference-numerics mode (see the kernel's TF32 notes): fp32 NHWC activations (pixel stride act_ld floats), fp32
+// weights [c_out_rows][taps][k_per_tap] with k_per_tap = c_in rounded up to 32, fp32 bias / residual; output fp32 NHWC
+// (out_mode 0, or fp16 NHWC with out_f16) or fp32 NCHW (out_mode 1).  (h_in, w_in) are the input extents.
+int conv_tf32_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_in, int64_t act_ld, const void* wpack,
+                   int64_t c_out, int64_t c_out_rows, int taps, int64_t k_per_tap, int stride, const float* bias, int act_fn,
+                   const void* residual, int64_t res_ld, void* out, int64_t out_ld, int out_mode, int out_f16, void* stream) {
+    constexpr int KE = BLOCK_K / 2;
+    AZB_CHECK_PTR(act);
+    AZB_CHECK_PTR(wpack);
+    AZB_CHECK_PTR(out);
+    if (n <= 0 || h_in <= 0 || w_in <= 0 || c_in <= 0 || c_out <= 0) return AZB_E_SHAPE;
+    if ((taps != 1 && taps != 9) || (stride != 1 && stride != 2)) return AZB_E_SHAPE;
+    if (act_fn < AZB_ACT_NONE || act_fn > AZB_ACT_RELU2) return AZB_E_SHAPE;
+    if (k_per_tap % KE || k_per_tap < c_in) return AZB_E_SHAPE;
+    if (c_in % 4 || act_ld % 4 || act_ld < c_in) return AZB_E_ALIGN;
+    if (!azb_aligned(act, 16) || !azb_aligned(wpack, 16) || !azb_aligned(out, 16)) return AZB_E_ALIGN;
+    if (out_mode != 0 && out_mode != 1) return AZB_E_SHAPE;
+    if (out_mode == 0 && (c_out % 8 || out_ld % (out_f16 ? 8 : 4) || out_ld < c_out)) return AZB_E_ALIGN;
+    if (residual && (out_mode != 0 || res_ld % 4 || res_ld < c_out || !azb_aligned(residual, 16))) return AZB_E_ALIGN;
+    if (bias && !azb_aligned(bias, 16)) return AZB_E_ALIGN;
+    if (out_mode == 1 && (act_fn != AZB_ACT_NONE || out_f16)) return AZB_E_UNSUPPORTED;
+    const int64_t h = (h_in + stride - 1) / stride, w = (w_in + stride - 1) / stride;
+
+    ConvParams p{};
+    p.N = (int)n, p.H = (int)h, p.W = (int)w;
+    patch_shape(h, w, p.BW, p.BH, p.BN);
+    p.tiles_w = (int)((w + p.BW - 1) / p.BW);
+    p.tiles_h = (int)((h + p.BH - 1) / p.BH);
+    const int64_t m_tiles = (int64_t)p.tiles_w * p.tiles_h * ((n + p.BN - 1) / p.BN);
+    int block_n = 16;
+    const int sms = sm_count();
+    const int cand[5] = {256, 128, 64, 32, 16};
+    for (int i = 0; i < 5; ++i) {
+        if (c_out_rows % cand[i]) continue;
+        block_n = cand[i];
+        if (m_tiles * (c_out_rows / cand[i]) >= (sms * 3) / 4 || cand[i] <= 64) break;
+    }
+    if (c_out_rows % block_n || c_out_rows < c_out) return AZB_E_SHAPE;
+    p.n_tiles = (int)(c_out_rows / block_n);
+    if (m_tiles * p.n_tiles > 0x7fffffffLL) return AZB_E_SHAPE;
+    p.tiles_out = (int)(m_tiles * p.n_tiles);
+    p.total_tiles = p.tiles_out;
+    p.phases = 1, p.splits = 1;
+    p.taps = taps, p.ksize = taps == 9 ? 3 : 1, p.pad = taps == 9 ? 1 : 0;
+    p.kb_per_tap = (int)(k_per_tap / KE);
+    p.c_out = (int)c_out;
+    p.bias = bias;
+    p.res = reinterpret_cast<const __nv_bfloat16*>(residual);  // (fp32 in this mode: the EPI 3 epilogue casts it back)
+    p.res_ld = res_ld;
+    p.out = out, p.out_ld = out_ld, p.out_mode = out_mode, p.out_f16 = out_f16;
+    p.stat_gran = 1, p.stride = stride, p.act = act_fn;
+    p.prefetch_kb = g_knob[AZB_CONV_KNOB_PREFETCH] >= 0 ? g_knob[AZB_CONV_KNOB_PREFETCH] : (m_tiles <= 32 ? 24 : 0);
+    p.c_in = (int)c_in;
+
+    CUtensorMap ta, tb;
+    {
+        const uint32_t st = (uint32_t)stride;
+        uint64_t dims[4] = {(uint64_t)c_in, (uint64_t)w_in, (uint64_t)h_in, (uint64_t)n};
+        uint64_t str[3] = {(uint64_t)act_ld * 4, (uint64_t)act_ld * 4 * w_in, (uint64_t)act_ld * 4 * w_in * h_in};
+        uint32_t box[4] = {KE, (uint32_t)p.BW * st, (uint32_t)p.BH * st, (uint32_t)p.BN};
+        uint32_t es[4] = {1, st, st, 1};
+        if (box[1] > 256 || box[2] > 256) return AZB_E_SHAPE;
+        const int rc = tc::make_map_typed(&ta, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, act, 4, dims, str, box, es);
+        if (rc) return rc == -1 ? AZB_E_DRIVER : AZB_E_SHAPE;
+    }
+    {
+        const int64_t k_total = (int64_t)taps * k_per_tap;
+        uint64_t dims[2] = {(uint64_t)k_total, (uint64_t)c_out_rows};
+        uint64_t str[1] = {(uint64_t)k_total * 4};
+        uint32_t box[2] = {KE, (uint32_t)block_n};
+        const int rc = tc::make_map_typed(&tb, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, wpack, 2, dims, str, box);
+        if (rc) return rc == -1 ? AZB_E_DRIVER : AZB_E_SHAPE;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (out_mode == 1) {
+        switch (block_n) {
+            case 16: return launch<16, false, 0, false, true>(ta, tb, ta, p, s);
+            case 32: return launch<32, false, 0, false, true>(ta, tb, ta, p, s);
+            default: return AZB_E_UNSUPPORTED;  // (the network's output convolution has 3 or 6 channels)
+        }
+    }
+    switch (block_n) {
+        case 256: return launch<256, false, 3, false, true>(ta, tb, ta, p, s);
+        case 128: return launch<128, false, 3, false, true>(ta, tb, ta, p, s);
+        case 64: return launch<64, false, 3, false, true>(ta, tb, ta, p, s);
+        case 32: return launch<32, false, 3, false, true>(ta, tb, ta, p, s);
+        default: return launch<16, false, 3, false, true>(ta, tb, ta, p, s);
+    }
+}
+
 }  // namespace
+
+extern "C" int azb_conv_tf32(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld, const void* wpack,
+                             int64_t c_out, int64_t c_out_rows, int taps, int64_t k_per_tap, int stride, const float* bias,
+                             int act_fn, const void* residual, int64_t res_ld, void* out, int64_t out_ld, int out_mode,
+                             int out_f16, void* stream) {
+    return conv_tf32_impl(act, n, h, w, c_in, act_ld, wpack, c_out, c_out_rows, taps, k_per_tap, stride, bias, act_fn, residual,
+                          res_ld, out, out_ld, out_mode, out_f16, stream);
+}
 
 extern "C" int azb_conv_gemm_bf16(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld,
                                   const void* wpack, int64_t c_out, int64_t c_out_rows, int taps, int64_t k_per_tap,

@@ -165,7 +165,7 @@ struct StepArgs {
     uint64_t seed;
     const int64_t* off_dev;
     int64_t off_host, off_inc, T, elem_off;
-    int row_floats, xin_copies;
+    int row_floats, xin_copies, noise_hint;
     unsigned long long np_magic;  // floor(2^64 / n_per_sample) + 1: exact i / n_per_sample for i < 2^32 by one multiply-high
 };
 
@@ -247,7 +247,10 @@ __device__ __forceinline__ void finish4(const StepArgs& a, const Row& r, float* 
     (acc).w = fmaf((s), (v).w, (acc).w)
 
 // Vector path: numel, n_per_sample, f_bstride, elem_off multiples of 4; 16-byte aligned pointers.
-template <typename FT, typename IT, bool CFG>
+// NOISE = false: the caller guarantees that no row draws noise (AzbStep::noise_hint < 0) -- the Philox / Box-Muller code
+// is not compiled in, which halves the register count and lets the streaming path run at the HBM rate; a row that asks
+// for noise nevertheless poisons the output with NaN instead of silently dropping the term.
+template <typename FT, typename IT, bool CFG, bool NOISE>
 __global__ void __launch_bounds__(256) step_vec4_kernel(const StepArgs a) {
     pdl_enter();
     RowX rx;
@@ -300,7 +303,8 @@ __global__ void __launch_bounds__(256) step_vec4_kernel(const StepArgs a) {
     }
 
     const bool generate = (a.eps == nullptr) && (r.n != 0.0f);
-    if (!generate) {
+    if (!NOISE || !generate) {
+        const float poison = (!NOISE && generate) ? __int_as_float(0x7fc00000) : 0.f;
         const int64_t n4 = a.numel >> 2;
         constexpr int U = 4;
         for (int64_t base = tid; base < n4; base += nthreads * U) {
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(256) step_vec4_kernel(const StepArgs a) {
                     const int64_t fi = f_index(a, i);
                     f[u] = Vec4<FT>::load(a.f, fi);
                     fn[u] = CFG ? Vec4<FT>::load(a.fneg, fi) : zero4;
-                    e[u] = a.eps ? ldg_stream4(a.eps + i) : zero4;
+                    e[u] = a.eps ? ldg_stream4(a.eps + i) : make_float4(poison, poison, poison, poison);
                 }
             }
 #pragma unroll
@@ -325,6 +329,7 @@ __global__ void __launch_bounds__(256) step_vec4_kernel(const StepArgs a) {
         return;
     }
 
+    if constexpr (!NOISE) return;
     // In-register noise.  Work item (g, j): Philox streams 4g..4g+3 at call j produce 16 normals
     // that belong to the four float4 groups at global elements (4j+ii)*T + 4g, ii = 0..3.  The grid is two-dimensional
     // (x over the T/4 stream groups, y over the calls), so no index is ever divided.
@@ -476,7 +481,8 @@ int grid_for(int64_t work_items, int per_sm) {
 template <typename FT, typename IT, bool CFG>
 int launch_step(const StepArgs& a, bool vec, cudaStream_t s) {
     if (vec) {
-        if (a.eps) return azb_launch(step_vec4_kernel<FT, IT, CFG>, dim3(grid_for(a.numel >> 2, 16)), dim3(256), 0, s, a);
+        if (a.eps || a.noise_hint < 0)
+            return azb_launch(step_vec4_kernel<FT, IT, CFG, false>, dim3(grid_for(a.numel >> 2, 16)), dim3(256), 0, s, a);
         // the row may ask for in-register noise: x over the T/4 Philox stream groups, y over the calls that cover this
         // tensor, about 16 CTAs per SM in total (the paths without noise treat the grid as a flat one)
         const int64_t T4 = a.T >> 2;
@@ -487,7 +493,7 @@ int launch_step(const StepArgs& a, bool vec, cudaStream_t s) {
         int64_t gy = cap / gx < 1 ? 1 : cap / gx;
         if (gy > spans) gy = spans;
         if (gy > 65535) gy = 65535;
-        return azb_launch(step_vec4_kernel<FT, IT, CFG>, dim3((unsigned)gx, (unsigned)gy), dim3(256), 0, s, a);
+        return azb_launch(step_vec4_kernel<FT, IT, CFG, true>, dim3((unsigned)gx, (unsigned)gy), dim3(256), 0, s, a);
     }
     return azb_launch(step_scalar_kernel<FT, IT, CFG>, dim3(grid_for(a.numel, 16)), dim3(256), 0, s, a);
 }
@@ -553,7 +559,7 @@ extern "C" int azb_step_ex_f32(const AzbStep* d, void* stream) {
     a.n_per_sample = n_per_sample, a.numel = n_per_sample * batch, a.f_bstride = d->f_batch_stride;
     a.hist_stride = d->hist_stride, a.table = d->table, a.step_idx = d->step_idx, a.seed = d->seed;
     a.off_dev = d->philox_state, a.off_host = d->offset_host, a.off_inc = d->offset_inc, a.T = d->rng_threads;
-    a.elem_off = d->rng_elem_offset, a.row_floats = d->row_floats, a.xin_copies = d->x_in_copies;
+    a.elem_off = d->rng_elem_offset, a.row_floats = d->row_floats, a.xin_copies = d->x_in_copies, a.noise_hint = d->noise_hint;
     a.np_magic = (a.numel < (1ll << 32) && n_per_sample > 1) ? (~0ull / (unsigned long long)n_per_sample) + 1ull : 0ull;
     const bool vec = (n_per_sample % 4 == 0) && (d->f_batch_stride % 4 == 0) && (d->rng_elem_offset % 4 == 0) &&
                      azb_aligned(a.src[0], 16) && azb_aligned(a.src[1], 16) && azb_aligned(a.dst[0], 16) &&

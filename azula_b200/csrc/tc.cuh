@@ -176,6 +176,17 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uin
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same with TF32 inputs (fp32 words in shared memory, 10-bit mantissa taken by the tensor core; K = 8 per
+// instruction, i.e. the same 32 bytes per operand row as K = 16 of bf16): the reference-numerics mode.
+__device__ __forceinline__ void mma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // mbarrier arrives once every MMA issued so far by this thread has completed.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -257,6 +268,10 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t smem_addr, uint
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Instruction descriptor, kind::tf32: D fp32, A/B TF32 (format code 2), both K-major, shape M x N (K = 8).
+__host__ __device__ constexpr uint32_t idesc_tf32_f32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // Same with an MN-major B operand (bit 16): B is stored [K][N] with N contiguous, e.g. V (keys x channels) in P V.
 __host__ __device__ constexpr uint32_t idesc_bf16_f32_b_mn(int M, int N) { return idesc_bf16_f32(M, N) | (1u << 16); }
 
@@ -277,6 +292,25 @@ inline EncodeTiledFn encode_fn() {
             fn = reinterpret_cast<EncodeTiledFn>(ptr);
     }
     return fn;
+}
+
+// Tensor map with 128-byte swizzle and zero fill of out-of-bounds elements; returns 0, -1 (no driver entry
+// point) or -2 (rejected by the driver).
+inline int make_map_typed(CUtensorMap* m, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return -1;
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = elem_strides ? elem_strides[i] : 1;
+        if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+    }
+    CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
 }
 
 // bf16 tensor map with 128-byte swizzle and zero fill of out-of-bounds elements; returns 0, -1 (no driver entry

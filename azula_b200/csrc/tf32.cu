@@ -1,0 +1,188 @@
+// Element-wise / reduction kernels of the REFERENCE-NUMERICS mode (fp32 NHWC activations, TF32 tensor-core
+// contractions: csrc/conv_gemm.cu TF32 = true).  They restate, in fp32 and one pass each, what the reference does around
+// its convolutions in eager PyTorch with fp32 modules:
+//
+//   azb_gn_stats_f32      GroupNorm32 statistics (azula/plugins/adm/_src/nn.py:80-87 -> native_group_norm): mean and
+//                         rstd per (image, group), two-level fp32 / fp64 accumulation
+//   azb_gn_apply_f32      y = act((x - mean) rstd gamma + beta [(1 + scale) . + shift]) with optional nearest 2x
+//                         upsampling or 2 x 2 average pooling of the result (_src/unet.py:101-109,135-137,177-181,
+//                         203-207,229-243); stats NULL = resampling only (the skip branch's x_upd)
+//   azb_nchw_to_nhwc_f32  network input (N, C, H, W) -> (N, H, W, C_pad), zero padded channels
+//
+// All HBM-bound streaming kernels; 128-bit accesses, grid sized in multiples of the SM count.
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int THREADS = 256;
+
+// One CTA per (image, group): the group's channels are contiguous per pixel (cg floats), pixels ld apart.
+__global__ void __launch_bounds__(THREADS) gn_stats_f32_kernel(const float* __restrict__ x, int64_t ld, int64_t hw, int c,
+                                                               int groups, float eps, float* __restrict__ stats) {
+    pdl_enter();
+    const int g = blockIdx.x, n = blockIdx.y;
+    const int cg = c / groups, v4 = cg >> 2;  // float4 per pixel and group
+    const float* base = x + (int64_t)n * hw * ld + (int64_t)g * cg;
+    const int64_t items = hw * v4;
+    // pass over the data in chunks: fp32 sums of <= 64 values, folded in fp64 (matches torch's Welford result to ~1e-7)
+    double s = 0.0, q = 0.0;
+    for (int64_t i0 = threadIdx.x; i0 < items; i0 += (int64_t)THREADS * 16) {
+        float fs = 0.f, fq = 0.f;
+#pragma unroll 4
+        for (int u = 0; u < 16; ++u) {
+            const int64_t i = i0 + (int64_t)u * THREADS;
+            if (i < items) {
+                const int64_t pix = i / v4;
+                const int j = (int)(i - pix * v4);
+                const float4 v = __ldg(reinterpret_cast<const float4*>(base + pix * ld) + j);
+                fs += (v.x + v.y) + (v.z + v.w);
+                fq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, fq))));
+            }
+        }
+        s += (double)fs, q += (double)fq;
+    }
+    __shared__ double sh[2][THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if ((threadIdx.x & 31) == 0) sh[0][threadIdx.x >> 5] = s, sh[1][threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tq = 0.0;
+        for (int w = 0; w < THREADS / 32; ++w) ts += sh[0][w], tq += sh[1][w];
+        const double cnt = (double)hw * cg;
+        const double mean = ts / cnt;
+        double var = tq / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float* o = stats + ((int64_t)n * groups + g) * 2;
+        o[0] = (float)mean;
+        o[1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+}
+
+struct ApplyParams {
+    const float* x;
+    int64_t x_ld;
+    float* y;
+    int64_t y_ld;
+    int n, h, w, c, groups;
+    const float* stats;  // [n][groups][2] or null (resampling only)
+    const float* gamma;
+    const float* beta;
+    const float* ss;     // [scale(c) | shift(c)] per sample (stride ss_stride; 0 = shared) or null
+    int64_t ss_stride;
+    int silu, mode;      // mode 0: same size, 1: nearest 2x upsampling of the result, 2: 2 x 2 average pooling of the result
+};
+
+__device__ __forceinline__ float silu_exact(float v) { return v / (1.0f + __expf(-v)); }
+
+// item = (output pixel, float4 of channels).  The transform is applied per INPUT pixel; pooling averages the four
+// transformed values (the reference pools act(norm(x)), _src/unet.py:229-233).
+__global__ void __launch_bounds__(THREADS) gn_apply_f32_kernel(const ApplyParams p) {
+    pdl_enter();
+    const int v4 = p.c >> 2;
+    const int ho = p.mode == 1 ? 2 * p.h : p.mode == 2 ? p.h / 2 : p.h;
+    const int wo = p.mode == 1 ? 2 * p.w : p.mode == 2 ? p.w / 2 : p.w;
+    const int64_t items = (int64_t)p.n * ho * wo * v4;
+    const int cg = p.c / max(p.groups, 1);
+    for (int64_t it = (int64_t)blockIdx.x * THREADS + threadIdx.x; it < items; it += (int64_t)gridDim.x * THREADS) {
+        const int j = (int)(it % v4);
+        const int64_t opix = it / v4;
+        const int ow = (int)(opix % wo), oh = (int)((opix / wo) % ho), n = (int)(opix / ((int64_t)wo * ho));
+        const int ch = j * 4;
+        float a[4] = {1.f, 1.f, 1.f, 1.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.stats) {
+            const float* st = p.stats + ((int64_t)n * p.groups + ch / cg) * 2;  // (4 consecutive channels share a group: cg % 4 == 0)
+            const float mean = __ldg(st), rstd = __ldg(st + 1);
+            const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + ch)), be = __ldg(reinterpret_cast<const float4*>(p.beta + ch));
+            const float g4[4] = {ga.x, ga.y, ga.z, ga.w}, b4[4] = {be.x, be.y, be.z, be.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) a[e] = rstd * g4[e], b[e] = fmaf(-mean, a[e], b4[e]);
+            if (p.ss) {
+                const float* ss = p.ss + (int64_t)n * p.ss_stride;
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(ss + ch)), sf = __ldg(reinterpret_cast<const float4*>(ss + p.c + ch));
+                const float s4[4] = {sc.x, sc.y, sc.z, sc.w}, f4[4] = {sf.x, sf.y, sf.z, sf.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a[e] *= 1.f + s4[e], b[e] = fmaf(b[e], 1.f + s4[e], f4[e]);
+            }
+        }
+        auto load = [&](int ih, int iw) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.x + (((int64_t)n * p.h + ih) * p.w + iw) * p.x_ld + ch));
+            float f[4] = {fmaf(a[0], v.x, b[0]), fmaf(a[1], v.y, b[1]), fmaf(a[2], v.z, b[2]), fmaf(a[3], v.w, b[3])};
+            if (p.silu) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) f[e] = silu_exact(f[e]);
+            }
+            return make_float4(f[0], f[1], f[2], f[3]);
+        };
+        float4 o;
+        if (p.mode == 2) {
+            const float4 v0 = load(2 * oh, 2 * ow), v1 = load(2 * oh, 2 * ow + 1), v2 = load(2 * oh + 1, 2 * ow), v3 = load(2 * oh + 1, 2 * ow + 1);
+            o = make_float4(0.25f * ((v0.x + v1.x) + (v2.x + v3.x)), 0.25f * ((v0.y + v1.y) + (v2.y + v3.y)),
+                            0.25f * ((v0.z + v1.z) + (v2.z + v3.z)), 0.25f * ((v0.w + v1.w) + (v2.w + v3.w)));
+        } else if (p.mode == 1) {
+            o = load(oh >> 1, ow >> 1);
+        } else {
+            o = load(oh, ow);
+        }
+        *reinterpret_cast<float4*>(p.y + opix * p.y_ld + ch) = o;
+    }
+}
+
+__global__ void __launch_bounds__(THREADS) nchw_to_nhwc_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int c,
+                                                                   int h, int w, int c_pad) {
+    pdl_enter();
+    const int64_t items = (int64_t)n * h * w;
+    for (int64_t pix = (int64_t)blockIdx.x * THREADS + threadIdx.x; pix < items; pix += (int64_t)gridDim.x * THREADS) {
+        const int64_t hw = (int64_t)h * w;
+        const int64_t img = pix / hw, sp = pix - img * hw;
+        for (int z = 0; z < c_pad; ++z) y[pix * c_pad + z] = z < c ? __ldg(x + (img * c + z) * hw + sp) : 0.f;
+    }
+}
+
+int grid_of(int64_t items) {
+    int64_t blocks = (items + THREADS - 1) / THREADS;
+    const int64_t cap = (int64_t)azb_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+
+extern "C" int azb_gn_stats_f32(const float* x, int64_t ld, int64_t n, int64_t hw, int64_t c, int64_t groups, float eps,
+                                float* stats, void* stream) {
+    AZB_CHECK_PTR(x);
+    AZB_CHECK_PTR(stats);
+    if (n <= 0 || hw <= 0 || c <= 0 || groups <= 0 || c % groups || (c / groups) % 4 || n > 65535) return AZB_E_SHAPE;
+    if (ld % 4 || ld < c || !azb_aligned(x, 16)) return AZB_E_ALIGN;
+    return azb_launch(gn_stats_f32_kernel, dim3((unsigned)groups, (unsigned)n), dim3(THREADS), 0, reinterpret_cast<cudaStream_t>(stream),
+                      x, ld, hw, (int)c, (int)groups, eps, stats);
+}
+
+extern "C" int azb_gn_apply_f32(const float* x, int64_t x_ld, float* y, int64_t y_ld, int64_t n, int64_t h, int64_t w, int64_t c,
+                                int64_t groups, const float* stats, const float* gamma, const float* beta,
+                                const float* scale_shift, int64_t ss_stride, int silu, int mode, void* stream) {
+    AZB_CHECK_PTR(x);
+    AZB_CHECK_PTR(y);
+    if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 4 || mode < 0 || mode > 2 || (mode == 2 && ((h | w) & 1))) return AZB_E_SHAPE;
+    if (stats && (!gamma || !beta || groups <= 0 || c % groups || (c / groups) % 4)) return AZB_E_SHAPE;
+    if (x_ld % 4 || y_ld % 4 || x_ld < c || y_ld < c || !azb_aligned(x, 16) || !azb_aligned(y, 16)) return AZB_E_ALIGN;
+    if ((gamma && !azb_aligned(gamma, 16)) || (beta && !azb_aligned(beta, 16)) || (scale_shift && (!azb_aligned(scale_shift, 16) || ss_stride % 4)))
+        return AZB_E_ALIGN;
+    ApplyParams p{x, x_ld, y, y_ld, (int)n, (int)h, (int)w, (int)c, (int)(stats ? groups : 1), stats, gamma, beta, stats ? scale_shift : nullptr,
+                  ss_stride, silu, mode};
+    const int64_t ho = mode == 1 ? 2 * h : mode == 2 ? h / 2 : h, wo = mode == 1 ? 2 * w : mode == 2 ? w / 2 : w;
+    return azb_launch(gn_apply_f32_kernel, dim3((unsigned)grid_of(n * ho * wo * (c / 4))), dim3(THREADS), 0,
+                      reinterpret_cast<cudaStream_t>(stream), p);
+}
+
+extern "C" int azb_nchw_to_nhwc_f32(const float* x, float* y, int64_t n, int64_t c, int64_t h, int64_t w, int64_t c_pad, void* stream) {
+    AZB_CHECK_PTR(x);
+    AZB_CHECK_PTR(y);
+    if (n <= 0 || c <= 0 || h <= 0 || w <= 0 || c_pad < c || c_pad % 4) return AZB_E_SHAPE;
+    return azb_launch(nchw_to_nhwc_f32_kernel, dim3((unsigned)grid_of(n * h * w)), dim3(THREADS), 0, reinterpret_cast<cudaStream_t>(stream),
+                      x, y, (int)n, (int)c, (int)h, (int)w, (int)c_pad);
+}

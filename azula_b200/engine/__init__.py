@@ -26,3 +26,21 @@ def eager_torch():
         yield
     finally:
         _NATIVE = previous
+
+
+def set_precision(module, precision: str):
+    r"""Selects the arithmetic of the native ADM backbone(s) inside ``module``: :py:`"bf16"` (default: bf16 activations
+    and tensor-core operands, the fast path with a stated bf16 tolerance) or :py:`"tf32"` (the reference-numerics
+    path: fp32 activations in HBM, ``tcgen05.mma.kind::tf32`` contractions, fp32 GroupNorm / SiLU / residuals -- what
+    the reference's fp32 modules compute under PyTorch's default flags).  Returns ``module``."""
+    if precision not in ("bf16", "tf32"):
+        raise ValueError(f"unknown precision {precision!r} (expected 'bf16' or 'tf32')")
+    from ..plugins.adm.unet import UNetModel
+
+    found = False
+    for m in module.modules():
+        if isinstance(m, UNetModel):
+            m.precision, found = precision, True
+    if not found:
+        raise ValueError("no ADM U-Net inside the module: the precision switch exists for plugins.adm backbones")
+    return module

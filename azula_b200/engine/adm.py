@@ -568,7 +568,8 @@ def forward(model, x: Tensor, timesteps: Tensor, y: Tensor | None = None) -> Ten
         cache = model._native
         packed = cache.get("packed")
         if packed is None or packed.fingerprint != fingerprint(model) or packed.emb_w.device != device:
-            cache.clear()
+            for k in [k for k in cache if k == "packed" or (isinstance(k, tuple) and k[0] != "tf32")]:
+                del cache[k]
             packed = cache["packed"] = Packed(model, device)
 
         timesteps = timesteps.reshape(-1)
@@ -587,7 +588,7 @@ def forward(model, x: Tensor, timesteps: Tensor, y: Tensor | None = None) -> Ten
         key = (n, h, w, rows)
         plan = cache.get(key)
         if plan is None:
-            plans = [k for k in cache if k != "packed"]
+            plans = [k for k in cache if isinstance(k, tuple) and k[0] != "tf32"]
             while len(plans) >= _MAX_PLANS:
                 del cache[plans.pop(0)]
             plan = cache[key] = Plan(model, packed, n, h, w, rows, device)

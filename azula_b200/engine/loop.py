@@ -109,6 +109,7 @@ def signature(sampler, x: Tensor, kwargs: dict):
         type(sampler), tuple(x.shape), x.device, sampler.start, sampler.stop, sampler.steps, sampler._signature(),
         sampler.dtype, sampler.device, sampler.shard, sampler.graph, sampler.unroll, type(den), _describe(inner),
         _describe(inner.schedule), get_module_dtype(inner.backbone),
+        tuple(getattr(m, "precision", None) for m in inner.backbone.modules() if hasattr(m, "precision")),
         # the guidance strength lives in device memory: its VALUE is not part of the key
         tuple(sorted((k, ("scalar",) if (k == "guidance" and _guided(den) and not torch.is_tensor(v)) else _freeze(v))
                      for k, v in kwargs.items())),
@@ -251,6 +252,7 @@ class FusedLoop:
         d.seed = 0
         d.f_dtype, d.in_dtype = _lib.DTYPE_CODE[out.dtype], _lib.DTYPE_CODE[self.in_dtype]
         d.row_floats, d.x_in_copies = _lib.ROW_COLS, copies
+        d.noise_hint = -1 if tab.noiseless else 0
         lib = _lib.lib()
         stream = _lib.stream_ptr(self.device)
         _lib.check(lib.azb_step_ex_f32(ctypes.byref(d), stream), "azb_step_ex_f32")

@@ -57,6 +57,22 @@ _lib.register({
          c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
     ),
     "azb_conv_tuning": (c_int, [c_int, c_int]),
+    "azb_conv_tf32": (
+        c_int,
+        [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_void_p,
+         c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p],
+    ),
+    "azb_gn_stats_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p]),
+    "azb_gn_apply_f32": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+         c_void_p, c_int64, c_int, c_int, c_void_p],
+    ),
+    "azb_nchw_to_nhwc_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "azb_attention_f16": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p],
+    ),
     "azb_zero_bytes": (c_int, [c_void_p, c_int64, c_void_p]),
     "azb_gn_apply_acc_bf16": (
         c_int,
@@ -715,4 +731,96 @@ def gn_apply_acc(x: Tensor, parts: list[tuple[Tensor, int]], gamma: Tensor, beta
         ),
         "azb_gn_apply_acc_bf16",
     )
+    return out
+
+
+# ------------------------------------------------------------------------- reference-numerics (TF32) mode
+
+
+def pack_conv_f32(weight: Tensor, bias: Tensor | None, c_in_pad: int | None = None) -> PackedConv:
+    r"""(C_out, C_in[, kh, kw]) -> fp32 (C_out_rows, taps, K_tap) with K_tap = C_in rounded up to 32 (one 128-byte row of
+    fp32): the weights of ``azb_conv_tf32``.  ``c_in_pad``: the (zero padded) channel count the activation is stored
+    with (the 3-channel network input is padded to 4)."""
+    if weight.ndim == 3:
+        weight = weight[..., 0]
+    if weight.ndim == 2:
+        weight = weight[:, :, None, None]
+    c_out, c_in, kh, kw = weight.shape
+    assert (kh, kw) in ((1, 1), (3, 3))
+    taps = kh * kw
+    c_store = c_in if c_in_pad is None else c_in_pad
+    k_pad = -(-c_store // 32) * 32
+    tile = 128 if c_out >= 128 else 64 if c_out >= 64 else 32 if c_out >= 32 else 16
+    rows = -(-c_out // tile) * tile
+    w = torch.zeros(rows, taps, k_pad, dtype=torch.float32, device=weight.device)
+    w[:c_out, :, :c_in] = weight.detach().permute(0, 2, 3, 1).reshape(c_out, taps, c_in).to(torch.float32)
+    b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    return PackedConv(w=w.contiguous(), bias=b, c_in=c_store, c_out=c_out, taps=taps)
+
+
+def conv_tf32(x: Tensor, pc: PackedConv, out: Tensor | None = None, stride: int = 1, act: str | None = None,
+              residual: Tensor | None = None, nchw: bool = False, out_f16: bool = False) -> Tensor:
+    r"""``azb_conv_tf32``: x fp32 NHWC (or (rows, C) tokens) -> fp32 NHWC / fp16 NHWC / fp32 NCHW."""
+    assert x.dtype == torch.float32 and x.is_cuda and pc.w.dtype == torch.float32
+    tokens = x.ndim == 2
+    n, h, w = token_grid(x.shape[0]) if tokens else x.shape[:3]
+    ho, wo = -(-h // stride), -(-w // stride)
+    if out is None:
+        if nchw:
+            out = torch.empty((n, pc.c_out, ho, wo), dtype=torch.float32, device=x.device)
+        else:
+            shape = (x.shape[0], pc.c_out) if tokens else (n, ho, wo, pc.c_out)
+            out = torch.empty(shape, dtype=torch.float16 if out_f16 else torch.float32, device=x.device)
+    _lib.check(
+        _lib.lib().azb_conv_tf32(
+            x.data_ptr(), n, h, w, pc.c_in, _ld(x), pc.w.data_ptr(), pc.c_out, pc.c_out_rows, pc.taps, pc.k_per_tap, stride,
+            _lib.ptr(pc.bias), ACT[act], _lib.ptr(residual), 0 if residual is None else _ld(residual), out.data_ptr(),
+            0 if nchw else _ld(out), int(nchw), int(out_f16), _lib.stream_ptr(x.device),
+        ),
+        "azb_conv_tf32",
+    )
+    return out
+
+
+def gn_stats_f32(x: Tensor, groups: int = GN_GROUPS, eps: float = GN_EPS, stats: Tensor | None = None) -> Tensor:
+    r"""``azb_gn_stats_f32``: (N, groups, 2) = {mean, rstd} of an fp32 NHWC tensor."""
+    n, h, w, c = x.shape
+    if stats is None:
+        stats = torch.empty(n, groups, 2, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().azb_gn_stats_f32(x.data_ptr(), _ld(x), n, h * w, c, groups, eps, stats.data_ptr(),
+                                           _lib.stream_ptr(x.device)), "azb_gn_stats_f32")
+    return stats
+
+
+def gn_apply_f32(x: Tensor, stats: Tensor | None = None, gamma: Tensor | None = None, beta: Tensor | None = None,
+                 scale_shift: Tensor | None = None, silu: bool = False, mode: int = 0, out: Tensor | None = None,
+                 groups: int = GN_GROUPS) -> Tensor:
+    r"""``azb_gn_apply_f32``: normalise (+ scale / shift) (+ SiLU) (+ nearest 2x upsampling / 2 x 2 pooling), fp32 NHWC."""
+    n, h, w, c = x.shape
+    ho, wo = (2 * h, 2 * w) if mode == 1 else (h // 2, w // 2) if mode == 2 else (h, w)
+    if out is None:
+        out = torch.empty(n, ho, wo, c, dtype=torch.float32, device=x.device)
+    ss_stride = 0
+    if scale_shift is not None and scale_shift.ndim == 2 and scale_shift.shape[0] > 1:
+        ss_stride = scale_shift.stride(0)
+    _lib.check(
+        _lib.lib().azb_gn_apply_f32(x.data_ptr(), _ld(x), out.data_ptr(), _ld(out), n, h, w, c, groups, _lib.ptr(stats),
+                                    _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(scale_shift), ss_stride, int(silu), mode,
+                                    _lib.stream_ptr(x.device)),
+        "azb_gn_apply_f32",
+    )
+    return out
+
+
+def attention_f16(qkv: Tensor, heads: int, new_order: bool = False, out: Tensor | None = None) -> Tensor:
+    r"""``azb_attention_f16``: qkv fp16 (N, T, 3C) -> fp32 (N, T, C)."""
+    assert qkv.dtype == torch.float16
+    n, t, c3 = qkv.shape
+    c = c3 // 3
+    d = c // heads
+    if out is None:
+        out = torch.empty(n, t, c, dtype=torch.float32, device=qkv.device)
+    hs, kd, vd = (d, c, 2 * c) if new_order else (3 * d, d, 2 * d)
+    _lib.check(_lib.lib().azb_attention_f16(qkv.data_ptr(), qkv.stride(1), out.data_ptr(), out.stride(1), n, t, heads, d, hs, kd,
+                                            vd, _lib.stream_ptr(qkv.device)), "azb_attention_f16")
     return out

@@ -37,6 +37,7 @@ class StepTable:
     draws: int = 0  # noise draws of the whole loop (each advances the generator by one randn_like)
     slots: int = 0  # history slots the rows address
     alt: bool = False  # whether rows address the second state buffer
+    noiseless: bool = False  # no affine row has n != 0: the kernel variant without the in-register generator serves
 
 
 def transition_scalars(alpha_t, sigma_t, alpha_s, sigma_s, eta: float | None):
@@ -107,8 +108,9 @@ class Grid:
 
         dtype = get_module_dtype(den.backbone)
         time = den.time_rows(c.c_time, dtype).contiguous()
+        noiseless = hist is not None or not bool((coef[:, 5] != 0).any().item())
         return StepTable(coef=coef.contiguous(), time=time, c_in0=c_in[0].to(torch.float32), steps=S, per_step=per_step,
-                         draws=int(draws.sum().item()), slots=slots, alt=alt)
+                         draws=int(draws.sum().item()), slots=slots, alt=alt, noiseless=noiseless)
 
 
 def build(sampler, device: torch.device) -> StepTable:

@@ -44,10 +44,24 @@ def download(url: str, filename: str | None = None, hash_prefix: str | None = No
     archive and the directory ``<file>+x`` holding its contents is returned (``azula/hub.py:40-125``)."""
     path = cache_path(url) if filename is None else os.path.abspath(os.path.expanduser(filename))
     os.makedirs(os.path.dirname(path), exist_ok=True)
+    fetched = False
     if not os.path.exists(path):
         if not quiet:
             print(f"Downloading {url} to {path}", file=sys.stderr)
-        torch.hub.download_url_to_file(url, path, progress=not quiet)
+        if "drive.google" in url:
+            # Google Drive answers plain HTTP clients with an HTML interstitial: the reference goes through gdown
+            # (azula/hub.py:78-79); without it, fail loudly instead of caching that page as a checkpoint
+            try:
+                import gdown
+            except ImportError as e:
+                raise RuntimeError(
+                    f"{url} is a Google Drive link and needs the `gdown` package (pip install gdown), "
+                    f"or place the file at {path} by hand"
+                ) from e
+            gdown.download(url, path, quiet=quiet)
+        else:
+            torch.hub.download_url_to_file(url, path, progress=not quiet)
+        fetched = True
     elif not quiet:
         print(f"Loading from {path}", file=sys.stderr)
     if hash_prefix is not None:
@@ -57,6 +71,8 @@ def download(url: str, filename: str | None = None, hash_prefix: str | None = No
             for block in iter(lambda: f.read(1 << 20), b""):
                 digest.update(block)
         if not digest.hexdigest().startswith(prefix):
+            if fetched:  # never leave a bad download in the cache, where the next call would trust it
+                os.remove(path)
             raise AssertionError(f"hash of {path} ({alg}:{digest.hexdigest()}) does not start with {alg}:{prefix}")
     if extract:
         xd = f"{path}+x"
@@ -67,7 +83,7 @@ def download(url: str, filename: str | None = None, hash_prefix: str | None = No
         with tempfile.TemporaryDirectory() as td:
             if tarfile.is_tarfile(path):
                 with tarfile.open(path, "r") as f:
-                    f.extractall(td)
+                    f.extractall(td, filter="data")  # no absolute paths, links out of the tree or device nodes
             elif zipfile.is_zipfile(path):
                 with zipfile.ZipFile(path, "r") as f:
                     f.extractall(td)

@@ -250,6 +250,9 @@ class UNetModel(nn.Module):
             nn.init.zeros_(self.out.get_submodule("2").weight), nn.init.zeros_(self.out.get_submodule("2").bias)
 
         self._native = {}  # (device, signature) -> engine plan, see azula_b200.engine.adm
+        # "bf16" (default): the fast native path, bf16 activations and tensor-core operands, stated bf16 tolerance;
+        # "tf32": the reference-numerics path (engine/adm_tf32.py): fp32 activations, TF32 operands, fp32 everything else
+        self.precision = "bf16"
 
     def _plant(self, path: str, module: nn.Module) -> None:
         node = self
@@ -277,6 +280,10 @@ class UNetModel(nn.Module):
             from ...engine import adm as engine
 
             if _engine.native_enabled():
+                if getattr(self, "precision", "bf16") == "tf32":  # reference numerics: fp32 activations, TF32 contractions
+                    from ...engine import adm_tf32
+
+                    return adm_tf32.forward(self, x, timesteps, y)
                 return engine.forward(self, x, timesteps, y)
         state = dict(self.named_parameters())
         return forward_torch(self.layout, state, x, timesteps, y, dropout=self.layout.dropout if self.training else 0.0)

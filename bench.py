@@ -234,9 +234,16 @@ def step_kernel_bandwidth(device, noise: bool) -> dict:
     lib, s = _lib.lib(), _lib.stream_ptr(device)
     T, _ = _lib.rng_policy(n)
 
+    import ctypes
+
+    d = _lib.AzbStep()
+    d.src[0], d.dst[0], d.f, d.table, d.step_idx = x.data_ptr(), out.data_ptr(), f.data_ptr(), row.data_ptr(), idx.data_ptr()
+    d.f_batch_stride, d.n_per_sample, d.batch, d.rng_threads, d.seed = n, n, 1, T, 1234
+    d.f_dtype, d.in_dtype, d.row_floats, d.x_in_copies = _lib.F32, _lib.F32, 8, 1
+    d.noise_hint = 0 if noise else -1  # what the fused loop passes: DDIM eta 0 tables never draw
+
     def launch():
-        _lib.check(lib.azb_step_f32(x.data_ptr(), f.data_ptr(), _lib.F32, n, None, out.data_ptr(), None, _lib.F32, n, 1,
-                                    row.data_ptr(), idx.data_ptr(), 1234, None, 0, T, 0, s), "azb_step_f32")
+        _lib.check(lib.azb_step_ex_f32(ctypes.byref(d), s), "azb_step_ex_f32")
 
     for _ in range(3):
         launch()

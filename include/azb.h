@@ -133,6 +133,10 @@ typedef struct AzbStep {
     int64_t offset_host, offset_inc, rng_threads, rng_elem_offset;
     uint64_t seed;
     int32_t f_dtype, in_dtype, row_floats, x_in_copies;
+    int32_t noise_hint;     /* < 0: the caller guarantees that no row of the table draws noise (n == 0 everywhere or eps
+                             * given): the kernel variant without the in-register generator runs (half the registers,
+                             * HBM rate); a row with n != 0 then yields NaN.  0: unknown (generator compiled in).       */
+    int32_t reserved_;
 } AzbStep;
 
 int azb_step_ex_f32(const AzbStep* desc, void* stream);
@@ -294,6 +298,36 @@ int azb_conv_choice(const AzbConv* desc, AzbConvChoice* choice);
 #define AZB_CONV_KNOB_ROWEPI 11 /* row-domain epilogue with TMA stores: 0 never, 1 wherever possible, -1 (default) for layers without activation / gate */
 #define AZB_CONV_KNOBS 12
 int azb_conv_tuning(int knob, int value);
+
+/*
+ * The REFERENCE-NUMERICS mode: the same contraction with fp32 operands in HBM and tcgen05.mma.kind::tf32 (10-bit operand
+ * mantissa, fp32 accumulation) -- what cuDNN runs for the reference's fp32 modules under PyTorch's default flags
+ * (torch.backends.cudnn.allow_tf32; azula/plugins/adm/_src/unet.py:182,207,213-215,277,285,471,602).
+ *   act    fp32 NHWC, pixel stride act_ld floats; c_in % 4 == 0 (the 3-channel network input is padded to 4)
+ *   wpack  fp32 [c_out_rows][taps][k_per_tap], k_per_tap = c_in rounded up to 32, zero padded
+ *   out    out_mode 0: fp32 NHWC (pixel stride out_ld), or fp16 NHWC when out_f16 (operands of azb_attention_f16);
+ *          out_mode 1: fp32 NCHW.  residual: fp32 NHWC (stride res_ld) or NULL; bias fp32 or NULL; act_fn AZB_ACT_*.
+ * (h, w) are the INPUT extents; stride 1 or 2.
+ */
+int azb_conv_tf32(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in, int64_t act_ld, const void* wpack,
+                  int64_t c_out, int64_t c_out_rows, int taps, int64_t k_per_tap, int stride, const float* bias, int act_fn,
+                  const void* residual, int64_t res_ld, void* out, int64_t out_ld, int out_mode, int out_f16, void* stream);
+
+/* GroupNorm32 of the reference-numerics mode, fp32 NHWC in and out (azula/plugins/adm/_src/nn.py:80-87 and the uses in
+ * _src/unet.py:177-181,203-207,229-243,276,599-601): statistics {mean, rstd} per (image, group), then
+ *   y = act(((x - mean) rstd gamma + beta) (1 + scale) + shift)   followed by nearest 2x upsampling (mode 1) or 2 x 2
+ * average pooling (mode 2) of the result; stats NULL = resampling only.  scale_shift: [scale(c) | shift(c)] per sample. */
+int azb_gn_stats_f32(const float* x, int64_t ld, int64_t n, int64_t hw, int64_t c, int64_t groups, float eps, float* stats,
+                     void* stream);
+int azb_gn_apply_f32(const float* x, int64_t x_ld, float* y, int64_t y_ld, int64_t n, int64_t h, int64_t w, int64_t c,
+                     int64_t groups, const float* stats, const float* gamma, const float* beta, const float* scale_shift,
+                     int64_t ss_stride, int silu, int mode, void* stream);
+/* fp32 (n, c, h, w) -> fp32 (n, h, w, c_pad) with zero padded channels (the network input of the TF32 mode). */
+int azb_nchw_to_nhwc_f32(const float* x, float* y, int64_t n, int64_t c, int64_t h, int64_t w, int64_t c_pad, void* stream);
+/* azb_attention_bf16 with fp16 operands (N, T, ld) and an fp32 result (N, T, out_ld): the reference-numerics mode's
+ * QKVAttention (_src/unet.py:328-345,361-381); d in {32, 64, 128, 256}. */
+int azb_attention_f16(const void* qkv, int64_t ld, float* out, int64_t out_ld, int64_t n, int64_t t, int64_t heads, int64_t d,
+                      int64_t head_stride, int64_t k_delta, int64_t v_delta, void* stream);
 
 /* Rows of the colsum buffer for an (n, h, w) activation; *slab_in_image = 1 when every 32-row slab
  * lies inside one image (the condition for azb_gn_finalize_f32), else 0.  Host-side helper. */

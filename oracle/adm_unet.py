@@ -214,7 +214,7 @@ def forward(
 
     ``taps`` (optional dict) receives every block output keyed by its state_dict prefix.
     """
-    emb = time_features(timesteps, tab.model_ch)
+    emb = time_features(timesteps, tab.model_ch).to(sd["time_embed.0.weight"].dtype)  # (float64 state: the tie-breaker run)
     emb = F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])
     emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
     if tab.num_classes is not None:

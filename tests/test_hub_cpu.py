@@ -60,3 +60,22 @@ def test_load_model_from_cached_checkpoint(cache, monkeypatch):
     x = torch.randn(2, 3, 16, 16)
     with torch.no_grad():
         assert torch.equal(den(x, torch.tensor(0.5)).mean, src.eval()(x, torch.tensor(0.5)).mean)
+
+
+def test_bad_download_is_not_cached_and_drive_links_need_gdown(cache, monkeypatch):
+    """a download whose hash does not match must not stay in the cache; Google-Drive links go through
+    gdown as in the reference (azula/hub.py:78-79) or fail loudly -- never cache the HTML interstitial."""
+    import sys
+
+    url = "https://example.org/weights.pt"
+    monkeypatch.setattr(torch.hub, "download_url_to_file", lambda u, dst, progress=True: open(dst, "wb").write(b"garbage"))
+    with pytest.raises(AssertionError):
+        hub.download(url, hash_prefix="sha256:ffffffff", quiet=True)
+    assert not os.path.exists(hub.cache_path(url))
+    monkeypatch.setitem(sys.modules, "gdown", None)  # import gdown -> ImportError
+    with pytest.raises(RuntimeError, match="gdown"):
+        hub.download("https://drive.google.com/uc?id=abc", quiet=True)
+    assert not os.path.exists(hub.cache_path("https://drive.google.com/uc?id=abc"))
+    fake = SimpleNamespace(download=lambda u, dst, quiet=False: open(dst, "wb").write(b"ok"))
+    monkeypatch.setitem(sys.modules, "gdown", fake)
+    assert open(hub.download("https://drive.google.com/uc?id=abc", quiet=True), "rb").read() == b"ok"
