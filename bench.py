@@ -447,6 +447,11 @@ def run_engine(args) -> None:
         return float(t.item())
 
     den = build_denoiser("azula_b200", config, device)
+    precision = os.environ.get("AZB_PRECISION", args.precision)
+    if precision != "bf16":  # the reference-numerics mode (fp32 activations, TF32 contractions), ADM backbones only
+        from azula_b200 import engine
+
+        engine.set_precision(den, precision)
     if rank == 0:
         seed_backbone(den)
     if world > 1:  # the ONE collective of the path: weights from rank 0 at init (no per-step collective)
@@ -538,9 +543,9 @@ def run_engine(args) -> None:
         line = {
             "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if plan is not None else "f32", "data": "synthetic",
+            "dtype": ("tf32" if precision == "tf32" else "bf16") if plan is not None else "f32", "data": "synthetic",
             "config": {"workload": f"{wl['what']}, batch {batch}/GPU x {world} GPU, {'x'.join(map(str, shape[1:]))} fp32 state"
-                                   + (", bf16 backbone" if plan is not None else ""),
+                                   + ((", tf32 backbone (fp32 activations)" if precision == "tf32" else ", bf16 backbone") if plan is not None else ""),
                        "global_batch": world * batch, "parallelism": f"replicas x{world} (batch-sharded, no per-step collective)",
                        "graph": loop.graph is not None, "stages_per_graph_replay": loop.unroll,
                        "l2": "256 MiB flush write between timed iterations"},
@@ -558,7 +563,10 @@ def run_engine(args) -> None:
             for _ in range(2):  # second pass: warm instruction caches / clocks as inside the loop
                 detail.clear()
                 table = plan.profile(detail)
-            line["roofline"] = roofline_of(config, table, detail, batch, pk)
+            line["roofline"] = roofline_of(config if precision == "bf16" else config + "_tf32", table, detail, batch, pk)
+            if precision == "tf32":
+                line["roofline"]["note"] = ("reference-numerics mode: tcgen05 kind::tf32 runs at HALF the bf16 tensor rate; "
+                                            "`peak` is still the measured bf16 figure")
             line["forward_kernels"] = {k: {"launches": r["launches"], "ms": round(r["ms"], 3)} for k, r in table.items()}
         if shard_check is not None:
             line["shard_check"] = shard_check
@@ -639,6 +647,8 @@ def main() -> None:
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--config", default="adm", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="items per GPU (0 = the workload's)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"],
+                    help="arithmetic of the native ADM backbone: bf16 (headline) or tf32 (reference numerics)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-gpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the stand-alone step-kernel bandwidth measurements")

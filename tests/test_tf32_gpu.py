@@ -146,7 +146,7 @@ def _models(cfg, seed):
 
 @pytest.mark.parametrize("tag,cfg,shape", [
     ("wide", WIDE_ADM, (4, 3, 32, 32)),
-    ("w128", dict(WIDE_ADM, num_channels=128, channel_mult=(1, 2, 3), attention_resolutions=(2, 4)), (2, 3, 64, 48)),
+    ("w128", dict(WIDE_ADM, num_channels=128, channel_mult=(1, 2, 3), attention_resolutions=(16, 8)), (2, 3, 64, 48)),
     ("card_64px", None, (2, 3, 64, 64)),  # the imagenet_256x256 card itself at a reduced spatial size
 ])
 def test_tf32_forward_error_is_that_of_the_reference_default_flags(tag, cfg, shape):
