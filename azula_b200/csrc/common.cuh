@@ -90,6 +90,16 @@ __device__ __forceinline__ void stg_stream4(float* p, float4 v) {
                  : "memory");
 }
 
+// Coherent (not .nc) streaming load: for kernels that may run in place (output aliases the input).
+__device__ __forceinline__ float4 ld_stream4_coherent(const float* p) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p)
+                 : "memory");
+    return r;
+}
+
 __device__ __forceinline__ uint4 ldg_stream16(const void* p) {
     uint4 r;
     // plain (coherent) streaming load: the apply pass may run in place (y == x)

@@ -17,15 +17,19 @@ namespace {
 
 constexpr int THREADS = 256;
 
-// One CTA per (image, group): the group's channels are contiguous per pixel (cg floats), pixels ld apart.
+// CTA (g, n, s) reduces pixel range s of S of group g of image n: the group's channels are contiguous per pixel
+// (cg floats), pixels ld apart.  fp32 sums of <= 64 values are folded in fp64; with S > 1 the partials meet in a
+// workspace and the LAST CTA of an (image, group) to arrive folds them in a fixed order (deterministic) and resets the
+// arrival counter for the next launch.
 __global__ void __launch_bounds__(THREADS) gn_stats_f32_kernel(const float* __restrict__ x, int64_t ld, int64_t hw, int c,
-                                                               int groups, float eps, float* __restrict__ stats) {
+                                                               int groups, float eps, float* __restrict__ stats,
+                                                               double* __restrict__ partial, int* __restrict__ counters) {
     pdl_enter();
-    const int g = blockIdx.x, n = blockIdx.y;
+    const int g = blockIdx.x, n = blockIdx.y, S = gridDim.z, sp = blockIdx.z;
     const int cg = c / groups, v4 = cg >> 2;  // float4 per pixel and group
-    const float* base = x + (int64_t)n * hw * ld + (int64_t)g * cg;
-    const int64_t items = hw * v4;
-    // pass over the data in chunks: fp32 sums of <= 64 values, folded in fp64 (matches torch's Welford result to ~1e-7)
+    const int64_t p_lo = hw * sp / S, p_hi = hw * (sp + 1) / S;
+    const float* base = x + ((int64_t)n * hw + p_lo) * ld + (int64_t)g * cg;
+    const int64_t items = (p_hi - p_lo) * v4;
     double s = 0.0, q = 0.0;
     for (int64_t i0 = threadIdx.x; i0 < items; i0 += (int64_t)THREADS * 16) {
         float fs = 0.f, fq = 0.f;
@@ -43,6 +47,7 @@ __global__ void __launch_bounds__(THREADS) gn_stats_f32_kernel(const float* __re
         s += (double)fs, q += (double)fq;
     }
     __shared__ double sh[2][THREADS / 32];
+    __shared__ int last;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -53,13 +58,32 @@ __global__ void __launch_bounds__(THREADS) gn_stats_f32_kernel(const float* __re
     if (threadIdx.x == 0) {
         double ts = 0.0, tq = 0.0;
         for (int w = 0; w < THREADS / 32; ++w) ts += sh[0][w], tq += sh[1][w];
-        const double cnt = (double)hw * cg;
-        const double mean = ts / cnt;
-        double var = tq / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        float* o = stats + ((int64_t)n * groups + g) * 2;
-        o[0] = (float)mean;
-        o[1] = (float)(1.0 / sqrt(var + (double)eps));
+        const int64_t slot = (int64_t)n * groups + g;
+        last = 1;
+        if (S > 1) {
+            double* mine = partial + (slot * S + sp) * 2;
+            mine[0] = ts, mine[1] = tq;
+            __threadfence();
+            last = atomicAdd(counters + slot, 1) == S - 1;
+            if (last) {
+                __threadfence();
+                ts = tq = 0.0;
+                for (int k = 0; k < S; ++k) {
+                    const volatile double* pk = partial + (slot * S + k) * 2;
+                    ts += pk[0], tq += pk[1];
+                }
+                counters[slot] = 0;
+            }
+        }
+        if (last) {
+            const double cnt = (double)hw * cg;
+            const double mean = ts / cnt;
+            double var = tq / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            float* o = stats + slot * 2;
+            o[0] = (float)mean;
+            o[1] = (float)(1.0 / sqrt(var + (double)eps));
+        }
     }
 }
 
@@ -79,22 +103,28 @@ struct ApplyParams {
 
 __device__ __forceinline__ float silu_exact(float v) { return v / (1.0f + __expf(-v)); }
 
-// item = (output pixel, float4 of channels).  The transform is applied per INPUT pixel; pooling averages the four
-// transformed values (the reference pools act(norm(x)), _src/unet.py:229-233).
+// Grid (x, output row, image); a thread walks the row's (pixel, float4-of-channels) items with a stride that is a
+// multiple of the channel vectors for the common widths, so its channel vector -- and with it the affine coefficients
+// (statistics, gamma / beta, scale / shift: five loads) -- stays the same and is computed once.  The transform is
+// applied per INPUT pixel; pooling averages the four transformed values (the reference pools act(norm(x)),
+// _src/unet.py:229-233).
 __global__ void __launch_bounds__(THREADS) gn_apply_f32_kernel(const ApplyParams p) {
     pdl_enter();
     const int v4 = p.c >> 2;
-    const int ho = p.mode == 1 ? 2 * p.h : p.mode == 2 ? p.h / 2 : p.h;
     const int wo = p.mode == 1 ? 2 * p.w : p.mode == 2 ? p.w / 2 : p.w;
-    const int64_t items = (int64_t)p.n * ho * wo * v4;
+    const int ho = p.mode == 1 ? 2 * p.h : p.mode == 2 ? p.h / 2 : p.h;
+    const int oh = blockIdx.y, n = blockIdx.z;
     const int cg = p.c / max(p.groups, 1);
-    for (int64_t it = (int64_t)blockIdx.x * THREADS + threadIdx.x; it < items; it += (int64_t)gridDim.x * THREADS) {
-        const int j = (int)(it % v4);
-        const int64_t opix = it / v4;
-        const int ow = (int)(opix % wo), oh = (int)((opix / wo) % ho), n = (int)(opix / ((int64_t)wo * ho));
+    const int items = wo * v4;
+    const float* xin = p.x + (int64_t)n * p.h * p.w * p.x_ld;
+    float* yout = p.y + ((int64_t)n * ho + oh) * wo * p.y_ld;
+    int jc = -1;
+    float a[4] = {1.f, 1.f, 1.f, 1.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int it = blockIdx.x * THREADS + threadIdx.x; it < items; it += gridDim.x * THREADS) {
+        const int ow = it / v4, j = it - ow * v4;
         const int ch = j * 4;
-        float a[4] = {1.f, 1.f, 1.f, 1.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p.stats) {
+        if (p.stats && j != jc) {
+            jc = j;
             const float* st = p.stats + ((int64_t)n * p.groups + ch / cg) * 2;  // (4 consecutive channels share a group: cg % 4 == 0)
             const float mean = __ldg(st), rstd = __ldg(st + 1);
             const float4 ga = __ldg(reinterpret_cast<const float4*>(p.gamma + ch)), be = __ldg(reinterpret_cast<const float4*>(p.beta + ch));
@@ -110,7 +140,7 @@ __global__ void __launch_bounds__(THREADS) gn_apply_f32_kernel(const ApplyParams
             }
         }
         auto load = [&](int ih, int iw) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p.x + (((int64_t)n * p.h + ih) * p.w + iw) * p.x_ld + ch));
+            const float4 v = ld_stream4_coherent(xin + ((int64_t)ih * p.w + iw) * p.x_ld + ch);  // (y may alias x)
             float f[4] = {fmaf(a[0], v.x, b[0]), fmaf(a[1], v.y, b[1]), fmaf(a[2], v.z, b[2]), fmaf(a[3], v.w, b[3])};
             if (p.silu) {
 #pragma unroll
@@ -128,7 +158,7 @@ __global__ void __launch_bounds__(THREADS) gn_apply_f32_kernel(const ApplyParams
         } else {
             o = load(oh, ow);
         }
-        *reinterpret_cast<float4*>(p.y + opix * p.y_ld + ch) = o;
+        stg_stream4(yout + (int64_t)ow * p.y_ld + ch, o);
     }
 }
 
@@ -153,13 +183,22 @@ int grid_of(int64_t items) {
 }  // namespace
 
 extern "C" int azb_gn_stats_f32(const float* x, int64_t ld, int64_t n, int64_t hw, int64_t c, int64_t groups, float eps,
-                                float* stats, void* stream) {
+                                float* stats, void* workspace, int64_t workspace_bytes, void* stream) {
     AZB_CHECK_PTR(x);
     AZB_CHECK_PTR(stats);
     if (n <= 0 || hw <= 0 || c <= 0 || groups <= 0 || c % groups || (c / groups) % 4 || n > 65535) return AZB_E_SHAPE;
     if (ld % 4 || ld < c || !azb_aligned(x, 16)) return AZB_E_ALIGN;
-    return azb_launch(gn_stats_f32_kernel, dim3((unsigned)groups, (unsigned)n), dim3(THREADS), 0, reinterpret_cast<cudaStream_t>(stream),
-                      x, ld, hw, (int)c, (int)groups, eps, stats);
+    // pixel ranges per (image, group): enough CTAs to fill the machine on large maps, one on small ones
+    int64_t S = hw / 2048;
+    if (S > 16) S = 16;
+    if (S < 1) S = 1;
+    const int64_t slots = n * groups;
+    const int64_t need = ((slots * 4 + 255) / 256) * 256 + slots * S * 16;
+    if (S > 1 && (!workspace || workspace_bytes < need || !azb_aligned(workspace, 256))) S = 1;  // no scratch: one CTA per slot
+    int* counters = reinterpret_cast<int*>(workspace);
+    double* partial = S > 1 ? reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + ((slots * 4 + 255) / 256) * 256) : nullptr;
+    return azb_launch(gn_stats_f32_kernel, dim3((unsigned)groups, (unsigned)n, (unsigned)S), dim3(THREADS), 0,
+                      reinterpret_cast<cudaStream_t>(stream), x, ld, hw, (int)c, (int)groups, eps, stats, partial, counters);
 }
 
 extern "C" int azb_gn_apply_f32(const float* x, int64_t x_ld, float* y, int64_t y_ld, int64_t n, int64_t h, int64_t w, int64_t c,
@@ -175,7 +214,11 @@ extern "C" int azb_gn_apply_f32(const float* x, int64_t x_ld, float* y, int64_t 
     ApplyParams p{x, x_ld, y, y_ld, (int)n, (int)h, (int)w, (int)c, (int)(stats ? groups : 1), stats, gamma, beta, stats ? scale_shift : nullptr,
                   ss_stride, silu, mode};
     const int64_t ho = mode == 1 ? 2 * h : mode == 2 ? h / 2 : h, wo = mode == 1 ? 2 * w : mode == 2 ? w / 2 : w;
-    return azb_launch(gn_apply_f32_kernel, dim3((unsigned)grid_of(n * ho * wo * (c / 4))), dim3(THREADS), 0,
+    if (ho > 65535 || n > 65535 || wo * (c / 4) > 0x7fffffffLL) return AZB_E_SHAPE;
+    // a row of items per (output row, image); up to 4 items per thread so that the stride keeps the channel vector fixed
+    int64_t gx = (wo * (c / 4) + 4 * THREADS - 1) / (4 * THREADS);
+    if (gx < 1) gx = 1;
+    return azb_launch(gn_apply_f32_kernel, dim3((unsigned)gx, (unsigned)ho, (unsigned)n), dim3(THREADS), 0,
                       reinterpret_cast<cudaStream_t>(stream), p);
 }
 

@@ -123,6 +123,7 @@ class PlanTF32:
         self.emb = torch.empty(rows, D, **f32)
         self.emb_all = torch.empty(rows, packed.emb_total, **f32)
         self.x_nhwc = torch.empty(n, h, w, packed.c_in_pad, **f32)
+        self.stats_ws = ops.gn_stats_workspace_f32(n, ops.GN_GROUPS, device)
 
         L = len(lay.encoder)
         sizes, hh, ww = [], h, w
@@ -175,7 +176,7 @@ class PlanTF32:
         st = torch.empty(n, ops.GN_GROUPS, 2, dtype=torch.float32, device=self.device)
         self.keep += [x, st]
         self._emit("gn_stats", 0.0, 4.0 * n * h * w * c, self.lib.azb_gn_stats_f32, x.data_ptr(), ops._ld(x), n, h * w, c,
-                   ops.GN_GROUPS, ops.GN_EPS, st.data_ptr(), desc=f"{n}x{h}x{w}x{c}")
+                   ops.GN_GROUPS, ops.GN_EPS, st.data_ptr(), self.stats_ws.data_ptr(), self.stats_ws.numel(), desc=f"{n}x{h}x{w}x{c}")
         return st
 
     def _apply(self, x: Tensor, out: Tensor, stats: Tensor | None, affine, emb_offset: int | None, silu: bool, mode: int) -> None:

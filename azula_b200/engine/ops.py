@@ -62,7 +62,8 @@ _lib.register({
         [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_void_p,
          c_int, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p],
     ),
-    "azb_gn_stats_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p]),
+    "azb_gn_stats_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p, c_void_p, c_int64,
+                                 c_void_p]),
     "azb_gn_apply_f32": (
         c_int,
         [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
@@ -782,13 +783,21 @@ def conv_tf32(x: Tensor, pc: PackedConv, out: Tensor | None = None, stride: int 
     return out
 
 
-def gn_stats_f32(x: Tensor, groups: int = GN_GROUPS, eps: float = GN_EPS, stats: Tensor | None = None) -> Tensor:
+def gn_stats_workspace_f32(n: int, groups: int, device) -> Tensor:
+    r"""Zeroed scratch for :func:`gn_stats_f32` (arrival counters + fp64 partial sums of up to 16 CTAs per slot)."""
+    slots = n * groups
+    return torch.zeros(-(-slots * 4 // 256) * 256 + slots * 16 * 16, dtype=torch.uint8, device=device)
+
+
+def gn_stats_f32(x: Tensor, groups: int = GN_GROUPS, eps: float = GN_EPS, stats: Tensor | None = None,
+                 workspace: Tensor | None = None) -> Tensor:
     r"""``azb_gn_stats_f32``: (N, groups, 2) = {mean, rstd} of an fp32 NHWC tensor."""
     n, h, w, c = x.shape
     if stats is None:
         stats = torch.empty(n, groups, 2, dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().azb_gn_stats_f32(x.data_ptr(), _ld(x), n, h * w, c, groups, eps, stats.data_ptr(),
-                                           _lib.stream_ptr(x.device)), "azb_gn_stats_f32")
+    _lib.check(_lib.lib().azb_gn_stats_f32(x.data_ptr(), _ld(x), n, h * w, c, groups, eps, stats.data_ptr(), _lib.ptr(workspace),
+                                           0 if workspace is None else workspace.numel(), _lib.stream_ptr(x.device)),
+               "azb_gn_stats_f32")
     return stats
 
 

@@ -318,7 +318,10 @@ int azb_conv_tf32(const void* act, int64_t n, int64_t h, int64_t w, int64_t c_in
  *   y = act(((x - mean) rstd gamma + beta) (1 + scale) + shift)   followed by nearest 2x upsampling (mode 1) or 2 x 2
  * average pooling (mode 2) of the result; stats NULL = resampling only.  scale_shift: [scale(c) | shift(c)] per sample. */
 int azb_gn_stats_f32(const float* x, int64_t ld, int64_t n, int64_t hw, int64_t c, int64_t groups, float eps, float* stats,
-                     void* stream);
+                     void* workspace, int64_t workspace_bytes, void* stream);
+/* (workspace: optional scratch, 256-byte aligned, ZERO-initialised once by the caller and left zeroed by the kernel --
+ * 256-byte-rounded n * groups * 4 bytes of arrival counters + n * groups * 16 * 16 bytes of fp64 partial sums let large
+ * maps be reduced by up to 16 CTAs per (image, group), folded in a fixed order by the last one to arrive.) */
 int azb_gn_apply_f32(const float* x, int64_t x_ld, float* y, int64_t y_ld, int64_t n, int64_t h, int64_t w, int64_t c,
                      int64_t groups, const float* stats, const float* gamma, const float* beta, const float* scale_shift,
                      int64_t ss_stride, int silu, int mode, void* stream);

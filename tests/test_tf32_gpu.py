@@ -92,7 +92,7 @@ def test_conv_tf32_channel_slices_and_activation():
     assert _rel(wide[..., :128], ref) <= 1.5e-3 and (wide[..., 128:] == 7.0).all()
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 16, 256), (3, 8, 12, 128), (1, 64, 64, 512)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 256), (3, 8, 12, 128), (1, 64, 64, 512), (2, 128, 64, 768), (1, 8, 8, 2048)])
 def test_groupnorm_f32(shape):
     n, h, w, c = shape
     g = torch.Generator(device=DEV).manual_seed(7)
@@ -100,6 +100,10 @@ def test_groupnorm_f32(shape):
     gamma, beta = 1 + 0.1 * torch.randn(c, device=DEV, generator=g), 0.1 * torch.randn(c, device=DEV, generator=g)
     ss = 0.2 * torch.randn(n, 2 * c, device=DEV, generator=g)
     st = ops.gn_stats_f32(x)
+    ws = ops.gn_stats_workspace_f32(n, 32, DEV)  # large maps: several CTAs per (image, group), fixed fold order
+    for _ in range(2):
+        assert torch.allclose(ops.gn_stats_f32(x, workspace=ws), st, rtol=1e-6, atol=1e-7)
+    assert (ws[: n * 32 * 4] == 0).all(), "arrival counters must be left zeroed"
     xc = x.permute(0, 3, 1, 2)
     grp = xc.double().reshape(n, 32, -1)
     assert torch.allclose(st[..., 0].double(), grp.mean(-1), atol=1e-5)
@@ -185,7 +189,7 @@ def test_tf32_sampler_through_the_graph():
     x1 = torch.randn(4, 3, 32, 32, device=DEV, generator=torch.Generator(device=DEV).manual_seed(13))
     sched = lambda t: RM.vp_alpha_sigma(t, 1e-2, 1e-2)  # noqa: E731
     sig = RM.adm_sigmas().to(DEV)
-    net = lambda xx, tt, y_=None: AU.forward(sd, tab, xx, tt, y_)  # noqa: E731
+    net = lambda xx, tt, y=None: AU.forward(sd, tab, xx, tt, y)  # noqa: E731
     mean = lambda xx, tt: RM.adm_mean_var(net, sched, sig, xx, tt, label=y)[0]  # noqa: E731
     ref = RM.sample_loop(mean, sched, x1, steps=6, eta=0.0)  # fp32, TF32 off
     smp = DDIMSampler(den, steps=6, silent=True, graph=True)
