@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                      const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_out,
                      const ConvParams p) {
     constexpr bool LEAN = EPI == 1;
-    static_assert(!TF32 || (!HALO && !PAIR), "the TF32 mode uses the tap-wise single-CTA kernels");
+    static_assert(!TF32 || !HALO, "the TF32 mode uses the tap-wise kernels");
     static_assert((EPI == 3) == (TF32 && EPI != 0), "EPI 3 is the TF32 mode's NHWC epilogue");
     constexpr int KE = TF32 ? BLOCK_K / 2 : BLOCK_K;  // elements per k-block (128 bytes)
     using C = Cfg<BLOCK_N, PAIR, HALO>;
@@ -611,7 +611,8 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (leader && tc::elect_one()) {
-            constexpr uint32_t idesc = TF32 ? tc::idesc_tf32_f32(BLOCK_M, BLOCK_N) : tc::idesc_bf16_f32(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+            constexpr uint32_t idesc = TF32 ? tc::idesc_tf32_f32(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N)
+                                            : tc::idesc_bf16_f32(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
             int s = 0;
             uint32_t parity = 0;
             for (int local = 0; local < tile_count; ++local) {
@@ -629,7 +630,9 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // +32 bytes per K=16 step inside the 128-byte swizzle row (address field is >>4)
-                        if constexpr (PAIR)
+                        if constexpr (PAIR && TF32)
+                            tc::mma_tf32_ss_pair(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        else if constexpr (PAIR)
                             tc::mma_f16_ss_pair(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                         else if constexpr (TF32)  // K = 8 fp32 words = the same 32 bytes per operand row
                             tc::mma_tf32_ss(tmem_acc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
@@ -731,7 +734,10 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
             }
             tc::fence_before_sync();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[as]));
+            if (lane == 0) {
+                if (PAIR && !leader) tc::mbar_arrive_cluster(tc::mapa(tc::smem_u32(&bar_acc_empty[as]), 0));
+                else tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[as]));
+            }
         }
     } else if constexpr (EPI == 2) {
         // ===== epilogue, row domain + TMA store (see the kernel's header) =====
@@ -1673,11 +1679,17 @@ int conv_tf32_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64
         block_n = cand[i];
         if (m_tiles * (c_out_rows / cand[i]) >= (sms * 3) / 4 || cand[i] <= 64) break;
     }
+    if (g_knob[AZB_CONV_KNOB_BLOCKN] >= 16 && c_out_rows % g_knob[AZB_CONV_KNOB_BLOCKN] == 0 && out_mode == 0) block_n = g_knob[AZB_CONV_KNOB_BLOCKN];
     if (c_out_rows % block_n || c_out_rows < c_out) return AZB_E_SHAPE;
     p.n_tiles = (int)(c_out_rows / block_n);
     if (m_tiles * p.n_tiles > 0x7fffffffLL) return AZB_E_SHAPE;
     p.tiles_out = (int)(m_tiles * p.n_tiles);
-    p.total_tiles = p.tiles_out;
+    // CTA pairs (two SMs share a 256-pixel x N tile, each stages half of the weight tile): as in the bf16 kernels, for wide
+    // tiles, an even number of M tiles and reductions of at least 16 k-blocks
+    const int64_t num_kb_total = (int64_t)taps * (k_per_tap / KE);
+    bool pair = out_mode == 0 && block_n >= 128 && m_tiles % 2 == 0 && g_knob[AZB_CONV_KNOB_PAIR] != 0;
+    if (pair && g_knob[AZB_CONV_KNOB_PAIR] < 0) pair = num_kb_total >= 16;
+    p.total_tiles = pair ? p.tiles_out / 2 : p.tiles_out;
     p.phases = 1, p.splits = 1;
     p.taps = taps, p.ksize = taps == 9 ? 3 : 1, p.pad = taps == 9 ? 1 : 0;
     p.kb_per_tap = (int)(k_per_tap / KE);
@@ -1705,7 +1717,7 @@ int conv_tf32_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64
         const int64_t k_total = (int64_t)taps * k_per_tap;
         uint64_t dims[2] = {(uint64_t)k_total, (uint64_t)c_out_rows};
         uint64_t str[1] = {(uint64_t)k_total * 4};
-        uint32_t box[2] = {KE, (uint32_t)block_n};
+        uint32_t box[2] = {KE, (uint32_t)(pair ? block_n / 2 : block_n)};  // a pair member stages half the rows
         const int rc = tc::make_map_typed(&tb, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, wpack, 2, dims, str, box);
         if (rc) return rc == -1 ? AZB_E_DRIVER : AZB_E_SHAPE;
     }
@@ -1717,6 +1729,7 @@ int conv_tf32_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64
             default: return AZB_E_UNSUPPORTED;  // (the network's output convolution has 3 or 6 channels)
         }
     }
+    if (pair) return block_n == 256 ? launch<256, true, 3, false, true>(ta, tb, ta, p, s) : launch<128, true, 3, false, true>(ta, tb, ta, p, s);
     switch (block_n) {
         case 256: return launch<256, false, 3, false, true>(ta, tb, ta, p, s);
         case 128: return launch<128, false, 3, false, true>(ta, tb, ta, p, s);

@@ -697,6 +697,12 @@ if os.environ.get("AZB_PDL", "") == "0":  # A/B switch: plain stream-ordered lau
     except Exception:  # library not built yet: the first real call reports it
         pass
 
+if os.environ.get("AZB_PAIR", "") in ("0", "1"):  # A/B switch: CTA pairs never / whenever possible
+    try:
+        conv_tuning(KNOB_PAIR, int(os.environ["AZB_PAIR"]))
+    except Exception:
+        pass
+
 if os.environ.get("AZB_ROWEPI", "") == "0":  # A/B switch: the shared-memory-transpose epilogue instead of TMA stores
     try:
         conv_tuning(KNOB_ROWEPI, 0)

@@ -80,6 +80,31 @@ def test_conv_tf32_against_float64_and_cudnn_tf32(shape):
     assert half.dtype == torch.float16 and _rel(half, ref64 - res.double()) <= 2e-3
 
 
+@pytest.mark.parametrize("blockn", [128, 256])
+@pytest.mark.parametrize("shape", [(2, 32, 32, 256, 256, 3), (1, 64, 64, 128, 512, 3), (2, 20, 24, 96, 256, 3), (4, 16, 16, 1024, 256, 1)])
+def test_conv_tf32_cta_pairs_equal_single_cta_bits(shape, blockn):
+    """cta_group::2 pairs (two SMs share a 256-pixel tile) accumulate every output element in the same K order as the
+    single-CTA kernel: bit-equal results."""
+    n, h, w, ci, co, k = shape
+    g = torch.Generator(device=DEV).manual_seed(17)
+    x = torch.randn(n, h, w, ci, device=DEV, generator=g)
+    wt = torch.randn(co, ci, k, k, device=DEV, generator=g) / (ci * k * k) ** 0.5
+    pc = ops.pack_conv_f32(wt, torch.randn(co, device=DEV, generator=g))
+    res = torch.randn(n, h, w, co, device=DEV, generator=g)
+    try:
+        ops.conv_tuning(ops.KNOB_BLOCKN, blockn)
+        ops.conv_tuning(ops.KNOB_PAIR, 1)
+        pair = ops.conv_tf32(x, pc, residual=res)
+        ops.conv_tuning(ops.KNOB_PAIR, 0)
+        single = ops.conv_tf32(x, pc, residual=res)
+    finally:
+        ops.conv_tuning(ops.KNOB_BLOCKN, -1)
+        ops.conv_tuning(ops.KNOB_PAIR, -1)
+    assert torch.equal(pair, single)
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), wt.double(), pc.bias.double(), padding=k // 2).permute(0, 2, 3, 1) + res.double()
+    assert _rel(pair, ref) <= 1e-3
+
+
 def test_conv_tf32_channel_slices_and_activation():
     g = torch.Generator(device=DEV).manual_seed(5)
     x_wide = torch.randn(2, 16, 16, 192, device=DEV, generator=g)
