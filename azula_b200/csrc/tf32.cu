@@ -29,17 +29,17 @@ __global__ void __launch_bounds__(THREADS) gn_stats_f32_kernel(const float* __re
     const int cg = c / groups, v4 = cg >> 2;  // float4 per pixel and group
     const int64_t p_lo = hw * sp / S, p_hi = hw * (sp + 1) / S;
     const float* base = x + ((int64_t)n * hw + p_lo) * ld + (int64_t)g * cg;
-    const int64_t items = (p_hi - p_lo) * v4;
+    const uint32_t items = (uint32_t)((p_hi - p_lo) * v4);  // (the host keeps a CTA's share below 2^31 items)
     double s = 0.0, q = 0.0;
-    for (int64_t i0 = threadIdx.x; i0 < items; i0 += (int64_t)THREADS * 16) {
+    for (uint32_t i0 = threadIdx.x; i0 < items; i0 += THREADS * 16u) {
         float fs = 0.f, fq = 0.f;
 #pragma unroll 4
         for (int u = 0; u < 16; ++u) {
-            const int64_t i = i0 + (int64_t)u * THREADS;
+            const uint32_t i = i0 + (uint32_t)u * THREADS;
             if (i < items) {
-                const int64_t pix = i / v4;
-                const int j = (int)(i - pix * v4);
-                const float4 v = __ldg(reinterpret_cast<const float4*>(base + pix * ld) + j);
+                const uint32_t pix = i / (uint32_t)v4;  // 32-bit: a 64-bit division per 16 bytes made this pass ALU-bound
+                const uint32_t j = i - pix * (uint32_t)v4;
+                const float4 v = ldg_stream4(base + (int64_t)pix * ld + 4 * j);
                 fs += (v.x + v.y) + (v.z + v.w);
                 fq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, fq))));
             }
@@ -101,7 +101,7 @@ struct ApplyParams {
     int silu, mode;      // mode 0: same size, 1: nearest 2x upsampling of the result, 2: 2 x 2 average pooling of the result
 };
 
-__device__ __forceinline__ float silu_exact(float v) { return v / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu_exact(float v) { return __fdividef(v, 1.0f + __expf(-v)); }  // ~2e-6 relative
 
 // Grid (x, output row, image); a thread walks the row's (pixel, float4-of-channels) items with a stride that is a
 // multiple of the channel vectors for the common widths, so its channel vector -- and with it the affine coefficients
@@ -192,6 +192,7 @@ extern "C" int azb_gn_stats_f32(const float* x, int64_t ld, int64_t n, int64_t h
     int64_t S = hw / 2048;
     if (S > 16) S = 16;
     if (S < 1) S = 1;
+    if ((hw / S + 1) * (c / groups / 4) > 0x7fffffffLL) return AZB_E_SHAPE;
     const int64_t slots = n * groups;
     const int64_t need = ((slots * 4 + 255) / 256) * 256 + slots * S * 16;
     if (S > 1 && (!workspace || workspace_bytes < need || !azb_aligned(workspace, 256))) S = 1;  // no scratch: one CTA per slot
@@ -215,8 +216,9 @@ extern "C" int azb_gn_apply_f32(const float* x, int64_t x_ld, float* y, int64_t 
                   ss_stride, silu, mode};
     const int64_t ho = mode == 1 ? 2 * h : mode == 2 ? h / 2 : h, wo = mode == 1 ? 2 * w : mode == 2 ? w / 2 : w;
     if (ho > 65535 || n > 65535 || wo * (c / 4) > 0x7fffffffLL) return AZB_E_SHAPE;
-    // a row of items per (output row, image); up to 4 items per thread so that the stride keeps the channel vector fixed
-    int64_t gx = (wo * (c / 4) + 4 * THREADS - 1) / (4 * THREADS);
+    // a row of items per (output row, image); up to 16 items per thread (the stride keeps the channel vector fixed for
+    // the common widths, so the coefficient set-up is amortised over them)
+    int64_t gx = (wo * (c / 4) + 16 * THREADS - 1) / (16 * THREADS);
     if (gx < 1) gx = 1;
     return azb_launch(gn_apply_f32_kernel, dim3((unsigned)gx, (unsigned)ho, (unsigned)n), dim3(THREADS), 0,
                       reinterpret_cast<cudaStream_t>(stream), p);
