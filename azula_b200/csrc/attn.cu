@@ -253,7 +253,19 @@ int launch_attn(const AttnParams& p, int n, cudaStream_t s) {
 }  // namespace
 
 int azb_attention_tc_launch(const void* qkv, int64_t ld, void* out, int64_t out_ld, int64_t n, int64_t t, int64_t heads,
-                            int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta, void* stream);  // attn_tc.cu
+                            int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta, int qk_norm, float qk_eps,
+                            void* stream);  // attn_tc.cu
+
+// Attention with the per-head RMS normalisation of q and k folded into the logits (T <= 256, d = 64: DiT tokens):
+// replaces azb_segment_rmsnorm_bf16 + azb_attention_bf16 (azula/nn/attention.py:103,110-116).
+extern "C" int azb_attention_qknorm_bf16(const void* qkv, int64_t ld, void* out, int64_t out_ld, int64_t n, int64_t t,
+                                         int64_t heads, int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta,
+                                         float qk_eps, void* stream) {
+    AZB_CHECK_PTR(qkv);
+    AZB_CHECK_PTR(out);
+    if (n <= 0 || t <= 0 || heads <= 0 || n > 65535 || heads > 65535) return AZB_E_SHAPE;
+    return azb_attention_tc_launch(qkv, ld, out, out_ld, n, t, heads, d, head_stride, k_delta, v_delta, 1, qk_eps, stream);
+}
 
 extern "C" int azb_attention_bf16(const void* qkv, int64_t ld, void* out, int64_t out_ld, int64_t n, int64_t t,
                                   int64_t heads, int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta,
@@ -262,7 +274,7 @@ extern "C" int azb_attention_bf16(const void* qkv, int64_t ld, void* out, int64_
     AZB_CHECK_PTR(out);
     if (n <= 0 || t <= 0 || heads <= 0 || n > 65535 || heads > 65535) return AZB_E_SHAPE;
     // head width 64 (every ADM card, DiT-B): tcgen05 kernel; other widths: the mma.sync kernel below
-    const int rc = azb_attention_tc_launch(qkv, ld, out, out_ld, n, t, heads, d, head_stride, k_delta, v_delta, stream);
+    const int rc = azb_attention_tc_launch(qkv, ld, out, out_ld, n, t, heads, d, head_stride, k_delta, v_delta, 0, 0.f, stream);
     if (rc != AZB_E_UNSUPPORTED) return rc;
     return azb_attention_mma_bf16(qkv, ld, out, out_ld, n, t, heads, d, head_stride, k_delta, v_delta, stream);
 }

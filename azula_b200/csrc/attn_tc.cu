@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "tc.cuh"
 
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace {
@@ -54,6 +55,13 @@ __device__ __forceinline__ float ex2_fast(float v) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
+// Two positive fp32 values -> packed bf16 pair, round to nearest (ties away) with integer adds and one byte permute: the
+// conversion instruction (F2FP.BF16.PACK_AB) shares the MUFU pipe with the exponentials (ncu: XU pipe 1.5 x the ex2 count).
+__device__ __forceinline__ uint32_t pack_bf16_pos(float lo, float hi) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(r) : "r"(__float_as_uint(lo) + 0x8000u), "r"(__float_as_uint(hi) + 0x8000u));
+    return r;
+}
 __device__ __forceinline__ void softmax_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * SOFTMAX_WARPS) : "memory"); }
 
 struct AttnTcParams {
@@ -62,6 +70,8 @@ struct AttnTcParams {
     int T, heads;
     int head_stride, k_delta, v_delta;
     float scale_log2e;
+    int turns;         // short-sequence kernel: the two softmax groups exponentiate in turns (AZB_ATTN_TURNS, A/B switch)
+    long long* trace;  // diagnosis only (AZB_ATTN_TRACE=<file>, short-sequence kernel): clock64 per (CTA, role, item, event)
 };
 
 template <int BK>
@@ -300,6 +310,406 @@ __global__ void __launch_bounds__(THREADS, Cfg<BK>::CTAS_PER_SM)
     if (warp == SOFTMAX_WARPS + 1) tc::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Short sequences (T <= 256: DiT-B/2 tokens, the 16 x 16 and 8 x 8 levels of ADM): a PERSISTENT kernel, one CTA per SM,
+// work item = one (image, head) = 2 tiles of 128 queries x all (<= 256) keys.  Everything a tile needs stays on chip:
+//   tensor memory   group g owns columns [256 g, 256 g + 256): the fp32 logits S_g of its 128 queries, then P_g as bf16
+//                   PAIRS written back by tcgen05.st over logits that are already consumed, and the output accumulator
+//                   O_g (64 columns) -- P is the A operand of P V straight from tensor memory (tcgen05.mma with A in
+//                   TMEM), so the probabilities never touch shared memory.  T > 224: P chunks 0-3 in [0, 64), O in
+//                   [64, 128), P chunks 4-7 in [128, 192), and P V starts on the first half while the second is still
+//                   being exponentiated; shorter sequences: P in [0, 16 chunks), O in [128, 192)
+//   shared memory   two stages of {Q, K} (64 KiB) and two of V (32 KiB): the {Q, K} stage of item j + 2 is released as
+//                   soon as the two logit MMAs of item j retire, a whole item ahead of its use
+//   warps 0-3 / 4-7 softmax groups 0 / 1: thread = query row (the whole row of logits sits in the thread's TMEM lane: no
+//                   shuffles, no exchange through shared memory); exact two-pass softmax out of tensor memory (row
+//                   maximum, then P = exp2(c1 s + c0), the sum of the unrounded values), O / sum -> bf16 -> global
+//   warp 8          TMA producer (Q, K, V of an item are three boxes of 256 tokens x 64 channels of one tensor map; rows
+//                   beyond T are zero-filled)
+//   warps 9, 10     MMA issuers, one per group (a single thread each, asleep on the group's barriers between issues):
+//                   S_g of the next item once group g has drained O_g, P_g V once P_g is written.  Nothing couples the
+//                   groups except the stage rings, so they drift apart and one exponentiates (the MUFU pipe, 16 / clk /
+//                   SM, is the floor of this kernel) while the other waits for its MMAs and reads O.  (A single polling
+//                   issuer was measured first: its spin loop took issue slots from the softmax warps of its scheduler.)
+// QKNORM: the per-head RMS normalisation of q and k (azula/nn/attention.py:103, elementwise_affine = False) is applied
+// to the landed Q / K rows IN PLACE in shared memory by the softmax threads (row t of both by thread t, one item ahead of
+// the logits), with the arithmetic of azb_segment_rmsnorm_bf16 -- the separate pass over the qkv projection is gone.
+constexpr int TQ = 256;                       // tokens per item
+constexpr int T256_THREADS = 352;         // 2 softmax groups x 4 warps, TMA producer, one MMA issuer per group
+constexpr int T256_QK_STAGE = 2 * TQ * 128;   // Q + K
+constexpr int T256_V_STAGE = TQ * 128;
+constexpr int T256_SMEM = 2 * T256_QK_STAGE + 2 * T256_V_STAGE + 2 * BQ * 128 + 1024;  // + one output staging tile per group
+
+template <bool QKNORM>
+__global__ void __launch_bounds__(T256_THREADS, 1)
+    attention_t256_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const AttnTcParams p,
+                          const int items, const float qk_eps) {
+    pdl_enter();
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    auto q_smem = [&](int s) -> uint32_t { return smem_base + (uint32_t)s * T256_QK_STAGE; };
+    auto k_smem = [&](int s) -> uint32_t { return smem_base + (uint32_t)s * T256_QK_STAGE + TQ * 128; };
+    auto v_smem = [&](int s) -> uint32_t { return smem_base + 2 * T256_QK_STAGE + (uint32_t)s * T256_V_STAGE; };
+
+    __shared__ __align__(8) uint64_t bar_qk_full[2], bar_qk_ready[2], bar_qk_free[2], bar_v_full[2], bar_v_free[2];
+    __shared__ __align__(8) uint64_t bar_s[2], bar_p[2], bar_o[2], bar_sfree[2], bar_turn[2];
+    __shared__ uint32_t tmem_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto mark = [&](int role, int j, int e) {  // role 0 / 1: softmax groups, 2 / 3: their MMA issuers
+        if (p.trace && j < 8) p.trace[(((int64_t)blockIdx.x * 4 + role) * 8 + j) * 8 + e] = clock64();
+    };
+    const int n_my = (int)blockIdx.x < items ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int tiles = p.T > BQ ? 2 : 1;       // query tiles per item (group 1 idles on sequences of <= 128 tokens)
+    const int nkc = (p.T + 31) >> 5;          // 32-key chunks that hold valid keys
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(tc::smem_u32(&bar_qk_full[s]), 1);
+            tc::mbar_init(tc::smem_u32(&bar_qk_ready[s]), 8);
+            tc::mbar_init(tc::smem_u32(&bar_qk_free[s]), tiles);
+            tc::mbar_init(tc::smem_u32(&bar_v_full[s]), 1);
+            tc::mbar_init(tc::smem_u32(&bar_v_free[s]), tiles);
+            tc::mbar_init(tc::smem_u32(&bar_s[s]), 1);
+            tc::mbar_init(tc::smem_u32(&bar_p[s]), 4);
+            tc::mbar_init(tc::smem_u32(&bar_o[s]), 1);
+            tc::mbar_init(tc::smem_u32(&bar_sfree[s]), 4);
+            tc::mbar_init(tc::smem_u32(&bar_turn[s]), 4);
+        }
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tmap);
+        tc::prefetch_tmap(&tmap_out);
+    }
+    if (warp == 9) {
+        tc::tmem_alloc(tc::smem_u32(&tmem_slot), 512);
+        tc::tmem_relinquish();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = tmem_slot;
+
+    if (warp == 8) {
+        // ===== TMA producer =====
+        if (tc::elect_one()) {
+            for (int j = 0; j < n_my; ++j) {
+                const int item = (int)blockIdx.x + j * (int)gridDim.x;
+                const int img = item / p.heads, hd = item - img * p.heads;
+                const int ch_q = hd * p.head_stride, s = j & 1;
+                const uint32_t par = ((uint32_t)(j >> 1) & 1u) ^ 1u;
+                tc::mbar_wait(tc::smem_u32(&bar_qk_free[s]), par);
+                const uint32_t full = tc::smem_u32(&bar_qk_full[s]);
+                tc::mbar_expect_tx(full, T256_QK_STAGE);
+                tc::tma_load_3d(q_smem(s), &tmap, full, ch_q, 0, img);
+                tc::tma_load_3d(k_smem(s), &tmap, full, ch_q + p.k_delta, 0, img);
+                tc::mbar_wait(tc::smem_u32(&bar_v_free[s]), par);
+                const uint32_t vfull = tc::smem_u32(&bar_v_full[s]);
+                tc::mbar_expect_tx(vfull, T256_V_STAGE);
+                tc::tma_load_3d(v_smem(s), &tmap, vfull, ch_q + p.v_delta, 0, img);
+            }
+        }
+    } else if (warp >= 9) {
+        // ===== MMA issuers: warp 9 + g issues the MMAs of group g, in order, sleeping on the group's barriers =====
+        const int g = warp - 9;
+        if (g < tiles && tc::elect_one()) {
+            constexpr uint32_t idesc_s = tc::idesc_bf16_f32(BQ, TQ);
+            constexpr uint32_t idesc_o = tc::idesc_bf16_f32_b_mn(BQ, D);
+            // P in two halves when all 8 chunks are in use (see the softmax groups): P chunks [0, 4) in columns [0, 64), O in
+            // [64, 128) (logits consumed by the first half), P chunks [4, 8) in [128, 192); otherwise P in [0, 16 nkc), O in
+            // [128, 192) and no early start
+            const int nh = nkc == 8 ? 4 : 0;
+            const uint32_t p2_col = nh ? 128u : 0u, o_col = nh ? 64u : 128u;
+            const uint32_t tmem_g = tmem_base + (uint32_t)(g * 256);
+            for (int j = 0; j < n_my; ++j) {
+                const int s = j & 1;
+                const uint32_t par = (uint32_t)(j >> 1) & 1u;
+                // S_g = Q_g K^T once the group has drained O_g of the previous item and Q / K have landed (and are normalised)
+                tc::mbar_wait(tc::smem_u32(&bar_sfree[g]), ((uint32_t)j & 1u) ^ 1u);
+                mark(2 + g, j, 0);
+                tc::mbar_wait(tc::smem_u32(QKNORM ? &bar_qk_ready[s] : &bar_qk_full[s]), par);
+                mark(2 + g, j, 1);
+                tc::fence_after_sync();
+                const uint64_t desc_q = tc::smem_desc_sw128(q_smem(s) + (uint32_t)g * (BQ * 128));
+                const uint64_t desc_k = tc::smem_desc_sw128(k_smem(s));
+#pragma unroll
+                for (int k = 0; k < D / 16; ++k)
+                    tc::mma_f16_ss(tmem_g, desc_q + (uint64_t)(2 * k), desc_k + (uint64_t)(2 * k), idesc_s, k != 0);
+                tc::mma_commit(tc::smem_u32(&bar_s[g]));
+                if (j + 2 < n_my) tc::mma_commit(tc::smem_u32(&bar_qk_free[s]));  // (both groups' logit MMAs: count = tiles)
+                // P_g V -> O_g, in two halves: the first k-steps run while the group still exponentiates the rest
+                tc::mbar_wait(tc::smem_u32(&bar_v_full[s]), par);
+                mark(2 + g, j, 2);
+                const uint32_t v_src = v_smem(s);
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    tc::mbar_wait(tc::smem_u32(&bar_p[g]), (uint32_t)half);
+                    mark(2 + g, j, 3 + half);
+                    tc::fence_after_sync();
+                    const int k0 = half ? 2 * nh : 0, k1 = half ? 2 * nkc : 2 * nh;
+                    for (int k = k0; k < k1; ++k)  // 16 keys per step: 8 packed columns of P, 2048 bytes of V
+                        tc::mma_f16_ts(tmem_g + o_col, tmem_g + (k < 2 * nh ? 8u * (uint32_t)k : p2_col + 8u * (uint32_t)(k - 2 * nh)),
+                                       tc::smem_desc_sw128(v_src + (uint32_t)k * 2048u), idesc_o, k != 0);
+                }
+                tc::mma_commit(tc::smem_u32(&bar_o[g]));
+                mark(2 + g, j, 5);
+                if (j + 2 < n_my) tc::mma_commit(tc::smem_u32(&bar_v_free[s]));
+            }
+        }
+    } else {
+        // ===== softmax groups =====
+        const int g = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;  // == TMEM lane; query g * 128 + row
+        const uint32_t tmem_g = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * 256);
+        const int t = (int)threadIdx.x;          // 0 .. 255: the Q / K row this thread normalises
+        const uint32_t o_stage = smem_base + 2 * T256_QK_STAGE + 2 * T256_V_STAGE + (uint32_t)g * (BQ * 128);
+        const bool tracer_thread = (warp & 3) == 0 && lane == 0;  // the group's thread that talks to the TMA unit
+        bool store_pending = false;
+        auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+        auto normalise = [&](int j) {
+            const int s = j & 1;
+            tc::mbar_wait(tc::smem_u32(&bar_qk_full[s]), (uint32_t)(j >> 1) & 1u);
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                // the eight 16-byte slots of a row in an order that keeps a quarter warp on distinct banks (a sum of
+                // squares does not care which channels a slot holds, and every slot is scaled alike)
+                const uint32_t base = (which ? k_smem(s) : q_smem(s)) + (uint32_t)t * 128u;
+                uint32_t w[8][4];
+                float ss = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(w[i][0]), "=r"(w[i][1]), "=r"(w[i][2]), "=r"(w[i][3])
+                                 : "r"(base + (uint32_t)(((i + t) & 7) << 4))
+                                 : "memory");
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float a = bf16_bits_to_f32(w[i][c] & 0xffffu), b = __uint_as_float(w[i][c] & 0xffff0000u);
+                        ss = fmaf(a, a, ss), ss = fmaf(b, b, ss);
+                    }
+                const float rstd = rsqrtf(ss / (float)D + qk_eps);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        __nv_bfloat162 r2 = __floats2bfloat162_rn(bf16_bits_to_f32(w[i][c] & 0xffffu) * rstd,
+                                                                  __uint_as_float(w[i][c] & 0xffff0000u) * rstd);
+                        w[i][c] = *reinterpret_cast<uint32_t*>(&r2);
+                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + (uint32_t)(((i + t) & 7) << 4)), "r"(w[i][0]),
+                                 "r"(w[i][1]), "r"(w[i][2]), "r"(w[i][3])
+                                 : "memory");
+                }
+            }
+            tc::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_qk_ready[s]));
+        };
+        if (QKNORM && n_my > 0) normalise(0);
+        for (int j = 0; j < n_my; ++j) {
+            if (QKNORM && j + 1 < n_my) normalise(j + 1);  // a whole item ahead of its logits
+            if (g >= tiles) continue;
+            const int item = (int)blockIdx.x + j * (int)gridDim.x;
+            const int img = item / p.heads, hd = item - img * p.heads;
+            const uint32_t par = (uint32_t)j & 1u;
+            const bool tracer = tracer_thread;
+            if (tracer) mark(g, j, 0);
+            tc::mbar_wait(tc::smem_u32(&bar_s[g]), par);
+            if (tracer) mark(g, j, 1);
+            tc::fence_after_sync();
+            // Pass 1: the exact row maximum.  Not needed with QKNORM: the rows of q and k are RMS-normalised, |q| |k| <= 64,
+            // so every logit is <= 64 and the constant shift 64 keeps exp2 in [2^-23, 1] -- softmax does not care which
+            // shift is used, bf16 / fp32 are floating point, and a quarter of the group's instructions disappears.
+            float m = (float)D;
+            if constexpr (!QKNORM) {
+                m = -INFINITY;
+                auto fold = [&](const uint32_t (&acc)[32], int c) {
+                    if (c * 32 + 32 <= p.T) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(acc[i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i < p.T) m = fmaxf(m, __uint_as_float(acc[i]));
+                    }
+                };
+                uint32_t a0[32], a1[32];
+                tc::tmem_ld_32x32b_x32(tmem_g, a0);
+#pragma unroll 1
+                for (int c = 0; c < nkc; c += 2) {  // the load of chunk c + 1 is in flight while chunk c is folded
+                    tc::tmem_ld_wait();
+                    if (c + 1 < nkc) tc::tmem_ld_32x32b_x32(tmem_g + (uint32_t)((c + 1) * 32), a1);
+                    fold(a0, c);
+                    if (c + 1 < nkc) {
+                        tc::tmem_ld_wait();
+                        if (c + 2 < nkc) tc::tmem_ld_32x32b_x32(tmem_g + (uint32_t)((c + 2) * 32), a0);
+                        fold(a1, c + 1);
+                    }
+                }
+            }
+            if (tracer) mark(g, j, 2);
+            const float c1 = p.scale_log2e, c0 = -m * p.scale_log2e;
+            float sum0 = 0.f, sum1 = 0.f;
+            // Pass 2: P = exp2(c1 s + c0) as bf16 pairs over consumed logits.  The load of chunk c + 1 is in flight while
+            // chunk c is exponentiated; after the first half of the chunks the MMA warp is told to start on P V.
+            const int nh = nkc == 8 ? 4 : 0;
+            const uint32_t p2_col = nh ? 128u : 0u, o_col = nh ? 64u : 128u;
+            auto exponentiate = [&](const uint32_t (&acc)[32], int c) {
+                uint32_t packed[16];
+                if (c * 32 + 32 <= p.T) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float e0 = ex2_fast(fmaf(__uint_as_float(acc[2 * i]), c1, c0));
+                        const float e1 = ex2_fast(fmaf(__uint_as_float(acc[2 * i + 1]), c1, c0));
+                        sum0 += e0, sum1 += e1;
+                        packed[i] = pack_bf16_pos(e0, e1);
+                    }
+                } else {  // the ragged end of the sequence: keys >= T contribute nothing
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float e0 = ex2_fast(fmaf(__uint_as_float(acc[2 * i]), c1, c0));
+                        float e1 = ex2_fast(fmaf(__uint_as_float(acc[2 * i + 1]), c1, c0));
+                        if (c * 32 + 2 * i >= p.T) e0 = 0.f;
+                        if (c * 32 + 2 * i + 1 >= p.T) e1 = 0.f;
+                        sum0 += e0, sum1 += e1;
+                        packed[i] = pack_bf16_pos(e0, e1);
+                    }
+                }
+                tc::tmem_st_32x32b_x16(tmem_g + (c < nh ? (uint32_t)(c * 16) : p2_col + (uint32_t)((c - nh) * 16)), packed);
+                if (c + 1 == nh || c + 1 == nkc) {  // first half / all of P is in tensor memory
+                    tc::tmem_st_wait();
+                    tc::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tc::mbar_arrive(tc::smem_u32(&bar_p[g]));
+                        if (c + 1 == nkc && tiles == 2 && p.turns) tc::mbar_arrive(tc::smem_u32(&bar_turn[g ^ 1]));
+                    }
+                    if (tracer) mark(g, j, c + 1 == nkc ? 4 : 3);
+                }
+            };
+            // The exponentials of the two groups take turns: alone on the MUFU pipe a group is done in half the time, and its
+            // other phases (P V, draining O, the next logits, the row maximum) then overlap the other group's exponentials
+            // instead of both groups contending for the pipe and idling together (measured: in phase without this).
+            if (tiles == 2 && p.turns) tc::mbar_wait(tc::smem_u32(&bar_turn[g]), g == 0 ? (par ^ 1u) : par);
+            if (nh == 0) {  // no early start: the "first half" is empty
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_p[g]));
+            }
+            {
+                uint32_t a0[32], a1[32];
+                tc::tmem_ld_32x32b_x32(tmem_g, a0);
+#pragma unroll 1
+                for (int c = 0; c < nkc; c += 2) {
+                    tc::tmem_ld_wait();
+                    if (c + 1 < nkc) tc::tmem_ld_32x32b_x32(tmem_g + (uint32_t)((c + 1) * 32), a1);
+                    exponentiate(a0, c);
+                    if (c + 1 < nkc) {
+                        tc::tmem_ld_wait();
+                        if (c + 2 < nkc) tc::tmem_ld_32x32b_x32(tmem_g + (uint32_t)((c + 2) * 32), a0);
+                        exponentiate(a1, c + 1);
+                    }
+                }
+            }
+            const float sum = sum0 + sum1;
+            // O_g / sum -> bf16 -> 128-byte-swizzled staging tile -> ONE TMA store per tile (rows beyond T are clipped by
+            // the tensor map).  Per-thread row stores were measured at 2000 - 4000 clk per tile: 32 lanes x 8 partial-sector
+            // writes to 32 different lines per warp.
+            tc::mbar_wait(tc::smem_u32(&bar_o[g]), par);
+            if (tracer) mark(g, j, 5);
+            tc::fence_after_sync();
+            const float inv = 1.0f / sum;
+            if (tracer && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            group_sync();  // the TMA unit has read the previous tile out of the staging block
+            const uint32_t my_row = o_stage + (uint32_t)row * 128u;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t acc[32];
+                tc::tmem_ld_32x32b_x32(tmem_g + o_col + (uint32_t)(h * 32), acc);
+                tc::tmem_ld_wait();
+                if (h == 1) {  // O is in registers: the MMA warp may overwrite the group's columns with the next logits
+                    tc::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_sfree[g]));
+                }
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(acc[8 * v + 2 * i]) * inv,
+                                                                  __uint_as_float(acc[8 * v + 2 * i + 1]) * inv);
+                        w[i] = *reinterpret_cast<uint32_t*>(&t2);
+                    }
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + (uint32_t)(((h * 4 + v) ^ (row & 7)) << 4)), "r"(w[0]),
+                                 "r"(w[1]), "r"(w[2]), "r"(w[3])
+                                 : "memory");
+                }
+            }
+            tc::fence_proxy_async();
+            group_sync();
+            if (tracer) {
+                tc::tma_store_3d(&tmap_out, o_stage, hd * D, g * BQ, img);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                mark(g, j, 6);
+            }
+            store_pending = true;
+        }
+        if (tracer_thread && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // complete before exit
+    }
+
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 9) tc::tmem_dealloc(tmem_base, 512);
+}
+
+template <bool QKNORM>
+int launch_t256(const void* qkv, int64_t ld, int64_t n, int64_t t, const AttnTcParams& p, float qk_eps, cudaStream_t stream) {
+    CUtensorMap tm;
+    uint64_t dims[3] = {(uint64_t)ld, (uint64_t)t, (uint64_t)n};
+    uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)t};
+    uint32_t box[3] = {D, TQ, 1};
+    int rc = tc::make_map_bf16(&tm, qkv, 3, dims, str, box);
+    if (rc) return rc == -1 ? AZB_E_DRIVER : AZB_E_SHAPE;
+    CUtensorMap tmo;  // (channels, tokens, images) of the output; a store box = 128 tokens x one head
+    uint64_t odims[3] = {(uint64_t)p.heads * D, (uint64_t)t, (uint64_t)n};
+    uint64_t ostr[2] = {(uint64_t)p.out_ld * 2, (uint64_t)p.out_ld * 2 * (uint64_t)t};
+    uint32_t obox[3] = {D, BQ, 1};
+    rc = tc::make_map_bf16(&tmo, p.out, 3, odims, ostr, obox);
+    if (rc) return rc == -1 ? AZB_E_DRIVER : AZB_E_SHAPE;
+    static AzbPerDevice<bool> configured_dev;
+    bool& configured = configured_dev.get();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attention_t256_kernel<QKNORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, T256_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const int64_t items = n * p.heads;
+    if (items > 0x7fffffffLL) return AZB_E_SHAPE;
+    const int sms = azb_sm_count();
+    const int grid = items < sms ? (int)items : sms;
+    if (const char* path = getenv("AZB_ATTN_TRACE")) {  // diagnosis: one synchronous launch with event timestamps
+        AttnTcParams pt = p;
+        const size_t bytes = (size_t)grid * 4 * 8 * 8 * sizeof(long long);
+        if (cudaMalloc(&pt.trace, bytes) != cudaSuccess) return AZB_E_DRIVER;
+        cudaMemsetAsync(pt.trace, 0, bytes, stream);
+        azb_launch(attention_t256_kernel<QKNORM>, dim3((unsigned)grid), dim3(T256_THREADS), T256_SMEM, stream, tm, tmo, pt, (int)items, qk_eps);
+        cudaStreamSynchronize(stream);
+        long long* host = (long long*)malloc(bytes);
+        cudaMemcpy(host, pt.trace, bytes, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(path, "wb")) {
+            fwrite(host, 1, bytes, f);
+            fclose(f);
+        }
+        free(host);
+        cudaFree(pt.trace);
+        return azb_launch_status();
+    }
+    azb_launch(attention_t256_kernel<QKNORM>, dim3((unsigned)grid), dim3(T256_THREADS), T256_SMEM, stream, tm, tmo, p, (int)items, qk_eps);
+    return azb_launch_status();
+}
+
 template <int BK>
 int launch_tc(const void* qkv, int64_t ld, int64_t n, int64_t t, const AttnTcParams& p, cudaStream_t stream) {
     using C = Cfg<BK>;
@@ -327,14 +737,22 @@ int launch_tc(const void* qkv, int64_t ld, int64_t n, int64_t t, const AttnTcPar
 // Returns AZB_E_UNSUPPORTED when the shape is not the one this kernel serves (the caller then uses the
 // mma.sync kernel of attn.cu).
 int azb_attention_tc_launch(const void* qkv, int64_t ld, void* out, int64_t out_ld, int64_t n, int64_t t, int64_t heads,
-                            int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta, void* stream) {
+                            int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta, int qk_norm, float qk_eps,
+                            void* stream) {
     if (d != D || out_ld % 8 || !azb_aligned(out, 16) || ld % 8 || !azb_aligned(qkv, 16)) return AZB_E_UNSUPPORTED;
     if (head_stride % 8 || k_delta % 8 || v_delta % 8) return AZB_E_UNSUPPORTED;
+    if (qk_norm && t > 256) return AZB_E_UNSUPPORTED;  // the fused normalisation lives in the short-sequence kernel
     AttnTcParams p{};
     p.out = reinterpret_cast<__nv_bfloat16*>(out), p.out_ld = out_ld;
     p.T = (int)t, p.heads = (int)heads;
     p.head_stride = (int)head_stride, p.k_delta = (int)k_delta, p.v_delta = (int)v_delta;
     p.scale_log2e = 1.4426950408889634f / sqrtf((float)d);
+    static int turns = -1;
+    if (turns < 0) {
+        const char* e = getenv("AZB_ATTN_TURNS");
+        turns = e ? atoi(e) : 1;
+    }
+    p.turns = turns;
     static int forced = -1;  // AZB_ATTN_BK=64|128 pins the tile (experiments); default 64: two CTAs per SM
     if (forced < 0) {
         const char* e = getenv("AZB_ATTN_BK");
@@ -344,5 +762,12 @@ int azb_attention_tc_launch(const void* qkv, int64_t ld, void* out, int64_t out_
     // 100 us, T = 256: 21 vs 25 us) -- the second resident CTA hides the barrier round trips of the first
     const int bk = forced == 128 ? 128 : 64;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    static int small = -1;  // AZB_ATTN_SMALL=0 keeps short sequences on the ring kernel below (A/B measurements)
+    if (small < 0) {
+        const char* e = getenv("AZB_ATTN_SMALL");
+        small = e ? atoi(e) : 1;
+    }
+    if (t <= TQ && (small || qk_norm))
+        return qk_norm ? launch_t256<true>(qkv, ld, n, t, p, qk_eps, s) : launch_t256<false>(qkv, ld, n, t, p, 0.f, s);
     return bk == 128 ? launch_tc<128>(qkv, ld, n, t, p, s) : launch_tc<64>(qkv, ld, n, t, p, s);
 }

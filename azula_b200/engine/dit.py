@@ -33,6 +33,7 @@ from .plan import LaunchPlan, ModulationBank, fingerprint, note_use
 
 _MAX_PLANS = 2
 _ACTS = {"silu": 1, "relu": 2, "relu2": 3}
+FOLD_QK_NORM = True  # A/B switch: q / k RMS normalisation inside the short-sequence attention kernel
 
 
 def structure_ok(model) -> bool:
@@ -156,7 +157,11 @@ class Plan(LaunchPlan):
             qkv = arena.take(R, 3 * hid)
             self.conv(y, w["qkv"], qkv, grid=self.grid)
             heads, d = w["heads"], hid // w["heads"]
-            if rot is not None:  # RMS norm (if any) + rotary embedding of q and k in one in-place pass
+            # short sequences, no rotation: the q / k RMS normalisation is folded into the attention kernel's logits
+            fold = w["qk_norm"] and rot is None and L <= 256 and d == 64 and FOLD_QK_NORM
+            if fold:
+                pass
+            elif rot is not None:  # RMS norm (if any) + rotary embedding of q and k in one in-place pass
                 self.keep += [qkv, rot]
                 self._emit("qk_norm", 0.0, 2.0 * 2 * R * 2 * hid, self.lib.azb_qk_norm_rope_bf16, qkv.data_ptr(), 3 * hid, R,
                            heads, d, int(w["qk_norm"]), w["qk_eps"], rot.data_ptr(), L, desc=f"{R}x{2 * heads}x{d} +rope")
@@ -166,9 +171,14 @@ class Plan(LaunchPlan):
                            R, 2 * heads, d, w["qk_eps"], desc=f"{R}x{2 * heads}x{d}")
             att = arena.take(R, hid)
             self.keep += [qkv, att]
-            self._emit("attention", 4.0 * B * heads * L * L * d, 2.0 * R * 4 * hid, self.lib.azb_attention_bf16,
-                       qkv.data_ptr(), 3 * hid, att.data_ptr(), hid, B, L, heads, d, d, hid, 2 * hid,
-                       desc=f"{B}x{heads}x{L}x{d}")
+            if fold:
+                self._emit("attention", 4.0 * B * heads * L * L * d, 2.0 * R * 4 * hid, self.lib.azb_attention_qknorm_bf16,
+                           qkv.data_ptr(), 3 * hid, att.data_ptr(), hid, B, L, heads, d, d, hid, 2 * hid, w["qk_eps"],
+                           desc=f"{B}x{heads}x{L}x{d} +qk-norm")
+            else:
+                self._emit("attention", 4.0 * B * heads * L * L * d, 2.0 * R * 4 * hid, self.lib.azb_attention_bf16,
+                           qkv.data_ptr(), 3 * hid, att.data_ptr(), hid, B, L, heads, d, d, hid, 2 * hid,
+                           desc=f"{B}x{heads}x{L}x{d}")
             arena.give(qkv)
             y2 = arena.take(R, hid)
             self.conv(att, w["y"], y2, grid=self.grid, residual=y)

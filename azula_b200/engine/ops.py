@@ -70,6 +70,10 @@ _lib.register({
          c_void_p, c_int64, c_int, c_int, c_void_p],
     ),
     "azb_nchw_to_nhwc_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "azb_attention_qknorm_bf16": (
+        c_int,
+        [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_void_p],
+    ),
     "azb_attention_f16": (
         c_int,
         [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p],
@@ -824,6 +828,19 @@ def gn_apply_f32(x: Tensor, stats: Tensor | None = None, gamma: Tensor | None = 
                                     _lib.stream_ptr(x.device)),
         "azb_gn_apply_f32",
     )
+    return out
+
+
+def attention_qknorm(qkv: Tensor, heads: int, eps: float = 1e-5, out: Tensor | None = None) -> Tensor:
+    r"""``azb_attention_qknorm_bf16``: attention over a (N, T, 3C) bf16 projection in [q | k | v] channel order with the
+    per-head RMS normalisation of q and k folded into the logits (T <= 256, head width 64)."""
+    n, t, c3 = qkv.shape
+    c = c3 // 3
+    d = c // heads
+    if out is None:
+        out = torch.empty(n, t, c, dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(_lib.lib().azb_attention_qknorm_bf16(qkv.data_ptr(), qkv.stride(1), out.data_ptr(), out.stride(1), n, t, heads, d, d,
+                                                    c, 2 * c, eps, _lib.stream_ptr(qkv.device)), "azb_attention_qknorm_bf16")
     return out
 
 

@@ -401,6 +401,12 @@ int azb_gn_coef_f32(int64_t n, int64_t h, int64_t w, int64_t c, int64_t groups, 
 int azb_attention_bf16(const void* qkv, int64_t ld, void* out, int64_t out_ld, int64_t n, int64_t t,
                        int64_t heads, int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta,
                        void* stream);
+/* The same with the per-head RMS normalisation of q and k (torch.nn.RMSNorm(elementwise_affine = False), eps = qk_eps;
+ * azula/nn/attention.py:103) folded into the logits: s'_ij = s_ij rq_i rk_j.  Replaces the in-place pass
+ * azb_segment_rmsnorm_bf16 for sequences of T <= 256 tokens and head width 64; AZB_E_UNSUPPORTED otherwise. */
+int azb_attention_qknorm_bf16(const void* qkv, int64_t ld, void* out, int64_t out_ld, int64_t n, int64_t t, int64_t heads,
+                              int64_t d, int64_t head_stride, int64_t k_delta, int64_t v_delta, float qk_eps, void* stream);
+
 /* The same contract served by the warp-level mma.sync kernel only (azb_attention_bf16 uses the tcgen05 / TMEM
  * kernel for d = 64 and this one for the other widths); exported so that tests can compare the two. */
 int azb_attention_mma_bf16(const void* qkv, int64_t ld, void* out, int64_t out_ld, int64_t n, int64_t t,

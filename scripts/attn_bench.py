@@ -41,6 +41,21 @@ def main():
             torch.cuda.synchronize()
             us = 1e3 * e0.elapsed_time(e1) / reps
             print(f"{what:28s} {'tcgen05' if kernel == 'auto' else 'mma.sync':9s} {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s")
+        if t <= 256 and not once:  # the q / k RMS normalisation folded into the short-sequence kernel vs the separate pass
+            for what2, fn in (("fused qk-norm", lambda: ops.attention_qknorm(qkv, heads, out=out)),
+                              ("rmsnorm pass + attention", lambda: (ops.segment_rmsnorm_(qkv.reshape(n * t, -1), 2 * heads, 64), ops.attention(qkv, heads, True, out=out)))):
+                if not new_order:
+                    continue
+                for _ in range(3):
+                    fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(20):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                print(f"{what:28s} {what2:26s} {1e3 * e0.elapsed_time(e1) / 20:8.1f} us")
         torch.cuda.synchronize()
 
 

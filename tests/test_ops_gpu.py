@@ -163,3 +163,28 @@ def test_time_embedding_path():
     idx = torch.tensor([1, 9, 0, 1], device=DEV)
     ref3 = y + table[idx]
     assert torch.allclose(ops.add_rows(y, table, idx), ref3)
+
+
+@pytest.mark.parametrize("case", [(3, 256, 12, 64), (2, 64, 4, 64), (2, 100, 2, 64), (1, 200, 3, 64), (4, 16, 1, 64),
+                                  (40, 256, 12, 64), (33, 100, 11, 64), (70, 64, 9, 64), (50, 129, 7, 64)])
+def test_attention_with_folded_qk_norm(case):
+    """azb_attention_qknorm_bf16 (persistent short-sequence kernel: logits and probabilities resident in tensor memory,
+    q / k RMS-normalised in place in shared memory) == RMS-normalise q and k per head, then attention
+    (azula/nn/attention.py:103,110-116), and the same kernel without the normalisation == plain attention; the
+    two-launch route (azb_segment_rmsnorm_bf16 first) rounds q and k to bf16 like the fused one.  The large cases give
+    every CTA several (image, head) items: the stage rings and the event-driven MMA issue order are exercised."""
+    n, t, heads, d = case
+    c = heads * d
+    g = torch.Generator(device=DEV).manual_seed(t)
+    qkv = (torch.randn(n, t, 3 * c, device=DEV, generator=g) * 2).to(torch.bfloat16)
+    got = ops.attention_qknorm(qkv, heads, eps=1e-5)
+    q, k, v = (z.reshape(n, t, heads, d).transpose(1, 2) for z in qkv.float().chunk(3, dim=-1))
+    rms = lambda z: (z * torch.rsqrt(z.square().mean(-1, keepdim=True) + 1e-5)).to(torch.bfloat16).float()  # noqa: E731
+    ref = (torch.softmax(rms(q) @ rms(k).transpose(-1, -2) / d**0.5, dim=-1) @ v).transpose(1, 2).reshape(n, t, c)
+    _close(got, ref, (case, "folded"), rel=2.0**-6)
+    two = qkv.clone()
+    ops.segment_rmsnorm_(two.reshape(n * t, 3 * c), 2 * heads, d)
+    _close(ops.attention(two, heads, True), ref, (case, "two launches"), rel=2.0**-6)
+    plain = (torch.softmax(q @ k.transpose(-1, -2) / d**0.5, dim=-1) @ v).transpose(1, 2).reshape(n, t, c)
+    _close(ops.attention(qkv, heads, True), plain, (case, "no normalisation"), rel=2.0**-6)
+    assert torch.equal(ops.attention_qknorm(qkv, heads, eps=1e-5), got), "not reproducible"
