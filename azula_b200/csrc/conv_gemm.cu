@@ -145,19 +145,28 @@ __device__ __forceinline__ void fixed_add(unsigned long long* acc, float v) {
     if (lo) atomicAdd(acc + 1, lo);
 }
 
-__device__ __forceinline__ float activate(float v, int act) {
-    switch (act) {
-        // x sigmoid(x) = t + t tanh(t) with t = x / 2: ONE special-function instruction per element (tanh.approx, 2^-11
-        // relative) instead of an exponential and a reciprocal -- the activation epilogue of the 768 -> 3072 token GEMM
-        // was bound by the SFU pipe (38 % tensor-pipe activity against 64 % of the same GEMM without activation)
-        case AZB_ACT_SILU: {
-            const float t = 0.5f * v;
-            return fmaf(t, tanh_approx(t), t);
+// The activation of N register values with the (runtime, CTA-uniform) selector tested ONCE, outside the element loop: with
+// the switch inside, ptxas kept two compares and a branch per ELEMENT (ncu source page of the 768 -> 3072 token GEMM).
+// SiLU: x sigmoid(x) = t + t tanh(t) with t = x / 2 -- ONE special-function instruction per element (tanh.approx, 2^-11
+// relative) instead of an exponential and a reciprocal.
+template <int N>
+__device__ __forceinline__ void activate_all(float (&v)[N], int act) {
+    if (act == AZB_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const float t = 0.5f * v[j];
+            v[j] = fmaf(t, tanh_approx(t), t);
         }
-        case AZB_ACT_RELU: return fmaxf(v, 0.f);
-        case AZB_ACT_RELU2: v = fmaxf(v, 0.f); return v * v;
+    } else if (act == AZB_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == AZB_ACT_RELU2) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const float r = fmaxf(v[j], 0.f);
+            v[j] = r * r;
+        }
     }
-    return v;
 }
 
 template <int BLOCK_N, bool PAIR = false, bool HALO = false>
@@ -698,10 +707,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                         v[4 * q] = __uint_as_float(acc[4 * q]) + b4.x, v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + b4.y;
                         v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + b4.z, v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + b4.w;
                     }
-                    if (p.act) {
-#pragma unroll
-                        for (int j = 0; j < CHUNK; ++j) v[j] = activate(v[j], p.act);
-                    }
+                    activate_all(v, p.act);
                     if (use_res) {
 #pragma unroll
                         for (int q = 0; q < CHUNK / 4; ++q)
@@ -820,10 +826,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                         v[4 * q] = __uint_as_float(acc[4 * q]) + b4.x, v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + b4.y;
                         v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + b4.z, v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + b4.w;
                     }
-                    if (p.act) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = activate(v[j], p.act);
-                    }
+                    activate_all(v, p.act);
                     if (gatep && ok) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
@@ -1122,10 +1125,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                             }
 #pragma unroll
                             for (int j = 0; j < 8; ++j) f[j] += bias8[j];
-                            if (act) {
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) f[j] = activate(f[j], act);
-                            }
+                            activate_all(f, act);
                             if (gate && col_ok && okc[it]) {
                                 const float* gp = gate + (pixc[it] / p.gate_rows) * p.gate_ld + col;
                                 const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp));
@@ -1401,14 +1401,15 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
         return AZB_E_ALIGN;
     const int64_t h = (h_in + ex.stride - 1) / ex.stride, w = (w_in + ex.stride - 1) / ex.stride;
 
-    // the row-domain epilogue (EPI == 2) brings activation and gate to the halo kernels
-    // Measured (gpurun_out/bench_r2b_*): neutral to +3 % on the ADM layers (no activation / gate, long reductions), but
-    // -10..-20 % on the short-K token GEMMs and the small U-Net convolutions with activation / gate epilogues, where
-    // the wait for the TMA unit to drain the staging block is exposed: those keep the transposing epilogue unless the
-    // knob is forced to 1.
+    // The row-domain epilogue (EPI == 2) brings activation and gate to the halo kernels.  Measured: neutral to +3 % on the
+    // ADM layers (no activation / gate, long reductions); on the token GEMMs with activation / gate epilogues and wide
+    // tiles +25 % (768 -> 3072 + SiLU: 87 -> 70 us, scripts/gemm_one.py) once the activation selector is tested outside
+    // the element loop; the small U-Net convolutions with 64-column tiles (four of the eight epilogue warps idle in this
+    // epilogue) keep the transposing one unless the knob is forced to 1.
+    const bool epi_plain = ex.act == AZB_ACT_NONE && !ex.gate;
     const bool rowepi_ok = g_knob[AZB_CONV_KNOB_ROWEPI] != 0 && out_mode == 0 && !colsum && (!ex.gn_acc || stat_gran == 8) &&
                            (phases == 1 || (c_out % 64 == 0 && out_ld % 8 == 0)) &&
-                           (g_knob[AZB_CONV_KNOB_ROWEPI] == 1 || (ex.act == AZB_ACT_NONE && !ex.gate));
+                           (g_knob[AZB_CONV_KNOB_ROWEPI] == 1 || epi_plain || (taps == 1 && c_out_rows % 128 == 0));
     // Halo tiles: 3 x 3, stride 1, maps of at least one 8 x 16 patch, whole 64-channel blocks (see the kernel's header)
     bool halo = g_knob[AZB_CONV_KNOB_HALO] != 0 && taps == 9 &&
                 ex.stride == 1 && h >= HALO_H && w >= HALO_W &&
@@ -1576,7 +1577,8 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     // Row-domain epilogue with TMA stores (EPI == 2): every bf16 NHWC layer with an N tile of whole 64-channel store
     // blocks, without split-K / per-channel statistics; activation, gate, residual and exact GroupNorm sums included.
     // A halo kernel needs a wide tile unless it is this epilogue's 64-column instantiation.
-    const bool rowepi = rowepi_ok && splits == 1 && block_n >= 64 && (!halo || block_n >= 128);
+    const bool rowepi = rowepi_ok && splits == 1 && block_n >= 64 && (!halo || block_n >= 128) &&
+                        (epi_plain || g_knob[AZB_CONV_KNOB_ROWEPI] == 1 || block_n >= 128);
     if (halo && (ex.act != AZB_ACT_NONE || ex.gate) && !rowepi) return AZB_E_UNSUPPORTED;  // (unreachable: wide halo tiles)
     if (ex.choice) {
         ex.choice->halo = halo, ex.choice->pair = pair, ex.choice->lean = lean || rowepi, ex.choice->block_n = block_n, ex.choice->splits = splits;
