@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libazb.so")
 if os.environ.get("AZB_LIBRARY"):  # A/B measurements of two builds on one box (scripts/build_ab.sh)
     LIB_PATH = os.environ["AZB_LIBRARY"]
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 F32, BF16, F16, I64 = 0, 1, 2, 3
 DTYPE_CODE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16, torch.int64: I64}

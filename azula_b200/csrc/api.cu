@@ -12,6 +12,14 @@ extern "C" int azb_conv_tuning(int knob, int value) {
     return AZB_OK;
 }
 
+// Diagnostics: device buffer of 64-bit words {launch counter, then per convolution launch: earliest CTA entry, earliest
+// CTA start (after the programmatic-launch wait), latest CTA end, CTAs} in %globaltimer nanoseconds; see azb.h.
+void* azb_trace_buf = nullptr;
+extern "C" int azb_debug_trace(void* buf) {
+    azb_trace_buf = buf;
+    return AZB_OK;
+}
+
 extern "C" const char* azb_strerror(int code) {
     switch (code) {
         case AZB_OK: return "ok";

@@ -14,6 +14,12 @@
     } while (0)
 
 extern int azb_knob[AZB_CONV_KNOBS];  // api.cu
+extern void* azb_trace_buf;           // api.cu (azb_debug_trace)
+__device__ __forceinline__ unsigned long long azb_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 static inline int azb_launch_status() {
     cudaError_t e = cudaGetLastError();

@@ -72,7 +72,7 @@ constexpr int HALO_BYTES = HALO_ROWS * 128;
 // replication dimensions have stride 0 -- (2 x 6) x (2 x 10) = 12 x 20 pixels that cover the 10 x 18 halo region, whose
 // origin sits one row and one column inside
 constexpr int UP_PITCH = 12, UP_ROWS = 20 * UP_PITCH, UP_BYTES = UP_ROWS * 128, UP_ORIGIN = UP_PITCH + 1;
-constexpr int SMEM_BUDGET = 193 * 1024;  // operand ring; + 32 KiB epilogue staging + alignment <= 227 KiB
+constexpr int SMEM_BUDGET = 192 * 1024;  // operand ring; + 32 KiB epilogue staging + alignment + ~1.5 KiB static <= 227 KiB
 
 struct ConvParams {
     int N, H, W;              // activation extent (pixels)
@@ -98,6 +98,7 @@ struct ConvParams {
     const float* gate;        // per-(sample, channel) multiplier of act(acc + bias), or null
     int64_t gate_ld;          // floats between the gate rows of consecutive samples (0 = one shared row)
     int gate_rows;            // output pixels per sample (sample = pixel index / gate_rows)
+    int gate_uniform;         // every 32-row slab of an M tile lies in ONE sample (row-domain epilogue: gate row held per lane)
     int kb_extra;             // K blocks of the second (1x1, same resolution) operand appended after the taps
     unsigned long long* gn_acc;  // [N][c_out / stat_gran][4] exact fixed-point {sum hi, sum lo, sumsq hi, sumsq lo}
     int chunked;              // 1: CTA b owns the contiguous tile range [b * per, (b + 1) * per) instead of b, b + grid, ...
@@ -113,6 +114,18 @@ struct ConvParams {
     int phases;               // 4: phase-decomposed upsampling convolution (see conv_impl), tile / tiles_out = phase; else 1
     int a_slot;               // halo kernels: bytes per A slot
     int sa, sb;               // halo kernels: A slots and weight stages in the shared-memory budget
+    int b_resident;           // halo kernels, one channel block, one N tile: the nine weight tiles are loaded ONCE per CTA and
+                              // stay in stages 0 .. 8 (a 64 -> 64 layer streams 72 KiB of weights per 128-pixel tile otherwise:
+                              // 8 KiB stages in flight against ~1 us of L2 latency paced its MMAs at a third of their rate)
+    // halo kernels, per-pixel normalisation of the input (UNetBlock, azula/nn/unet.py:97-107): the convolution reads
+    // bf16((1 + a[n][c]) norm_C(x)[pixel] + b[n][c]); statistics from the producer's epilogue (rowstat)
+    int in_norm;                   // 0: none, 1: LayerNorm over the channels of a pixel, 2: RMSNorm
+    float in_eps;
+    const float2* in_rowstat;      // [pixels][c_in / 64] {sum, sum of squares} of each 64-channel block of the input
+    const float* in_mod;           // [a(c_in) | b(c_in)] per sample (fp32), in_mod_ld floats between samples (0 = shared)
+    int64_t in_mod_ld;
+    float2* rowstat;               // EPI 2: [pixels][c_out / 64] {sum, sum of squares} of the stored values, or null
+    unsigned long long* trace;     // azb_debug_trace buffer or null
     unsigned long long item_mask;  // halo kernels: bit i = item i of a tile is a halo item (else a 1 x 1 block): the blocks
                                    // of the fused 1 x 1 operand are spread between the halo items, so that every halo item
                                    // is preceded by >= 9 k-blocks of MMA time in which it can land and be transformed
@@ -182,7 +195,9 @@ struct Cfg {
     static constexpr int STAGE_BYTES = HALO ? B_SLOT : A_BYTES + B_BYTES;
     // halo kernels split the budget at run time (ConvParams::sa A slots, ::sb weight stages); STAGES is the most the
     // barrier arrays must hold
-    static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES > 8 ? 8 : SMEM_BUDGET / STAGE_BYTES;
+    // (halo kernels: up to 9, so that ALL nine weight tiles of a 64-channel layer can stay resident, ConvParams::b_resident)
+    static constexpr int STAGES_CAP = HALO ? 9 : 8;
+    static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES > STAGES_CAP ? STAGES_CAP : SMEM_BUDGET / STAGE_BYTES;
     static constexpr int RING_BYTES = HALO ? SMEM_BUDGET : STAGES * STAGE_BYTES;
     static constexpr int weight_stages(int sa) {
         return (SMEM_BUDGET - sa * A_SLOT) / STAGE_BYTES > 8 ? 8 : (SMEM_BUDGET - sa * A_SLOT) / STAGE_BYTES;
@@ -256,6 +271,53 @@ __device__ __forceinline__ void transform_tile(uint32_t slot, int rg, int chunk,
     }
 }
 
+// The same pass for the per-pixel normalisation (ConvParams::in_norm): row k of this thread's rows is scaled with its own
+// {rstd, mean * rstd} (r[k], mr[k]; zero for pixels outside the image, which stay zero), then modulated per channel:
+// f = fma(fma(x, r, -mr), A, B) with A = 1 + a[n][c], B = b[n][c] -- (1 + a) * norm(x) + b of UNetBlock._forward.
+template <int PITCH, int ROWS, int OFF>
+__device__ __forceinline__ void transform_tile_norm(uint32_t slot, int rg, int chunk, const float (&a)[8], const float (&b)[8],
+                                                    const float (&r)[(ROWS + 15) / 16], const float (&mr)[(ROWS + 15) / 16], int h0,
+                                                    int w0, int H, int W) {
+    const uint32_t base = slot + (uint32_t)rg * 128u + ((uint32_t)(chunk ^ (rg & 7)) << 4);
+    constexpr int KS = (ROWS + 15) / 16;
+#pragma unroll
+    for (int k0 = 0; k0 < KS; k0 += 4) {
+        uint32_t v[4][4];
+        bool inside[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = rg + 16 * (k0 + u);
+            const int y = i / PITCH, x = i - y * PITCH;
+            inside[u] = (unsigned)(h0 - OFF + y) < (unsigned)H && (unsigned)(w0 - OFF + x) < (unsigned)W;
+            if (16 * (k0 + u) + 15 < ROWS || i < ROWS)
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3])
+                             : "r"(base + (uint32_t)(k0 + u) * 2048u)
+                             : "memory");
+            else v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float ru = k0 + u < KS ? r[k0 + u < KS ? k0 + u : 0] : 0.f, mu = k0 + u < KS ? mr[k0 + u < KS ? k0 + u : 0] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float f0 = fmaf(fmaf(bf16_bits_to_f32(v[u][j] & 0xffffu), ru, -mu), a[2 * j], b[2 * j]);
+                const float f1 = fmaf(fmaf(__uint_as_float(v[u][j] & 0xffff0000u), ru, -mu), a[2 * j + 1], b[2 * j + 1]);
+                __nv_bfloat162 t = __floats2bfloat162_rn(f0, f1);
+                v[u][j] = inside[u] ? *reinterpret_cast<uint32_t*>(&t) : 0u;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = rg + 16 * (k0 + u);
+            if (16 * (k0 + u) + 15 < ROWS || i < ROWS)
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + (uint32_t)(k0 + u) * 2048u), "r"(v[u][0]),
+                             "r"(v[u][1]), "r"(v[u][2]), "r"(v[u][3])
+                             : "memory");
+        }
+    }
+}
+
 // LEAN: the epilogue of the common case -- bf16 NHWC output, no activation, no gate, no split-K, GroupNorm sums (if
 // any) as exact accumulators per 8-channel block -- with those switches resolved at compile time.
 //
@@ -275,13 +337,14 @@ __device__ __forceinline__ void transform_tile(uint32_t slot, int rg, int chunk,
 // operands with a 10-bit mantissa, fp32 accumulation -- what cuDNN does for the reference under PyTorch's default
 // flags (torch.backends.cudnn.allow_tf32).  Tap-wise single-CTA kernels with EPI == 3 (row domain: one fp32 / fp16
 // NHWC row segment per lane, direct 16-byte stores of whole 128-byte lines, fp32 residual) or the fp32 NCHW epilogue.
-template <int BLOCK_N, bool PAIR, int EPI, bool HALO, bool TF32 = false>
+template <int BLOCK_N, bool PAIR, int EPI, bool HALO, bool TF32 = false, bool NORM = false>
 __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
     conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_out,
                      const ConvParams p) {
     constexpr bool LEAN = EPI == 1;
     static_assert(!TF32 || !HALO, "the TF32 mode uses the tap-wise kernels");
+    static_assert(!NORM || (HALO && EPI == 2), "the per-pixel normalisation lives in the halo kernels' input transform");
     static_assert((EPI == 3) == (TF32 && EPI != 0), "EPI 3 is the TF32 mode's NHWC epilogue");
     constexpr int KE = TF32 ? BLOCK_K / 2 : BLOCK_K;  // elements per k-block (128 bytes)
     using C = Cfg<BLOCK_N, PAIR, HALO>;
@@ -289,6 +352,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
     static_assert(!PAIR || BLOCK_N >= 128, "a CTA pair splits the weight tile in two halves of >= 64 rows");
 
     pdl_trigger();  // the next kernel of the stream may begin launching; it waits for this grid before touching memory
+    const unsigned long long t_enter = p.trace ? azb_globaltimer() : 0ull;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     __shared__ __align__(8) uint64_t bar_full[STAGES];
@@ -346,6 +410,16 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
     // barrier setup, tensor-memory allocation and descriptor prefetch overlapped the tail of the previous kernel; its
     // results (activations, GroupNorm sums, coefficients) are read and this kernel's outputs written only from here on
     pdl_wait();
+    // tile timeline of CTA 0 (diagnostics): words [1 << 16, ...) of the trace buffer, 16 stamps per (tile < 16)
+    auto mark = [&](int local, int e) {
+        if (p.trace && blockIdx.x == 0 && local < 16) p.trace[(1 << 16) + local * 16 + e] = azb_globaltimer();
+    };
+    unsigned long long* trace_slot = nullptr;
+    if (p.trace && threadIdx.x == 0) {
+        trace_slot = p.trace + 8 + 4 * *reinterpret_cast<volatile unsigned long long*>(p.trace);
+        atomicMin(trace_slot, t_enter);
+        atomicMin(trace_slot + 1, azb_globaltimer());
+    }
 
     const int num_kb_taps = p.taps * p.kb_per_tap;
     const int num_kb = num_kb_taps + p.kb_extra;
@@ -388,7 +462,14 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
             int sb = 0;
             uint32_t pb = 1;  // parity of the `empty` barriers: the first pass finds every slot free
             const uint32_t full_b0 = PAIR ? tc::mapa(tc::smem_u32(&bar_full[0]), 0) : tc::smem_u32(&bar_full[0]);
-            for (int local = 0; local < tile_count; ++local) {
+            if (p.b_resident) {
+                for (int t = 0; t < 9 && tile_count > 0; ++t) {
+                    const uint32_t full = tc::smem_u32(&bar_full[t]);
+                    tc::mbar_expect_tx(full, C::B_BYTES);
+                    tc::tma_load_2d(b_ring + t * C::STAGE_BYTES, &tmap_b, full, t * p.kb_per_tap * BLOCK_K, 0);
+                }
+            }
+            for (int local = 0; local < (p.b_resident ? 0 : tile_count); ++local) {
                 const int tile = unit_to_tile(tile_first + local * tile_step);
                 int n_tile, w0, h0, n0;
                 tile_coords(p, tile % p.tiles_out, n_tile, w0, h0, n0);
@@ -477,7 +558,9 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
             };
             for (int local = 0; local < tile_count; ++local) {
                 const int as = local & 1;
+                mark(local, 0);
                 tc::mbar_wait(tc::smem_u32(&bar_acc_empty[as]), ((local >> 1) & 1) ^ 1);
+                mark(local, 1);
                 tc::fence_after_sync();
                 const uint32_t tmem_acc = tmem_base + (uint32_t)(as * C::ACC_COLS);
                 const int phase = HALO && p.phases > 1 ? unit_to_tile(tile_first + local * tile_step) / p.tiles_out : 0;
@@ -487,6 +570,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                         // they arrive with release.cluster after fence.proxy.async, and what they wrote is read by each
                         // CTA's own tensor core, never by this thread: the CTA-scope acquire of try_wait suffices)
                         tc::mbar_wait(tc::smem_u32(&bar_a_ready[sa]), pa);
+                        if (it == 0) mark(local, 2);
                         tc::fence_after_sync();
                         // tap (0, 0): the view that starts at halo pixel (0, 0)
                         uint32_t a_src = smem_base + (uint32_t)(sa * p.a_slot) + (p.in_up ? UP_ORIGIN * 128u : 0u);
@@ -495,13 +579,22 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                         // half-resolution pixels at rows dy, dy + 1 and columns dx, dx + 1 of it
                         const int kw_end = halo_taps == 9 ? 3 : 2;
                         if (halo_taps != 9) a_src += ((uint32_t)(phase >> 1) * pitch + (uint32_t)(phase & 1)) * 128u;
-                        for (int t = 0, kw = 0; t < halo_taps; ++t) {
-                            tc::mbar_wait(tc::smem_u32(&bar_full[sb]), pb);
+                        if (p.b_resident && local == 0) {  // resident weights: stage = tap, loaded once, never released
+                            for (int t = 0; t < 9; ++t) tc::mbar_wait(tc::smem_u32(&bar_full[t]), 0u);
                             tc::fence_after_sync();
-                            mma4(tc::smem_desc_sw128_sbo(a_src, pitch * 128u), tc::smem_desc_sw128(b_ring + sb * C::STAGE_BYTES),
+                        }
+                        for (int t = 0, kw = 0; t < halo_taps; ++t) {
+                            const int st = p.b_resident ? t : sb;
+                            if (!p.b_resident) {
+                                tc::mbar_wait(tc::smem_u32(&bar_full[st]), pb);
+                                tc::fence_after_sync();
+                            }
+                            mma4(tc::smem_desc_sw128_sbo(a_src, pitch * 128u), tc::smem_desc_sw128(b_ring + st * C::STAGE_BYTES),
                                  tmem_acc, (it | t) == 0);
-                            release(&bar_empty[sb]);
-                            if (++sb == SB) sb = 0, pb ^= 1u;
+                            if (!p.b_resident) {
+                                release(&bar_empty[sb]);
+                                if (++sb == SB) sb = 0, pb ^= 1u;
+                            }
                             // next tap: one pixel to the right, or back to column 0 of the next halo row
                             if (++kw == kw_end) kw = 0, a_src += (pitch - (uint32_t)kw_end + 1u) * 128u;
                             else a_src += 128u;
@@ -523,6 +616,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                     }
                 }
                 release(&bar_acc_full[as]);
+                mark(local, 3);
             }
         }
     } else if (HALO && warp >= 2 + EPI_WARPS && warp < 2 + EPI_WARPS + XF_WARPS) {
@@ -536,13 +630,66 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
         uint32_t pa = 0;
         const uint32_t ready0 = PAIR ? tc::mapa(tc::smem_u32(&bar_a_ready[0]), 0) : tc::smem_u32(&bar_a_ready[0]);
         const bool xf = p.in_coef != nullptr;
+        constexpr int KS = (HALO_ROWS + 15) / 16;
+        // Per-pixel normalisation: the producer's per-block sums of this thread's rows, requested ONE TILE AHEAD (all loads
+        // of a tile are independent and in flight together: a single L2 round trip, hidden behind the previous tile)
+        float ps1[NORM ? KS : 1], ps2[NORM ? KS : 1];
+        auto request_stats = [&](int local) {
+#pragma unroll
+            for (int k = 0; k < (NORM ? KS : 1); ++k) ps1[k] = ps2[k] = 0.f;
+            if (!NORM || local >= tile_count) return;
+            const int tile = unit_to_tile(tile_first + local * tile_step);
+            int n_tile, w0, h0, n0;
+            tile_coords(p, tile % p.tiles_out, n_tile, w0, h0, n0);
+            const int nblk = p.c_in >> 6;
+            const float2* sp[KS];
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+                const int i = rg + 16 * k;
+                const int y = i / HALO_PITCH, x = i - y * HALO_PITCH;
+                const int hh = h0 - 1 + y, ww = w0 - 1 + x;
+                const bool in = i < HALO_ROWS && (unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W;
+                sp[k] = in ? p.in_rowstat + (((int64_t)n0 * p.H + hh) * p.W + ww) * nblk : nullptr;
+            }
+            for (int bk = 0; bk < nblk; ++bk) {
+                float2 v[KS];
+#pragma unroll
+                for (int k = 0; k < KS; ++k) v[k] = sp[k] ? __ldg(sp[k] + bk) : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < KS; ++k) ps1[k] += v[k].x, ps2[k] += v[k].y;
+            }
+        };
+        if constexpr (NORM) request_stats(0);
         for (int local = 0; local < tile_count; ++local) {
             const int tile = unit_to_tile(tile_first + local * tile_step);
             int n_tile, w0, h0, n0;
             tile_coords(p, tile % p.tiles_out, n_tile, w0, h0, n0);
+            float nr[NORM ? KS : 1], nmr[NORM ? KS : 1];
+            if constexpr (NORM) {
+                const float inv_c = 1.0f / (float)p.c_in, inv_cm1 = 1.0f / (float)(p.c_in - 1);
+#pragma unroll
+                for (int k = 0; k < KS; ++k) {
+                    // LayerNorm: torch.var_mean's UNBIASED variance (azula/nn/layers.py:152-155); RMSNorm: the mean square
+                    const float s1 = ps1[k], s2 = ps2[k];
+                    const float mean = p.in_norm == 1 ? s1 * inv_c : 0.f;
+                    const float var = p.in_norm == 1 ? fmaxf(fmaf(-mean, s1, s2), 0.f) * inv_cm1 : s2 * inv_c;
+                    nr[k] = rsqrtf(var + p.in_eps);
+                    nmr[k] = mean * nr[k];
+                }
+                request_stats(local + 1);
+            }
             for (int hi = 0; hi < p.kb_per_tap; ++hi) {
                 float a[8], b[8];
-                if (xf) {
+                if (NORM) {
+                    const float* mp = p.in_mod + (int64_t)n0 * p.in_mod_ld + hi * BLOCK_K + chunk * 8;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const float4 va = __ldg(reinterpret_cast<const float4*>(mp) + j);
+                        const float4 vb = __ldg(reinterpret_cast<const float4*>(mp + p.c_in) + j);
+                        a[4 * j] = 1.f + va.x, a[4 * j + 1] = 1.f + va.y, a[4 * j + 2] = 1.f + va.z, a[4 * j + 3] = 1.f + va.w;
+                        b[4 * j] = vb.x, b[4 * j + 1] = vb.y, b[4 * j + 2] = vb.z, b[4 * j + 3] = vb.w;
+                    }
+                } else if (xf) {
                     const float4* cp = reinterpret_cast<const float4*>(p.in_coef + (int64_t)n0 * p.c_in + hi * BLOCK_K + chunk * 8);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -551,7 +698,11 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                     }
                 }
                 tc::mbar_wait(tc::smem_u32(&bar_a_full[sa]), pa);
-                if (xf) {
+                if constexpr (NORM) {
+                    const uint32_t slot = smem_base + (uint32_t)(sa * p.a_slot);
+                    transform_tile_norm<HALO_PITCH, HALO_ROWS, 1>(slot, rg, chunk, a, b, nr, nmr, h0, w0, p.H, p.W);
+                    tc::fence_proxy_async();
+                } else if (xf) {
                     const uint32_t slot = smem_base + (uint32_t)(sa * p.a_slot);
                     if (p.in_up) transform_tile<UP_PITCH, UP_ROWS, 2>(slot, rg, chunk, a, b, p.in_silu, h0, w0, p.H, p.W);
                     else transform_tile<HALO_PITCH, HALO_ROWS, 1>(slot, rg, chunk, a, b, p.in_silu, h0, w0, p.H, p.W);
@@ -749,13 +900,29 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
         // ===== epilogue, row domain + TMA store (see the kernel's header) =====
         const int e = warp - 2;
         const int quarter = warp & 3;
-        constexpr int CPW = BLOCK_N >= 128 ? BLOCK_N / 2 : BLOCK_N;  // columns per warp: whole 64-column store blocks
-        static_assert(CPW % 64 == 0, "row-domain epilogue: BLOCK_N >= 64");
-        const int half = BLOCK_N >= 128 ? (e >> 2) : 0;
-        const bool active = BLOCK_N >= 128 || e < 4;
-        const uint32_t stage = smem_base + C::RING_BYTES + e * (32 * 128);  // 32 pixels x 128 bytes, 1024-byte aligned
-        const uint32_t my_row = stage + (uint32_t)lane * 128u;
+        // columns per warp: whole 64-column store blocks -- or, for 64-column tiles, HALF a block: the two warps of a TMEM lane
+        // quarter (e and e + 4) fill one staging block together and meet at a 64-thread named barrier, so that all eight
+        // epilogue warps work on the short tiles of the narrow layers (with four, the epilogue of a 64 -> 64 layer of the
+        // in-repo U-Net took 1.7 - 2.3 us per tile against 1.3 us of MMA issue)
+        constexpr bool SPLIT64 = BLOCK_N == 64;
+        constexpr int CPW = BLOCK_N >= 128 ? BLOCK_N / 2 : SPLIT64 ? 32 : BLOCK_N;
+        static_assert(CPW % 64 == 0 || SPLIT64, "row-domain epilogue: BLOCK_N >= 64");
+        const int half = e >> 2;
+        const bool active = true;
+        __shared__ float2 pair_sums[4][32];  // SPLIT64 + rowstat: the upper half's per-pixel sums on their way to the lower half
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory"); };
+        // 32 pixels x 128 bytes per warp, 1024-byte aligned.  With 64-column tiles only four warps are active: each uses
+        // the idle partner's block as a SECOND staging buffer, so that a tile never waits for the TMA unit to finish reading
+        // the previous one (measured on the 64-channel U-Net layers: that wait was most of a 1.4 us epilogue)
+        constexpr bool TWO_STAGING = BLOCK_N == 64;
+        const uint32_t stage0 = smem_base + C::RING_BYTES + (SPLIT64 ? quarter : e) * (32 * 128);
         const int sw = lane & 7;
+        // this lane's pixel inside the tile (fixed for the whole kernel: the divisions are done once)
+        const int row = quarter * 32 + lane;
+        const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
+        const int r0 = quarter * 32;  // first pixel of the 32 this warp stores: tile rows [32 quarter, 32 quarter + 32)
+        const int r0h = (r0 / p.BW) % p.BH, r0n = r0 / (p.BW * p.BH);
+        const bool short_k = num_kb <= 36;  // tiles of a microsecond: no sleeping between polls of the accumulator barrier
         // the lanes with (lane & 7) == 0 own 8-channel block (lane >> 3) of every chunk: GroupNorm sums carried across
         // the tiles of an image (chunked mode), slot = n_tile * 4 + chunk
         float carry_s[8], carry_q[8];
@@ -788,46 +955,82 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                 flush_carry(carry_img);
                 carry_img = n0;
             }
-            tc::mbar_wait_backoff(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
+            // everything that does not depend on the accumulator happens BEFORE the wait for it: this lane's pixel, its
+            // residual / gate rows and the residual of the first chunk (an L2 round trip on layers whose whole reduction
+            // lasts a microsecond)
+            const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
+            const bool ok = active && (n < p.N) && (h < p.H) && (w < p.W);
+            const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
+            const int64_t rpix = p.res_up ? ((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : pix;
+            const __nv_bfloat16* resp = p.res ? p.res + rpix * p.res_ld + col_base : nullptr;
+            const float* gatep = p.gate ? p.gate + (int64_t)((uint32_t)pix / (uint32_t)p.gate_rows) * p.gate_ld + col_base : nullptr;
+            const bool use_res = resp != nullptr && ok;
+            // (narrow tiles only: with N = 256 the extra 16 registers spill, and those layers have long reductions)
+            constexpr bool RES_AHEAD = BLOCK_N <= 128;
+            uint4 rsd_next[RES_AHEAD ? 4 : 1];
+            if (RES_AHEAD && use_res) {
+#pragma unroll
+                for (int q = 0; q < (RES_AHEAD ? 4 : 1); ++q)
+                    rsd_next[q] = col_base + 8 * q < p.c_out ? __ldg(reinterpret_cast<const uint4*>(resp) + q) : make_uint4(0, 0, 0, 0);
+            }
+            // bias and gate of this warp's columns, ONE value per lane and 32-column chunk, broadcast with shuffles when the
+            // chunk is processed: these kernels leave the SM no L1 cache (the shared-memory carve-out is the whole array), so
+            // every per-chunk __ldg of a bias / gate row was a full L2 round trip on the critical path of a short tile
+            float bias_l[CPW / 32], gate_l[CPW / 32];
+            int gate_sample = -1;
+            if (p.gate && p.gate_uniform) gate_sample = __reduce_max_sync(0xffffffffu, ok ? (int)((uint32_t)pix / (uint32_t)p.gate_rows) : -1);
+#pragma unroll
+            for (int c = 0; c < CPW / 32; ++c) {
+                const int cl = col_base + 32 * c + lane;
+                bias_l[c] = (p.bias && cl < p.c_out) ? __ldg(p.bias + cl) : 0.f;
+                gate_l[c] = (gate_sample >= 0 && cl < p.c_out) ? __ldg(p.gate + (int64_t)gate_sample * p.gate_ld + cl) : 1.f;
+            }
+            const uint32_t stage = TWO_STAGING ? stage0 + 4 * (local & 1) * (32 * 128) : stage0;
+            const uint32_t my_row = stage + (uint32_t)lane * 128u;
+            if (e == 0 && lane == 0) mark(local, 4);
+            if (short_k) tc::mbar_wait(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
+            else tc::mbar_wait_backoff(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
+            if (e == 0 && lane == 0) mark(local, 5);
             tc::fence_after_sync();
             if (active) {
-                // this lane's pixel
-                const int row = quarter * 32 + lane;
-                const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
-                const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
-                const bool ok = (n < p.N) && (h < p.H) && (w < p.W);
-                const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
-                const int64_t rpix = p.res_up ? ((int64_t)n * (p.H >> 1) + (h >> 1)) * (p.W >> 1) + (w >> 1) : pix;
-                const __nv_bfloat16* resp = p.res ? p.res + rpix * p.res_ld + col_base : nullptr;
-                const float* gatep = p.gate ? p.gate + (pix / p.gate_rows) * p.gate_ld + col_base : nullptr;
-                // first pixel of the 32 this warp stores: tile rows [32 quarter, 32 quarter + 32)
-                const int r0 = quarter * 32;
-                const int sh = h0 + (r0 / p.BW) % p.BH, sn = n0 + r0 / (p.BW * p.BH);
+                const int sh = h0 + r0h, sn = n0 + r0n;
+                float rs_sum = 0.f, rs_sq = 0.f;
 #pragma unroll 1
                 for (int c0 = 0; c0 < CPW; c0 += 32) {
                     uint32_t acc[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * C::ACC_COLS + half * CPW + c0);
                     tc::tmem_ld_32x32b_x32(taddr, acc);
                     const int col = col_base + c0;
-                    // loads that do not depend on the accumulator go first
+                    // this chunk's residual was requested one chunk (or one barrier wait) ago; request the next one
                     uint4 rsd[4];
-                    const bool use_res = resp != nullptr && ok;
-                    if (use_res) {
+                    if constexpr (RES_AHEAD) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) rsd[q] = rsd_next[q];
+                        if (use_res && c0 + 32 < CPW) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                rsd_next[q] = col + 32 + 8 * q < p.c_out ? __ldg(reinterpret_cast<const uint4*>(resp + c0 + 32) + q) : make_uint4(0, 0, 0, 0);
+                        }
+                    } else if (use_res) {  // loads that do not depend on the accumulator go first
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
                             rsd[q] = col + 8 * q < p.c_out ? __ldg(reinterpret_cast<const uint4*>(resp + c0) + q) : make_uint4(0, 0, 0, 0);
                     }
                     tc::tmem_ld_wait();
+                    if (e == 0 && lane == 0) mark(local, c0 == 0 ? 7 : 11);
                     float v[32];
+                    float bias_c = bias_l[0], gate_c = gate_l[0];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (p.bias && col + 4 * q < p.c_out) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + q);
-                        v[4 * q] = __uint_as_float(acc[4 * q]) + b4.x, v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + b4.y;
-                        v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + b4.z, v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + b4.w;
-                    }
+                    for (int c = 1; c < CPW / 32; ++c)
+                        if (c0 == 32 * c) bias_c = bias_l[c], gate_c = gate_l[c];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + __shfl_sync(0xffffffffu, bias_c, j);
                     activate_all(v, p.act);
-                    if (gatep && ok) {
+                    if (e == 0 && lane == 0) mark(local, c0 == 0 ? 8 : 12);
+                    if (gate_sample >= 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= __shfl_sync(0xffffffffu, gate_c, j);
+                    } else if (gatep && ok) {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             if (col + 4 * q < p.c_out) {
@@ -853,9 +1056,57 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                         __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
                         packed[j] = *reinterpret_cast<uint32_t*>(&t);
                     }
+                    if (e == 0 && lane == 0) mark(local, c0 == 0 ? 9 : 13);
+                    if (p.rowstat) {
+                        // {sum, sum of squares} of the STORED values of this pixel's 64-channel block, for the per-pixel
+                        // normalisation in the consumer's input transform (ConvParams::in_norm)
+                        float s_ = 0.f, q_ = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float lo = bf16_bits_to_f32(packed[j] & 0xffffu), hi = __uint_as_float(packed[j] & 0xffff0000u);
+                            s_ += lo + hi, q_ = fmaf(lo, lo, fmaf(hi, hi, q_));
+                        }
+                        if constexpr (SPLIT64) rs_sum = s_, rs_sq = q_;
+                        else if ((c0 & 32) == 0) rs_sum = s_, rs_sq = q_;
+                        else if (ok && col < p.c_out + 32)
+                            p.rowstat[pix * (p.c_out >> 6) + ((col_base + (c0 & ~63)) >> 6)] = make_float2(rs_sum + s_, rs_sq + q_);
+                    }
+                    if (e == 0 && lane == 0) mark(local, c0 == 0 ? 10 : 14);
+                    if constexpr (SPLIT64) {
+                        // the pair's staging block is free once the TMA unit has read the store of two tiles ago out of it
+                        if (store_pending) {
+                            if (half == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            pair_sync();
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t slot = (uint32_t)((4 * half + q) ^ sw);
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + (slot << 4)), "r"(packed[4 * q]),
+                                         "r"(packed[4 * q + 1]), "r"(packed[4 * q + 2]), "r"(packed[4 * q + 3])
+                                         : "memory");
+                        }
+                        if (p.rowstat && half == 1) pair_sums[quarter][lane] = make_float2(rs_sum, rs_sq);
+                        tc::fence_proxy_async();
+                        pair_sync();
+                        if (half == 0) {
+                            if (lane == 0) {
+                                const int cblk = n_tile * BLOCK_N;
+                                if (cblk < p.c_out) tc::tma_store_4d(&tmap_out, stage, cblk, w0, sh, sn);
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                            }
+                            if (p.rowstat && ok) {
+                                const float2 up = pair_sums[quarter][lane];
+                                p.rowstat[pix * (p.c_out >> 6) + n_tile] = make_float2(rs_sum + up.x, rs_sq + up.y);
+                            }
+                        }
+                        store_pending = true;
+                    } else {
                     // the staging block is free once the TMA unit has read the previous store out of it
                     if ((c0 & 32) == 0 && store_pending) {
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        if (lane == 0) {
+                            if (TWO_STAGING) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        }
                         __syncwarp();
                     }
                     // 32 channels = slots (c0 & 63) / 8 + 0..3 of this pixel's 128-byte row; slot s lives at s ^ (row & 7)
@@ -880,6 +1131,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
                         store_pending = true;
+                    }
                     }
                     if (p.gn_acc) {
                         // sums of the STORED (rounded) values: 8 channels in the lane, then the 32 rows of the slab
@@ -935,6 +1187,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                 if (PAIR && !leader) tc::mbar_arrive_cluster(tc::mapa(tc::smem_u32(&bar_acc_empty[as]), 0));
                 else tc::mbar_arrive(tc::smem_u32(&bar_acc_empty[as]));
             }
+            if (e == 0 && lane == 0) mark(local, 6);
         }
         if (p.chunked) flush_carry(carry_img);
         if (lane == 0 && store_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete before exit
@@ -1260,6 +1513,10 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
 
     tc::fence_before_sync();
     __syncthreads();
+    if (trace_slot) {
+        atomicMax(trace_slot + 2, azb_globaltimer());
+        if (blockIdx.x == 0) atomicAdd(p.trace, 1ull);
+    }
     if constexpr (PAIR) {
         tc::cluster_sync();  // neither CTA retires (shared memory, barriers, tensor memory) while its peer still works
         if (warp == 1) tc::tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
@@ -1280,12 +1537,12 @@ int sm_count() { return azb_sm_count(); }
 
 #define g_knob azb_knob
 
-template <int BLOCK_N, bool PAIR = false, int EPI = 0, bool HALO = false, bool TF32 = false>
+template <int BLOCK_N, bool PAIR = false, int EPI = 0, bool HALO = false, bool TF32 = false, bool NORM = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const ConvParams& p, cudaStream_t s,
            const CUtensorMap* tout = nullptr) {
     constexpr int smem = Cfg<BLOCK_N, PAIR, HALO>::SMEM;
     constexpr int threads = HALO ? THREADS_HALO : THREADS;
-    auto kernel = conv_gemm_kernel<BLOCK_N, PAIR, EPI, HALO, TF32>;
+    auto kernel = conv_gemm_kernel<BLOCK_N, PAIR, EPI, HALO, TF32, NORM>;
     const CUtensorMap& to = tout ? *tout : ta;
     static AzbPerDevice<bool> configured_dev;
     bool& configured = configured_dev.get();
@@ -1355,6 +1612,12 @@ struct ConvExtra {
     int in_up = 0;               // act given at half resolution: the convolution reads its nearest 2x upsampling (halo + in_coef)
     const float* in_coef = nullptr;  // [N][c_in] {a, b}: the input is act(a x + b), applied on the fly (halo kernels only)
     int in_silu = 0;
+    int in_norm = 0;             // per-pixel LayerNorm (1) / RMSNorm (2) + modulation of the input (halo kernels)
+    float in_eps = 1e-5f;
+    const float* in_rowstat = nullptr;
+    const float* in_mod = nullptr;
+    int64_t in_mod_ld = 0;
+    float* rowstat = nullptr;    // per-(pixel, 64-channel block) sums of the output (row-domain epilogue only)
     AzbConvChoice* choice = nullptr;  // dry run: report the launcher's choice instead of launching
 };
 
@@ -1394,6 +1657,7 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     if ((colsum || ex.gn_acc) && (out_mode != 0 || (stat_gran != 1 && stat_gran != 8))) return AZB_E_SHAPE;
     if (colsum && (ex.gn_acc || !azb_aligned(colsum, 8))) return AZB_E_SHAPE;
     if (ex.gn_acc && !azb_aligned(ex.gn_acc, 8)) return AZB_E_ALIGN;
+    if (ex.gate && n * ((h_in + ex.stride - 1) / ex.stride) * ((w_in + ex.stride - 1) / ex.stride) >= 0x7fffffffLL) return AZB_E_SHAPE;
     if (ex.gate && (out_mode != 0 || ex.gate_rows <= 0 || ex.gate_ld % 4 || !azb_aligned(ex.gate, 16))) return AZB_E_ALIGN;
     if (out_mode == 1 && ex.act != AZB_ACT_NONE) return AZB_E_UNSUPPORTED;
     if (ex.act2 && (ex.c_in2 <= 0 || ex.c_in2 % 8 || ex.act2_ld % 8 || ex.act2_ld < ex.c_in2 || ex.k2 % BLOCK_K ||
@@ -1402,16 +1666,25 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     const int64_t h = (h_in + ex.stride - 1) / ex.stride, w = (w_in + ex.stride - 1) / ex.stride;
 
     // The row-domain epilogue (EPI == 2) brings activation and gate to the halo kernels.  Measured: neutral to +3 % on the
-    // ADM layers (no activation / gate, long reductions); on the token GEMMs with activation / gate epilogues and wide
-    // tiles +25 % (768 -> 3072 + SiLU: 87 -> 70 us, scripts/gemm_one.py) once the activation selector is tested outside
-    // the element loop; the small U-Net convolutions with 64-column tiles (four of the eight epilogue warps idle in this
-    // epilogue) keep the transposing one unless the knob is forced to 1.
-    const bool epi_plain = ex.act == AZB_ACT_NONE && !ex.gate;
+    // ADM layers (no activation / gate, long reductions); +25 % on the token GEMMs with activation / gate epilogues
+    // (768 -> 3072 + SiLU: 87 -> 70 us, scripts/gemm_one.py) and 2 - 7 us per launch on the in-repo U-Net's 3 x 3 layers
+    // (scripts/unet_conv_ab.py) once the activation selector is tested outside the element loop, bias / gate rows are held
+    // per lane instead of re-read through an L1 these kernels do not have, and 64-column tiles use all eight warps.
     const bool rowepi_ok = g_knob[AZB_CONV_KNOB_ROWEPI] != 0 && out_mode == 0 && !colsum && (!ex.gn_acc || stat_gran == 8) &&
-                           (phases == 1 || (c_out % 64 == 0 && out_ld % 8 == 0)) &&
-                           (g_knob[AZB_CONV_KNOB_ROWEPI] == 1 || epi_plain || (taps == 1 && c_out_rows % 128 == 0));
+                           (phases == 1 || (c_out % 64 == 0 && out_ld % 8 == 0));
+    if (ex.in_norm < 0 || ex.in_norm > 2) return AZB_E_SHAPE;
+    if (ex.in_norm && (!ex.in_rowstat || !ex.in_mod || ex.in_coef || ex.in_up || taps != 9 || ex.stride != 1 || c_in % BLOCK_K ||
+                       ex.in_mod_ld % 4 || !azb_aligned(ex.in_mod, 16) || !azb_aligned(ex.in_rowstat, 8)))
+        return AZB_E_SHAPE;
+    if (ex.rowstat && (out_mode != 0 || c_out % 64 || phases != 1 || !azb_aligned(ex.rowstat, 8))) return AZB_E_SHAPE;
     // Halo tiles: 3 x 3, stride 1, maps of at least one 8 x 16 patch, whole 64-channel blocks (see the kernel's header)
+    // ... and, unless the input transform / upsampling on load needs them, only when every SM gets several tiles: with one
+    // or two tiles per CTA the tap-wise kernel's plain load -> MMA stream starts up faster than load -> transform slot ->
+    // MMA (in-repo U-Net, 128 / 256 channels at 32 x 32 / 16 x 16 x batch 32: 14 - 15 us tap-wise against 18 us)
+    const bool halo_needed = ex.in_coef || ex.in_norm || ex.in_up;
+    const int64_t halo_m_tiles = ((w + HALO_W - 1) / HALO_W) * ((h + HALO_H - 1) / HALO_H) * n;
     bool halo = g_knob[AZB_CONV_KNOB_HALO] != 0 && taps == 9 &&
+                (halo_needed || g_knob[AZB_CONV_KNOB_HALO] == 1 || halo_m_tiles * ((c_out + 255) / 256) > 2 * sm_count()) &&
                 ex.stride == 1 && h >= HALO_H && w >= HALO_W &&
                 c_in % BLOCK_K == 0 && k_per_tap == c_in && (!ex.act2 || (ex.c_in2 % BLOCK_K == 0 && ex.k2 == ex.c_in2)) &&
                 !colsum && ((ex.act == AZB_ACT_NONE && !ex.gate) || rowepi_ok) && (!ex.gn_acc || stat_gran == 8) &&
@@ -1451,14 +1724,19 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     int splits = 1;
     const int64_t num_kb_total = (int64_t)taps_k * (k_per_tap / BLOCK_K) + (ex.act2 ? ex.k2 / BLOCK_K : 0);
     // halo kernels exist for the wide lean tiles and for the narrowest generic one (the network's output convolution)
-    if (halo && !((out_mode == 0 && block_n >= 128) || (out_mode == 1 && block_n == 16))) {
-        if (ex.in_coef) return AZB_E_UNSUPPORTED;
+    // ... and, with the row-domain epilogue, for 64-column tiles (the 64-channel level of the in-repo U-Net)
+    // (one channel block: resident weights; with more, the 8 KiB weight stages stream too slowly -- 192 -> 64: 57 us against
+    // 40 us tap-wise)
+    const bool halo64 = out_mode == 0 && block_n == 64 && rowepi_ok && !ex.act2 && phases == 1 && !ex.gn_acc && splits == 1 &&
+                        !ex.in_coef && !ex.in_up && (k_per_tap == BLOCK_K || ex.in_norm);
+    if (halo && !((out_mode == 0 && block_n >= 128) || (out_mode == 1 && block_n == 16) || halo64)) {
+        if (ex.in_coef || ex.in_norm) return AZB_E_UNSUPPORTED;
         // recompute the tiling for the tap-wise kernel
         ExtraGuard guard(g_knob[AZB_CONV_KNOB_HALO]);
         return conv_impl(act, n, h_in, w_in, c_in, act_ld, wpack, c_out, c_out_rows, taps, k_per_tap, bias, residual, res_ld,
                          out, out_ld, out_mode, colsum, stat_gran, stream, ex);
     }
-    if (!halo && ex.in_coef) return AZB_E_UNSUPPORTED;
+    if (!halo && (ex.in_coef || ex.in_norm)) return AZB_E_UNSUPPORTED;
     if (!halo && !ex.res_up && g_knob[AZB_CONV_KNOB_SPLITK] != 0 && ex.workspace && out_mode == 0 && m_tiles * (c_out_rows / block_n) <= sms && (block_n <= 64 || m_tiles * (c_out_rows / block_n) < sms / 2)) {
         const int try_n[2] = {128, 256}, try_s[2] = {2, 4};
         for (int i = 0; i < 2 && splits == 1; ++i) {
@@ -1505,6 +1783,9 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     p.stat_gran = stat_gran;
     p.stride = ex.stride, p.act = ex.act;
     p.gate = ex.gate, p.gate_ld = ex.gate_ld, p.gate_rows = (int)ex.gate_rows;
+    // a slab = 32 consecutive tile rows: inside one image when the per-image patch has >= 32 pixels; a sample is then a
+    // whole number of images (gate_rows = k H W), or -- one image, 16-column token grids -- a whole number of slabs
+    p.gate_uniform = (p.BW * p.BH >= 32 && (ex.gate_rows % (h * w) == 0 || (n == 1 && p.BW == w && ex.gate_rows % 32 == 0))) ? 1 : 0;
     p.kb_extra = ex.act2 ? (int)(ex.k2 / BLOCK_K) : 0;
     if (ex.gn_acc && (p.BW * p.BH) % 32) return AZB_E_SHAPE;  // a 32-row slab would straddle two images
     p.gn_acc = reinterpret_cast<unsigned long long*>(ex.gn_acc);
@@ -1515,6 +1796,9 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     // STAGES loads in flight the main loop would run at HBM latency; prefetch the weight stream into L2 ahead of use
     p.prefetch_kb = halo ? 0 : g_knob[AZB_CONV_KNOB_PREFETCH] >= 0 ? g_knob[AZB_CONV_KNOB_PREFETCH] : (m_tiles <= 32 ? 24 : 0);
     p.in_coef = reinterpret_cast<const float2*>(ex.in_coef), p.in_silu = ex.in_silu, p.c_in = (int)c_in;
+    p.trace = reinterpret_cast<unsigned long long*>(azb_trace_buf);
+    p.in_norm = ex.in_norm, p.in_eps = ex.in_eps, p.in_rowstat = reinterpret_cast<const float2*>(ex.in_rowstat);
+    p.in_mod = ex.in_mod, p.in_mod_ld = ex.in_mod_ld, p.rowstat = reinterpret_cast<float2*>(ex.rowstat);
     p.in_up = ex.in_up == 1;
     p.a_slot = p.in_up ? UP_BYTES : Cfg<256, true, true>::A_SLOT;
     p.sa = g_knob[AZB_CONV_KNOB_HALO_SA] >= 2 && g_knob[AZB_CONV_KNOB_HALO_SA] <= 4 ? g_knob[AZB_CONV_KNOB_HALO_SA] : 3;
@@ -1577,12 +1861,13 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     // Row-domain epilogue with TMA stores (EPI == 2): every bf16 NHWC layer with an N tile of whole 64-channel store
     // blocks, without split-K / per-channel statistics; activation, gate, residual and exact GroupNorm sums included.
     // A halo kernel needs a wide tile unless it is this epilogue's 64-column instantiation.
-    const bool rowepi = rowepi_ok && splits == 1 && block_n >= 64 && (!halo || block_n >= 128) &&
-                        (epi_plain || g_knob[AZB_CONV_KNOB_ROWEPI] == 1 || block_n >= 128);
+    const bool rowepi = rowepi_ok && splits == 1 && block_n >= 64 && !(block_n == 64 && ex.gn_acc);
+    if (ex.rowstat && !rowepi) return AZB_E_UNSUPPORTED;  // the per-pixel sums come from the row-domain epilogue only
     if (halo && (ex.act != AZB_ACT_NONE || ex.gate) && !rowepi) return AZB_E_UNSUPPORTED;  // (unreachable: wide halo tiles)
     if (ex.choice) {
         ex.choice->halo = halo, ex.choice->pair = pair, ex.choice->lean = lean || rowepi, ex.choice->block_n = block_n, ex.choice->splits = splits;
         ex.choice->tiles = p.total_tiles;
+        ex.choice->epi = rowepi ? 2 : lean ? 1 : 0;
         return AZB_OK;
     }
     if (rowepi) {
@@ -1608,10 +1893,21 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
         if (halo) {
             const int b_stage = pair ? Cfg<256, true, true>::STAGE_BYTES * block_n / 256 : Cfg<256, false, true>::STAGE_BYTES * block_n / 256;
             p.sb = (SMEM_BUDGET - p.sa * p.a_slot) / b_stage;
+            // one channel block, one N tile, all nine weight tiles fit next to the A slots: resident weights
+            p.b_resident = (!pair && p.kb_per_tap == 1 && p.kb_extra == 0 && phases == 1 && p.n_tiles == 1 && p.sb >= 9 &&
+                            g_knob[AZB_CONV_KNOB_HALO_SB] < 0) ? 1 : 0;
             if (p.sb > 8) p.sb = 8;
             if (g_knob[AZB_CONV_KNOB_HALO_SB] >= 2 && g_knob[AZB_CONV_KNOB_HALO_SB] < p.sb) p.sb = g_knob[AZB_CONV_KNOB_HALO_SB];
             if (p.sb < 2) return AZB_E_SHAPE;
+            if (p.in_norm) {  // the instantiations whose transform warps normalise per pixel
+                if (pair) return block_n == 256 ? launch<256, true, 2, true, false, true>(ta, tb, ta2, p, s, &tout)
+                                                : launch<128, true, 2, true, false, true>(ta, tb, ta2, p, s, &tout);
+                if (block_n == 64) return launch<64, false, 2, true, false, true>(ta, tb, ta2, p, s, &tout);
+                return block_n == 256 ? launch<256, false, 2, true, false, true>(ta, tb, ta2, p, s, &tout)
+                                      : launch<128, false, 2, true, false, true>(ta, tb, ta2, p, s, &tout);
+            }
             if (pair) return block_n == 256 ? launch<256, true, 2, true>(ta, tb, ta2, p, s, &tout) : launch<128, true, 2, true>(ta, tb, ta2, p, s, &tout);
+            if (block_n == 64) return launch<64, false, 2, true>(ta, tb, ta2, p, s, &tout);
             return block_n == 256 ? launch<256, false, 2, true>(ta, tb, ta2, p, s, &tout) : launch<128, false, 2, true>(ta, tb, ta2, p, s, &tout);
         }
         if (pair) return block_n == 256 ? launch<256, true, 2>(ta, tb, ta2, p, s, &tout) : launch<128, true, 2>(ta, tb, ta2, p, s, &tout);
@@ -1812,6 +2108,8 @@ extern "C" int azb_conv_bf16(const AzbConv* d, void* stream) {
     ex.workspace = d->workspace, ex.workspace_bytes = d->workspace_bytes;
     ex.in_coef = d->in_coef, ex.in_silu = d->in_silu;
     ex.res_up = d->res_up, ex.in_up = d->in_up;
+    ex.in_norm = d->in_norm, ex.in_eps = d->in_eps, ex.in_rowstat = d->in_rowstat, ex.in_mod = d->in_mod, ex.in_mod_ld = d->in_mod_ld;
+    ex.rowstat = d->rowstat;
     return conv_impl(d->act, d->n, d->h, d->w, d->c_in, d->act_ld, d->wpack, d->c_out, d->c_out_rows, d->taps, d->k_per_tap,
                      d->bias, d->residual, d->res_ld, d->out, d->out_ld, d->out_mode, d->colsum,
                      (d->colsum || d->gn_acc) ? d->stat_gran : 1, stream, ex);
@@ -1828,6 +2126,8 @@ extern "C" int azb_conv_choice(const AzbConv* d, AzbConvChoice* choice) {
     ex.workspace = d->workspace, ex.workspace_bytes = d->workspace_bytes;
     ex.in_coef = d->in_coef, ex.in_silu = d->in_silu;
     ex.res_up = d->res_up, ex.in_up = d->in_up;
+    ex.in_norm = d->in_norm, ex.in_eps = d->in_eps, ex.in_rowstat = d->in_rowstat, ex.in_mod = d->in_mod, ex.in_mod_ld = d->in_mod_ld;
+    ex.rowstat = d->rowstat;
     ex.choice = choice;
     return conv_impl(d->act, d->n, d->h, d->w, d->c_in, d->act_ld, d->wpack, d->c_out, d->c_out_rows, d->taps, d->k_per_tap,
                      d->bias, d->residual, d->res_ld, d->out, d->out_ld, d->out_mode, d->colsum,

@@ -310,7 +310,7 @@ class Plan:
         n, h, w, _ = x.shape
         grid = (n, 2 * h, 2 * w) if in_up else (n, h, w)
         d = ops.conv_desc(x, pc, out, grid=grid, residual=residual, x2=x2, gran=self.stat_gran, nchw_f32=nchw_f32,
-                          in_up=in_up, in_coef=self._probe_coef(n, pc.c_in) if in_up else None)
+                          in_up=in_up, in_coef=self._probe_coef(n, pc.c_in))  # (the transform itself is what asks for halo tiles)
         try:
             return bool(ops.conv_choice(d).halo)
         except _lib.AzbError:  # e.g. the phase-decomposed form on a map below 16 x 8 half-resolution pixels

@@ -33,6 +33,8 @@ class AzbConv(ctypes.Structure):
         ("act2", c_void_p), ("c_in2", c_int64), ("act2_ld", c_int64), ("k2", c_int64), ("gn_acc", c_void_p),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
         ("in_coef", c_void_p), ("in_silu", c_int32), ("in_up", c_int32),
+        ("in_norm", c_int32), ("in_eps", c_float), ("in_rowstat", c_void_p), ("in_mod", c_void_p), ("in_mod_ld", c_int64),
+        ("rowstat", c_void_p),
     ]
 
 
@@ -40,7 +42,7 @@ class AzbConvChoice(ctypes.Structure):
     r"""``AzbConvChoice`` of ``include/azb.h``: what the convolution launcher would do for a descriptor."""
 
     _fields_ = [("halo", c_int32), ("pair", c_int32), ("lean", c_int32), ("block_n", c_int32), ("splits", c_int32),
-                ("tiles", c_int32)]
+                ("tiles", c_int32), ("epi", c_int32)]
 
 
 _lib.register({
@@ -57,6 +59,7 @@ _lib.register({
          c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p],
     ),
     "azb_conv_tuning": (c_int, [c_int, c_int]),
+    "azb_debug_trace": (c_int, [c_void_p]),
     "azb_conv_tf32": (
         c_int,
         [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int64, c_int, c_void_p,
@@ -611,7 +614,9 @@ def conv_desc(x: Tensor, pc, out: Tensor, *, grid: tuple[int, int, int] | None =
               gate: int | None = None, gate_ld: int = 0, gate_rows: int = 0, residual: Tensor | None = None,
               nchw_f32: bool = False, x2: Tensor | None = None, gn_acc: Tensor | None = None, gran: int = 8,
               workspace: Tensor | None = None, in_coef: Tensor | None = None, in_silu: bool = False,
-              res_up: bool = False, in_up: bool = False) -> AzbConv:
+              res_up: bool = False, in_up: bool = False, in_norm: int = 0, in_eps: float = 1e-5,
+              in_rowstat: Tensor | None = None, in_mod: int | None = None, in_mod_ld: int = 0,
+              rowstat: Tensor | None = None) -> AzbConv:
     r"""Fills an :class:`AzbConv` for ``azb_conv_bf16``; ``pc`` is a :class:`PackedConv` or, with ``x2``, a
     :class:`PackedConvSkip``.  ``gn_acc``: int64 (N, C_out / gran, 4) exact GroupNorm accumulators (zeroed by the
     caller).  ``in_coef``: fp32 (N, C_in, 2) from :func:`gn_coef` -- the convolution then reads
@@ -639,6 +644,16 @@ def conv_desc(x: Tensor, pc, out: Tensor, *, grid: tuple[int, int, int] | None =
     # x is (n, h / 2, w / 2, c), `grid` = the upsampled extents: 1 = read through a nearest 2x upsampling tensor map,
     # 2 = phase-decomposed (weights from pack_conv_up, 2.25 x fewer FLOPs)
     d.in_up = (2 if getattr(pc, "taps", 9) == 16 else 1) if in_up else 0
+    # per-pixel LayerNorm (1) / RMSNorm (2) + modulation of the input, statistics from the producer's `rowstat`;
+    # `in_mod` is a raw device address of [a(C_in) | b(C_in)] fp32 rows
+    if in_norm:
+        assert in_rowstat is not None and in_rowstat.dtype == torch.float32 and in_rowstat.is_contiguous()
+        assert in_rowstat.numel() == n * h * w * (pc.c_in // 64) * 2 and in_mod
+        d.in_norm, d.in_eps, d.in_rowstat, d.in_mod, d.in_mod_ld = in_norm, in_eps, in_rowstat.data_ptr(), in_mod, in_mod_ld
+    if rowstat is not None:
+        ho, wo = -(-h // stride), -(-w // stride)
+        assert rowstat.dtype == torch.float32 and rowstat.is_contiguous() and rowstat.numel() == n * ho * wo * (pc.c_out // 64) * 2
+        d.rowstat = rowstat.data_ptr()
     return d
 
 

@@ -5,9 +5,12 @@ Replaces ``UNet.forward`` of the reference (``azula/nn/unet.py:207-259`` and ``U
 SiLU and a gated residual -- 8 ATen launches and as many HBM round trips in fp32 NCHW) by a launch
 plan over NHWC bf16 buffers:
 
-    per block   azb_rownorm_mod_bf16   y = (1 + a) * LayerNorm_C(x) + b           (one pass)
-                azb_conv2d_bf16        h = SiLU(conv3x3(y) + bias)                 (tcgen05, epilogue act)
-                azb_conv2d_bf16        out = x + c * (conv3x3(h) + bias)           (tcgen05, epilogue gate + residual)
+    per block   azb_conv_bf16          h = SiLU(conv3x3((1 + a) * LayerNorm_C(x) + b) + bias)
+                                       (tcgen05 halo tiles; the per-pixel normalisation and the modulation are applied to the
+                                       landed tile in shared memory from the per-pixel sums the PRODUCER of x wrote in its
+                                       epilogue -- no normalisation pass over HBM; azb_rownorm_mod_bf16 + azb_conv2d_bf16
+                                       where the producer has no row-domain epilogue or the channels are not whole 64-blocks)
+                azb_conv_bf16          out = x + c * (conv3x3(h) + bias)           (epilogue gate + residual + per-pixel sums)
     down        azb_conv2d_bf16 stride 2 (TMA element strides: no im2col, no gather pass)
     up          azb_gn_apply_bf16 mode 1 (nearest x2) writing straight into the concatenation buffer
     (a, b, c)   all blocks' Ada-Norm-Zero MLPs in two fp32 launches (:class:`ModulationBank`)
@@ -23,12 +26,15 @@ import torch.nn as nn
 
 from torch import Tensor
 
+from ctypes import byref
+
 from .. import _lib
 from . import ops
 from .plan import LaunchPlan, ModulationBank, fingerprint, note_use
 
 _MAX_PLANS = 2
 _NORM_KIND = {"layer": 0, "rms": 1}
+FUSE_NORM = True  # A/B switch: per-pixel normalisation inside the convolution's input transform (else a separate pass)
 
 
 def _is_block(m) -> bool:
@@ -142,6 +148,8 @@ class Plan(LaunchPlan):
         self.mod_ld = self.abc.stride(0) if (rows == n and n > 1) else 0
         self.gn_partial_need = 0
         self.counters = torch.zeros(max(n, 1), dtype=torch.int32, device=device)
+        self.rowstat: dict[int, Tensor] = {}  # id(activation view) -> per-(pixel, 64-channel block) sums from its producer
+        self.fused_norms = 0
 
         depth = len(model.descent)
         first = model.descent[0][0]
@@ -164,9 +172,9 @@ class Plan(LaunchPlan):
                 if _is_block(m):
                     self._block(m, cur, out)
                 elif m is first:
-                    self.conv(self.patches, packed.conv[id(m)], out, kind="gemm")
+                    self.conv_stat(self.patches, packed.conv[id(m)], out, kind="gemm")
                 else:
-                    self.conv(cur, packed.conv[id(m)], out, stride=2)
+                    self.conv_stat(cur, packed.conv[id(m)], out, stride=2)
                 self._release(cur)
                 cur = out
         # ---- ascent
@@ -191,7 +199,7 @@ class Plan(LaunchPlan):
                     break
                 else:
                     out = arena.take(n, hi, wi, m.out_channels)
-                    self.conv(cur, packed.conv[id(m)], out)
+                    self.conv_stat(cur, packed.conv[id(m)], out)
                 self._release(cur)
                 cur = out
         assert self.out_conv is not None
@@ -205,22 +213,69 @@ class Plan(LaunchPlan):
         if t is not None and id(t) in self.arena.owner:
             self.arena.give(t)
 
+    def conv_stat(self, x: Tensor, pc, out: Tensor, *, stride: int = 1, act: int = 0, gate: int | None = None,
+                  gate_ld: int = 0, gate_rows: int = 0, residual: Tensor | None = None, kind: str | None = None,
+                  norm: tuple | None = None) -> bool:
+        r"""Queues a convolution through the descriptor entry (``azb_conv_bf16``).  Where the launcher takes the row-domain
+        epilogue, the per-(pixel, 64-channel block) sums of ``out`` are written too (``self.rowstat[id(out)]``) for a
+        normalisation fused into the NEXT convolution; ``norm = (kind, eps, sums of x, address of [a | b], stride)`` asks
+        for that fusion here.  Returns False (nothing queued) when ``norm`` is given but the launcher cannot fuse it."""
+        n, h, w = x.shape[:3]
+        ho, wo = -(-h // stride), -(-w // stride)
+        kw = dict(stride=stride, act=act, gate=gate, gate_ld=gate_ld, gate_rows=gate_rows, residual=residual)
+        if norm is not None:
+            kw.update(in_norm=norm[0], in_eps=norm[1], in_rowstat=norm[2], in_mod=norm[3], in_mod_ld=norm[4])
+        stat = None
+        if FUSE_NORM and pc.c_out % 64 == 0:
+            stat = torch.empty(n * ho * wo, pc.c_out // 64, 2, dtype=torch.float32, device=self.device)
+        d, choice = None, None
+        for st in ([stat, None] if stat is not None else [None]):
+            d = ops.conv_desc(x, pc, out, rowstat=st, **kw)
+            c = ops.AzbConvChoice()
+            if self.lib.azb_conv_choice(byref(d), byref(c)) == 0 and (st is None or c.epi == 2) and (norm is None or c.halo):
+                choice, stat = c, st
+                break
+        if choice is None:
+            if norm is not None:
+                return False
+            raise _lib.AzbError("azb_conv_choice rejected a convolution of the U-Net plan")
+        if stat is not None:
+            self.rowstat[id(out)] = stat
+        self.keep += [x, out, pc.w, d, stat] + ([residual] if residual is not None else []) + ([pc.bias] if pc.bias is not None else [])
+        if norm is not None:
+            self.keep.append(norm[2])
+        flops = 2.0 * n * ho * wo * pc.c_out * pc.taps * pc.c_in
+        nbytes = 2.0 * (n * h * w * pc.c_in + pc.c_out * pc.taps * pc.c_in) + n * ho * wo * pc.c_out * 2.0 * (2 if residual is not None else 1)
+        desc = f"{n}x{h}x{w} {pc.c_in}->{pc.c_out}" + (f" s{stride}" if stride > 1 else "") + (" norm+" if norm else "") + (
+            " +act" if act else "") + (" +gate" if gate else "") + (" +res" if residual is not None else "") + (
+            " +sums" if stat is not None else "") + (" [halo]" if choice.halo else "")
+        self._emit(kind or ("conv3x3" if pc.taps == 9 else "gemm"), flops, nbytes, self.lib.azb_conv_bf16, byref(d), desc=desc)
+        return True
+
     def _block(self, m, x: Tensor, out: Tensor) -> None:
         r"""``UNetBlock._forward`` (``azula/nn/unet.py:97-107``)."""
         arena, pk = self.arena, self.packed
         n, h, w, c = x.shape
         off = pk.bank.offset[id(m)]
         abc = self.abc.data_ptr() + 4 * off
-        y = arena.take(n, h, w, c)
-        if m.norm_kind == "group":
-            self._group_norm(m, x, y, abc)
-        else:
-            self.rownorm(x, y, _NORM_KIND[m.norm_kind], abc, self.mod_ld, h * w, eps=m.norm.eps)
         c1, c2 = pk.conv[id(m.ffn[0])], pk.conv[id(m.ffn[3])]
         hbuf = arena.take(n, h, w, c1.c_out)
-        self.conv(y, c1, hbuf, act=ops.ACT["silu"])
-        arena.give(y)
-        self.conv(hbuf, c2, out, gate=abc + 4 * 2 * c, gate_ld=self.mod_ld, gate_rows=h * w, residual=x)
+        fused = False
+        stat = self.rowstat.get(id(x))
+        if FUSE_NORM and m.norm_kind in _NORM_KIND and stat is not None and c % 64 == 0:
+            # the normalisation and the modulation ride in the input transform of the first convolution
+            fused = self.conv_stat(x, c1, hbuf, act=ops.ACT["silu"],
+                                   norm=(1 + _NORM_KIND[m.norm_kind], float(m.norm.eps), stat, abc, self.mod_ld))
+            self.fused_norms += int(fused)
+        if not fused:
+            y = arena.take(n, h, w, c)
+            if m.norm_kind == "group":
+                self._group_norm(m, x, y, abc)
+            else:
+                self.rownorm(x, y, _NORM_KIND[m.norm_kind], abc, self.mod_ld, h * w, eps=m.norm.eps)
+            self.conv_stat(y, c1, hbuf, act=ops.ACT["silu"])
+            arena.give(y)
+        self.conv_stat(hbuf, c2, out, gate=abc + 4 * 2 * c, gate_ld=self.mod_ld, gate_rows=h * w, residual=x)
         arena.give(hbuf)
 
     def _group_norm(self, m, x: Tensor, y: Tensor, abc: int) -> None:

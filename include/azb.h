@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define AZB_VERSION 3
+#define AZB_VERSION 4
 
 enum {
     AZB_OK = 0,
@@ -262,6 +262,22 @@ typedef struct AzbConv {
      * upsampling, (h, w) being the upsampled extents: conv(up(act(A x + B))) of an upsampling ResBlock
      * (_src/unet.py:101-109,229-233) without the 4x larger intermediate. */
     int32_t in_up;
+    /* Fused per-pixel normalisation of the input (same conditions as in_coef, instead of it): the convolution reads
+     *     bf16((1 + a[n][c]) * norm_C(x)[pixel] + b[n][c])
+     * i.e. the LayerNorm / RMSNorm over the channels of every pixel and the Ada-Norm-Zero modulation that open
+     * UNetBlock._forward (azula/nn/unet.py:97-104, azula/nn/layers.py LayerNorm / RMSNorm) without a pass over HBM.
+     * in_norm: 0 none, 1 LayerNorm, 2 RMSNorm (eps = in_eps); in_rowstat: fp32 [pixels][c_in / 64][2] = {sum, sum of
+     * squares} of every 64-channel block of x, as written by the producer of x through `rowstat`; in_mod: fp32
+     * [a(c_in) | b(c_in)] per sample, in_mod_ld floats between samples (0 = one shared row). */
+    int32_t in_norm;
+    float in_eps;
+    const float* in_rowstat;
+    const float* in_mod;
+    int64_t in_mod_ld;
+    /* rowstat (c_out % 64 == 0; needs the row-domain epilogue, AzbConvChoice.epi == 2, AZB_E_UNSUPPORTED otherwise): the
+     * epilogue also writes {sum, sum of squares} of the stored (bf16-rounded) values of every (pixel, 64-channel block) of
+     * `out` to fp32 rowstat[pixels][c_out / 64][2]. */
+    float* rowstat;
 } AzbConv;
 
 int azb_conv_bf16(const AzbConv* desc, void* stream);
@@ -270,6 +286,7 @@ int azb_conv_bf16(const AzbConv* desc, void* stream);
  * operand is staged as halo tiles (the condition for in_coef), pair / lean / block_n / splits as described above. */
 typedef struct AzbConvChoice {
     int32_t halo, pair, lean, block_n, splits, tiles;
+    int32_t epi;  /* epilogue: 0 transposing (generic), 1 lean, 2 row domain with TMA stores */
 } AzbConvChoice;
 int azb_conv_choice(const AzbConv* desc, AzbConvChoice* choice);
 
@@ -283,7 +300,8 @@ int azb_conv_choice(const AzbConv* desc, AzbConvChoice* choice);
  *                           vectors per thread, the pre-wave policy)
  *   AZB_CONV_KNOB_BLOCKN    force the N tile (16 .. 256; ignored unless it divides the padded C_out)
  *   AZB_CONV_KNOB_LEAN      0: always the generic epilogue (all switches at run time)
- *   AZB_CONV_KNOB_HALO      0: never stage 3 x 3 operands as halo tiles (tap-wise TMA loads instead) */
+ *   AZB_CONV_KNOB_HALO      0: never stage 3 x 3 operands as halo tiles (tap-wise TMA loads instead), 1: wherever the shape
+ *                           allows, -1: where an input transform needs them or every SM gets more than two tiles */
 #define AZB_CONV_KNOB_PAIR 0
 #define AZB_CONV_KNOB_PREFETCH 1
 #define AZB_CONV_KNOB_SPLITK 2
@@ -295,9 +313,14 @@ int azb_conv_choice(const AzbConv* desc, AzbConvChoice* choice);
 #define AZB_CONV_KNOB_HALO_SB 8    /* halo kernels: cap on the weight stages */
 #define AZB_CONV_KNOB_HALO_SPREAD 9 /* halo kernels: 0 = the fused 1 x 1 blocks follow the last halo item (default: spread) */
 #define AZB_KNOB_PDL 10 /* 0: plain stream-ordered launches instead of programmatic dependent launches */
-#define AZB_CONV_KNOB_ROWEPI 11 /* row-domain epilogue with TMA stores: 0 never, 1 wherever possible, -1 (default) for layers without activation / gate */
+#define AZB_CONV_KNOB_ROWEPI 11 /* row-domain epilogue with TMA stores: 0 never, 1 / -1 (default) wherever possible */
 #define AZB_CONV_KNOBS 12
 int azb_conv_tuning(int knob, int value);
+/* Diagnostics (scripts/graph_trace.py): `buf` = device array of uint64 {launch counter, 7 unused, then 4 words per
+ * convolution launch in stream order: earliest CTA entry, earliest CTA start after the programmatic-launch wait, latest
+ * CTA end (%globaltimer ns; initialise mins to ~0, max to 0), unused} or NULL to switch tracing off.  Launch descriptors
+ * built (or graphs captured) while a buffer is set carry it; no reference counterpart. */
+int azb_debug_trace(void* buf);
 
 /*
  * The REFERENCE-NUMERICS mode: the same contraction with fp32 operands in HBM and tcgen05.mma.kind::tf32 (10-bit operand

@@ -142,6 +142,57 @@ __global__ void __launch_bounds__(512, 1) rate_kernel(int mode, int iters, long 
     if (warp == 0) tc::tmem_dealloc(tmem_slot, 512);
 }
 
+// tcgen05.mma issue / execution rate: `iters` back-to-back M = 128, K = 16 MMAs with N columns (SS operands in shared memory,
+// contents irrelevant), one commit at the end; clocks per MMA
+template <int N>
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int iters, long long* cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    __shared__ __align__(8) uint64_t bar_done;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        tc::mbar_init(tc::smem_u32(&bar_done), 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) {
+        tc::tmem_alloc(tc::smem_u32(&tmem_slot), 256);
+        tc::tmem_relinquish();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    if (threadIdx.x == 0) {
+        constexpr uint32_t idesc = tc::idesc_bf16_f32(128, N);
+        const uint64_t da = tc::smem_desc_sw128(base), db = tc::smem_desc_sw128(base + 16384);
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) tc::mma_f16_ss(tmem, da + (uint64_t)(2 * (i & 3)), db + (uint64_t)(2 * (i & 3)), idesc, 1);
+        const long long t1 = clock64();
+        tc::mma_commit(tc::smem_u32(&bar_done));
+        tc::mbar_wait(tc::smem_u32(&bar_done), 0);
+        const long long t2 = clock64();
+        cycles[0] = t1 - t0, cycles[1] = t2 - t0;
+    }
+    __syncthreads();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+template <int N>
+void mma_rate(long long* dc) {
+    const int iters = 2048;
+    cudaFuncSetAttribute(mma_rate_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    mma_rate_kernel<N><<<1, 128, 64 * 1024>>>(iters, dc);
+    mma_rate_kernel<N><<<1, 128, 64 * 1024>>>(iters, dc);
+    cudaDeviceSynchronize();
+    long long c[2];
+    cudaMemcpy(c, dc, 16, cudaMemcpyDeviceToHost);
+    printf("tcgen05.mma M 128 N %3d K 16 (SS): issue %6.1f clk / MMA, complete %6.1f clk / MMA  (%.0f MAC / clk)\n", N, (double)c[0] / iters,
+           (double)c[1] / iters, 128.0 * N * 16 * iters / (double)c[1]);
+}
+
 // D[128 x 64] = A[128 x 64] B[64 x 64]^T: A in tensor memory (written by tcgen05.st), B K-major in swizzled shared memory
 __global__ void __launch_bounds__(128, 1) ts_kernel(const __nv_bfloat16* a, const __nv_bfloat16* b, float* d) {
     extern __shared__ uint8_t smem_raw[];
@@ -226,6 +277,7 @@ int main() {
             }
         }
     }
+    mma_rate<32>(dc), mma_rate<64>(dc), mma_rate<128>(dc), mma_rate<256>(dc);
     // D
     std::vector<__nv_bfloat16> ha(128 * 64), hb(64 * 64);
     std::vector<float> fa(128 * 64), fb(64 * 64);

@@ -170,9 +170,13 @@ def test_fused_groupnorm_path_end_to_end_at_card_width():
     oracle within the stated bf16 tolerance, and equal the un-fused plan (GroupNorm as a separate pass over HBM, same
     halo kernels) BIT FOR BIT -- the transform warps and azb_gn_apply_acc_bf16 share coefficients and arithmetic."""
     from azula_b200.engine import adm as engine_adm
+    from azula_b200.engine import ops as engine_ops
 
     den, sd = _seeded(WIDE_ADM, seed=11)
     tab = AU.block_table(**WIDE_ADM)
+    # halo tiles wherever the shape allows, for BOTH plans: by default a convolution without an input transform takes the
+    # tap-wise kernel on feature maps this small (another K order), and the comparison below is bit for bit
+    engine_ops.conv_tuning(engine_ops.KNOB_HALO, 1)
     # (batch 8: enough 8 x 16 patches that the launcher picks the wide N tiles the halo kernels exist for)
     x = torch.randn(8, 3, 32, 32, device=DEV, generator=torch.Generator(device=DEV).manual_seed(5))
     ts = torch.randint(0, 1000, (8,), device=DEV)
@@ -190,6 +194,7 @@ def test_fused_groupnorm_path_end_to_end_at_card_width():
     finally:
         engine_adm.FUSE_NORM = True
         den.backbone._native.clear()
+        engine_ops.conv_tuning(engine_ops.KNOB_HALO, -1)
     assert torch.equal(fused, plain), (fused - plain).abs().max().item()
 
 

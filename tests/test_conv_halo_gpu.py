@@ -25,14 +25,19 @@ DEV = "cuda"
 def _exact_reference():
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
+    # halo tiles wherever the shape allows: by default a layer WITHOUT an input transform takes them only when every SM gets
+    # several tiles, and these small test problems would compare a halo launch with a tap-wise one (another K order)
+    ops.conv_tuning(ops.KNOB_HALO, 1)
     yield
     for knob in (ops.KNOB_HALO, ops.KNOB_PAIR, ops.KNOB_BLOCKN):
         ops.conv_tuning(knob, -1)
 
 
 def _wide_tiles(co):
-    """Small test problems would get narrow N tiles (to fill the SMs); the halo kernels exist for N >= 128."""
+    """Small test problems would get narrow N tiles (to fill the SMs) and, without an input transform, the tap-wise
+    kernel (few tiles per SM); the halo kernels exist for N >= 128 -- force both."""
     ops.conv_tuning(ops.KNOB_BLOCKN, 256 if co % 256 == 0 else 128)
+    ops.conv_tuning(ops.KNOB_HALO, 1)
 
 
 def _choice(x, pc, out, **kw):
@@ -81,7 +86,7 @@ def test_halo_conv_matches_torch_and_tapwise(shape, pair):
     o = got.double().reshape(n, h * w, co // 8, 8)
     want = torch.stack((o.sum(dim=(1, 3)), o.square().sum(dim=(1, 3))), dim=-1)
     assert torch.allclose(_acc_to_sums(acc), want, rtol=1e-5, atol=1e-3)
-    ops.conv_tuning(ops.KNOB_HALO, -1)
+    ops.conv_tuning(ops.KNOB_HALO, 1)
     got2, acc2 = ops.conv_acc(x, pc, residual=res)
     assert torch.equal(got, got2) and torch.equal(acc, acc2)
 
@@ -295,3 +300,89 @@ def test_phase_decomposed_upsampling_convolution(shape, pair):
     o = four.double().reshape(n, 4 * h * w, co // 8, 8)
     want = torch.stack((o.sum(dim=(1, 3)), o.square().sum(dim=(1, 3))), dim=-1)
     assert torch.allclose(_acc_to_sums(acc), want, rtol=1e-5, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Per-pixel normalisation fused into the input transform (UNetBlock of azula/nn/unet.py:97-107) and the per-pixel sums
+# the producer writes for it (AzbConv.rowstat / in_norm)
+
+def _launch(d):
+    _lib.check(_lib.lib().azb_conv_bf16(byref(d), _lib.stream_ptr(torch.device(DEV))), "azb_conv_bf16")
+
+
+PIXNORM_SHAPES = [
+    # n, h, w, c (the block keeps the channel count), kind
+    (2, 16, 16, 64, "layer"),     # 64-column tiles: the halo kernel's N = 64 instantiation
+    (3, 32, 32, 64, "rms"),
+    (2, 32, 32, 128, "layer"),    # two 64-channel blocks per pixel: sums from two epilogue warps
+    (1, 16, 24, 256, "layer"),    # four blocks; partial tiles
+    (2, 16, 16, 256, "rms"),
+    (5, 64, 64, 64, "layer"),     # several tiles per CTA
+]
+
+
+@pytest.mark.parametrize("shape", PIXNORM_SHAPES)
+def test_pixel_norm_fused_into_the_convolution(shape):
+    n, h, w, c, kind = shape
+    g = torch.Generator(device=DEV).manual_seed(c + h)
+    # producer: gated residual convolution (the tail of the previous block), row-domain epilogue + per-pixel sums
+    x0, wt0, b0 = _mk(n, h, w, c, c, 3, seed=5)
+    res = (torch.randn(n, h, w, c, device=DEV, generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    gate = torch.randn(n, c, device=DEV, generator=g)
+    pc0 = ops.pack_conv(wt0.float(), b0)
+    x = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=DEV)
+    stat = torch.full((n * h * w, c // 64, 2), float("nan"), device=DEV)
+    d0 = ops.conv_desc(x0, pc0, x, gate=gate.data_ptr(), gate_ld=gate.stride(0), gate_rows=h * w, residual=res, rowstat=stat)
+    ch0 = ops.conv_choice(d0)
+    assert ch0.epi == 2, (shape, ch0.epi, ch0.block_n)
+    _launch(d0)
+    ref0 = _ref(x0, wt0, b0) * gate[:, None, None, :] + res.float()
+    _check(x, ref0, ("producer", shape))
+    blocks = x.float().reshape(n * h * w, c // 64, 64)
+    assert torch.allclose(stat[..., 0], blocks.sum(-1), rtol=1e-5, atol=1e-4), ("sums", shape)
+    assert torch.allclose(stat[..., 1], blocks.square().sum(-1), rtol=1e-5, atol=1e-4), ("sums of squares", shape)
+
+    # consumer: SiLU(conv3x3((1 + a) * norm(x) + b)) with the normalisation in the input transform
+    _, wt1, b1 = _mk(n, h, w, c, c, 3, seed=6)
+    pc1 = ops.pack_conv(wt1.float(), b1)
+    mod = 0.3 * torch.randn(n, 3 * c, device=DEV, generator=g)
+    out = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=DEV)
+    d1 = ops.conv_desc(x, pc1, out, act=ops.ACT["silu"], in_norm=1 if kind == "layer" else 2, in_eps=1e-5, in_rowstat=stat,
+                       in_mod=mod.data_ptr(), in_mod_ld=mod.stride(0))
+    ch1 = ops.conv_choice(d1)
+    assert ch1.halo == 1 and ch1.epi == 2, (shape, ch1.halo, ch1.epi, ch1.block_n)
+    _launch(d1)
+    xf = x.float()
+    if kind == "layer":
+        v, m = torch.var_mean(xf, dim=-1, keepdim=True)  # unbiased, as azula.nn.layers.layer_norm
+        nx = (xf - m) * torch.rsqrt(v + 1e-5)
+    else:
+        nx = xf * torch.rsqrt(xf.square().mean(-1, keepdim=True) + 1e-5)
+    y = ((1 + mod[:, None, None, :c]) * nx + mod[:, None, None, c : 2 * c]).to(torch.bfloat16)
+    ref1 = F.silu(_ref(y, wt1, b1))
+    # the transform rounds y to bf16 from statistics summed in another order than torch's: single-ulp differences of y
+    err = (out.float() - ref1).abs()
+    tol = 2.0**-6 * ref1.abs() + 2.0**-6 * ref1.abs().mean()
+    assert (err > tol).sum().item() == 0, (shape, err.max().item(), ref1.abs().mean().item())
+    # ... and agrees with the two-launch route (azb_rownorm_mod_bf16, then the same convolution) to the same bar
+    y2 = ops.rownorm_mod(x, kind=kind, mod=mod, rows_per_sample=h * w)
+    two = ops.conv2d(y2, pc1, act="silu")
+    err2 = (out.float() - two.float()).abs()
+    assert (err2 > tol).sum().item() == 0, (shape, "vs two launches", err2.max().item())
+    out2 = torch.empty_like(out)
+    d1.out = out2.data_ptr()
+    _launch(d1)
+    assert torch.equal(out, out2), "not reproducible"
+
+
+def test_pixel_norm_needs_the_halo_kernel():
+    """Shapes the halo kernels do not serve report AZB_E_UNSUPPORTED for in_norm (the plan then keeps the separate pass)."""
+    n, h, w, c = 2, 8, 4, 64  # smaller than one 8 x 16 patch
+    x, wt, b = _mk(n, h, w, c, c, 3)
+    pc = ops.pack_conv(wt.float(), b)
+    stat = torch.zeros(n * h * w, 1, 2, device=DEV)
+    mod = torch.zeros(n, 3 * c, device=DEV)
+    out = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=DEV)
+    d = ops.conv_desc(x, pc, out, in_norm=1, in_rowstat=stat, in_mod=mod.data_ptr(), in_mod_ld=mod.stride(0))
+    c_ = ops.AzbConvChoice()
+    assert _lib.lib().azb_conv_choice(byref(d), byref(c_)) == -6  # AZB_E_UNSUPPORTED
