@@ -922,7 +922,9 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
         const int bw = row % p.BW, bh = (row / p.BW) % p.BH, bn = row / (p.BW * p.BH);
         const int r0 = quarter * 32;  // first pixel of the 32 this warp stores: tile rows [32 quarter, 32 quarter + 32)
         const int r0h = (r0 / p.BW) % p.BH, r0n = r0 / (p.BW * p.BH);
-        const bool short_k = num_kb <= 36;  // tiles of a microsecond: no sleeping between polls of the accumulator barrier
+        // tiles of a microsecond: no sleeping between polls of the accumulator barrier (only there: eight spinning warps cost
+        // the power-capped 36-k-block layers of ADM 1.3 % of the sustained step)
+        const bool short_k = num_kb < 24;
         // the lanes with (lane & 7) == 0 own 8-channel block (lane >> 3) of every chunk: GroupNorm sums carried across
         // the tiles of an image (chunked mode), slot = n_tile * 4 + chunk
         float carry_s[8], carry_q[8];
@@ -955,9 +957,19 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                 flush_carry(carry_img);
                 carry_img = n0;
             }
-            // everything that does not depend on the accumulator happens BEFORE the wait for it: this lane's pixel, its
-            // residual / gate rows and the residual of the first chunk (an L2 round trip on layers whose whole reduction
-            // lasts a microsecond)
+            auto wait_accumulator = [&]() {
+                if (e == 0 && lane == 0) mark(local, 4);
+                if (short_k) tc::mbar_wait(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
+                else tc::mbar_wait_backoff(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
+                if (e == 0 && lane == 0) mark(local, 5);
+                tc::fence_after_sync();
+            };
+            // Narrow tiles (<= 128 columns): everything that does not depend on the accumulator happens BEFORE the wait for
+            // it -- this lane's pixel, its residual / gate rows and the residual of the first chunk (an L2 round trip on
+            // layers whose whole reduction lasts a microsecond).  The N = 256 layers (long reductions; the power-capped ADM
+            // step) keep the order wait -> addresses: nothing to hide there, and fewer values live across the wait.
+            constexpr bool PREP_FIRST = BLOCK_N <= 128;
+            if constexpr (!PREP_FIRST) wait_accumulator();
             const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
             const bool ok = active && (n < p.N) && (h < p.H) && (w < p.W);
             const int64_t pix = ((int64_t)n * p.H + h) * p.W + w;
@@ -976,22 +988,23 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
             // bias and gate of this warp's columns, ONE value per lane and 32-column chunk, broadcast with shuffles when the
             // chunk is processed: these kernels leave the SM no L1 cache (the shared-memory carve-out is the whole array), so
             // every per-chunk __ldg of a bias / gate row was a full L2 round trip on the critical path of a short tile
-            float bias_l[CPW / 32], gate_l[CPW / 32];
+            // (narrow tiles, like RES_AHEAD: the N = 256 layers have long reductions that hide the round trip, and on the
+            // power-capped ADM step the extra shuffles cost more than they save -- same-box A/B, 8.47 vs 8.35 images/s)
+            constexpr bool LANE_ROWS = BLOCK_N <= 128;
+            float bias_l[LANE_ROWS ? CPW / 32 : 1], gate_l[LANE_ROWS ? CPW / 32 : 1];
             int gate_sample = -1;
-            if (p.gate && p.gate_uniform) gate_sample = __reduce_max_sync(0xffffffffu, ok ? (int)((uint32_t)pix / (uint32_t)p.gate_rows) : -1);
+            if constexpr (LANE_ROWS) {
+                if (p.gate && p.gate_uniform) gate_sample = __reduce_max_sync(0xffffffffu, ok ? (int)((uint32_t)pix / (uint32_t)p.gate_rows) : -1);
 #pragma unroll
-            for (int c = 0; c < CPW / 32; ++c) {
-                const int cl = col_base + 32 * c + lane;
-                bias_l[c] = (p.bias && cl < p.c_out) ? __ldg(p.bias + cl) : 0.f;
-                gate_l[c] = (gate_sample >= 0 && cl < p.c_out) ? __ldg(p.gate + (int64_t)gate_sample * p.gate_ld + cl) : 1.f;
+                for (int c = 0; c < CPW / 32; ++c) {
+                    const int cl = col_base + 32 * c + lane;
+                    bias_l[c] = (p.bias && cl < p.c_out) ? __ldg(p.bias + cl) : 0.f;
+                    gate_l[c] = (gate_sample >= 0 && cl < p.c_out) ? __ldg(p.gate + (int64_t)gate_sample * p.gate_ld + cl) : 1.f;
+                }
             }
             const uint32_t stage = TWO_STAGING ? stage0 + 4 * (local & 1) * (32 * 128) : stage0;
             const uint32_t my_row = stage + (uint32_t)lane * 128u;
-            if (e == 0 && lane == 0) mark(local, 4);
-            if (short_k) tc::mbar_wait(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
-            else tc::mbar_wait_backoff(tc::smem_u32(&bar_acc_full[as]), (local >> 1) & 1);
-            if (e == 0 && lane == 0) mark(local, 5);
-            tc::fence_after_sync();
+            if constexpr (PREP_FIRST) wait_accumulator();
             if (active) {
                 const int sh = h0 + r0h, sn = n0 + r0n;
                 float rs_sum = 0.f, rs_sq = 0.f;
@@ -1019,12 +1032,24 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                     tc::tmem_ld_wait();
                     if (e == 0 && lane == 0) mark(local, c0 == 0 ? 7 : 11);
                     float v[32];
-                    float bias_c = bias_l[0], gate_c = gate_l[0];
+                    float gate_c = 1.f;
+                    if constexpr (LANE_ROWS) {
+                        float bias_c = bias_l[0];
+                        gate_c = gate_l[0];
 #pragma unroll
-                    for (int c = 1; c < CPW / 32; ++c)
-                        if (c0 == 32 * c) bias_c = bias_l[c], gate_c = gate_l[c];
+                        for (int c = 1; c < CPW / 32; ++c)
+                            if (c0 == 32 * c) bias_c = bias_l[c], gate_c = gate_l[c];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + __shfl_sync(0xffffffffu, bias_c, j);
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + __shfl_sync(0xffffffffu, bias_c, j);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (p.bias && col + 4 * q < p.c_out) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + q);
+                            v[4 * q] = __uint_as_float(acc[4 * q]) + b4.x, v[4 * q + 1] = __uint_as_float(acc[4 * q + 1]) + b4.y;
+                            v[4 * q + 2] = __uint_as_float(acc[4 * q + 2]) + b4.z, v[4 * q + 3] = __uint_as_float(acc[4 * q + 3]) + b4.w;
+                        }
+                    }
                     activate_all(v, p.act);
                     if (e == 0 && lane == 0) mark(local, c0 == 0 ? 8 : 12);
                     if (gate_sample >= 0) {

@@ -52,7 +52,8 @@ __device__ __forceinline__ float group_sum(float v, int lanes) {
 // A group of `lpr` lanes owns one row; lane l of the group holds vectors l, l + lpr, ... (VPL of them).
 // Two passes over registers: mean, then the centred sum of squares (as torch.var_mean does).
 template <int VPL>
-__global__ void __launch_bounds__(THREADS) rownorm_mod_kernel(const RowNormParams p) {
+__global__ void __launch_bounds__(THREADS, VPL <= 4 ? 4 : 2) rownorm_mod_kernel(const RowNormParams p) {
+    pdl_enter();  // (programmatic dependent launch: the CTAs are resident when the producer of x retires)
     const int lane = threadIdx.x & 31;
     const int sub = lane & (p.lpr - 1);
     const int rows_per_warp = 32 / p.lpr;
@@ -300,13 +301,13 @@ extern "C" int azb_rownorm_mod_bf16(const void* x, int64_t x_ld, void* y, int64_
     const unsigned grid = stream_grid(rows, rows_per_cta);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     switch (vpl) {
-        case 1: rownorm_mod_kernel<1><<<grid, THREADS, 0, s>>>(p); break;
-        case 2: rownorm_mod_kernel<2><<<grid, THREADS, 0, s>>>(p); break;
-        case 3: rownorm_mod_kernel<3><<<grid, THREADS, 0, s>>>(p); break;
-        case 4: rownorm_mod_kernel<4><<<grid, THREADS, 0, s>>>(p); break;
+        case 1: azb_launch(rownorm_mod_kernel<1>, dim3(grid), dim3(THREADS), 0, s, p); break;
+        case 2: azb_launch(rownorm_mod_kernel<2>, dim3(grid), dim3(THREADS), 0, s, p); break;
+        case 3: azb_launch(rownorm_mod_kernel<3>, dim3(grid), dim3(THREADS), 0, s, p); break;
+        case 4: azb_launch(rownorm_mod_kernel<4>, dim3(grid), dim3(THREADS), 0, s, p); break;
         case 5:
-        case 6: rownorm_mod_kernel<6><<<grid, THREADS, 0, s>>>(p); break;
-        default: rownorm_mod_kernel<8><<<grid, THREADS, 0, s>>>(p); break;
+        case 6: azb_launch(rownorm_mod_kernel<6>, dim3(grid), dim3(THREADS), 0, s, p); break;
+        default: azb_launch(rownorm_mod_kernel<8>, dim3(grid), dim3(THREADS), 0, s, p); break;
     }
     return azb_launch_status();
 }

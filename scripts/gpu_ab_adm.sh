@@ -1,0 +1,13 @@
+# Same-box A/B of the ADM headline between build/old_tree (previous commit) and the working tree: 3 interleaved rounds
+mkdir -p gpurun_out
+for i in 1; do
+  timeout 600 python bench.py --no-cpu-baseline --no-eager-gpu --steps 3 --warmup 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('new-first $i', round(d['value'],3), d['roofline']['frac'], d['roofline']['us_per_launch'], d['clocks']['sm_mhz'])"
+  (cd build/old_tree && timeout 600 python bench.py --no-cpu-baseline --no-eager-gpu --steps 3 --warmup 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('old $i', round(d['value'],3), d['roofline']['frac'], d['roofline']['us_per_launch'], d['clocks']['sm_mhz'])")
+  timeout 600 python bench.py --no-cpu-baseline --no-eager-gpu --steps 3 --warmup 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('new $i', round(d['value'],3), d['roofline']['frac'], d['roofline']['us_per_launch'], d['clocks']['sm_mhz'])"
+done 2>&1 | tee gpurun_out/ab_adm.txt
