@@ -21,6 +21,10 @@ NVCC_FLAGS = [
 ]
 
 
+# extra compile flags for diagnostics builds, e.g. AZB_NVCC_EXTRA=-DAZB_TIMELINE (per-tile stamps for scripts/conv_timeline.py)
+NVCC_FLAGS += os.environ.get("AZB_NVCC_EXTRA", "").split()
+
+
 def nvcc() -> str:
     exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(exe):

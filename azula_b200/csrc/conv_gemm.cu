@@ -410,9 +410,14 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
     // barrier setup, tensor-memory allocation and descriptor prefetch overlapped the tail of the previous kernel; its
     // results (activations, GroupNorm sums, coefficients) are read and this kernel's outputs written only from here on
     pdl_wait();
-    // tile timeline of CTA 0 (diagnostics): words [1 << 16, ...) of the trace buffer, 16 stamps per (tile < 16)
+    // tile timeline of CTA 0 (diagnostics, scripts/conv_timeline.py; compiled in with AZB_NVCC_EXTRA=-DAZB_TIMELINE only):
+    // words [1 << 16, ...) of the trace buffer, 16 stamps per (tile < 16)
     auto mark = [&](int local, int e) {
+#ifdef AZB_TIMELINE
         if (p.trace && blockIdx.x == 0 && local < 16) p.trace[(1 << 16) + local * 16 + e] = azb_globaltimer();
+#else
+        (void)local, (void)e;
+#endif
     };
     unsigned long long* trace_slot = nullptr;
     if (p.trace && threadIdx.x == 0) {

@@ -582,10 +582,17 @@ def run_engine(args) -> None:
             "clocks": clocks.summary(),
         }
         if plan is not None:
-            detail: list = []
-            for _ in range(2):  # second pass: warm instruction caches / clocks as inside the loop
-                detail.clear()
-                table = plan.profile(detail)
+            # per-launch CUDA-event timing of one forward: one warm-up pass (instruction caches, clocks as inside the loop), then
+            # five measured passes; the pass with the MEDIAN total is reported (single passes scatter by +-7 % on the power-capped
+            # part: the dominant kernel was seen between 824 and 955 us in back-to-back runs of one build)
+            passes = []
+            for i in range(6):
+                d_: list = []
+                t_ = plan.profile(d_)
+                if i:
+                    passes.append((sum(r["ms"] for r in t_.values()), t_, d_))
+            passes.sort(key=lambda x: x[0])
+            _, table, detail = passes[len(passes) // 2]
             line["roofline"] = roofline_of(config if precision == "bf16" else config + "_tf32", table, detail, batch, pk)
             if precision == "tf32":
                 line["roofline"]["note"] = ("reference-numerics mode: tcgen05 kind::tf32 runs at HALF the bf16 tensor rate; "

@@ -1,5 +1,6 @@
 """Tile timeline of CTA 0 of one convolution launch (diagnostics stamps of conv_gemm_kernel): MMA issuer and first epilogue
-warp.  python scripts/conv_timeline.py --only plain,-1,-1 [--c 64 --hw 64]"""
+warp.  Needs a diagnostics build: AZB_NVCC_EXTRA=-DAZB_TIMELINE python -m azula_b200.csrc.build --force
+python scripts/conv_timeline.py --only plain,-1,-1 [--c 64 --hw 64]"""
 import os
 import subprocess
 import sys
