@@ -335,7 +335,10 @@ __global__ void __launch_bounds__(THREADS, Cfg<BK>::CTAS_PER_SM)
 // to the landed Q / K rows IN PLACE in shared memory by the softmax threads (row t of both by thread t, one item ahead of
 // the logits), with the arithmetic of azb_segment_rmsnorm_bf16 -- the separate pass over the qkv projection is gone.
 constexpr int TQ = 256;                       // tokens per item
-constexpr int T256_THREADS = 352;         // 2 softmax groups x 4 warps, TMA producer, one MMA issuer per group
+constexpr int T256_GROUP_WARPS = 8;           // softmax warps per group: warps w and w + 4 share TMEM lane quarter w % 4 and
+                                              // split the key columns ([0, 128) / [128, 256))
+constexpr int T256_SOFTMAX = 2 * T256_GROUP_WARPS;
+constexpr int T256_THREADS = 32 * (T256_SOFTMAX + 3);  // + TMA producer + one MMA issuer per group
 constexpr int T256_QK_STAGE = 2 * TQ * 128;   // Q + K
 constexpr int T256_V_STAGE = TQ * 128;
 constexpr int T256_SMEM = 2 * T256_QK_STAGE + 2 * T256_V_STAGE + 2 * BQ * 128 + 1024;  // + one output staging tile per group
@@ -352,8 +355,11 @@ __global__ void __launch_bounds__(T256_THREADS, 1)
     auto v_smem = [&](int s) -> uint32_t { return smem_base + 2 * T256_QK_STAGE + (uint32_t)s * T256_V_STAGE; };
 
     __shared__ __align__(8) uint64_t bar_qk_full[2], bar_qk_ready[2], bar_qk_free[2], bar_v_full[2], bar_v_free[2];
-    __shared__ __align__(8) uint64_t bar_s[2], bar_p[2], bar_o[2], bar_sfree[2], bar_turn[2];
+    __shared__ __align__(8) uint64_t bar_s[2], bar_p[2][2], bar_o[2], bar_sfree[2], bar_turn[2];
     __shared__ uint32_t tmem_slot;
+    // [group][row]: the two key halves of a row meet here in two steps (half 1 deposits, half 0 combines and deposits the
+    // result) -- one array per group is all the static shared memory that is left next to 225 KiB of stages
+    __shared__ float red[2][BQ];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto mark = [&](int role, int j, int e) {  // role 0 / 1: softmax groups, 2 / 3: their MMA issuers
@@ -362,25 +368,30 @@ __global__ void __launch_bounds__(T256_THREADS, 1)
     const int n_my = (int)blockIdx.x < items ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int tiles = p.T > BQ ? 2 : 1;       // query tiles per item (group 1 idles on sequences of <= 128 tokens)
     const int nkc = (p.T + 31) >> 5;          // 32-key chunks that hold valid keys
+    // Tensor-memory columns of a group: logits chunk c in [32 c, 32 c + 32); P chunks 0-3 (key half 0) in [0, 64), O in
+    // [64, 128), P chunks 4-7 (key half 1) in [128, 192): a half's P only ever overwrites logits of the SAME half that are
+    // already consumed, and O overwrites logits of half 0, whose P is complete before the first P V step is issued.
+    constexpr uint32_t O_COL = 64, P1_COL = 128;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
             tc::mbar_init(tc::smem_u32(&bar_qk_full[s]), 1);
-            tc::mbar_init(tc::smem_u32(&bar_qk_ready[s]), 8);
+            tc::mbar_init(tc::smem_u32(&bar_qk_ready[s]), T256_SOFTMAX);
             tc::mbar_init(tc::smem_u32(&bar_qk_free[s]), tiles);
             tc::mbar_init(tc::smem_u32(&bar_v_full[s]), 1);
             tc::mbar_init(tc::smem_u32(&bar_v_free[s]), tiles);
             tc::mbar_init(tc::smem_u32(&bar_s[s]), 1);
-            tc::mbar_init(tc::smem_u32(&bar_p[s]), 4);
+            tc::mbar_init(tc::smem_u32(&bar_p[s][0]), 4);
+            tc::mbar_init(tc::smem_u32(&bar_p[s][1]), 4);
             tc::mbar_init(tc::smem_u32(&bar_o[s]), 1);
-            tc::mbar_init(tc::smem_u32(&bar_sfree[s]), 4);
-            tc::mbar_init(tc::smem_u32(&bar_turn[s]), 4);
+            tc::mbar_init(tc::smem_u32(&bar_sfree[s]), T256_GROUP_WARPS);
+            tc::mbar_init(tc::smem_u32(&bar_turn[s]), T256_GROUP_WARPS);
         }
         tc::fence_barrier_init();
         tc::prefetch_tmap(&tmap);
         tc::prefetch_tmap(&tmap_out);
     }
-    if (warp == 9) {
+    if (warp == T256_SOFTMAX + 1) {
         tc::tmem_alloc(tc::smem_u32(&tmem_slot), 512);
         tc::tmem_relinquish();
     }
@@ -389,7 +400,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1)
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
 
-    if (warp == 8) {
+    if (warp == T256_SOFTMAX) {
         // ===== TMA producer =====
         if (tc::elect_one()) {
             for (int j = 0; j < n_my; ++j) {
@@ -408,18 +419,14 @@ __global__ void __launch_bounds__(T256_THREADS, 1)
                 tc::tma_load_3d(v_smem(s), &tmap, vfull, ch_q + p.v_delta, 0, img);
             }
         }
-    } else if (warp >= 9) {
-        // ===== MMA issuers: warp 9 + g issues the MMAs of group g, in order, sleeping on the group's barriers =====
-        const int g = warp - 9;
+    } else if (warp > T256_SOFTMAX) {
+        // ===== MMA issuers: one per group, in order, asleep on the group's barriers between issues =====
+        const int g = warp - (T256_SOFTMAX + 1);
         if (g < tiles && tc::elect_one()) {
             constexpr uint32_t idesc_s = tc::idesc_bf16_f32(BQ, TQ);
             constexpr uint32_t idesc_o = tc::idesc_bf16_f32_b_mn(BQ, D);
-            // P in two halves when all 8 chunks are in use (see the softmax groups): P chunks [0, 4) in columns [0, 64), O in
-            // [64, 128) (logits consumed by the first half), P chunks [4, 8) in [128, 192); otherwise P in [0, 16 nkc), O in
-            // [128, 192) and no early start
-            const int nh = nkc == 8 ? 4 : 0;
-            const uint32_t p2_col = nh ? 128u : 0u, o_col = nh ? 64u : 128u;
             const uint32_t tmem_g = tmem_base + (uint32_t)(g * 256);
+            const int ksteps = 2 * nkc;  // 16 keys per P V step
             for (int j = 0; j < n_my; ++j) {
                 const int s = j & 1;
                 const uint32_t par = (uint32_t)(j >> 1) & 1u;
@@ -436,18 +443,18 @@ __global__ void __launch_bounds__(T256_THREADS, 1)
                     tc::mma_f16_ss(tmem_g, desc_q + (uint64_t)(2 * k), desc_k + (uint64_t)(2 * k), idesc_s, k != 0);
                 tc::mma_commit(tc::smem_u32(&bar_s[g]));
                 if (j + 2 < n_my) tc::mma_commit(tc::smem_u32(&bar_qk_free[s]));  // (both groups' logit MMAs: count = tiles)
-                // P_g V -> O_g, in two halves: the first k-steps run while the group still exponentiates the rest
+                // P_g V -> O_g: the steps of key half 0, then those of key half 1, each as soon as its P is written
                 tc::mbar_wait(tc::smem_u32(&bar_v_full[s]), par);
                 mark(2 + g, j, 2);
                 const uint32_t v_src = v_smem(s);
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
-                    tc::mbar_wait(tc::smem_u32(&bar_p[g]), (uint32_t)half);
+                    tc::mbar_wait(tc::smem_u32(&bar_p[g][half]), (uint32_t)j & 1u);
                     mark(2 + g, j, 3 + half);
                     tc::fence_after_sync();
-                    const int k0 = half ? 2 * nh : 0, k1 = half ? 2 * nkc : 2 * nh;
-                    for (int k = k0; k < k1; ++k)  // 16 keys per step: 8 packed columns of P, 2048 bytes of V
-                        tc::mma_f16_ts(tmem_g + o_col, tmem_g + (k < 2 * nh ? 8u * (uint32_t)k : p2_col + 8u * (uint32_t)(k - 2 * nh)),
+                    const int k0 = half ? 8 : 0, k1 = half ? ksteps : (ksteps < 8 ? ksteps : 8);
+                    for (int k = k0; k < k1; ++k)  // 8 packed columns of P, 2048 bytes of V per step
+                        tc::mma_f16_ts(tmem_g + O_COL, tmem_g + (k < 8 ? 8u * (uint32_t)k : P1_COL + 8u * (uint32_t)(k - 8)),
                                        tc::smem_desc_sw128(v_src + (uint32_t)k * 2048u), idesc_o, k != 0);
                 }
                 tc::mma_commit(tc::smem_u32(&bar_o[g]));
@@ -456,23 +463,25 @@ __global__ void __launch_bounds__(T256_THREADS, 1)
             }
         }
     } else {
-        // ===== softmax groups =====
-        const int g = warp >> 2;
+        // ===== softmax groups: thread = (query row, key half) =====
+        const int g = warp >> 3;
+        const int half = (warp >> 2) & 1;
         const int row = (warp & 3) * 32 + lane;  // == TMEM lane; query g * 128 + row
         const uint32_t tmem_g = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * 256);
-        const int t = (int)threadIdx.x;          // 0 .. 255: the Q / K row this thread normalises
+        const int t = (int)threadIdx.x;          // 0 .. 511: Q row t, or K row t - 256, is normalised by this thread
         const uint32_t o_stage = smem_base + 2 * T256_QK_STAGE + 2 * T256_V_STAGE + (uint32_t)g * (BQ * 128);
-        const bool tracer_thread = (warp & 3) == 0 && lane == 0;  // the group's thread that talks to the TMA unit
+        const bool tracer_thread = (warp & 7) == 0 && lane == 0;  // the group's thread that talks to the TMA unit
         bool store_pending = false;
-        auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); };
+        auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); };
+        // this thread's chunks: [c_lo, c_hi) of the 32-key chunks (key half 0: 0-3, half 1: 4-7, clipped to the valid ones)
+        const int c_lo = 4 * half, c_hi = nkc < 4 * half + 4 ? nkc : 4 * half + 4;
         auto normalise = [&](int j) {
             const int s = j & 1;
             tc::mbar_wait(tc::smem_u32(&bar_qk_full[s]), (uint32_t)(j >> 1) & 1u);
-#pragma unroll
-            for (int which = 0; which < 2; ++which) {
+            {
                 // the eight 16-byte slots of a row in an order that keeps a quarter warp on distinct banks (a sum of
                 // squares does not care which channels a slot holds, and every slot is scaled alike)
-                const uint32_t base = (which ? k_smem(s) : q_smem(s)) + (uint32_t)t * 128u;
+                const uint32_t base = (t < TQ ? q_smem(s) : k_smem(s)) + (uint32_t)(t & (TQ - 1)) * 128u;
                 uint32_t w[8][4];
                 float ss = 0.f;
 #pragma unroll
@@ -519,13 +528,17 @@ __global__ void __launch_bounds__(T256_THREADS, 1)
             tc::mbar_wait(tc::smem_u32(&bar_s[g]), par);
             if (tracer) mark(g, j, 1);
             tc::fence_after_sync();
-            // Pass 1: the exact row maximum.  Not needed with QKNORM: the rows of q and k are RMS-normalised, |q| |k| <= 64,
-            // so every logit is <= 64 and the constant shift 64 keeps exp2 in [2^-23, 1] -- softmax does not care which
-            // shift is used, bf16 / fp32 are floating point, and a quarter of the group's instructions disappears.
+            // Pass 1: the exact row maximum (the two key halves meet in shared memory).  Not needed with QKNORM: the rows of
+            // q and k are RMS-normalised, |q| |k| <= 64, so every logit is <= 64 and the constant shift 64 keeps exp2 in
+            // [2^-23, 1] -- softmax does not care which shift is used, bf16 / fp32 are floating point.
             float m = (float)D;
             if constexpr (!QKNORM) {
                 m = -INFINITY;
-                auto fold = [&](const uint32_t (&acc)[32], int c) {
+#pragma unroll 1
+                for (int c = c_lo; c < c_hi; ++c) {
+                    uint32_t acc[32];
+                    tc::tmem_ld_32x32b_x32(tmem_g + (uint32_t)(c * 32), acc);
+                    tc::tmem_ld_wait();
                     if (c * 32 + 32 <= p.T) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(acc[i]));
@@ -534,29 +547,25 @@ __global__ void __launch_bounds__(T256_THREADS, 1)
                         for (int i = 0; i < 32; ++i)
                             if (c * 32 + i < p.T) m = fmaxf(m, __uint_as_float(acc[i]));
                     }
-                };
-                uint32_t a0[32], a1[32];
-                tc::tmem_ld_32x32b_x32(tmem_g, a0);
-#pragma unroll 1
-                for (int c = 0; c < nkc; c += 2) {  // the load of chunk c + 1 is in flight while chunk c is folded
-                    tc::tmem_ld_wait();
-                    if (c + 1 < nkc) tc::tmem_ld_32x32b_x32(tmem_g + (uint32_t)((c + 1) * 32), a1);
-                    fold(a0, c);
-                    if (c + 1 < nkc) {
-                        tc::tmem_ld_wait();
-                        if (c + 2 < nkc) tc::tmem_ld_32x32b_x32(tmem_g + (uint32_t)((c + 2) * 32), a0);
-                        fold(a1, c + 1);
-                    }
                 }
+                if (half) red[g][row] = m;
+                group_sync();
+                if (!half) red[g][row] = m = fmaxf(m, red[g][row]);
+                group_sync();
+                m = red[g][row];
+                group_sync();  // red is reused for the sums
             }
             if (tracer) mark(g, j, 2);
             const float c1 = p.scale_log2e, c0 = -m * p.scale_log2e;
             float sum0 = 0.f, sum1 = 0.f;
-            // Pass 2: P = exp2(c1 s + c0) as bf16 pairs over consumed logits.  The load of chunk c + 1 is in flight while
-            // chunk c is exponentiated; after the first half of the chunks the MMA warp is told to start on P V.
-            const int nh = nkc == 8 ? 4 : 0;
-            const uint32_t p2_col = nh ? 128u : 0u, o_col = nh ? 64u : 128u;
-            auto exponentiate = [&](const uint32_t (&acc)[32], int c) {
+            // The exponentials of the two groups may take turns on the MUFU pipe (AZB_ATTN_TURNS, A/B switch)
+            if (tiles == 2 && p.turns) tc::mbar_wait(tc::smem_u32(&bar_turn[g]), g == 0 ? (par ^ 1u) : par);
+            // Pass 2: P = exp2(c1 s + c0) as bf16 pairs over consumed logits of this thread's key half
+#pragma unroll 1
+            for (int c = c_lo; c < c_hi; ++c) {
+                uint32_t acc[32];
+                tc::tmem_ld_32x32b_x32(tmem_g + (uint32_t)(c * 32), acc);
+                tc::tmem_ld_wait();
                 uint32_t packed[16];
                 if (c * 32 + 32 <= p.T) {
 #pragma unroll
@@ -577,62 +586,39 @@ __global__ void __launch_bounds__(T256_THREADS, 1)
                         packed[i] = pack_bf16_pos(e0, e1);
                     }
                 }
-                tc::tmem_st_32x32b_x16(tmem_g + (c < nh ? (uint32_t)(c * 16) : p2_col + (uint32_t)((c - nh) * 16)), packed);
-                if (c + 1 == nh || c + 1 == nkc) {  // first half / all of P is in tensor memory
-                    tc::tmem_st_wait();
-                    tc::fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tc::mbar_arrive(tc::smem_u32(&bar_p[g]));
-                        if (c + 1 == nkc && tiles == 2 && p.turns) tc::mbar_arrive(tc::smem_u32(&bar_turn[g ^ 1]));
-                    }
-                    if (tracer) mark(g, j, c + 1 == nkc ? 4 : 3);
-                }
-            };
-            // The exponentials of the two groups take turns: alone on the MUFU pipe a group is done in half the time, and its
-            // other phases (P V, draining O, the next logits, the row maximum) then overlap the other group's exponentials
-            // instead of both groups contending for the pipe and idling together (measured: in phase without this).
-            if (tiles == 2 && p.turns) tc::mbar_wait(tc::smem_u32(&bar_turn[g]), g == 0 ? (par ^ 1u) : par);
-            if (nh == 0) {  // no early start: the "first half" is empty
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_p[g]));
+                tc::tmem_st_32x32b_x16(tmem_g + (c < 4 ? (uint32_t)(c * 16) : P1_COL + (uint32_t)((c - 4) * 16)), packed);
             }
-            {
-                uint32_t a0[32], a1[32];
-                tc::tmem_ld_32x32b_x32(tmem_g, a0);
-#pragma unroll 1
-                for (int c = 0; c < nkc; c += 2) {
-                    tc::tmem_ld_wait();
-                    if (c + 1 < nkc) tc::tmem_ld_32x32b_x32(tmem_g + (uint32_t)((c + 1) * 32), a1);
-                    exponentiate(a0, c);
-                    if (c + 1 < nkc) {
-                        tc::tmem_ld_wait();
-                        if (c + 2 < nkc) tc::tmem_ld_32x32b_x32(tmem_g + (uint32_t)((c + 2) * 32), a0);
-                        exponentiate(a1, c + 1);
-                    }
-                }
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+                tc::mbar_arrive(tc::smem_u32(&bar_p[g][half]));  // this key half of P is in tensor memory
+                if (tiles == 2 && p.turns) tc::mbar_arrive(tc::smem_u32(&bar_turn[g ^ 1]));
             }
-            const float sum = sum0 + sum1;
+            if (tracer) mark(g, j, 4);
+            float sum = sum0 + sum1;
+            if (half) red[g][row] = sum;
             // O_g / sum -> bf16 -> 128-byte-swizzled staging tile -> ONE TMA store per tile (rows beyond T are clipped by
             // the tensor map).  Per-thread row stores were measured at 2000 - 4000 clk per tile: 32 lanes x 8 partial-sector
-            // writes to 32 different lines per warp.
+            // writes to 32 different lines per warp.  Key half h of the threads converts channels [32 h, 32 h + 32).
+            // (the sums meet and the staging block is checked WHILE P V runs: nothing of it is left for after the wait)
+            if (tracer && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            group_sync();  // half 1's partial sums are visible; the TMA unit has read the previous tile out of the staging block
+            if (!half) red[g][row] = sum = sum + red[g][row];
+            group_sync();
+            const float inv = 1.0f / red[g][row];
             tc::mbar_wait(tc::smem_u32(&bar_o[g]), par);
             if (tracer) mark(g, j, 5);
             tc::fence_after_sync();
-            const float inv = 1.0f / sum;
-            if (tracer && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            group_sync();  // the TMA unit has read the previous tile out of the staging block
             const uint32_t my_row = o_stage + (uint32_t)row * 128u;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            {
                 uint32_t acc[32];
-                tc::tmem_ld_32x32b_x32(tmem_g + o_col + (uint32_t)(h * 32), acc);
+                tc::tmem_ld_32x32b_x32(tmem_g + O_COL + (uint32_t)(half * 32), acc);
                 tc::tmem_ld_wait();
-                if (h == 1) {  // O is in registers: the MMA warp may overwrite the group's columns with the next logits
-                    tc::fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_sfree[g]));
-                }
+                // O is in registers: the MMA warp may overwrite the group's columns with the next logits
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bar_sfree[g]));
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     uint32_t w[4];
@@ -642,7 +628,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1)
                                                                   __uint_as_float(acc[8 * v + 2 * i + 1]) * inv);
                         w[i] = *reinterpret_cast<uint32_t*>(&t2);
                     }
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + (uint32_t)(((h * 4 + v) ^ (row & 7)) << 4)), "r"(w[0]),
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(my_row + (uint32_t)(((half * 4 + v) ^ (row & 7)) << 4)), "r"(w[0]),
                                  "r"(w[1]), "r"(w[2]), "r"(w[3])
                                  : "memory");
                 }
@@ -661,7 +647,7 @@ __global__ void __launch_bounds__(T256_THREADS, 1)
 
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 9) tc::tmem_dealloc(tmem_base, 512);
+    if (warp == T256_SOFTMAX + 1) tc::tmem_dealloc(tmem_base, 512);
 }
 
 template <bool QKNORM>
