@@ -360,9 +360,11 @@ def test_pixel_norm_fused_into_the_convolution(shape):
         nx = xf * torch.rsqrt(xf.square().mean(-1, keepdim=True) + 1e-5)
     y = ((1 + mod[:, None, None, :c]) * nx + mod[:, None, None, c : 2 * c]).to(torch.bfloat16)
     ref1 = F.silu(_ref(y, wt1, b1))
-    # the transform rounds y to bf16 from statistics summed in another order than torch's: single-ulp differences of y
+    # the transform evaluates y with two packed bf16 multiply-adds (two roundings, bf16 row scales) from statistics summed
+    # in another order than torch's: y is within ~1 bf16 ulp of torch's (0.5 ulp), and the convolution sums 9 C of them
     err = (out.float() - ref1).abs()
-    tol = 2.0**-6 * ref1.abs() + 2.0**-6 * ref1.abs().mean()
+    tol = 2.0**-5 * ref1.abs() + 2.0**-5 * ref1.abs().mean()
+    assert (err.square().sum() / ref1.square().sum()).sqrt().item() < 6e-3, (shape, "relative L2")
     assert (err > tol).sum().item() == 0, (shape, err.max().item(), ref1.abs().mean().item())
     # ... and agrees with the two-launch route (azb_rownorm_mod_bf16, then the same convolution) to the same bar
     y2 = ops.rownorm_mod(x, kind=kind, mod=mod, rows_per_sample=h * w)
