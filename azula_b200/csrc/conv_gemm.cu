@@ -1714,13 +1714,15 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
         return AZB_E_SHAPE;
     if (ex.rowstat && (out_mode != 0 || c_out % 64 || phases != 1 || !azb_aligned(ex.rowstat, 8))) return AZB_E_SHAPE;
     // Halo tiles: 3 x 3, stride 1, maps of at least one 8 x 16 patch, whole 64-channel blocks (see the kernel's header)
-    // ... and, unless the input transform / upsampling on load needs them, only when every SM gets several tiles: with one
-    // or two tiles per CTA the tap-wise kernel's plain load -> MMA stream starts up faster than load -> transform slot ->
-    // MMA (in-repo U-Net, 128 / 256 channels at 32 x 32 / 16 x 16 x batch 32: 14 - 15 us tap-wise against 18 us)
+    // ... and, unless the input transform / upsampling on load needs them, only on feature maps of at least 32 patches
+    // (64 x 64 pixels): on smaller maps a CTA gets one or two tiles and the tap-wise kernel's plain load -> MMA stream starts
+    // up faster than load -> transform slot -> MMA (in-repo U-Net, 128 / 256 channels at 32 x 32 / 16 x 16 x batch 32: 14 - 15
+    // us tap-wise against 18 us).  The rule looks at ONE image, not at the batch: a shard of a batch must choose the same
+    // kernels as the whole batch (the two classes sum K in different orders).
     const bool halo_needed = ex.in_coef || ex.in_norm || ex.in_up;
-    const int64_t halo_m_tiles = ((w + HALO_W - 1) / HALO_W) * ((h + HALO_H - 1) / HALO_H) * n;
+    const int64_t halo_tiles_per_image = ((w + HALO_W - 1) / HALO_W) * ((h + HALO_H - 1) / HALO_H);
     bool halo = g_knob[AZB_CONV_KNOB_HALO] != 0 && taps == 9 &&
-                (halo_needed || g_knob[AZB_CONV_KNOB_HALO] == 1 || halo_m_tiles * ((c_out + 255) / 256) > 2 * sm_count()) &&
+                (halo_needed || g_knob[AZB_CONV_KNOB_HALO] == 1 || halo_tiles_per_image >= 32) &&
                 ex.stride == 1 && h >= HALO_H && w >= HALO_W &&
                 c_in % BLOCK_K == 0 && k_per_tap == c_in && (!ex.act2 || (ex.c_in2 % BLOCK_K == 0 && ex.k2 == ex.c_in2)) &&
                 !colsum && ((ex.act == AZB_ACT_NONE && !ex.gate) || rowepi_ok) && (!ex.gn_acc || stat_gran == 8) &&

@@ -301,7 +301,7 @@ int azb_conv_choice(const AzbConv* desc, AzbConvChoice* choice);
  *   AZB_CONV_KNOB_BLOCKN    force the N tile (16 .. 256; ignored unless it divides the padded C_out)
  *   AZB_CONV_KNOB_LEAN      0: always the generic epilogue (all switches at run time)
  *   AZB_CONV_KNOB_HALO      0: never stage 3 x 3 operands as halo tiles (tap-wise TMA loads instead), 1: wherever the shape
- *                           allows, -1: where an input transform needs them or every SM gets more than two tiles */
+ *                           allows, -1: where an input transform needs them or the feature map has >= 32 patches of 8 x 16 */
 #define AZB_CONV_KNOB_PAIR 0
 #define AZB_CONV_KNOB_PREFETCH 1
 #define AZB_CONV_KNOB_SPLITK 2
