@@ -541,10 +541,10 @@ def run_engine(args) -> None:
                         m._native.clear()
 
             res = versus_global(x0)
-            # The noise streams are addressed by global element index (x1 slices are asserted equal above); what can
-            # differ between a 16-image and a 32-image launch is the convolution launcher's split-K choice on the
-            # smallest feature maps (another fp32 summation order, then bf16 rounding).  With split-K off the
-            # backbone is batch-invariant bit for bit:
+            # The noise streams are addressed by global element index (x1 slices are asserted equal above); what differs
+            # between a 16-image and a 32-image launch is the convolution launcher's split-K choice on the smallest feature
+            # maps and the grouping of the GroupNorm partial sums a CTA carries over its tile range (fp32 summation orders,
+            # then bf16 rounding).  The second comparison pins split-K off, which isolates the second effect:
             _ops.conv_tuning(_ops.KNOB_SPLITK, 0)
             drop_plans()
             x0_nosplit = sampler_of("azula_b200", config, den, graph=True, shard=(rank, world))(x1)
