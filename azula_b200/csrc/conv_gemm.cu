@@ -272,15 +272,15 @@ __device__ __forceinline__ void transform_tile(uint32_t slot, int rg, int chunk,
 }
 
 // The same pass for the per-pixel normalisation (ConvParams::in_norm): row k of this thread's rows is scaled with its own
-// {rstd, mean * rstd} (r[k], mr[k]; zero for pixels outside the image, which stay zero), then modulated per channel:
+// {rstd, -mean * rstd} (r2b[k], nm2b[k]: packed bf16 pairs; pixels outside the image stay zero), then modulated per channel:
 // (1 + a) * norm(x) + b of UNetBlock._forward as two PACKED bf16 fused multiply-adds per channel pair,
 //     t = fma(x, r, -m r),  y = fma(t, 1 + a[n][c], b[n][c])
 // (HFMA2.BF16: one rounding each, so y is within ~1 bf16 ulp of the fp32 evaluation; the data never leaves its packed form --
 // 1 instruction per element instead of 3.5, which is what the four transform warps of a microsecond-long tile can afford).
 template <int PITCH, int ROWS, int OFF>
 __device__ __forceinline__ void transform_tile_norm(uint32_t slot, int rg, int chunk, const float (&a)[8], const float (&b)[8],
-                                                    const float (&r)[(ROWS + 15) / 16], const float (&mr)[(ROWS + 15) / 16], int h0,
-                                                    int w0, int H, int W) {
+                                                    const uint32_t (&r2b)[(ROWS + 15) / 16], const uint32_t (&nm2b)[(ROWS + 15) / 16],
+                                                    int h0, int w0, int H, int W) {
     const uint32_t base = slot + (uint32_t)rg * 128u + ((uint32_t)(chunk ^ (rg & 7)) << 4);
     constexpr int KS = (ROWS + 15) / 16;
     __nv_bfloat162 a2[4], b2[4];
@@ -305,7 +305,7 @@ __device__ __forceinline__ void transform_tile_norm(uint32_t slot, int rg, int c
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int k = k0 + u < KS ? k0 + u : 0;
-            const __nv_bfloat162 r2 = __float2bfloat162_rn(r[k]), nm2 = __float2bfloat162_rn(-mr[k]);
+            const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&r2b[k]), nm2 = *reinterpret_cast<const __nv_bfloat162*>(&nm2b[k]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const __nv_bfloat162 x2 = *reinterpret_cast<const __nv_bfloat162*>(&v[u][j]);
@@ -642,32 +642,36 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
         const uint32_t ready0 = PAIR ? tc::mapa(tc::smem_u32(&bar_a_ready[0]), 0) : tc::smem_u32(&bar_a_ready[0]);
         const bool xf = p.in_coef != nullptr;
         constexpr int KS = (HALO_ROWS + 15) / 16;
-        // Per-pixel normalisation: the producer's per-block sums of this thread's rows, requested ONE TILE AHEAD (all loads
-        // of a tile are independent and in flight together: a single L2 round trip, hidden behind the previous tile)
-        float ps1[NORM ? KS : 1], ps2[NORM ? KS : 1];
+        // Per-pixel normalisation: the producer's per-block sums, requested ONE TILE AHEAD (all loads of a tile are independent
+        // and in flight together: a single L2 round trip, hidden behind the previous tile).  The eight lanes that share the
+        // rows rg, rg + 16, ... (one per 16-byte chunk) split them: lane `chunk` owns rows k = chunk and chunk + 8, turns their
+        // sums into packed {rstd, -mean rstd} and the group exchanges the twelve results with shuffles.
+        constexpr int KO = (KS + 7) / 8;  // rows per lane
+        float ps1[NORM ? KO : 1], ps2[NORM ? KO : 1];
         auto request_stats = [&](int local) {
 #pragma unroll
-            for (int k = 0; k < (NORM ? KS : 1); ++k) ps1[k] = ps2[k] = 0.f;
+            for (int o = 0; o < (NORM ? KO : 1); ++o) ps1[o] = ps2[o] = 0.f;
             if (!NORM || local >= tile_count) return;
             const int tile = unit_to_tile(tile_first + local * tile_step);
             int n_tile, w0, h0, n0;
             tile_coords(p, tile % p.tiles_out, n_tile, w0, h0, n0);
             const int nblk = p.c_in >> 6;
-            const float2* sp[KS];
+            const float2* sp[KO];
 #pragma unroll
-            for (int k = 0; k < KS; ++k) {
+            for (int o = 0; o < KO; ++o) {
+                const int k = chunk + 8 * o;
                 const int i = rg + 16 * k;
                 const int y = i / HALO_PITCH, x = i - y * HALO_PITCH;
                 const int hh = h0 - 1 + y, ww = w0 - 1 + x;
-                const bool in = i < HALO_ROWS && (unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W;
-                sp[k] = in ? p.in_rowstat + (((int64_t)n0 * p.H + hh) * p.W + ww) * nblk : nullptr;
+                const bool in = k < KS && i < HALO_ROWS && (unsigned)hh < (unsigned)p.H && (unsigned)ww < (unsigned)p.W;
+                sp[o] = in ? p.in_rowstat + (((int64_t)n0 * p.H + hh) * p.W + ww) * nblk : nullptr;
             }
             for (int bk = 0; bk < nblk; ++bk) {
-                float2 v[KS];
+                float2 v[KO];
 #pragma unroll
-                for (int k = 0; k < KS; ++k) v[k] = sp[k] ? __ldg(sp[k] + bk) : make_float2(0.f, 0.f);
+                for (int o = 0; o < KO; ++o) v[o] = sp[o] ? __ldg(sp[o] + bk) : make_float2(0.f, 0.f);
 #pragma unroll
-                for (int k = 0; k < KS; ++k) ps1[k] += v[k].x, ps2[k] += v[k].y;
+                for (int o = 0; o < KO; ++o) ps1[o] += v[o].x, ps2[o] += v[o].y;
             }
         };
         if constexpr (NORM) request_stats(0);
@@ -675,17 +679,24 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
             const int tile = unit_to_tile(tile_first + local * tile_step);
             int n_tile, w0, h0, n0;
             tile_coords(p, tile % p.tiles_out, n_tile, w0, h0, n0);
-            float nr[NORM ? KS : 1], nmr[NORM ? KS : 1];
+            uint32_t nr[NORM ? KS : 1], nmr[NORM ? KS : 1];
             if constexpr (NORM) {
                 const float inv_c = 1.0f / (float)p.c_in, inv_cm1 = 1.0f / (float)(p.c_in - 1);
+                uint32_t own_r[KO], own_m[KO];
 #pragma unroll
-                for (int k = 0; k < KS; ++k) {
+                for (int o = 0; o < KO; ++o) {
                     // LayerNorm: torch.var_mean's UNBIASED variance (azula/nn/layers.py:152-155); RMSNorm: the mean square
-                    const float s1 = ps1[k], s2 = ps2[k];
+                    const float s1 = ps1[o], s2 = ps2[o];
                     const float mean = p.in_norm == 1 ? s1 * inv_c : 0.f;
                     const float var = p.in_norm == 1 ? fmaxf(fmaf(-mean, s1, s2), 0.f) * inv_cm1 : s2 * inv_c;
-                    nr[k] = rsqrtf(var + p.in_eps);
-                    nmr[k] = mean * nr[k];
+                    const float r = rsqrtf(var + p.in_eps);
+                    const __nv_bfloat162 r2 = __float2bfloat162_rn(r), m2 = __float2bfloat162_rn(-mean * r);
+                    own_r[o] = *reinterpret_cast<const uint32_t*>(&r2), own_m[o] = *reinterpret_cast<const uint32_t*>(&m2);
+                }
+#pragma unroll
+                for (int k = 0; k < KS; ++k) {  // row k lives in lane (k & 7) of this thread's group of eight
+                    nr[k] = __shfl_sync(0xffffffffu, own_r[k >> 3], (lane & 24) | (k & 7));
+                    nmr[k] = __shfl_sync(0xffffffffu, own_m[k >> 3], (lane & 24) | (k & 7));
                 }
                 request_stats(local + 1);
             }
