@@ -1970,6 +1970,10 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
         const int b_stage = out_mode == 1 ? Cfg<16, false, true>::STAGE_BYTES
                                           : pair ? Cfg<256, true, true>::STAGE_BYTES * block_n / 256 : Cfg<256, false, true>::STAGE_BYTES * block_n / 256;
         p.sb = (SMEM_BUDGET - p.sa * p.a_slot) / b_stage;
+        // (one channel block, one N tile: resident weights, as in the row-domain branch -- the 64 -> 3 output convolution of
+        // the in-repo U-Net streamed nine 2 KiB weight tiles per 128-pixel tile through the ring)
+        p.b_resident = (!pair && p.kb_per_tap == 1 && p.kb_extra == 0 && phases == 1 && p.n_tiles == 1 && p.sb >= 9 &&
+                        g_knob[AZB_CONV_KNOB_HALO_SB] < 0) ? 1 : 0;
         if (p.sb > 8) p.sb = 8;
         if (g_knob[AZB_CONV_KNOB_HALO_SB] >= 2 && g_knob[AZB_CONV_KNOB_HALO_SB] < p.sb) p.sb = g_knob[AZB_CONV_KNOB_HALO_SB];
         if (p.sb < 2) return AZB_E_SHAPE;
