@@ -1774,8 +1774,9 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     const int64_t num_kb_total = (int64_t)taps_k * (k_per_tap / BLOCK_K) + (ex.act2 ? ex.k2 / BLOCK_K : 0);
     // halo kernels exist for the wide lean tiles and for the narrowest generic one (the network's output convolution)
     // ... and, with the row-domain epilogue, for 64-column tiles (the 64-channel level of the in-repo U-Net)
-    // (one channel block: resident weights; with more, the 8 KiB weight stages stream too slowly -- 192 -> 64: 57 us against
-    // 40 us tap-wise)
+    // (one channel block: resident weights.  With more, the layer is bound by the MMA issuer's per-k-block loop -- wait, fence,
+    // four 48-clk MMAs, commit: ~190 ns against 100 ns of tensor work -- in both kernel classes, and the halo one adds its
+    // slot handshakes: 192 -> 64 took 57 us with 8 weight stages and 56 us with 15, against 40 us tap-wise)
     const bool halo64 = out_mode == 0 && block_n == 64 && rowepi_ok && !ex.act2 && phases == 1 && !ex.gn_acc && splits == 1 &&
                         !ex.in_coef && !ex.in_up && (k_per_tap == BLOCK_K || ex.in_norm);
     if (halo && !((out_mode == 0 && block_n >= 128) || (out_mode == 1 && block_n == 16) || halo64)) {
