@@ -590,9 +590,29 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                         // half-resolution pixels at rows dy, dy + 1 and columns dx, dx + 1 of it
                         const int kw_end = halo_taps == 9 ? 3 : 2;
                         if (halo_taps != 9) a_src += ((uint32_t)(phase >> 1) * pitch + (uint32_t)(phase & 1)) * 128u;
-                        if (p.b_resident && local == 0) {  // resident weights: stage = tap, loaded once, never released
-                            for (int t = 0; t < 9; ++t) tc::mbar_wait(tc::smem_u32(&bar_full[t]), 0u);
-                            tc::fence_after_sync();
+                        if (p.b_resident) {
+                            // Resident weights (one channel block, nine taps, stage = tap, loaded once): a straight line of 36
+                            // MMAs whose descriptors differ from two base descriptors by COMPILE-TIME offsets -- the generic
+                            // loop below spends ~70 clk of this one thread per MMA on waits, descriptor arithmetic and commits,
+                            // against 48 clk of tensor time for a 64-column MMA.
+                            if (local == 0) {
+                                for (int t = 0; t < 9; ++t) tc::mbar_wait(tc::smem_u32(&bar_full[t]), 0u);
+                                tc::fence_after_sync();
+                            }
+                            const uint64_t da0 = tc::smem_desc_sw128_sbo(a_src, HALO_PITCH * 128u);
+                            const uint64_t db0 = tc::smem_desc_sw128(b_ring);
+#pragma unroll
+                            for (int t = 0; t < 9; ++t) {
+                                const uint32_t a_off = (uint32_t)(((t / 3) * HALO_PITCH + (t % 3)) * 128);
+                                const uint32_t b_off = (uint32_t)(t * C::STAGE_BYTES);
+#pragma unroll
+                                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                                    tc::mma_f16_ss(tmem_acc, da0 + (uint64_t)((a_off >> 4) + 2 * k), db0 + (uint64_t)((b_off >> 4) + 2 * k),
+                                                   idesc, (t | k) != 0);
+                            }
+                            release(&bar_a_empty[sa]);
+                            if (++sa == SA) sa = 0, pa ^= 1u;
+                            continue;
                         }
                         for (int t = 0, kw = 0; t < halo_taps; ++t) {
                             const int st = p.b_resident ? t : sb;
