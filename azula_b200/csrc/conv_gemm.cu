@@ -413,6 +413,18 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
     if constexpr (PAIR) tc::cluster_sync();  // the peer's barriers are initialised before anything is sent to them
     tc::fence_after_sync();
     const uint32_t tmem_base = tmem_slot;
+    // Resident weights are constants of the network, not results of the previous kernel: their nine tiles are requested
+    // BEFORE the programmatic-launch wait and land while the previous grid drains.
+    if constexpr (HALO && !PAIR) {
+        if (p.b_resident && warp == 0 && tc::elect_one()) {
+            const uint32_t ring = smem_base + (uint32_t)(p.sa * p.a_slot);
+            for (int t = 0; t < 9; ++t) {
+                const uint32_t full = tc::smem_u32(&bar_full[t]);
+                tc::mbar_expect_tx(full, C::B_BYTES);
+                tc::tma_load_2d(ring + t * C::STAGE_BYTES, &tmap_b, full, t * p.kb_per_tap * BLOCK_K, 0);
+            }
+        }
+    }
     // barrier setup, tensor-memory allocation and descriptor prefetch overlapped the tail of the previous kernel; its
     // results (activations, GroupNorm sums, coefficients) are read and this kernel's outputs written only from here on
     pdl_wait();
@@ -473,13 +485,7 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
             int sb = 0;
             uint32_t pb = 1;  // parity of the `empty` barriers: the first pass finds every slot free
             const uint32_t full_b0 = PAIR ? tc::mapa(tc::smem_u32(&bar_full[0]), 0) : tc::smem_u32(&bar_full[0]);
-            if (p.b_resident) {
-                for (int t = 0; t < 9 && tile_count > 0; ++t) {
-                    const uint32_t full = tc::smem_u32(&bar_full[t]);
-                    tc::mbar_expect_tx(full, C::B_BYTES);
-                    tc::tma_load_2d(b_ring + t * C::STAGE_BYTES, &tmap_b, full, t * p.kb_per_tap * BLOCK_K, 0);
-                }
-            }
+            // (resident weights were requested before the programmatic-launch wait, see above)
             for (int local = 0; local < (p.b_resident ? 0 : tile_count); ++local) {
                 const int tile = unit_to_tile(tile_first + local * tile_step);
                 int n_tile, w0, h0, n0;
