@@ -87,6 +87,8 @@ struct ConvParams {
     const __nv_bfloat16* res; // residual, NHWC bf16, or null
     int64_t res_ld;
     int res_up;               // 1: residual at (H / 2, W / 2), pixel (h, w) adds residual pixel (h / 2, w / 2)
+    int out_up;               // 1 (EPI 2): the output is written through a nearest-neighbour 2x upsampling -- every staged block
+                              // is stored four times, to (2 h + dy, 2 w + dx), through the 5-d map of the phase scatter
     void* out;
     int64_t out_ld;           // NHWC pixel stride (mode 0)
     int out_mode;             // 0: bf16 NHWC (TF32 mode: fp32 NHWC, or fp16 NHWC with out_f16), 1: fp32 NCHW
@@ -1196,10 +1198,15 @@ __global__ void __launch_bounds__(HALO ? THREADS_HALO : THREADS, 1)
                         if (lane == 0) {
                             const int cblk = col_base + (c0 & ~63);
                             if (cblk < p.c_out) {
-                                if (HALO && p.phases > 1)  // (channel + dx * ld, w, dy, h, n) of the full-resolution tensor
+                                if (HALO && p.phases > 1) {  // (channel + dx * ld, w, dy, h, n) of the full-resolution tensor
                                     tc::tma_store_5d(&tmap_out, stage, cblk + (phase & 1) * (int)p.out_ld, w0, phase >> 1, sh, sn);
-                                else
+                                } else if (p.out_up) {  // nn.Upsample(2, nearest) of the output: the same map, all four positions
+#pragma unroll
+                                    for (int ph = 0; ph < 4; ++ph)
+                                        tc::tma_store_5d(&tmap_out, stage, cblk + (ph & 1) * (int)p.out_ld, w0, ph >> 1, sh, sn);
+                                } else {
                                     tc::tma_store_4d(&tmap_out, stage, cblk, w0, sh, sn);
+                                }
                             }
                             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
@@ -1682,6 +1689,7 @@ struct ConvExtra {
     void* workspace = nullptr;   // split-K scratch: flags (zero between launches) + fp32 partial tiles
     int64_t workspace_bytes = 0;
     int res_up = 0;              // residual given at half resolution (nearest 2x upsampling on the fly)
+    int out_up = 0;              // output written through a nearest 2x upsampling: `out` is (n, 2 h, 2 w, ld)
     int in_up = 0;               // act given at half resolution: the convolution reads its nearest 2x upsampling (halo + in_coef)
     const float* in_coef = nullptr;  // [N][c_in] {a, b}: the input is act(a x + b), applied on the fly (halo kernels only)
     int in_silu = 0;
@@ -1854,6 +1862,7 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     p.res_ld = res_ld;
     if (ex.res_up && (!residual || (h & 1) || (w & 1) || out_mode != 0 || splits > 1)) return AZB_E_SHAPE;
     p.res_up = ex.res_up;
+    p.out_up = ex.out_up;
     p.out = out, p.out_ld = out_ld, p.out_mode = out_mode;
     p.colsum = reinterpret_cast<float2*>(colsum);
     p.stat_gran = stat_gran;
@@ -1939,6 +1948,9 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
     // A halo kernel needs a wide tile unless it is this epilogue's 64-column instantiation.
     const bool rowepi = rowepi_ok && splits == 1 && block_n >= 64 && !(block_n == 64 && ex.gn_acc);
     if (ex.rowstat && !rowepi) return AZB_E_UNSUPPORTED;  // the per-pixel sums come from the row-domain epilogue only
+    if (ex.out_up < 0 || ex.out_up > 1) return AZB_E_SHAPE;
+    if (ex.out_up && (out_mode != 0 || c_out % 64 || out_ld % 8 || phases != 1 || ex.rowstat || ex.gn_acc)) return AZB_E_SHAPE;
+    if (ex.out_up && (!rowepi || block_n < 128 || p.BW * p.BH < 32)) return AZB_E_UNSUPPORTED;
     if (halo && (ex.act != AZB_ACT_NONE || ex.gate) && !rowepi) return AZB_E_UNSUPPORTED;  // (unreachable: wide halo tiles)
     if (ex.choice) {
         ex.choice->halo = halo, ex.choice->pair = pair, ex.choice->lean = lean || rowepi, ex.choice->block_n = block_n, ex.choice->splits = splits;
@@ -1952,7 +1964,7 @@ int conv_impl(const void* act, int64_t n, int64_t h_in, int64_t w_in, int64_t c_
         const int imgs = p.BW * p.BH >= 32 ? 1 : 32 / (p.BW * p.BH);
         CUtensorMap tout;
         int rc;
-        if (phases > 1) {
+        if (phases > 1 || ex.out_up) {
             // full-resolution output (n, 2 H, 2 W, ld) seen as (channel + dx * ld, w, dy, h, n): one map serves all phases
             const uint64_t W2 = 2 * (uint64_t)w, H2 = 2 * (uint64_t)h;
             uint64_t dims[5] = {(uint64_t)out_ld + (uint64_t)c_out, (uint64_t)w, 2, (uint64_t)h, (uint64_t)n};
@@ -2189,7 +2201,7 @@ extern "C" int azb_conv_bf16(const AzbConv* d, void* stream) {
     ex.in_coef = d->in_coef, ex.in_silu = d->in_silu;
     ex.res_up = d->res_up, ex.in_up = d->in_up;
     ex.in_norm = d->in_norm, ex.in_eps = d->in_eps, ex.in_rowstat = d->in_rowstat, ex.in_mod = d->in_mod, ex.in_mod_ld = d->in_mod_ld;
-    ex.rowstat = d->rowstat;
+    ex.rowstat = d->rowstat, ex.out_up = d->out_up;
     return conv_impl(d->act, d->n, d->h, d->w, d->c_in, d->act_ld, d->wpack, d->c_out, d->c_out_rows, d->taps, d->k_per_tap,
                      d->bias, d->residual, d->res_ld, d->out, d->out_ld, d->out_mode, d->colsum,
                      (d->colsum || d->gn_acc) ? d->stat_gran : 1, stream, ex);
@@ -2207,7 +2219,7 @@ extern "C" int azb_conv_choice(const AzbConv* d, AzbConvChoice* choice) {
     ex.in_coef = d->in_coef, ex.in_silu = d->in_silu;
     ex.res_up = d->res_up, ex.in_up = d->in_up;
     ex.in_norm = d->in_norm, ex.in_eps = d->in_eps, ex.in_rowstat = d->in_rowstat, ex.in_mod = d->in_mod, ex.in_mod_ld = d->in_mod_ld;
-    ex.rowstat = d->rowstat;
+    ex.rowstat = d->rowstat, ex.out_up = d->out_up;
     ex.choice = choice;
     return conv_impl(d->act, d->n, d->h, d->w, d->c_in, d->act_ld, d->wpack, d->c_out, d->c_out_rows, d->taps, d->k_per_tap,
                      d->bias, d->residual, d->res_ld, d->out, d->out_ld, d->out_mode, d->colsum,

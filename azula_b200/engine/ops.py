@@ -34,7 +34,7 @@ class AzbConv(ctypes.Structure):
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
         ("in_coef", c_void_p), ("in_silu", c_int32), ("in_up", c_int32),
         ("in_norm", c_int32), ("in_eps", c_float), ("in_rowstat", c_void_p), ("in_mod", c_void_p), ("in_mod_ld", c_int64),
-        ("rowstat", c_void_p),
+        ("rowstat", c_void_p), ("out_up", c_int32), ("reserved_", c_int32),
     ]
 
 
@@ -616,7 +616,7 @@ def conv_desc(x: Tensor, pc, out: Tensor, *, grid: tuple[int, int, int] | None =
               workspace: Tensor | None = None, in_coef: Tensor | None = None, in_silu: bool = False,
               res_up: bool = False, in_up: bool = False, in_norm: int = 0, in_eps: float = 1e-5,
               in_rowstat: Tensor | None = None, in_mod: int | None = None, in_mod_ld: int = 0,
-              rowstat: Tensor | None = None) -> AzbConv:
+              rowstat: Tensor | None = None, out_up: bool = False) -> AzbConv:
     r"""Fills an :class:`AzbConv` for ``azb_conv_bf16``; ``pc`` is a :class:`PackedConv` or, with ``x2``, a
     :class:`PackedConvSkip``.  ``gn_acc``: int64 (N, C_out / gran, 4) exact GroupNorm accumulators (zeroed by the
     caller).  ``in_coef``: fp32 (N, C_in, 2) from :func:`gn_coef` -- the convolution then reads
@@ -654,6 +654,7 @@ def conv_desc(x: Tensor, pc, out: Tensor, *, grid: tuple[int, int, int] | None =
         ho, wo = -(-h // stride), -(-w // stride)
         assert rowstat.dtype == torch.float32 and rowstat.is_contiguous() and rowstat.numel() == n * ho * wo * (pc.c_out // 64) * 2
         d.rowstat = rowstat.data_ptr()
+    d.out_up = int(out_up)  # `out` is (n, 2 h, 2 w, c): the result is stored through a nearest 2x upsampling
     return d
 
 

@@ -185,11 +185,24 @@ class Plan(LaunchPlan):
             if i + 1 < depth:
                 self._release(cur)
                 cur = self.cat[i]
-            for m in level:
+            skip_upsample = False
+            for k, m in enumerate(level):
                 if _is_block(m):
+                    # the last block of a level stores straight through the nn.Upsample that follows it (four TMA stores
+                    # of the staged tile instead of a pass over HBM) where the launcher can
+                    nxt = level[k + 1] if k + 1 < len(level) else None
+                    if FUSE_NORM and isinstance(nxt, nn.Upsample) and i > 0:
+                        out = self.cat[i - 1][..., widths[i - 1] :]
+                        if self._block(m, cur, out, out_up=True):
+                            skip_upsample = True
+                            self._release(cur)
+                            cur = out
+                            continue
                     out = arena.take(n, hi, wi, widths[i])
                     self._block(m, cur, out)
                 elif isinstance(m, nn.Upsample):
+                    if skip_upsample:
+                        continue
                     out = self.cat[i - 1][..., widths[i - 1] :]
                     self._upsample(cur, out)
                 elif i == 0 and m is level[-1]:
@@ -215,18 +228,22 @@ class Plan(LaunchPlan):
 
     def conv_stat(self, x: Tensor, pc, out: Tensor, *, stride: int = 1, act: int = 0, gate: int | None = None,
                   gate_ld: int = 0, gate_rows: int = 0, residual: Tensor | None = None, kind: str | None = None,
-                  norm: tuple | None = None) -> bool:
+                  norm: tuple | None = None, out_up: bool = False) -> bool:
         r"""Queues a convolution through the descriptor entry (``azb_conv_bf16``).  Where the launcher takes the row-domain
         epilogue, the per-(pixel, 64-channel block) sums of ``out`` are written too (``self.rowstat[id(out)]``) for a
         normalisation fused into the NEXT convolution; ``norm = (kind, eps, sums of x, address of [a | b], stride)`` asks
-        for that fusion here.  Returns False (nothing queued) when ``norm`` is given but the launcher cannot fuse it."""
+        for that fusion here; ``out_up``: ``out`` is the (n, 2h, 2w, c) destination of the ``nn.Upsample`` that follows, written
+        by the epilogue itself.  Returns False (nothing queued) when ``norm`` / ``out_up`` is asked for but the launcher cannot
+        do it."""
         n, h, w = x.shape[:3]
         ho, wo = -(-h // stride), -(-w // stride)
         kw = dict(stride=stride, act=act, gate=gate, gate_ld=gate_ld, gate_rows=gate_rows, residual=residual)
         if norm is not None:
             kw.update(in_norm=norm[0], in_eps=norm[1], in_rowstat=norm[2], in_mod=norm[3], in_mod_ld=norm[4])
+        if out_up:
+            kw.update(out_up=True)
         stat = None
-        if FUSE_NORM and pc.c_out % 64 == 0:
+        if FUSE_NORM and pc.c_out % 64 == 0 and not out_up:
             stat = torch.empty(n * ho * wo, pc.c_out // 64, 2, dtype=torch.float32, device=self.device)
         d, choice = None, None
         for st in ([stat, None] if stat is not None else [None]):
@@ -236,7 +253,7 @@ class Plan(LaunchPlan):
                 choice, stat = c, st
                 break
         if choice is None:
-            if norm is not None:
+            if norm is not None or out_up:
                 return False
             raise _lib.AzbError("azb_conv_choice rejected a convolution of the U-Net plan")
         if stat is not None:
@@ -248,17 +265,22 @@ class Plan(LaunchPlan):
         nbytes = 2.0 * (n * h * w * pc.c_in + pc.c_out * pc.taps * pc.c_in) + n * ho * wo * pc.c_out * 2.0 * (2 if residual is not None else 1)
         desc = f"{n}x{h}x{w} {pc.c_in}->{pc.c_out}" + (f" s{stride}" if stride > 1 else "") + (" norm+" if norm else "") + (
             " +act" if act else "") + (" +gate" if gate else "") + (" +res" if residual is not None else "") + (
-            " +sums" if stat is not None else "") + (" [halo]" if choice.halo else "")
+            " +sums" if stat is not None else "") + (" +up2" if out_up else "") + (" [halo]" if choice.halo else "")
         self._emit(kind or ("conv3x3" if pc.taps == 9 else "gemm"), flops, nbytes, self.lib.azb_conv_bf16, byref(d), desc=desc)
         return True
 
-    def _block(self, m, x: Tensor, out: Tensor) -> None:
-        r"""``UNetBlock._forward`` (``azula/nn/unet.py:97-107``)."""
+    def _block(self, m, x: Tensor, out: Tensor, out_up: bool = False) -> bool:
+        r"""``UNetBlock._forward`` (``azula/nn/unet.py:97-107``).  ``out_up``: ``out`` is the destination of the
+        ``nn.Upsample`` that follows the block; returns False (nothing queued) if the launcher cannot store through it."""
         arena, pk = self.arena, self.packed
         n, h, w, c = x.shape
         off = pk.bank.offset[id(m)]
         abc = self.abc.data_ptr() + 4 * off
         c1, c2 = pk.conv[id(m.ffn[0])], pk.conv[id(m.ffn[3])]
+        if out_up:  # ask the launcher first: nothing may be queued if the tail cannot store through the upsampling
+            probe = ops.conv_desc(x, c2, out, gate=abc + 4 * 2 * c, gate_ld=self.mod_ld, gate_rows=h * w, residual=x, out_up=True)
+            if self.lib.azb_conv_choice(byref(probe), byref(ops.AzbConvChoice())) != 0:
+                return False
         hbuf = arena.take(n, h, w, c1.c_out)
         fused = False
         stat = self.rowstat.get(id(x))
@@ -275,8 +297,10 @@ class Plan(LaunchPlan):
                 self.rownorm(x, y, _NORM_KIND[m.norm_kind], abc, self.mod_ld, h * w, eps=m.norm.eps)
             self.conv_stat(y, c1, hbuf, act=ops.ACT["silu"])
             arena.give(y)
-        self.conv_stat(hbuf, c2, out, gate=abc + 4 * 2 * c, gate_ld=self.mod_ld, gate_rows=h * w, residual=x)
+        ok = self.conv_stat(hbuf, c2, out, gate=abc + 4 * 2 * c, gate_ld=self.mod_ld, gate_rows=h * w, residual=x, out_up=out_up)
+        assert ok
         arena.give(hbuf)
+        return True
 
     def _group_norm(self, m, x: Tensor, y: Tensor, abc: int) -> None:
         from ctypes import byref, c_int64

@@ -278,6 +278,11 @@ typedef struct AzbConv {
      * epilogue also writes {sum, sum of squares} of the stored (bf16-rounded) values of every (pixel, 64-channel block) of
      * `out` to fp32 rowstat[pixels][c_out / 64][2]. */
     float* rowstat;
+    /* out_up = 1 (row-domain epilogue, N tile >= 128, c_out % 64 == 0; AZB_E_UNSUPPORTED otherwise): `out` is
+     * (n, 2 h, 2 w, c_out) with pixel stride out_ld and receives the nearest-neighbour 2x upsampling of the result -- the
+     * nn.Upsample that follows the last block of an ascent level (azula/nn/unet.py:186-190) without its own pass. */
+    int32_t out_up;
+    int32_t reserved_;
 } AzbConv;
 
 int azb_conv_bf16(const AzbConv* desc, void* stream);

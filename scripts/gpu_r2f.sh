@@ -20,3 +20,7 @@ for f in sorted(glob.glob('gpurun_out/bench_*${tag}*.json')):
     except Exception as e:
         print(f, 'ERR', e)
 PY
+# launch list of the bench command's timed region (ncu, cold-cache, serialised: shares, not absolute times)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 1600 --csv \
+  --log-file gpurun_out/launches_$tag.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager-gpu --profile-range \
+  > gpurun_out/ncu_bench_$tag.log 2>&1; echo "ncu launch list rc=$?"
