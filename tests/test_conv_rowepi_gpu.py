@@ -174,3 +174,29 @@ def test_rowepi_residual_through_upsampling_and_phase_scatter():
     assert torch.equal(a, o)
     up = t.float().repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
     _check(a, _ref(x2, wt2, b2, up), "res_up")
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 256, 256, 3), (3, 32, 32, 128, 128, 3), (2, 16, 24, 128, 256, 1)])
+def test_output_stored_through_nearest_upsampling(shape):
+    """AzbConv.out_up: the row-domain epilogue stores every staged block four times, to (2 h + dy, 2 w + dx) of a channel
+    slice of a wider (n, 2 h, 2 w, .) buffer -- the nn.Upsample(2, nearest) after the last block of an ascent level of the
+    in-repo U-Net (azula/nn/unet.py:186-190) without its own pass; gate + residual epilogue as in that block."""
+    from ctypes import byref
+
+    from azula_b200 import _lib
+
+    n, h, w, ci, co, k = shape
+    x, wt, b = _mk(n, h, w, ci, co, k, seed=51)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    gate = torch.randn(n, co, device=DEV, generator=g)
+    res = torch.randn(n, h, w, co, device=DEV, generator=g).to(torch.bfloat16)
+    pc = ops.pack_conv(wt.float(), b)
+    wide = torch.full((n, 2 * h, 2 * w, co + 64), 7.0, device=DEV, dtype=torch.bfloat16)
+    d = ops.conv_desc(x, pc, wide[..., :co], gate=gate.data_ptr(), gate_ld=gate.stride(0), gate_rows=h * w, residual=res, out_up=True)
+    ch = ops.conv_choice(d)
+    assert ch.epi == 2 and ch.block_n >= 128
+    _lib.check(_lib.lib().azb_conv_bf16(byref(d), _lib.stream_ptr(torch.device(DEV))), "azb_conv_bf16")
+    plain = ops.conv2d(x, pc, gate=gate, residual=res)
+    up = plain.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    assert torch.equal(wide[..., :co], up), (wide[..., :co].float() - up.float()).abs().max().item()
+    assert (wide[..., co:] == 7.0).all()
