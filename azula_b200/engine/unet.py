@@ -12,7 +12,8 @@ plan over NHWC bf16 buffers:
                                        where the producer has no row-domain epilogue or the channels are not whole 64-blocks)
                 azb_conv_bf16          out = x + c * (conv3x3(h) + bias)           (epilogue gate + residual + per-pixel sums)
     down        azb_conv2d_bf16 stride 2 (TMA element strides: no im2col, no gather pass)
-    up          azb_gn_apply_bf16 mode 1 (nearest x2) writing straight into the concatenation buffer
+    up          the last block of an ascent level stores through the upsampling (AzbConv.out_up: four TMA stores of every staged
+                tile straight into the concatenation buffer); azb_gn_apply_bf16 mode 1 (nearest x2) where the launcher cannot
     (a, b, c)   all blocks' Ada-Norm-Zero MLPs in two fp32 launches (:class:`ModulationBank`)
 
 ``torch.cat((skip, x), dim=1)`` (``:257``) costs nothing: the last module of descent level *i* and the
