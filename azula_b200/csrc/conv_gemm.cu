@@ -51,6 +51,20 @@
 //   in_up = 2    phase decomposition: four 2 x 2 convolutions of the half-resolution tensor with pre-summed taps, each
 //                (M tile, N tile, phase) a tile of this kernel (conv_impl)
 // and the skip branch up(x) is read by the epilogue at pixel (h / 2, w / 2) (res_up).
+//
+// Short-reduction layers (the in-repo U-Net's 3 x 3 layers, K = 576 .. 2304 with 1 - 7 tiles per CTA; token GEMMs with
+// K = 768): a tile lasts about a microsecond, nothing hides behind the main loop, and the kernel has these extras:
+//   NORM         (template) the transform warps apply the per-pixel LayerNorm / RMSNorm + modulation that opens a UNetBlock
+//                (in_norm): statistics from the per-pixel sums the PRODUCER's row-domain epilogue wrote (rowstat), requested a
+//                tile ahead, shared among the eight lanes of a row group, applied with packed bf16 multiply-adds
+//   64-column    halo tiles with the row-domain epilogue; the two warps of a TMEM lane quarter share a staging block (all
+//   tiles        eight epilogue warps busy), two staging blocks per pair; one channel block + one N tile: the nine weight
+//                tiles stay RESIDENT (requested before the programmatic-launch wait) and the 36 MMAs of a tile are issued as
+//                a straight line with compile-time descriptor offsets
+//   epilogue     bias / gate rows held one value per lane and broadcast with shuffles, the residual requested a chunk
+//                ahead, all of it before the accumulator wait (tiles of <= 128 columns); out_up: every staged block stored
+//                four times through the phase-scatter map (nn.Upsample after the block)
+// Timelines behind these choices: scripts/conv_timeline.py (-DAZB_TIMELINE), scripts/graph_trace.py (azb_debug_trace).
 
 #include "common.cuh"
 #include "tc.cuh"
