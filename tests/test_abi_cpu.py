@@ -57,3 +57,35 @@ def test_argument_errors_without_gpu(lib_path):
     assert rc == -1
     with pytest.raises(_lib.AzbError):
         _lib.check(rc, "azb_step_f32")
+
+
+def test_descriptor_structs_match_the_header(tmp_path):
+    """The ctypes mirrors of the plain-C descriptors (AzbConv, AzbConvChoice, AzbStep) have the size and the field
+    offsets the C compiler gives the structs of include/azb.h: a field added on one side only would shift every later
+    argument silently."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    from azula_b200 import _lib as L
+    from azula_b200.engine import ops
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {"AzbConv": ops.AzbConv, "AzbConvChoice": ops.AzbConvChoice, "AzbStep": L.AzbStep}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "azb.h")}"', "int main(void) {"]
+    for name, cls in structs.items():
+        lines.append(f'  printf("{name} %zu\\n", sizeof({name}));')
+        for field, *_ in cls._fields_:
+            lines.append(f'  printf("{name}.{field} %zu\\n", offsetof({name}, {field}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(out[name]) == ctypes.sizeof(cls), (name, out[name], ctypes.sizeof(cls))
+        for field, *_ in cls._fields_:
+            assert int(out[f"{name}.{field}"]) == getattr(cls, field).offset, (name, field)
